@@ -1,0 +1,653 @@
+// raymarch.cu -- ray/AABB intersection, occupancy-grid ray marching and alpha compositing for sm_100a.
+//
+// Replaces the reference's raymarching extension (raymarching/src/raymarching.cu) behind the C ABI in
+// include/pvd_b200.h.  Design differences (B200-first, not a translation):
+//   * march_rays_train is ONE occupancy march per ray (the reference marches every ray twice), a
+//     stash of the accepted (t, dt) pairs, a block-scan that hands out DETERMINISTIC sample offsets in
+//     ray-id order (the reference uses atomicAdd arrival order), and a warp-per-ray expansion that
+//     writes xyzs/dirs/deltas with lane-contiguous stores.
+//   * composite_rays_train fwd/bwd run one WARP per ray: the transmittance product and the running
+//     colour / depth sums are warp shuffle scans over 32 samples at a time instead of a serial loop
+//     per thread, so sample reads are coalesced across the warp.
+//   * every launch goes to the caller's stream and reports launch errors.
+#include "common.cuh"
+
+namespace pvd {
+
+// =============================================================================================
+// utilities
+// =============================================================================================
+
+// ray / axis-aligned box slab test (raymarching.cu:94-147)
+__device__ __forceinline__ void near_far_one(const float* __restrict__ o, const float* __restrict__ d,
+                                             const float* __restrict__ aabb, float min_near, float& near_out,
+                                             float& far_out) {
+    const float ox = o[0], oy = o[1], oz = o[2];
+    const float rdx = __fdiv_rn(1.0f, d[0]), rdy = __fdiv_rn(1.0f, d[1]), rdz = __fdiv_rn(1.0f, d[2]);
+    float near = __fmul_rn(aabb[0] - ox, rdx), far = __fmul_rn(aabb[3] - ox, rdx);
+    if (near > far) { float s = near; near = far; far = s; }
+    float near_y = __fmul_rn(aabb[1] - oy, rdy), far_y = __fmul_rn(aabb[4] - oy, rdy);
+    if (near_y > far_y) { float s = near_y; near_y = far_y; far_y = s; }
+    if (near > far_y || near_y > far) { near_out = far_out = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(aabb[2] - oz, rdz), far_z = __fmul_rn(aabb[5] - oz, rdz);
+    if (near_z > far_z) { float s = near_z; near_z = far_z; far_z = s; }
+    if (near > far_z || near_z > far) { near_out = far_out = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    near_out = near;
+    far_out = far;
+}
+
+__global__ void k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                           const float* __restrict__ aabb, uint32_t N, float min_near, float* __restrict__ nears,
+                           float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float a, b;
+    near_far_one(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, aabb, min_near, a, b);
+    nears[n] = a;
+    fars[n] = b;
+}
+
+// background-sphere polar coordinates (raymarching.cu:165-200)
+__global__ void k_polar(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                        uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* o = rays_o + 3 * (size_t)n;
+    const float* d = rays_d + 3 * (size_t)n;
+    const float ox = o[0], oy = o[1], oz = o[2], dx = d[0], dy = d[1], dz = d[2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float Cq = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * Cq)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    coords[2 * (size_t)n] = 2 * theta * kRPi - 1;
+    coords[2 * (size_t)n + 1] = phi * kRPi;
+}
+
+__global__ void k_morton3D(const int32_t* __restrict__ coords, uint32_t N, int32_t* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int32_t* c = coords + 3 * (size_t)n;
+    indices[n] = (int32_t)morton3((uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2]);
+}
+
+__global__ void k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N, int32_t* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int32_t ind = indices[n];  // signed shifts, as raymarching.cu:251-255
+    int32_t* c = coords + 3 * (size_t)n;
+    c[0] = (int32_t)compact3((uint32_t)(ind >> 0));
+    c[1] = (int32_t)compact3((uint32_t)(ind >> 1));
+    c[2] = (int32_t)compact3((uint32_t)(ind >> 2));
+}
+
+// 8 density cells -> one byte; two float4 loads per thread (raymarching.cu:270-291)
+__global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float4* g = reinterpret_cast<const float4*>(grid) + 2 * (size_t)n;
+    const float4 a = __ldg(g), b = __ldg(g + 1);
+    uint32_t bits = 0;
+    bits |= (a.x > thresh) ? 1u : 0u;
+    bits |= (a.y > thresh) ? 2u : 0u;
+    bits |= (a.z > thresh) ? 4u : 0u;
+    bits |= (a.w > thresh) ? 8u : 0u;
+    bits |= (b.x > thresh) ? 16u : 0u;
+    bits |= (b.y > thresh) ? 32u : 0u;
+    bits |= (b.z > thresh) ? 64u : 0u;
+    bits |= (b.w > thresh) ? 128u : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// =============================================================================================
+// training march: count+stash -> scan -> expand
+// =============================================================================================
+
+// Pass 1 (one thread per ray, one warp per CTA so the 128 warps of a 4096-ray batch land on 128 SMs):
+// walk the occupancy grid exactly as raymarching.cu:357-403 does and stash (t, dt) of every accepted
+// sample.  num_steps[n] and t0[n] (jittered start) go to the workspace.
+__global__ void __launch_bounds__(32) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                   const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                   uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                   const float* __restrict__ nears, const float* __restrict__ fars,
+                                                   uint32_t perturb, Pcg32 rng, int32_t* __restrict__ num_steps_out,
+                                                   float* __restrict__ t0_out, float2* __restrict__ stash) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    MarchCtx c;
+    march_ctx_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
+    const float far = fars[n];
+    float t0 = nears[n];
+    if (perturb) {  // raymarching.cu:351-354: the same jitter every call (seed 42, advance(n))
+        pcg32_advance(rng, (uint64_t)n);
+        t0 = __fmaf_rn(c.dt_min, pcg32_next_float(rng), t0);
+    }
+    float2* st = stash + (size_t)n * max_steps;
+    float t = t0;
+    uint32_t num_steps = 0;
+    while (t < far && num_steps < max_steps) {
+        float x, y, z, tt;
+        march_pos(c, t, x, y, z);
+        const float dt = march_dt(c, t);
+        if (march_probe(c, grid, t, dt, x, y, z, tt)) {
+            st[num_steps] = make_float2(t, dt);
+            ++num_steps;
+            t = __fadd_rn(t, dt);
+        } else {
+            do { t = __fadd_rn(t, march_dt(c, t)); } while (t < tt);
+        }
+    }
+    num_steps_out[n] = (int32_t)num_steps;
+    t0_out[n] = t0;
+}
+
+// Pass 2 (one CTA): exclusive prefix sum of num_steps in ray-id order; rays[n] = (n, offset, count);
+// counter[0] += total, counter[1] += N  (what the reference's two atomics accumulate, raymarching.cu:408-409).
+__global__ void __launch_bounds__(1024) k_march_scan(const int32_t* __restrict__ num_steps, uint32_t N,
+                                                    int32_t* __restrict__ rays, int32_t* __restrict__ counter) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < N; base += blockDim.x) {
+        const uint32_t n = base + threadIdx.x;
+        const int32_t v = (n < N) ? num_steps[n] : 0;
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += u;
+            }
+            warp_tot[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        const int32_t excl = carry + (wid ? warp_tot[wid - 1] : 0) + inc - v;
+        if (n < N) {
+            rays[3 * (size_t)n] = (int32_t)n;
+            rays[3 * (size_t)n + 1] = excl;
+            rays[3 * (size_t)n + 2] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counter[0] += carry_s;
+        counter[1] += (int32_t)N;
+    }
+}
+
+// Pass 3 (one warp per ray): expand the stash into xyzs / dirs / deltas (raymarching.cu:454-469).
+__global__ void __launch_bounds__(128) k_march_expand(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                     float bound, uint32_t max_steps, uint32_t N, uint32_t M,
+                                                     const int32_t* __restrict__ rays, const float* __restrict__ t0s,
+                                                     const float2* __restrict__ stash, float* __restrict__ xyzs,
+                                                     float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    if (cnt == 0 || offset + cnt >= M) return;  // dropped exactly as raymarching.cu:418-419
+    const float ox = rays_o[3 * (size_t)n], oy = rays_o[3 * (size_t)n + 1], oz = rays_o[3 * (size_t)n + 2];
+    const float dx = rays_d[3 * (size_t)n], dy = rays_d[3 * (size_t)n + 1], dz = rays_d[3 * (size_t)n + 2];
+    const float t0 = t0s[n];
+    const float2* st = stash + (size_t)n * max_steps;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        const float2 s = st[i];
+        float last_t = t0;
+        if (i > 0) {
+            const float2 p = st[i - 1];
+            last_t = __fadd_rn(p.x, p.y);
+        }
+        const float t_next = __fadd_rn(s.x, s.y);
+        const size_t row = (size_t)offset + i;
+        xyzs[3 * row + 0] = clampf(__fmaf_rn(s.x, dx, ox), -bound, bound);
+        xyzs[3 * row + 1] = clampf(__fmaf_rn(s.x, dy, oy), -bound, bound);
+        xyzs[3 * row + 2] = clampf(__fmaf_rn(s.x, dz, oz), -bound, bound);
+        dirs[3 * row + 0] = dx;
+        dirs[3 * row + 1] = dy;
+        dirs[3 * row + 2] = dz;
+        *reinterpret_cast<float2*>(deltas + 2 * row) = make_float2(s.y, __fadd_rn(t_next, -last_t));
+    }
+}
+
+// =============================================================================================
+// training composite: one warp per ray, shuffle scans
+// =============================================================================================
+
+struct Chunk {
+    float w, T_after, r, g, b, tsum;
+};
+
+// inclusive scans over the warp
+__device__ __forceinline__ float warp_scan_mul(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += u;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                      const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                                                      uint32_t M, uint32_t N, float* __restrict__ weights_sum,
+                                                      float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n];
+    const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    if (cnt == 0 || offset + cnt >= M) {  // raymarching.cu:525-532
+        if (lane == 0) {
+            weights_sum[index] = 0;
+            depth[index] = 0;
+            image[3 * (size_t)index] = 0;
+            image[3 * (size_t)index + 1] = 0;
+            image[3 * (size_t)index + 2] = 0;
+        }
+        return;
+    }
+    float T = 1.0f, tcarry = 0.0f;           // carried across 32-sample chunks
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        const bool ok = i < cnt;
+        const size_t row = (size_t)offset + (ok ? i : 0);
+        const float sigma = ok ? sigmas[row] : 0.0f;
+        const float2 dl = ok ? *reinterpret_cast<const float2*>(deltas + 2 * row) : make_float2(0.f, 0.f);
+        const float alpha = ok ? 1.0f - __expf(-sigma * dl.x) : 0.0f;  // raymarching.cu:546
+        const float om = 1.0f - alpha;
+        const float incl = warp_scan_mul(om, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Ti = T * excl;
+        const float w = alpha * Ti;
+        const float tin = tcarry + warp_scan_add(dl.y, lane);
+        if (ok) {
+            r += w * rgbs[3 * row];
+            g += w * rgbs[3 * row + 1];
+            b += w * rgbs[3 * row + 2];
+            d += w * tin;
+            ws += w;
+        }
+        T *= __shfl_sync(0xffffffffu, incl, 31);
+        tcarry = __shfl_sync(0xffffffffu, tin, 31);
+    }
+    r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[3 * (size_t)index] = r;
+        image[3 * (size_t)index + 1] = g;
+        image[3 * (size_t)index + 2] = b;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_img,
+                                                      const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                      const float* __restrict__ deltas, const int32_t* __restrict__ rays,
+                                                      const float* __restrict__ weights_sum, const float* __restrict__ image,
+                                                      uint32_t M, uint32_t N, float* __restrict__ grad_sigmas,
+                                                      float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n];
+    const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    if (cnt == 0 || offset + cnt >= M) return;  // raymarching.cu:629
+    const float gws = grad_ws[index];
+    const float gr = grad_img[3 * (size_t)index], gg = grad_img[3 * (size_t)index + 1], gb = grad_img[3 * (size_t)index + 2];
+    const float r_final = image[3 * (size_t)index], g_final = image[3 * (size_t)index + 1],
+                b_final = image[3 * (size_t)index + 2], ws_final = weights_sum[index];
+    float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;  // carries (running sums up to the previous chunk)
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        const bool ok = i < cnt;
+        const size_t row = (size_t)offset + (ok ? i : 0);
+        const float sigma = ok ? sigmas[row] : 0.0f;
+        const float d0 = ok ? deltas[2 * row] : 0.0f;
+        const float cr = ok ? rgbs[3 * row] : 0.f, cg = ok ? rgbs[3 * row + 1] : 0.f, cb = ok ? rgbs[3 * row + 2] : 0.f;
+        const float alpha = ok ? 1.0f - __expf(-sigma * d0) : 0.0f;
+        const float om = 1.0f - alpha;
+        const float incl = warp_scan_mul(om, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float w = alpha * (T * excl);
+        const float T_after = T * incl;  // T after `T *= 1 - alpha` (raymarching.cu:660)
+        const float r_run = rc + warp_scan_add(w * cr, lane);
+        const float g_run = gc + warp_scan_add(w * cg, lane);
+        const float b_run = bc + warp_scan_add(w * cb, lane);
+        const float w_run = wc + warp_scan_add(w, lane);
+        if (ok) {
+            grad_rgbs[3 * row] = gr * w;
+            grad_rgbs[3 * row + 1] = gg * w;
+            grad_rgbs[3 * row + 2] = gb * w;
+            grad_sigmas[row] = d0 * (gr * (T_after * cr - (r_final - r_run)) + gg * (T_after * cg - (g_final - g_run)) +
+                                     gb * (T_after * cb - (b_final - b_run)) + gws * (T_after - (ws_final - w_run)));
+        }
+        T *= __shfl_sync(0xffffffffu, incl, 31);
+        rc = __shfl_sync(0xffffffffu, r_run, 31);
+        gc = __shfl_sync(0xffffffffu, g_run, 31);
+        bc = __shfl_sync(0xffffffffu, b_run, 31);
+        wc = __shfl_sync(0xffffffffu, w_run, 31);
+    }
+}
+
+// =============================================================================================
+// inference kernels: one thread per alive ray, n_step <= 8 samples per call
+// =============================================================================================
+
+__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                             const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                             uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ nears,
+                             const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+                             float* __restrict__ deltas, uint32_t perturb, Pcg32 rng) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    float t = rays_t[n];
+    MarchCtx c;
+    march_ctx_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
+    const float far = fars[index];
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float* pl = deltas + (size_t)n * n_step * 2;
+    if (perturb) {  // raymarching.cu:749-752 (advance by the slot n, not the ray id)
+        pcg32_advance(rng, (uint64_t)n);
+        t = __fmaf_rn(c.dt_min, pcg32_next_float(rng), t);
+    }
+    float last_t = t;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        float x, y, z, tt;
+        march_pos(c, t, x, y, z);
+        const float dt = march_dt(c, t);
+        if (march_probe(c, grid, t, dt, x, y, z, tt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz;
+            t = __fadd_rn(t, dt);
+            pl[0] = dt;
+            pl[1] = __fadd_rn(t, -last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            ++step;
+        } else {
+            do { t = __fadd_rn(t, march_dt(c, t)); } while (t < tt);
+        }
+    }
+}
+
+__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                                 float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                                 const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                 float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    float t = rays_t[n];
+    const float* ps = sigmas + (size_t)n * n_step;
+    const float* pc = rgbs + (size_t)n * n_step * 3;
+    const float* pl = deltas + (size_t)n * n_step * 2;
+    float ws = weights_sum[index], d = depth[index];
+    float r = image[3 * (size_t)index], g = image[3 * (size_t)index + 1], b = image[3 * (size_t)index + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (pl[0] == 0) break;  // ray ran out of samples (raymarching.cu:862)
+        const float alpha = 1.0f - __expf(-ps[0] * pl[0]);
+        const float T = 1 - ws;
+        const float w = alpha * T;
+        ws += w;
+        t += pl[1];
+        d += w * t;
+        r += w * pc[0];
+        g += w * pc[1];
+        b += w * pc[2];
+        if (T < 1e-4f) break;  // early termination (raymarching.cu:886)
+        ps += 1; pc += 3; pl += 2;
+        ++step;
+    }
+    rays_t[n] = (step < n_step) ? -1.0f : t;
+    weights_sum[index] = ws;
+    depth[index] = d;
+    image[3 * (size_t)index] = r;
+    image[3 * (size_t)index + 1] = g;
+    image[3 * (size_t)index + 2] = b;
+}
+
+// stable compaction of the alive list by one CTA (ballot + popc scan)
+__global__ void __launch_bounds__(1024) k_compact_rays(uint32_t n_alive, int32_t* __restrict__ rays_alive,
+                                                      const int32_t* __restrict__ rays_alive_old,
+                                                      float* __restrict__ rays_t, const float* __restrict__ rays_t_old,
+                                                      int32_t* __restrict__ alive_counter) {
+    __shared__ int32_t warp_cnt[32];
+    __shared__ int32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = alive_counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < n_alive; base += blockDim.x) {
+        const uint32_t n = base + threadIdx.x;
+        const float told = (n < n_alive) ? rays_t_old[n] : -1.0f;
+        const bool keep = (n < n_alive) && (told >= 0);  // raymarching.cu:934
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(mask);
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_cnt[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += u;
+            }
+            warp_cnt[lane] = w;
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        if (keep) {
+            const int32_t pos = carry + (wid ? warp_cnt[wid - 1] : 0) + __popc(mask & ((1u << lane) - 1u));
+            rays_alive[pos] = rays_alive_old[n];
+            rays_t[pos] = told;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_cnt[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) alive_counter[0] = carry_s;
+}
+
+}  // namespace pvd
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace pvd;
+
+extern "C" {
+
+int pvd_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                           float* nears, float* fars, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(rays_o && rays_d && aabb && nears && fars);
+    k_near_far<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_polar_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                       void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(rays_o && rays_d && coords);
+    k_polar<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(coords && indices);
+    k_morton3D<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(coords && indices);
+    k_morton3D_invert<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(grid && bitfield);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15u) == 0);
+    k_packbits<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+uint64_t pvd_march_rays_train_workspace_words(uint32_t N, uint32_t max_steps) {
+    // num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
+    const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
+    return head + 2ull * (uint64_t)N * max_steps;
+}
+
+int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars,
+                               int32_t* rays, int32_t* counter, uint32_t perturb, int32_t* ws_i32, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && ws_i32);
+    PVD_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(ws_i32) & 7u) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* num_steps = ws_i32;
+    float* t0 = reinterpret_cast<float*>(ws_i32 + N);
+    const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
+    float2* stash = reinterpret_cast<float2*>(ws_i32 + head);
+    const Pcg32 rng = pcg32_seeded(42u);  // hard-coded seed, raymarching.cu:488
+    k_march_count<<<ceil_div(N, 32), 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                  perturb, rng, num_steps, t0, stash);
+    PVD_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, st>>>(num_steps, N, rays, counter);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_march_rays_train_write(const float* rays_o, const float* rays_d, float bound, uint32_t max_steps, uint32_t N,
+                               uint32_t M, const int32_t* rays, const int32_t* ws_i32, float* xyzs, float* dirs,
+                               float* deltas, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(rays_o && rays_d && rays && ws_i32 && xyzs && dirs && deltas);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(ws_i32) & 7u) == 0 && (reinterpret_cast<uintptr_t>(deltas) & 7u) == 0);
+    const float* t0 = reinterpret_cast<const float*>(ws_i32 + N);
+    const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
+    const float2* stash = reinterpret_cast<const float2*>(ws_i32 + head);
+    k_march_expand<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, bound, max_steps, N, M, rays, t0, stash,
+                                                                     xyzs, dirs, deltas);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                         const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                         uint32_t perturb, int32_t* ws_i32, void* stream) {
+    int rc = pvd_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays, counter,
+                                        perturb, ws_i32, stream);
+    if (rc != PVD_OK) return rc;
+    return pvd_march_rays_train_write(rays_o, rays_d, bound, max_steps, N, M, rays, ws_i32, xyzs, dirs, deltas, stream);
+}
+
+int pvd_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                     uint32_t M, uint32_t N, float* weights_sum, float* depth, float* image,
+                                     void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image);
+    k_composite_fwd<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, weights_sum,
+                                                                      depth, image);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                      const float* rgbs, const float* deltas, const int32_t* rays,
+                                      const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                      float* grad_sigmas, float* grad_rgbs, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image &&
+                grad_sigmas && grad_rgbs);
+    k_composite_bwd<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
+                                                                      rays, weights_sum, image, M, N, grad_sigmas,
+                                                                      grad_rgbs);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                   uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                   float* dirs, float* deltas, uint32_t perturb, void* stream) {
+    if (n_alive == 0) return PVD_OK;
+    PVD_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas);
+    PVD_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1 && n_step >= 1);
+    const Pcg32 rng = pcg32_seeded((uint64_t)perturb);  // raymarching.cu:816
+    k_march_rays<<<ceil_div(n_alive, 64), 64, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o,
+                                                                         rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                                         nears, fars, xyzs, dirs, deltas, perturb, rng);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_composite_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, float* rays_t, const float* sigmas,
+                       const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
+                       void* stream) {
+    if (n_alive == 0) return PVD_OK;
+    PVD_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image);
+    k_composite_rays<<<ceil_div(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, sigmas,
+                                                                               rgbs, deltas, weights_sum, depth, image);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_alive_old, float* rays_t,
+                     const float* rays_t_old, int32_t* alive_counter, void* stream) {
+    if (n_alive == 0) return PVD_OK;
+    PVD_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter);
+    k_compact_rays<<<1, 1024, 0, (cudaStream_t)stream>>>(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old,
+                                                         alive_counter);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1 @@
+from .grid import GridEncoder, grid_encode  # noqa: F401
