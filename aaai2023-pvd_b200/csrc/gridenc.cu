@@ -153,6 +153,16 @@ __global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict
     tab_store(grad_inputs, t, r);
 }
 
+// per-level (scale, resolution) exactly as every kernel of this library derives them
+__global__ void k_grid_level_table(const int32_t* __restrict__ offsets, uint32_t L, float S, uint32_t H, float* __restrict__ scales,
+                                   int32_t* __restrict__ resolutions) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const GridLevel g = grid_level(offsets, l, S, H);
+    scales[l] = g.scale;
+    resolutions[l] = (int32_t)g.resolution;
+}
+
 template <typename T, uint32_t D, uint32_t C>
 int launch_fwd(const float* inputs, const void* emb, const int32_t* offsets, void* out, uint32_t B, uint32_t L, float S,
                uint32_t H, bool cgi, void* dy_dx, uint32_t gridtype, bool ac, bool sm, cudaStream_t st) {
@@ -206,6 +216,15 @@ int dispatch_bwd(uint32_t C, const void* grad, const float* inputs, const int32_
 using namespace pvd;
 
 extern "C" {
+
+int pvd_grid_level_table(const int32_t* offsets, uint32_t L, float S, uint32_t H, float* scales, int32_t* resolutions,
+                         void* stream) {
+    if (L == 0) return PVD_OK;
+    PVD_REQUIRE(offsets && scales && resolutions);
+    k_grid_level_table<<<ceil_div(L, 32), 32, 0, (cudaStream_t)stream>>>(offsets, L, S, H, scales, resolutions);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
 
 int pvd_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs, uint32_t B,
                             uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, void* dy_dx,

@@ -1,0 +1,143 @@
+// tc5.cuh -- hand-written inline-PTX wrappers for the 5th-generation tensor core (tcgen05), TMEM and
+// mbarriers on sm_100a, plus the shared-memory "chunk" tile layout the fused field kernels use.
+//
+// Tile layout ("chunk layout").  A tile of R rows x K columns of 2-byte elements is stored as K/8 chunks;
+// chunk j holds columns 8j..8j+7 of all R rows, 16 bytes per row, rows contiguous:
+//
+//        byte offset of element (r, k) = (k / 8) * (R * 16) + r * 16 + (k % 8) * 2
+//
+// so a thread that owns one row (one sample) writes a chunk of its row with a single 16-byte store and a
+// warp writes 512 contiguous bytes (no bank conflicts).  The same bytes are a valid tcgen05 operand in
+// BOTH of the no-swizzle canonical forms:
+//   * K-major  (rows = M/N index, columns = K):  core matrix = 8 rows x 16 B, SBO = 128 B between 8-row
+//     groups, LBO = R*16 B between the two 8-column chunks of one K=16 instruction;
+//   * MN-major (columns = M/N index, rows = K):  SBO = R*16 B between 8-column groups, LBO = 128 B between
+//     8-row groups -- this is what the weight-gradient GEMMs (reduction over the 128 samples) use.
+// Descriptor bit layout: CUTLASS cute/arch/mma_sm100_desc.hpp (UMMA::SmemDescriptor / InstrDescriptor).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace tc5 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- descriptors
+// 64-bit shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for Blackwell
+    return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+// 32-bit instruction descriptor for kind::f16 with fp16 A/B and fp32 accumulate.
+// a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
+__host__ __device__ constexpr uint32_t instr_desc_f16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return (1u << 4)            // c_format = F32
+           | (0u << 7)          // a_format = F16
+           | (0u << 10)         // b_format = F16
+           | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- TMEM allocation (one full warp)
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---------------------------------------------------------------- fences
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Bounded wait: returns false if the phase did not complete within ~`spins` polls (a wrong descriptor must not hang
+// the GPU).  parity = phase bit to wait for.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t spins = (1u << 22)) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t i = 0; i < spins; ++i) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- MMA issue (one thread) + commit
+// D[tmem] (+)= A[smem] * B[smem]^T ; accumulate = 0 overwrites D.
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- TMEM -> registers
+// 32 lanes x 32-bit, 16 consecutive columns: thread i of warp w reads TMEM lane 32*(w%4)+i.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// TMEM address of (lane, column) relative to an allocation base
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t lane, uint32_t col) { return base + (lane << 16) + col; }
+
+// ---------------------------------------------------------------- chunk-layout helpers
+// byte offset of the 16-byte chunk holding columns 8j..8j+7 of row r in a tile with R rows
+__device__ __forceinline__ uint32_t chunk_off(uint32_t R, uint32_t r, uint32_t j) { return j * (R * 16u) + r * 16u; }
+
+// pack 8 floats into 8 halves (one 16-byte chunk)
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c);
+    u.w = *reinterpret_cast<uint32_t*>(&d);
+    return u;
+}
+
+// K-major operand descriptor for a chunk tile of R rows starting at column k0 (multiple of 16... of 8)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, uint32_t R, uint32_t k0) {
+    return smem_desc(tile_saddr + (k0 >> 3) * (R * 16u), /*LBO*/ R * 16u, /*SBO*/ 128u);
+}
+// MN-major operand descriptor for a chunk tile of R rows (rows are the reduction index), reduction rows r0.., MN columns c0..
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, uint32_t R, uint32_t r0, uint32_t c0) {
+    return smem_desc(tile_saddr + (c0 >> 3) * (R * 16u) + r0 * 16u, /*LBO*/ 128u, /*SBO*/ R * 16u);
+}
+
+}  // namespace tc5

