@@ -174,7 +174,7 @@ def test_morton_packbits_exact(scene):
     assert np.array_equal(bits2.cpu().numpy(), scene["bitfield"])
 
 
-@pytest.mark.parametrize("L,desired", [(14, 2048), (16, 4096)])
+@pytest.mark.parametrize("L,desired", [(14, 2048), (16, 2048)])
 def test_grid_encode_fp32(ref_ext, L, desired):
     from gridencoder import GridEncoder, grid_encode
     from oracle import cpu, ref_glue
