@@ -1,0 +1,705 @@
+// field_hash.cu -- fused "hash" field query for sm_100a: multiresolution hash-grid encode + degree-4 SH +
+// sigma_net (2L->64->16) + color_net (31->64->64->3), forward and backward, one kernel per direction.
+//
+// Replaces, for model_type "hash", the chain of ~15 launches per direction that the reference issues from
+// NeRFNetwork.forward (distill_mutual/network.py:335-437): GridEncoder kernel + permute, 5 cuBLAS GEMMs with
+// ReLU/clamp/exp/sigmoid/cat kernels between them, the SH kernel, and their autograd mirrors.
+//
+// Work decomposition: one CTA = 128 threads = one tile of 128 consecutive samples; thread t owns sample row t.
+//   * gather phase: each thread interpolates its sample's 2L features from the (L2-resident) table with
+//     8-byte/4-byte vector loads, 32 independent gathers in flight per thread;
+//   * MLP phase: activations live in shared memory as fp16 "chunk" tiles (tc5.cuh) that are simultaneously valid
+//     K-major and MN-major tcgen05 operands; every layer is 2-4 tcgen05.mma instructions (M = 128 samples) issued by
+//     one thread, accumulating in TMEM; each thread then pulls ITS OWN row back with tcgen05.ld (32x32b: TMEM lane ==
+//     sample row), applies ReLU / clamp / exp / sigmoid in registers and writes the next operand tile;
+//   * backward: forward recomputed from the saved fp16 encoding, then per layer one weight-gradient GEMM
+//     (reduction over the 128 samples, both operands MN-major views of the SAME tiles, fp32 accumulators persistent
+//     in TMEM across all tiles a CTA processes) and one data-gradient GEMM (weights as MN-major operand, so no
+//     transposed weight copy exists); the encoding gradient is scattered with red.global.add.v2.f32.
+// CTAs are persistent (grid = min(#tiles, 2 x #SMs)) so weights are staged and TMEM is allocated once per CTA and
+// weight gradients leave the SM once.
+#include "gridenc.cuh"
+#include "shenc.cuh"
+#include "tc5.cuh"
+#include "../../include/pvd_b200_fused.h"
+
+namespace pvd {
+
+constexpr uint32_t kTile = 128;
+// byte offsets of the weight operand tiles inside the packed blob / shared memory
+constexpr uint32_t kWB1 = 0;      // sigma_net.0 : 64 rows (out) x 32 cols (in, 2L zero padded)
+constexpr uint32_t kWB2 = 4096;   // sigma_net.1 : 16 x 64
+constexpr uint32_t kWB3 = 6144;   // color_net.0 : 64 x 32 (in = 16 SH + 15 geo + 1 pad)
+constexpr uint32_t kWB4 = 10240;  // color_net.1 : 64 x 64
+constexpr uint32_t kWB5 = 18432;  // color_net.2 : 16 (3 + pad) x 64
+static_assert(kWB5 + 2048 == PVD_FIELD_WBLOB_BYTES, "blob size");
+
+// TMEM columns
+constexpr uint32_t kD = 0;      // [0,64)   layer output / data-gradient accumulator
+constexpr uint32_t kD16 = 64;   // [64,80)  sigma_net.1 output
+constexpr uint32_t kD5 = 80;    // [80,96)  color_net.2 output
+constexpr uint32_t kAW5 = 96;   // [96,112)   dW5^T  [64 in ][16 out]
+constexpr uint32_t kAW4 = 112;  // [112,176)  dW4    [64 out][64 in ]
+constexpr uint32_t kAW3 = 176;  // [176,208)  dW3    [64 out][32 in ]
+constexpr uint32_t kAW2 = 208;  // [208,224)  dW2^T  [64 in ][16 out]
+constexpr uint32_t kAW1 = 224;  // [224,256)  dW1    [64 out][32 in ]
+
+// layout of the weight-gradient workspace (floats), the kernel-native accumulator shapes
+constexpr uint32_t kGW1 = 0;                  // [64][32]
+constexpr uint32_t kGW2 = kGW1 + 64 * 32;     // [64][16]  (transposed: [in][out])
+constexpr uint32_t kGW3 = kGW2 + 64 * 16;     // [64][32]
+constexpr uint32_t kGW4 = kGW3 + 64 * 32;     // [64][64]
+constexpr uint32_t kGW5 = kGW4 + 64 * 64;     // [64][16]  (transposed: [in][out])
+constexpr uint32_t kGWTotal = kGW5 + 64 * 16; // 10240
+static_assert(kGWTotal == PVD_FIELD_GW_FLOATS, "workspace size");
+
+struct LevelInfo {
+    float scale;
+    uint32_t res1;    // resolution + 1 (dense stride)
+    uint32_t offset;  // first entry
+    uint32_t size;    // entries
+    uint32_t mode;    // 0 dense (index < size, no modulo), 1 hashed with power-of-two size, 2 generic
+    uint32_t mask;
+};
+
+__device__ __forceinline__ void level_info_init(LevelInfo* lv, const int32_t* offsets, uint32_t L, float S, uint32_t H) {
+    const uint32_t l = threadIdx.x;
+    if (l < L) {
+        const GridLevel g = grid_level(offsets, l, S, H);
+        LevelInfo v;
+        v.scale = g.scale;
+        v.res1 = g.resolution + 1;
+        v.offset = g.offset;
+        v.size = g.size;
+        v.mask = g.size - 1;
+        const uint64_t dense = (uint64_t)v.res1 * v.res1 * v.res1;
+        // gridencoder.cu:54-72: the running stride exceeds the level size exactly when the dense grid does not fit
+        const bool fits = ((uint64_t)v.res1 <= g.size) && ((uint64_t)v.res1 * v.res1 <= g.size) && (dense <= g.size);
+        v.mode = fits ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
+        lv[l] = v;
+    }
+}
+
+// one sample's corner set at one level: 8 entry indices (in entries) and weights, reference order (bit d of idx = upper
+// vertex along d, weight = ((wx)*wy)*wz)
+struct Corners {
+    uint32_t idx[8];
+    float w[8];
+};
+
+__device__ __forceinline__ void level_corners(const LevelInfo& lv, const float (&x01)[3], Corners& c) {
+    uint32_t cell[3];
+    float frac[3];
+    grid_locate<3>(x01, lv.scale, false, cell, frac);
+    const float wx[2] = {1.0f - frac[0], frac[0]}, wy[2] = {1.0f - frac[1], frac[1]}, wz[2] = {1.0f - frac[2], frac[2]};
+    if (lv.mode == 0) {
+        const uint32_t s1 = lv.res1, s2 = lv.res1 * lv.res1;
+        const uint32_t ix[2] = {cell[0], cell[0] + 1}, iy[2] = {cell[1] * s1, cell[1] * s1 + s1},
+                       iz[2] = {cell[2] * s2, cell[2] * s2 + s2};
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) c.idx[i] = ix[i & 1] + iy[(i >> 1) & 1] + iz[(i >> 2) & 1];
+    } else if (lv.mode == 1) {
+        const uint32_t hx[2] = {cell[0], cell[0] + 1}, hy[2] = {cell[1] * 2654435761u, (cell[1] + 1) * 2654435761u},
+                       hz[2] = {cell[2] * 805459861u, (cell[2] + 1) * 805459861u};
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) c.idx[i] = (hx[i & 1] ^ hy[(i >> 1) & 1] ^ hz[(i >> 2) & 1]) & lv.mask;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t v[3] = {cell[0] + (i & 1), cell[1] + ((i >> 1) & 1), cell[2] + ((i >> 2) & 1)};
+            c.idx[i] = grid_index<3>(0u, false, lv.size, lv.res1 - 1, v);
+        }
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) c.w[i] = __fmul_rn(__fmul_rn(wx[i & 1], wy[(i >> 1) & 1]), wz[(i >> 2) & 1]);
+}
+
+// map world position to the encoder's [0,1] range: (x + bound) / (2*bound)   (gridencoder/grid.py:211)
+__device__ __forceinline__ void to_unit(const float* __restrict__ p, float bound, float (&x01)[3], bool& oob) {
+    const float two_b = 2.0f * bound;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x01[d] = __fdiv_rn(__fadd_rn(p[d], bound), two_b);
+    oob = grid_oob<3>(x01);
+}
+
+// interpolate 8 consecutive features (4 levels) of one sample
+template <typename T>
+__device__ __forceinline__ void encode4(const T* __restrict__ table, const LevelInfo* lv, uint32_t l0, uint32_t L,
+                                        const float (&x01)[3], bool oob, float (&f)[8]) {
+#pragma unroll
+    for (uint32_t q = 0; q < 4; ++q) {
+        const uint32_t l = l0 + q;
+        float a0 = 0.0f, a1 = 0.0f;
+        if (l < L && !oob) {
+            const LevelInfo v = lv[l];
+            Corners c;
+            level_corners(v, x01, c);
+            const T* tab = table + (size_t)v.offset * 2;
+            float2 fv[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) fv[i] = tab_load2(tab, (size_t)c.idx[i] * 2);
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+                a0 = __fmaf_rn(c.w[i], fv[i].x, a0);
+                a1 = __fmaf_rn(c.w[i], fv[i].y, a1);
+            }
+        }
+        f[2 * q] = a0;
+        f[2 * q + 1] = a1;
+    }
+}
+
+struct Pipe {
+    uint64_t* bar;
+    uint32_t phase;
+    uint32_t tmem;
+    int32_t* status;
+};
+
+// Every thread: publish shared-memory operand writes to the async proxy and order prior TMEM reads, then barrier.
+__device__ __forceinline__ void operands_ready() {
+    tc5::fence_async_smem();
+    tc5::fence_before_sync();
+    __syncthreads();
+}
+// Every thread: wait for the MMAs committed by thread 0.
+__device__ __forceinline__ void mma_wait(Pipe& p) {
+    if (!tc5::mbar_wait(p.bar, p.phase)) atomicExch(p.status, 1);
+    p.phase ^= 1u;
+    tc5::fence_after_sync();
+}
+
+// D[128 x N] (=|+=) A[128 x K] * B[N x K]^T, both K-major chunk tiles (forward layer)
+__device__ __forceinline__ void issue_fwd(uint32_t d_tmem, uint32_t a_tile, uint32_t K, uint32_t b_tile, uint32_t b_rows, uint32_t N) {
+    const uint32_t idesc = tc5::instr_desc_f16(128, N, 0, 0);
+    for (uint32_t k0 = 0; k0 < K; k0 += 16)
+        tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, b_rows, k0), idesc, k0 > 0);
+}
+// D[128 x N] = G[128 x K] * W[K x N] with W stored as the forward operand tile [K rows(out) x N cols(in)] (data gradient)
+__device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, uint32_t g_tile, uint32_t K, uint32_t w_tile, uint32_t w_rows, uint32_t N) {
+    const uint32_t idesc = tc5::instr_desc_f16(128, N, 0, 1);
+    for (uint32_t k0 = 0; k0 < K; k0 += 16)
+        tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(g_tile, kTile, k0), tc5::desc_mnmajor(w_tile, w_rows, k0, 0), idesc, k0 > 0);
+}
+// D[64 x N] (+)= P[128 x 64]^T * Q[128 x N]  (weight gradient: reduction over the 128 samples of the tile)
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_tile, uint32_t q_tile, uint32_t N, bool first) {
+    const uint32_t idesc = tc5::instr_desc_f16(64, N, 1, 1);
+    for (uint32_t s0 = 0; s0 < kTile; s0 += 16)
+        tc5::mma_f16_ss(d_tmem, tc5::desc_mnmajor(p_tile, kTile, s0, 0), tc5::desc_mnmajor(q_tile, kTile, s0, 0), idesc,
+                        !(first && s0 == 0));
+}
+
+// this thread's row of a [128 x 16*NC16] TMEM accumulator -> ReLU -> fp16 chunk tile
+template <int NC16>
+__device__ __forceinline__ void relu_to_tile(uint32_t tmem_row, uint8_t* tile, uint32_t row) {
+#pragma unroll
+    for (int c = 0; c < NC16; ++c) {
+        float v[16];
+        tc5::tmem_ld16(tmem_row + 16 * c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        *reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c)) = tc5::pack8(v);
+        *reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c + 1)) = tc5::pack8(v + 8);
+    }
+}
+
+// this thread's row of a 64-wide data gradient, masked by the sign of the saved activation, written IN PLACE over it
+__device__ __forceinline__ void mask_grad_in_place(uint32_t tmem_row, uint8_t* tile, uint32_t row) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tc5::tmem_ld16(tmem_row + 16 * c, v);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint4* p = reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c + h));
+            const uint4 a = *p;
+            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+            float g[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 af = __half22float2(ah[i]);
+                g[2 * i] = af.x > 0.0f ? v[8 * h + 2 * i] : 0.0f;
+                g[2 * i + 1] = af.y > 0.0f ? v[8 * h + 2 * i + 1] : 0.0f;
+            }
+            *p = tc5::pack8(g);
+        }
+    }
+}
+
+struct FieldArgs {
+    const void* table;
+    const int32_t* offsets;
+    const uint8_t* wblob;
+    uint32_t L, H;
+    float S, bound, clip_min, clip_max, density_scale;
+};
+
+struct FwdRegs {  // what the backward needs from the recomputed forward of this thread's sample
+    float o0_raw, o0c, rgb[3];
+};
+
+// Layers 1..5 for one tile.  X tile must already hold the encoding.  Tiles: X, H1, CIN, H3, H4 (H3/H4 may alias X-independent
+// buffers in the forward-only kernel).  Returns sigma (scaled) and rgb for this thread's row.
+__device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t* smw, uint8_t* X, uint8_t* H1, uint8_t* CIN,
+                                            uint8_t* H3, uint8_t* H4, const float* __restrict__ dir, uint32_t row, float& sigma,
+                                            float (&o16)[16], FwdRegs& r) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane_base = (tid >> 5) * 32;
+    const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
+    const uint32_t sw = tc5::smem_u32(smw);
+    // ---- sigma_net.0 : [128 x 32] x [64 x 32]^T
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kD, tc5::smem_u32(X), 32, sw + kWB1, 64, 64);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    relu_to_tile<4>(trow + kD, H1, row);
+    // ---- sigma_net.1 : [128 x 64] x [16 x 64]^T
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kD16, tc5::smem_u32(H1), 64, sw + kWB2, 16, 16);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    tc5::tmem_ld16(trow + kD16, o16);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o16[i] = __half2float(__float2half_rn(o16[i]));  // the reference's fp16 activations
+    r.o0_raw = o16[0];
+    r.o0c = clampf(o16[0], a.clip_min, a.clip_max);  // network.py:418-420
+    o16[0] = r.o0c;
+    sigma = a.density_scale * __expf(r.o0c);          // trunc_exp forward (tools/activation.py:9-12), renderer.py:440
+    {
+        float sh[16];
+        sh_basis4(dir[0], dir[1], dir[2], sh);
+        float geo[16];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) geo[i] = o16[i + 1];
+        geo[15] = 0.0f;
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 0)) = tc5::pack8(sh);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 1)) = tc5::pack8(sh + 8);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 2)) = tc5::pack8(geo);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 3)) = tc5::pack8(geo + 8);
+    }
+    // ---- color_net.0 : [128 x 32] x [64 x 32]^T
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kD, tc5::smem_u32(CIN), 32, sw + kWB3, 64, 64);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    relu_to_tile<4>(trow + kD, H3, row);
+    // ---- color_net.1 : [128 x 64] x [64 x 64]^T
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kD, tc5::smem_u32(H3), 64, sw + kWB4, 64, 64);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    relu_to_tile<4>(trow + kD, H4, row);
+    // ---- color_net.2 : [128 x 64] x [16 x 64]^T , sigmoid
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kD5, tc5::smem_u32(H4), 64, sw + kWB5, 16, 16);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    float c16[16];
+    tc5::tmem_ld16(trow + kD5, c16);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.rgb[i] = 1.0f / (1.0f + __expf(-c16[i]));
+}
+
+__device__ __forceinline__ void stage_weights(uint8_t* smw, const uint8_t* __restrict__ blob) {
+    for (uint32_t i = threadIdx.x; i < PVD_FIELD_WBLOB_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smw)[i] = __ldg(reinterpret_cast<const uint4*>(blob) + i);
+}
+
+// =============================================================================================== forward kernel
+template <typename T>
+__global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                        uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
+                                                        __half* __restrict__ enc, float* __restrict__ feat16, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ LevelInfo lv[16];
+    uint8_t* smw = smem;                               // 20480
+    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;         // 8192
+    uint8_t* CIN = X + 8192;                           // 8192
+    uint8_t* HA = CIN + 8192;                          // 16384
+    uint8_t* HB = HA + 16384;                          // 16384
+    const uint32_t tid = threadIdx.x;
+
+    stage_weights(smw, a.wblob);
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_fence_init();
+    }
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    const T* table = reinterpret_cast<const T*>(a.table);
+
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTile + tid;
+        const bool live = row < M;
+        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+            }
+        }
+        float x01[3];
+        bool oob;
+        to_unit(pos, a.bound, x01, oob);
+#pragma unroll 1
+        for (uint32_t j = 0; j < 4; ++j) {
+            float f[8];
+            encode4<T>(table, lv, 4 * j, a.L, x01, oob, f);
+            const uint4 u = tc5::pack8(f);
+            *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
+            if (enc && live) *reinterpret_cast<uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = u;
+        }
+        float sigma, o16[16];
+        FwdRegs r;
+        mlp_forward(p, a, smw, X, HA, CIN, HB, HA, dir, tid, sigma, o16, r);
+        if (live) {
+            sigmas[row] = sigma;
+            rgbs[3 * (size_t)row] = r.rgb[0];
+            rgbs[3 * (size_t)row + 1] = r.rgb[1];
+            rgbs[3 * (size_t)row + 2] = r.rgb[2];
+            if (feat16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(feat16 + 16 * (size_t)row + 4 * q) =
+                        make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 128);
+}
+
+// =============================================================================================== backward kernel
+__device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint32_t ncols, float* __restrict__ dst) {
+    // M = 64 accumulator: row m lives in TMEM lane (m/16)*32 + m%16 (verified on B200, profiles/r01_tcgen05_probe.log)
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t m = warp * 16 + lane;
+    for (uint32_t c = 0; c < ncols; c += 16) {
+        float v[16];
+        tc5::tmem_ld16(tc5::tmem_addr(tmem_base, warp * 32, col + c), v);
+        if (lane < 16) {
+            float* d = dst + (size_t)m * ncols + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                             "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                             : "memory");
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                        const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
+                                                        const float* __restrict__ grad_rgbs, uint32_t M,
+                                                        const int32_t* __restrict__ n_valid_p, float* __restrict__ grad_table,
+                                                        float* __restrict__ gw, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ LevelInfo lv[16];
+    uint8_t* smw = smem;                        // 20480
+    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;  // 8192
+    uint8_t* CIN = X + 8192;                    // 8192
+    uint8_t* H1 = CIN + 8192;                   // 16384
+    uint8_t* H3 = H1 + 16384;                   // 16384
+    uint8_t* H4 = H3 + 16384;                   // 16384
+    uint8_t* G16 = H4 + 16384;                  // 4096
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane_base = (tid >> 5) * 32;
+
+    stage_weights(smw, a.wblob);
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_fence_init();
+    }
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
+    const uint32_t sw = tc5::smem_u32(smw);
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+
+    const uint32_t n_tiles = (n_valid + kTile - 1) / kTile;  // tiles made only of padding rows contribute nothing
+    bool first = true;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTile + tid;
+        const bool live = row < n_valid;
+        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+        float gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
+            }
+            gsig = __ldg(grad_sigmas + row);
+        }
+        // saved encoding -> X tile
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (live) u = __ldg(reinterpret_cast<const uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j));
+            *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
+        }
+        float sigma, o16[16];
+        FwdRegs r;
+        mlp_forward(p, a, smw, X, H1, CIN, H3, H4, dir, tid, sigma, o16, r);
+
+        // ---- d(color_net.2 pre-activation) = grad_rgb * rgb * (1 - rgb)
+        {
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) g[i] = grgb[i] * r.rgb[i] * (1.0f - r.rgb[i]);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = make_uint4(0, 0, 0, 0);
+        }
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW5, tc5::smem_u32(H4), tc5::smem_u32(G16), 16, first);   // dW5^T += H4^T G5
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB5, 16, 64);             // dH4 = G5 W5
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        mask_grad_in_place(trow + kD, H4, tid);                                              // G4 (over H4)
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW4, tc5::smem_u32(H4), tc5::smem_u32(H3), 64, first);    // dW4 += G4^T H3
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H4), 64, sw + kWB4, 64, 64);              // dH3 = G4 W4
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        mask_grad_in_place(trow + kD, H3, tid);                                              // G3 (over H3)
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW3, tc5::smem_u32(H3), tc5::smem_u32(CIN), 32, first);   // dW3 += G3^T CIN
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H3), 64, sw + kWB3, 64, 32);              // dCIN = G3 W3
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        // ---- d(sigma_net.1 output): channel 0 through trunc_exp + clamp, channels 1..15 = geo part of dCIN
+        {
+            float dc[16];
+            tc5::tmem_ld16(trow + kD + 16, dc);  // columns 16..31 = d(geo 0..14), pad
+            float g[16];
+            const bool inside = (r.o0_raw >= a.clip_min) && (r.o0_raw <= a.clip_max);  // clamp backward
+            // trunc_exp backward: g * exp(clamp(x, -12, 12)) (tools/activation.py:15-21)
+            g[0] = inside ? gsig * a.density_scale * __expf(clampf(r.o0c, -12.0f, 12.0f)) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 15; ++i) g[i + 1] = dc[i];
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = tc5::pack8(g + 8);
+        }
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW2, tc5::smem_u32(H1), tc5::smem_u32(G16), 16, first);   // dW2^T += H1^T G2
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB2, 16, 64);             // dH1 = G2 W2
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        mask_grad_in_place(trow + kD, H1, tid);                                              // G1 (over H1)
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW1, tc5::smem_u32(H1), tc5::smem_u32(X), 32, first);     // dW1 += G1^T X
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H1), 64, sw + kWB1, 64, 32);              // dX = G1 W1
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        first = false;
+        // ---- scatter d(encoding) into the table gradient (gridencoder.cu:227-314 semantics, fp32 accumulation)
+        float dx[32];
+        tc5::tmem_ld16(trow + kD, *reinterpret_cast<float(*)[16]>(&dx[0]));
+        tc5::tmem_ld16(trow + kD + 16, *reinterpret_cast<float(*)[16]>(&dx[16]));
+        if (live) {
+            float x01[3];
+            bool oob;
+            to_unit(pos, a.bound, x01, oob);
+            if (!oob) {
+#pragma unroll
+                for (uint32_t l = 0; l < 16; ++l) {
+                    if (l < a.L) {
+                        const LevelInfo v = lv[l];
+                        Corners c;
+                        level_corners(v, x01, c);
+                        float* gt = grad_table + (size_t)v.offset * 2;
+                        const float g0 = dx[2 * l], g1 = dx[2 * l + 1];
+#pragma unroll
+                        for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g0, c.w[i] * g1);
+                    }
+                }
+            }
+        }
+    }
+    // ---- weight gradients leave the SM once per CTA
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    if (!first) {
+        flush_acc(p.tmem, kAW1, 32, gw + kGW1);
+        flush_acc(p.tmem, kAW2, 16, gw + kGW2);
+        flush_acc(p.tmem, kAW3, 32, gw + kGW3);
+        flush_acc(p.tmem, kAW4, 64, gw + kGW4);
+        flush_acc(p.tmem, kAW5, 16, gw + kGW5);
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
+}
+
+// pack one fp32 [out, in] matrix into an fp16 chunk tile of R rows x K cols (zero padded)
+__device__ __forceinline__ void pack_matrix(const float* __restrict__ w, uint32_t out, uint32_t in, uint8_t* tile, uint32_t R,
+                                            uint32_t K) {
+    for (uint32_t e = threadIdx.x; e < R * K; e += blockDim.x) {
+        const uint32_t r = e / K, k = e - r * K;
+        const float v = (r < out && k < in) ? w[(size_t)r * in + k] : 0.0f;
+        *reinterpret_cast<__half*>(tile + tc5::chunk_off(R, r, k >> 3) + (k & 7u) * 2) = __float2half_rn(v);
+    }
+}
+
+__global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
+                               const float* __restrict__ wc1, const float* __restrict__ wc2, uint32_t in_dim,
+                               uint8_t* __restrict__ blob) {
+    pack_matrix(ws0, 64, in_dim, blob + kWB1, 64, 32);
+    pack_matrix(ws1, 16, 64, blob + kWB2, 16, 64);
+    pack_matrix(wc0, 64, 31, blob + kWB3, 64, 32);
+    pack_matrix(wc1, 64, 64, blob + kWB4, 64, 64);
+    pack_matrix(wc2, 3, 64, blob + kWB5, 16, 64);
+}
+
+// un-pad / transpose the kernel-native weight-gradient workspace into the parameter shapes (accumulating)
+__global__ void k_unpack_wgrads(const float* __restrict__ gw, uint32_t in_dim, float* __restrict__ g0, float* __restrict__ g1,
+                                float* __restrict__ g2, float* __restrict__ g3, float* __restrict__ g4) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 64 * in_dim) { const uint32_t o = t / in_dim, i = t - o * in_dim; g0[t] += gw[kGW1 + o * 32 + i]; }
+    if (t < 16 * 64) { const uint32_t o = t / 64, i = t - o * 64; g1[t] += gw[kGW2 + i * 16 + o]; }
+    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g2[t] += gw[kGW3 + o * 32 + i]; }
+    if (t < 64 * 64) { g3[t] += gw[kGW4 + t]; }
+    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g4[t] += gw[kGW5 + i * 16 + o]; }
+}
+
+static FieldArgs to_args(const PvdHashField* f) {
+    FieldArgs a;
+    a.table = f->table;
+    a.offsets = f->offsets;
+    a.wblob = reinterpret_cast<const uint8_t*>(f->wblob);
+    a.L = f->L;
+    a.H = f->H;
+    a.S = f->S;
+    a.bound = f->bound;
+    a.clip_min = f->sigma_clip_min;
+    a.clip_max = f->sigma_clip_max;
+    a.density_scale = f->density_scale;
+    return a;
+}
+
+static int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+constexpr size_t kFwdSmem = PVD_FIELD_WBLOB_BYTES + 8192 + 8192 + 16384 + 16384;            // 69632
+constexpr size_t kBwdSmem = PVD_FIELD_WBLOB_BYTES + 8192 + 8192 + 16384 * 3 + 4096;         // 90112
+
+}  // namespace pvd
+
+using namespace pvd;
+
+extern "C" {
+
+int pvd_field_pack_weights(const float* w_sigma0, const float* w_sigma1, const float* w_color0, const float* w_color1,
+                           const float* w_color2, uint32_t in_dim, void* wblob, void* stream) {
+    PVD_REQUIRE(w_sigma0 && w_sigma1 && w_color0 && w_color1 && w_color2 && wblob);
+    if (in_dim == 0 || in_dim > 32 || (in_dim & 1u)) return PVD_EUNSUPPORTED;
+    k_pack_weights<<<1, 256, 0, (cudaStream_t)stream>>>(w_sigma0, w_sigma1, w_color0, w_color1, w_color2, in_dim, (uint8_t*)wblob);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                           void* enc, float* feat16, int32_t* status, void* stream) {
+    if (M == 0) return PVD_OK;
+    PVD_REQUIRE(f && f->table && f->offsets && f->wblob && xyzs && dirs && sigmas && rgbs && status);
+    if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
+    const FieldArgs a = to_args(f);
+    const uint32_t tiles = (M + kTile - 1) / kTile;
+    const uint32_t grid = min(tiles, (uint32_t)(3 * sm_count()));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (f->table_dtype == PVD_DTYPE_F16) {
+        e = cudaFuncSetAttribute(k_hash_field_fwd<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_hash_field_fwd<__half><<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+    } else if (f->table_dtype == PVD_DTYPE_F32) {
+        e = cudaFuncSetAttribute(k_hash_field_fwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_hash_field_fwd<float><<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+    } else {
+        return PVD_EUNSUPPORTED;
+    }
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
+                            const float* grad_sigmas, const float* grad_rgbs, uint32_t M, const int32_t* n_valid,
+                            float* grad_table, float* gw_ws, int32_t* status, void* stream) {
+    if (M == 0) return PVD_OK;
+    PVD_REQUIRE(f && f->offsets && f->wblob && xyzs && dirs && enc && grad_sigmas && grad_rgbs && grad_table && gw_ws && status);
+    if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
+    const FieldArgs a = to_args(f);
+    const uint32_t tiles = (M + kTile - 1) / kTile;
+    const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the table is not read in the backward (the encoding was saved); one instantiation serves both table dtypes
+    cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, M, n_valid,
+                                                         grad_table, gw_ws, status);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,
+                            float* gw_color1, float* gw_color2, void* stream) {
+    PVD_REQUIRE(gw_ws && gw_sigma0 && gw_sigma1 && gw_color0 && gw_color1 && gw_color2);
+    if (in_dim == 0 || in_dim > 32) return PVD_EUNSUPPORTED;
+    k_unpack_wgrads<<<16, 256, 0, (cudaStream_t)stream>>>(gw_ws, in_dim, gw_sigma0, gw_sigma1, gw_color0, gw_color1, gw_color2);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -312,23 +312,44 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__
     }
 }
 
+// FUSED_MSE: instead of reading upstream gradients, derive them from the photometric loss of renderer.py:445 + the
+// trainer's criterion (just_train_tea/utils.py:841-846):  pred = image + (1 - ws) * bg ; loss = mean((pred - gt)^2).
+// grad_ws then points to gt [N,3], grad_img to bg [3]; `loss_scale` multiplies the gradients (GradScaler) and
+// loss_out[0] accumulates the UNSCALED loss, loss_out[1] the number of rays that contributed.
+template <bool FUSED_MSE>
 __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_img,
                                                       const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                       const float* __restrict__ deltas, const int32_t* __restrict__ rays,
                                                       const float* __restrict__ weights_sum, const float* __restrict__ image,
                                                       uint32_t M, uint32_t N, float* __restrict__ grad_sigmas,
-                                                      float* __restrict__ grad_rgbs) {
+                                                      float* __restrict__ grad_rgbs, float loss_scale, float* __restrict__ loss_out) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n];
     const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
     const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
-    if (cnt == 0 || offset + cnt >= M) return;  // raymarching.cu:629
-    const float gws = grad_ws[index];
-    const float gr = grad_img[3 * (size_t)index], gg = grad_img[3 * (size_t)index + 1], gb = grad_img[3 * (size_t)index + 2];
+    const bool skip = (cnt == 0 || offset + cnt >= M);  // raymarching.cu:629
     const float r_final = image[3 * (size_t)index], g_final = image[3 * (size_t)index + 1],
                 b_final = image[3 * (size_t)index + 2], ws_final = weights_sum[index];
+    float gws, gr, gg, gb;
+    if constexpr (FUSED_MSE) {
+        const float* gt = grad_ws + 3 * (size_t)index;
+        const float bgr = grad_img[0], bgg = grad_img[1], bgb = grad_img[2];
+        const float om = 1.0f - ws_final;
+        const float dr = r_final + om * bgr - gt[0], dg = g_final + om * bgg - gt[1], db = b_final + om * bgb - gt[2];
+        const float k = 2.0f / (3.0f * (float)N);
+        if (lane == 0) {
+            atomicAdd(loss_out, (dr * dr + dg * dg + db * db) / (3.0f * (float)N));
+            if (!skip) atomicAdd(loss_out + 1, 1.0f);
+        }
+        gr = k * dr * loss_scale; gg = k * dg * loss_scale; gb = k * db * loss_scale;
+        gws = -(gr * bgr + gg * bgg + gb * bgb);
+    } else {
+        gws = grad_ws[index];
+        gr = grad_img[3 * (size_t)index]; gg = grad_img[3 * (size_t)index + 1]; gb = grad_img[3 * (size_t)index + 2];
+    }
+    if (skip) return;
     float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;  // carries (running sums up to the previous chunk)
     for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t i = base + lane;
@@ -607,9 +628,23 @@ int pvd_composite_rays_train_backward(const float* grad_weights_sum, const float
     if (N == 0) return PVD_OK;
     PVD_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image &&
                 grad_sigmas && grad_rgbs);
-    k_composite_bwd<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
-                                                                      rays, weights_sum, image, M, N, grad_sigmas,
-                                                                      grad_rgbs);
+    k_composite_bwd<false><<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
+                                                                             rays, weights_sum, image, M, N, grad_sigmas,
+                                                                             grad_rgbs, 1.0f, nullptr);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_color, float loss_scale, const float* sigmas,
+                                          const float* rgbs, const float* deltas, const int32_t* rays,
+                                          const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                          float* grad_sigmas, float* grad_rgbs, float* loss_out, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(gt_rgb && bg_color && sigmas && rgbs && deltas && rays && weights_sum && image && grad_sigmas && grad_rgbs &&
+                loss_out);
+    k_composite_bwd<true><<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, sigmas, rgbs, deltas, rays,
+                                                                            weights_sum, image, M, N, grad_sigmas, grad_rgbs,
+                                                                            loss_scale, loss_out);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

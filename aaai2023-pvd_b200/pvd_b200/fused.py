@@ -1,0 +1,212 @@
+"""Host side of the fused field query (include/pvd_b200_fused.h): autograd op, parameter staging, network module.
+
+`fused_hash_field(xyzs, dirs, embeddings, w_sigma0, w_sigma1, w_color0, w_color1, w_color2, cfg)` is one autograd node
+that stands in for the whole of `NeRFNetwork.forward` for model_type "hash" (distill_mutual/network.py:335-437): autograd,
+AdamW and GradScaler see the same leaf parameters with the same names and shapes as in the reference.
+
+`HashNeRFField` is an nn.Module with the reference's parameter names (`encoder.embeddings`, `sigma_net.{0,1}.weight`,
+`color_net.{0,1,2}.weight`), so reference checkpoints load into it, and with the side-channel attributes the distillation
+trainer reads (`feature_sigma_color`, `sigma_l`, `color_l`, distill_mutual/utils.py:1049-1083).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _native as nv
+
+WBLOB_BYTES = 20480
+GW_FLOATS = 10240
+ENC_STRIDE = 32
+
+
+class PvdHashField(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("offsets", C.c_void_p), ("wblob", C.c_void_p), ("table_dtype", C.c_int32),
+                ("L", C.c_uint32), ("H", C.c_uint32), ("S", C.c_float), ("bound", C.c_float), ("sigma_clip_min", C.c_float),
+                ("sigma_clip_max", C.c_float), ("density_scale", C.c_float)]
+
+
+@dataclass
+class HashFieldConfig:
+    num_levels: int
+    base_resolution: int
+    per_level_scale: float
+    bound: float = 1.0
+    sigma_clip_min: float = -2.0   # main_distill_mutual.py:182
+    sigma_clip_max: float = 7.0    # main_distill_mutual.py:183
+    density_scale: float = 1.0
+    table_fp16: bool = True        # gather from the fp16 shadow (what autocast does in the reference, grid.py:51-52)
+
+
+def _cstruct(cfg: HashFieldConfig, table, offsets, wblob):
+    return PvdHashField(table=table.data_ptr(), offsets=offsets.data_ptr(), wblob=wblob.data_ptr(),
+                        table_dtype=nv.F16 if table.dtype == torch.float16 else nv.F32, L=cfg.num_levels,
+                        H=cfg.base_resolution, S=float(np.log2(cfg.per_level_scale)), bound=cfg.bound,
+                        sigma_clip_min=cfg.sigma_clip_min, sigma_clip_max=cfg.sigma_clip_max,
+                        density_scale=cfg.density_scale)
+
+
+class StagedParams:
+    """fp16 table shadow + packed tensor-core weight tiles, refreshed only when a parameter's version changes."""
+
+    def __init__(self):
+        self._table_key = None
+        self.table = None
+        self._w_key = None
+        self.wblob = None
+
+    def table_for(self, emb: torch.Tensor, fp16: bool):
+        if not fp16:
+            return emb.detach()
+        key = (emb.data_ptr(), emb._version)
+        if key != self._table_key:
+            if self.table is None or self.table.shape != emb.shape:
+                self.table = torch.empty_like(emb, dtype=torch.float16)
+            self.table.copy_(emb.detach())
+            self._table_key = key
+        return self.table
+
+    def wblob_for(self, ws, in_dim: int):
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if key != self._w_key:
+            if self.wblob is None:
+                self.wblob = torch.empty(WBLOB_BYTES, dtype=torch.uint8, device=ws[0].device)
+            w32 = [w.detach().float().contiguous() for w in ws]
+            with nv.on_device(self.wblob):
+                nv.check(nv.lib().pvd_field_pack_weights(nv.ptr(w32[0]), nv.ptr(w32[1]), nv.ptr(w32[2]), nv.ptr(w32[3]),
+                                                         nv.ptr(w32[4]), C.c_uint32(in_dim), nv.ptr(self.wblob),
+                                                         nv.stream_of(self.wblob)))
+            self._w_key = key
+        return self.wblob
+
+
+def hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, want_enc=True, want_feat=False, status=None):
+    M = xyzs.shape[0]
+    dev = xyzs.device
+    sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+    rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    enc = torch.empty(M, ENC_STRIDE, dtype=torch.float16, device=dev) if want_enc else None
+    feat = torch.empty(M, 16, dtype=torch.float32, device=dev) if want_feat else None
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    f = _cstruct(cfg, table, offsets, wblob)
+    with nv.on_device(xyzs):
+        nv.check(nv.lib().pvd_hash_field_forward(C.byref(f), nv.ptr(xyzs), nv.ptr(dirs), C.c_uint32(M), nv.ptr(sigmas),
+                                                 nv.ptr(rgbs), nv.ptr(enc), nv.ptr(feat), nv.ptr(status), nv.stream_of(xyzs)))
+    return sigmas, rgbs, enc, feat, status
+
+
+def hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_table, gw_ws, n_valid=None,
+                            status=None):
+    M = xyzs.shape[0]
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
+    f = _cstruct(cfg, table, offsets, wblob)
+    with nv.on_device(xyzs):
+        nv.check(nv.lib().pvd_hash_field_backward(C.byref(f), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(enc), nv.ptr(grad_sigmas),
+                                                  nv.ptr(grad_rgbs), C.c_uint32(M), nv.ptr(n_valid), nv.ptr(grad_table),
+                                                  nv.ptr(gw_ws), nv.ptr(status), nv.stream_of(xyzs)))
+    return status
+
+
+def unpack_wgrads(gw_ws, in_dim, like):
+    outs = [torch.zeros_like(w, dtype=torch.float32) for w in like]
+    with nv.on_device(gw_ws):
+        nv.check(nv.lib().pvd_field_unpack_wgrads(nv.ptr(gw_ws), C.c_uint32(in_dim), nv.ptr(outs[0]), nv.ptr(outs[1]),
+                                                  nv.ptr(outs[2]), nv.ptr(outs[3]), nv.ptr(outs[4]), nv.stream_of(gw_ws)))
+    return outs
+
+
+class _FusedHashField(Function):
+    @staticmethod
+    def forward(ctx, xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat):
+        xyzs = xyzs.detach().float().contiguous()
+        dirs = dirs.detach().float().contiguous()
+        table = staged.table_for(embeddings, cfg.table_fp16)
+        wblob = staged.wblob_for((w0, w1, w2, w3, w4), 2 * cfg.num_levels)
+        sigmas, rgbs, enc, feat, status = hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, True, want_feat)
+        ctx.save_for_backward(xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4)
+        ctx.cfg = cfg
+        ctx.status = status
+        if want_feat:
+            ctx.mark_non_differentiable(feat)
+            return sigmas, rgbs, feat
+        return sigmas, rgbs
+
+    @staticmethod
+    def backward(ctx, grad_sigmas, grad_rgbs, *unused):
+        xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4 = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = xyzs.device
+        gs = (grad_sigmas if grad_sigmas is not None else torch.zeros(xyzs.shape[0], device=dev)).float().contiguous()
+        gc = (grad_rgbs if grad_rgbs is not None else torch.zeros(xyzs.shape[0], 3, device=dev)).float().contiguous()
+        grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)
+        gw_ws = torch.zeros(GW_FLOATS, dtype=torch.float32, device=dev)
+        hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status)
+        g = unpack_wgrads(gw_ws, 2 * cfg.num_levels, (w0, w1, w2, w3, w4))
+        g = [gi.to(w.dtype) for gi, w in zip(g, (w0, w1, w2, w3, w4))]
+        return (None, None, grad_table.to(embeddings.dtype), g[0], g[1], g[2], g[3], g[4], None, None, None, None)
+
+
+def fused_hash_field(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat=False):
+    return _FusedHashField.apply(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat)
+
+
+class _Args:  # the few attributes of the reference's argparse namespace that forward() reads (network.py:358,422)
+    def __init__(self, sigma_clip_min=-2.0, sigma_clip_max=7.0, global_step=10 ** 9, stage_iters=None):
+        self.sigma_clip_min = sigma_clip_min
+        self.sigma_clip_max = sigma_clip_max
+        self.global_step = global_step
+        self.stage_iters = stage_iters or {"stage1": -1, "stage2": -1}
+
+
+class HashNeRFField(nn.Module):
+    """`NeRFNetwork(model_type="hash")` of the reference (distill_mutual/network.py:12-182) with a fused forward/backward.
+
+    Same parameter names/shapes: encoder.embeddings [5303704, 2] (L=14), sigma_net.{0,1}.weight, color_net.{0,1,2}.weight.
+    """
+
+    def __init__(self, num_levels=14, desired_resolution=2048, bound=1, hidden_dim=64, geo_feat_dim=15, args=None,
+                 density_scale=1.0, table_fp16=True):
+        super().__init__()
+        from gridencoder import GridEncoder
+        from shencoder import SHEncoder
+        assert hidden_dim == 64 and geo_feat_dim == 15, "the fused kernel is built for PVD's 64-wide / 15-feature heads"
+        self.bound = bound
+        self.args = args or _Args()
+        self.encoder = GridEncoder(num_levels=num_levels, desired_resolution=desired_resolution * bound)
+        self.in_dim = self.encoder.output_dim
+        self.encoder_dir = SHEncoder(degree=4)
+        self.sigma_net = nn.ModuleList([nn.Linear(self.in_dim, 64, bias=False), nn.Linear(64, 16, bias=False)])
+        self.color_net = nn.ModuleList([nn.Linear(31, 64, bias=False), nn.Linear(64, 64, bias=False),
+                                        nn.Linear(64, 3, bias=False)])
+        self.density_scale = density_scale
+        self.table_fp16 = table_fp16
+        self._staged = StagedParams()
+        self.feature_sigma_color = None
+        self.sigma_l = None
+        self.color_l = None
+
+    def config(self) -> HashFieldConfig:
+        e = self.encoder
+        return HashFieldConfig(num_levels=e.num_levels, base_resolution=e.base_resolution, per_level_scale=float(e.per_level_scale),
+                               bound=float(self.bound), sigma_clip_min=float(self.args.sigma_clip_min),
+                               sigma_clip_max=float(self.args.sigma_clip_max), density_scale=1.0, table_fp16=self.table_fp16)
+
+    def forward(self, x, d):
+        # x [M,3] in [-bound, bound], d [M,3] unit -> sigma [M], color [M,3]   (network.py:335-437, hash branch)
+        out = fused_hash_field(x, d, self.encoder.embeddings, self.sigma_net[0].weight, self.sigma_net[1].weight,
+                               self.color_net[0].weight, self.color_net[1].weight, self.color_net[2].weight,
+                               self.encoder.offsets, self.config(), self._staged, True)
+        sigma, color, feat = out
+        self.feature_sigma_color = feat
+        if self.training and self.args.global_step < self.args.stage_iters["stage1"]:
+            return None, None
+        self.sigma_l = feat[..., 0]
+        self.color_l = color
+        return sigma, color

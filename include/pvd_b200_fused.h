@@ -1,0 +1,83 @@
+/*
+ * pvd_b200_fused.h -- C ABI of the FUSED field query: hash-grid encode + SH + sigma/color MLPs in one kernel
+ * per direction, MLP GEMMs on tcgen05 tensor cores with TMEM accumulators (sm_100a only).
+ *
+ * These entry points are additive: they sit behind NeRFNetwork.forward / NeRFRenderer.run_cuda of the reference
+ * (distill_mutual/network.py:335-437, distill_mutual/renderer.py:359-448) and replace, for model_type "hash",
+ *   GridEncoder.forward (gridencoder/grid.py:207-232) -> sigma_net (network.py:413-417) -> clamp/trunc_exp (:418-425)
+ *   -> SHEncoder (shencoder/sphere_harmonics.py:83-95) -> color_net + sigmoid (network.py:428-437)
+ * and its autograd backward (5 cuBLAS GEMM pairs + the gridencoder scatter).
+ *
+ * Same conventions as pvd_b200.h: caller-owned device pointers, caller-allocated outputs, no hidden state,
+ * stream passed as void*, int return (0 ok / cudaError_t / negative PVD_E*).
+ */
+#ifndef PVD_B200_FUSED_H
+#define PVD_B200_FUSED_H
+
+#include <stdint.h>
+#include "pvd_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVD_FIELD_WBLOB_BYTES 20480u /* packed fp16 operand tiles of the five weight matrices */
+#define PVD_FIELD_ENC_STRIDE 32u     /* halves per sample in the saved encoding (2L <= 32, zero padded) */
+
+typedef struct PvdHashField {
+    const void* table;      /* [offsets[L], 2] hash-grid features, fp16 (PVD_DTYPE_F16) or fp32 */
+    const int32_t* offsets; /* [L+1] level offsets (gridencoder/grid.py:177-190) */
+    const void* wblob;      /* PVD_FIELD_WBLOB_BYTES from pvd_field_pack_weights */
+    int32_t table_dtype;
+    uint32_t L;             /* levels, 2L <= 32 */
+    uint32_t H;             /* base resolution */
+    float S;                /* log2(per_level_scale) */
+    float bound;            /* scene bound: xyz in [-bound, bound] is mapped to [0,1] (grid.py:211) */
+    float sigma_clip_min;   /* clamp of sigma_net channel 0 (network.py:418-420; defaults -2 / 7) */
+    float sigma_clip_max;
+    float density_scale;    /* renderer.py:440 */
+} PvdHashField;
+
+/* Convert the five nn.Linear weights (fp32, row-major [out, in]) of
+ *   sigma_net.0 [64, 2L], sigma_net.1 [16, 64], color_net.0 [64, 31], color_net.1 [64, 64], color_net.2 [3, 64]
+ * (network.py:103-152, bias=False) into the fp16 shared-memory operand tiles the kernels load. Run after every
+ * optimizer step. */
+int pvd_field_pack_weights(const float* w_sigma0, const float* w_sigma1, const float* w_color0, const float* w_color1,
+                           const float* w_color2, uint32_t in_dim, void* wblob, void* stream);
+
+/* Forward for M samples: xyzs [M,3], dirs [M,3] -> sigmas [M] (already multiplied by density_scale), rgbs [M,3].
+ * Optional outputs (NULL to skip): enc [M, 32] fp16 (hash features, needed by the backward),
+ * feat16 [M,16] fp32 = sigma_net output with channel 0 clamped (`feature_sigma_color`, network.py:421).
+ * `status` (device int, caller zeroes it) is set non-zero if a tensor-core wait timed out. */
+int pvd_hash_field_forward(const PvdHashField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas,
+                           float* rgbs, void* enc, float* feat16, int32_t* status, void* stream);
+
+/* Backward: d(loss)/d(sigmas) [M], d(loss)/d(rgbs) [M,3] -> ACCUMULATES into
+ *   grad_table [offsets[L], 2] fp32 and gw_ws, a PVD_FIELD_GW_FLOATS workspace holding the five weight gradients in the
+ *   kernel-native accumulator shapes  dW1[64][32] | dW2^T[64][16] | dW3[64][32] | dW4[64][64] | dW5^T[64][16]
+ *   (zero padded; pvd_field_unpack_wgrads adds them onto parameter-shaped [out, in] buffers).
+ * `enc` is the tensor the forward saved.  Rows >= *n_valid (device pointer, e.g. the march counter; NULL = all M)
+ * are padding and contribute nothing. */
+#define PVD_FIELD_GW_FLOATS 10240u
+int pvd_hash_field_backward(const PvdHashField* field, const float* xyzs, const float* dirs, const void* enc,
+                            const float* grad_sigmas, const float* grad_rgbs, uint32_t M, const int32_t* n_valid,
+                            float* grad_table, float* gw_ws, int32_t* status, void* stream);
+
+/* composite_rays_train_backward (pvd_b200.h) with the upstream gradients derived in the kernel from the photometric loss:
+ *   pred = image + (1 - weights_sum) * bg_color   (distill_mutual/renderer.py:445)
+ *   loss = mean((pred - gt_rgb)^2) over the N x 3 values (just_train_tea/utils.py:841-846, MSELoss)
+ * gradients are multiplied by loss_scale (GradScaler); loss_out[0] += unscaled loss, loss_out[1] += rays that carried
+ * samples.  gt_rgb [N,3], bg_color [3]. */
+int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_color, float loss_scale, const float* sigmas,
+                                          const float* rgbs, const float* deltas, const int32_t* rays,
+                                          const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                          float* grad_sigmas, float* grad_rgbs, float* loss_out, void* stream);
+
+/* gw_* += un-padded / transposed views of gw_ws; shapes [64,in_dim], [16,64], [64,31], [64,64], [3,64]. */
+int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,
+                            float* gw_color1, float* gw_color2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVD_B200_FUSED_H */

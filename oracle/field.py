@@ -1,0 +1,115 @@
+"""torch-CPU restatement of the field networks and of one training step.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The reference's field is built from ATen ops (F.linear, relu, sigmoid, exp, clamp, cat: distill_mutual/network.py:413-437)
+around its three extensions; ATen on the CPU is its own oracle, the extensions are restated in pvd_oracle.c.  This module
+glues them with autograd so that `loss.backward()` yields reference gradients for every parameter:
+
+    hash_field_forward   network.py:335-343,413-437  (GridEncoder -> sigma_net -> clamp -> trunc_exp -> SH -> color_net)
+    composite            raymarching.py:292-360
+    render_train_step    renderer.py:359-448 + the MSE criterion of just_train_tea/utils.py:841-846
+All math in float32 (the reference's autocast path differs from it by fp16 rounding, tolerance 1e-2 in the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import cpu
+
+
+class _GridEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x01, emb, offsets, per_level_scale, base_resolution):
+        out, _ = cpu.grid_encode_forward(x01.detach().numpy(), emb.detach().numpy(), offsets, per_level_scale, base_resolution)
+        ctx.save_for_backward(x01)
+        ctx.meta = (tuple(emb.shape), offsets, per_level_scale, base_resolution)
+        return torch.from_numpy(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x01,) = ctx.saved_tensors
+        shape, offsets, pls, H = ctx.meta
+        ge, _ = cpu.grid_encode_backward(g.contiguous().numpy(), x01.numpy(), shape, offsets, pls, H)
+        return None, torch.from_numpy(ge), None, None, None
+
+
+class _TruncExp(torch.autograd.Function):  # tools/activation.py:6-21
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-12, 12))
+
+
+class _Composite(torch.autograd.Function):  # raymarching.py:292-360
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, deltas, rays):
+        ws, depth, image = cpu.composite_rays_train_forward(sigmas.detach().numpy(), rgbs.detach().numpy(), deltas.numpy(),
+                                                            rays.numpy())
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, torch.from_numpy(ws), torch.from_numpy(image))
+        return torch.from_numpy(ws), torch.from_numpy(depth), torch.from_numpy(image)
+
+    @staticmethod
+    def backward(ctx, gws, gdepth, gimage):
+        sigmas, rgbs, deltas, rays, ws, image = ctx.saved_tensors
+        gs, gc = cpu.composite_rays_train_backward(gws.contiguous().numpy(), gimage.contiguous().numpy(), sigmas.detach().numpy(),
+                                                   rgbs.detach().numpy(), deltas.numpy(), rays.numpy(), ws.numpy(), image.numpy())
+        return torch.from_numpy(gs), torch.from_numpy(gc), None, None
+
+
+def hash_field_forward(x, d, emb, offsets, per_level_scale, base_resolution, weights, bound=1.0, clip_min=-2.0, clip_max=7.0,
+                       quantize_fp16=False):
+    """x [M,3] in [-bound,bound], d [M,3] -> sigma [M], color [M,3], feat [M,16].  weights = (ws0, ws1, wc0, wc1, wc2).
+
+    quantize_fp16 rounds table, weights and activations to fp16 where the reference's autocast does (grid.py:51-52 and
+    torch autocast's F.linear rule), keeping the arithmetic itself in fp32 -- a tight model of the fused kernel."""
+    q = (lambda t: t.half().float()) if quantize_fp16 else (lambda t: t)
+    ws0, ws1, wc0, wc1, wc2 = weights
+    x01 = (x + bound) / (2 * bound)  # grid.py:211
+    h = _GridEncode.apply(x01, q(emb), offsets, per_level_scale, base_resolution)
+    h = q(F.relu(F.linear(q(h), q(ws0))))
+    h = q(F.linear(h, q(ws1)))
+    h0 = torch.clamp(h[..., 0], clip_min, clip_max)  # network.py:418-420
+    feat = torch.cat([h0.unsqueeze(-1), h[..., 1:]], dim=-1)
+    sigma = _TruncExp.apply(h0)
+    sh = torch.from_numpy(cpu.sh_encode_forward(d.detach().numpy(), 4))
+    c = torch.cat([sh, h[..., 1:]], dim=-1)  # network.py:428-429
+    c = q(F.relu(F.linear(q(c), q(wc0))))
+    c = q(F.relu(F.linear(c, q(wc1))))
+    color = torch.sigmoid(F.linear(c, q(wc2)))
+    return sigma, color, feat
+
+
+def composite(sigmas, rgbs, deltas, rays):
+    return _Composite.apply(sigmas, rgbs, deltas, rays)
+
+
+def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cascade=1, grid_size=128, min_near=0.2, bg_color=1.0,
+                      density_scale=1.0, M=None, perturb=True, dt_gamma=0.0, max_steps=1024, aabb=None):
+    """One reference training step on the CPU: near/far -> march -> field -> composite -> bg mix -> MSE.
+
+    Returns dict(loss, image, depth, weights_sum, xyzs, dirs, deltas, rays, counter).  `field_fn(xyzs, dirs) -> (sigma, rgb)`.
+    """
+    ro, rd = rays_o.numpy(), rays_d.numpy()
+    if aabb is None:
+        aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = cpu.near_far_from_aabb(ro, rd, aabb, min_near)
+    xyzs, dirs, deltas, rays, counter = cpu.march_rays_train(ro, rd, bound, bitfield, cascade, grid_size, nears, fars, M=M,
+                                                            perturb=perturb, dt_gamma=dt_gamma, max_steps=max_steps)
+    if M is None:  # warm-up sizing: total rounded up strictly to 128 (raymarching.py:276-282)
+        m = int(counter[0])
+        m += 128 - m % 128
+        xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
+    txyz, tdir, tdl, trays = (torch.from_numpy(np.ascontiguousarray(a)) for a in (xyzs, dirs, deltas, rays))
+    sigma, rgb = field_fn(txyz, tdir)
+    ws, depth, image = composite(density_scale * sigma, rgb, tdl, trays)
+    pred = image + (1 - ws).unsqueeze(-1) * bg_color  # renderer.py:445
+    depth_n = torch.clamp(depth - torch.from_numpy(nears), min=0) / (torch.from_numpy(fars - nears) + 1e-6)  # renderer.py:446
+    loss = torch.mean((pred - gt_rgb) ** 2)
+    return dict(loss=loss, image=pred, depth=depth_n, weights_sum=ws, xyzs=txyz, dirs=tdir, deltas=tdl, rays=trays,
+                counter=counter, sigma=sigma, rgb=rgb)

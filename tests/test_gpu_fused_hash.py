@@ -1,0 +1,122 @@
+"""GPU parity of the fused hash-field kernels (tcgen05 MLP + gather + scatter) against the torch-CPU oracle.
+
+The fused path computes the MLP in fp16 with fp32 accumulation -- the precision the reference itself runs at (both CLIs force
+fp16 autocast, main_distill_mutual.py:251-254) -- so the comparison against the fp32 oracle uses BASELINE.json's fp16
+tolerance (1e-2 relative), and against the oracle with the same fp16 quantisation points a tighter one.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _make(L=14, seed=0, table_fp16=True):
+    from pvd_b200.fused import HashNeRFField
+    torch.manual_seed(seed)
+    net = HashNeRFField(num_levels=L, desired_resolution=2048, table_fp16=table_fp16).cuda()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    for m in list(net.sigma_net) + list(net.color_net):
+        m.weight.data.mul_(2.0)  # larger activations exercise ReLU masks and the clamp
+    return net
+
+
+def _oracle_inputs(net):
+    e = net.encoder
+    ws = [m.weight.detach().cpu().clone().requires_grad_(True) for m in list(net.sigma_net) + list(net.color_net)]
+    emb = e.embeddings.detach().cpu().clone().requires_grad_(True)
+    return emb, e.offsets.cpu().numpy(), float(e.per_level_scale), e.base_resolution, ws
+
+
+@pytest.mark.parametrize("L,table_fp16", [(14, True), (16, True), (14, False)])
+def test_fused_forward_matches_oracle(L, table_fp16):
+    from oracle import field
+    net = _make(L, 1, table_fp16)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M = 128 * 37 + 5  # ragged last tile
+    x = torch.rand(M, 3, device="cuda", generator=g) * 2 - 1
+    x[3] = torch.tensor([1.0, -1.0, 0.25], device="cuda")
+    d = torch.randn(M, 3, device="cuda", generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    net.eval()
+    sigma, color = net(x, d)
+    feat = net.feature_sigma_color
+    assert int(net._staged.wblob.numel()) == 20480
+    emb, offsets, pls, H, ws = _oracle_inputs(net)
+    with torch.no_grad():
+        so, co, fo = field.hash_field_forward(x.cpu(), d.cpu(), emb, offsets, pls, H, ws, quantize_fp16=True)
+        s32, c32, f32 = field.hash_field_forward(x.cpu(), d.cpu(), emb, offsets, pls, H, ws, quantize_fp16=False)
+    # same quantisation points, fp32 accumulate on both sides: a few fp16 ulps
+    torch.testing.assert_close(feat.cpu(), fo, rtol=4e-3, atol=4e-3)
+    torch.testing.assert_close(color.cpu(), co, rtol=4e-3, atol=2e-3)
+    torch.testing.assert_close(sigma.cpu(), so, rtol=1e-2, atol=1e-3)
+    # BASELINE tolerance against pure fp32
+    torch.testing.assert_close(color.cpu(), c32, rtol=1e-2, atol=1e-2)
+    assert _rel(feat.cpu(), f32) < 1e-2
+    assert float(feat[:, 0].min()) >= -2.0 and float(feat[:, 0].max()) <= 7.0
+
+
+def test_fused_backward_matches_oracle():
+    from oracle import field
+    net = _make(14, 3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    M = 128 * 24
+    x = torch.rand(M, 3, device="cuda", generator=g) * 2 - 1
+    d = torch.randn(M, 3, device="cuda", generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs = torch.randn(M, device="cuda", generator=g) * 0.05
+    gc = torch.randn(M, 3, device="cuda", generator=g)
+    net.train()
+    sigma, color = net(x, d)
+    (sigma * gs).sum().add((color * gc).sum()).backward()
+    emb, offsets, pls, H, ws = _oracle_inputs(net)
+    so, co, fo = field.hash_field_forward(x.cpu(), d.cpu(), emb, offsets, pls, H, ws, quantize_fp16=True)
+    (so * gs.cpu()).sum().add((co * gc.cpu()).sum()).backward()
+    params = list(net.sigma_net) + list(net.color_net)
+    for i, (m, w) in enumerate(zip(params, ws)):
+        assert _rel(m.weight.grad.cpu(), w.grad) < 2e-2, f"weight grad {i}"
+    ge = net.encoder.embeddings.grad.cpu()
+    assert _rel(ge, emb.grad) < 2e-2
+    # untouched table entries stay exactly zero; touched ones agree
+    assert float(ge.abs().sum()) > 0
+    assert float(((ge == 0) == (emb.grad == 0)).float().mean()) > 0.999
+
+
+def test_fused_field_in_a_full_training_step(scene):
+    """march -> fused field -> composite -> MSE, forward and backward, against the oracle's CPU training step."""
+    import raymarching
+    from oracle import field
+    net = _make(14, 5)
+    ro, rd = scene["batches"][0]
+    ro, rd = ro[:1024].contiguous(), rd[:1024].contiguous()
+    bf = torch.from_numpy(scene["bitfield"]).cuda()
+    gt = torch.rand(1024, 3, generator=torch.Generator().manual_seed(6))
+    gro, grd = ro.cuda(), rd.cuda()
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32, device="cuda")
+    nears, fars = raymarching.near_far_from_aabb(gro, grd, aabb, 0.2)
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(gro, grd, 1.0, bf, 1, 128, nears, fars, counter, -1, True, 128, False,
+                                                            0.0, 1024)
+    net.train()
+    sigma, color = net(xyzs, dirs)
+    ws, depth, image = raymarching.composite_rays_train(sigma, color, deltas, rays)
+    pred = image + (1 - ws).unsqueeze(-1) * 1.0
+    loss = torch.mean((pred - gt.cuda()) ** 2)
+    (loss * 1024.0).backward()  # loss scaling, as GradScaler does
+
+    emb, offsets, pls, H, wts = _oracle_inputs(net)
+    fn = lambda x, d: field.hash_field_forward(x, d, emb, offsets, pls, H, wts, quantize_fp16=True)[:2]
+    o = field.render_train_step(ro, rd, scene["bitfield"], gt, fn)
+    (o["loss"] * 1024.0).backward()
+    assert torch.equal(o["rays"], rays.cpu())
+    torch.testing.assert_close(pred.detach().cpu(), o["image"].detach(), rtol=1e-2, atol=5e-3)
+    assert abs(float(loss) - float(o["loss"])) < 1e-2 * float(o["loss"])
+    params = list(net.sigma_net) + list(net.color_net)
+    for i, (m, w) in enumerate(zip(params, wts)):
+        assert _rel(m.weight.grad.cpu(), w.grad) < 3e-2, f"weight grad {i}"
+    assert _rel(net.encoder.embeddings.grad.cpu(), emb.grad) < 3e-2
