@@ -335,6 +335,7 @@ def run_reference(args, rank, world, local):
     if rank != 0:
         return
     from pvd_b200 import synthetic as syn
+    why = "no CUDA device"
     try:
         from oracle import cpu, ref_pipeline
         ext = ref_pipeline.load_ext()
