@@ -110,16 +110,30 @@ __global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thr
 // training march: count+stash -> scan -> expand
 // =============================================================================================
 
-// Pass 1 (one thread per ray, one warp per CTA so the 128 warps of a 4096-ray batch land on 128 SMs):
-// walk the occupancy grid exactly as raymarching.cu:357-403 does and stash (t, dt) of every accepted
-// sample.  num_steps[n] and t0[n] (jittered start) go to the workspace.
-__global__ void __launch_bounds__(32) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                   const uint8_t* __restrict__ grid, float bound, float dt_gamma,
-                                                   uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                                                   const float* __restrict__ nears, const float* __restrict__ fars,
-                                                   uint32_t perturb, Pcg32 rng, int32_t* __restrict__ num_steps_out,
-                                                   float* __restrict__ t0_out, float2* __restrict__ stash) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+// Pass 1 -- ONE WARP PER RAY.  The reference walks each ray with one thread (raymarching.cu:357-403): a chain of several
+// hundred dependent iterations, each with a scattered byte load, at one warp per SM.  Here the 32 lanes of a warp test 32
+// CONSECUTIVE lattice points of the same ray at once and the serial skipping logic is replayed on ballots, which gives
+// 4096 resident warps instead of 128 and 32 independent occupancy loads in flight per ray.
+//
+// Why this is exact.  The marcher's parameter only ever advances by `t += clamp(t*dt_gamma, dt_min, dt_max)`, in the
+// occupied branch (:389) and in the skip loop (:400) alike, so the visited parameters are a subset of one fixed lattice
+// t_0 = t0, t_{k+1} = fl(t_k + dtf(t_k)) that does not depend on the grid.  A lattice point is "landed" if the serial loop
+// evaluates it: point 0 is; after an occupied landed point k, k+1 is; after an empty landed point k with cell exit tt_k,
+// the first j > k with t_j >= tt_k is.  Each lane evaluates its lattice point exactly as the serial loop would
+// (same position, cell, level, exit expressions), and the landed set is then resolved with ballots.  Lattice values are
+// produced either by the 32-step serial recurrence (every lane runs it redundantly and keeps its own element) or, when
+// dt is constant and the window stays inside one binade, from the observation that fl(t + dt) advances the bit pattern of
+// t by a constant number of ulps c (round-to-nearest of dt/ulp; ties are detected and sent to the serial path), so
+// bits(t_{k0+i}) = bits(t_{k0}) + i*c.
+// The accepted (t, dt) pairs go to the stash in march order; num_steps[n] and t0[n] to the workspace.
+__global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                    const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                    uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                    const float* __restrict__ nears, const float* __restrict__ fars,
+                                                    uint32_t perturb, Pcg32 rng, int32_t* __restrict__ num_steps_out,
+                                                    float* __restrict__ t0_out, float2* __restrict__ stash) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (n >= N) return;
     MarchCtx c;
     march_ctx_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
@@ -130,22 +144,104 @@ __global__ void __launch_bounds__(32) k_march_count(const float* __restrict__ ra
         t0 = __fmaf_rn(c.dt_min, pcg32_next_float(rng), t0);
     }
     float2* st = stash + (size_t)n * max_steps;
-    float t = t0;
-    uint32_t num_steps = 0;
-    while (t < far && num_steps < max_steps) {
-        float x, y, z, tt;
-        march_pos(c, t, x, y, z);
-        const float dt = march_dt(c, t);
-        if (march_probe(c, grid, t, dt, x, y, z, tt)) {
-            st[num_steps] = make_float2(t, dt);
-            ++num_steps;
-            t = __fadd_rn(t, dt);
-        } else {
-            do { t = __fadd_rn(t, march_dt(c, t)); } while (t < tt);
+    const bool const_dt = (dt_gamma == 0.0f);
+    const float dt_c = march_dt(c, 0.0f);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    float t_base = t0;
+    float carry_tt = 0.0f;
+    bool have_carry = false;
+    uint32_t count = 0;
+    while (true) {
+        // ---- the 32 lattice points of this window
+        float t_i, t_next;
+        bool fast = false;
+        if (const_dt && t_base > 0.0f) {
+            const uint32_t b = __float_as_uint(t_base);
+            const uint32_t e = b >> 23;
+            const float t1 = __fadd_rn(t_base, dt_c);
+            const uint32_t b1 = __float_as_uint(t1);
+            if (e > 0 && e < 254 && (b1 >> 23) == e) {
+                const uint32_t cstep = b1 - b;
+                // tie check: dt / ulp(t) has fractional part exactly one half -> rounding direction depends on parity
+                const float r = __fmul_rn(dt_c, __uint_as_float((uint32_t)(127 + 150 - (int)e) << 23));  // dt * 2^(23-(e-127))
+                const bool tie = (r - floorf(r)) == 0.5f;
+                const uint32_t bend = b + 32u * cstep;
+                if (!tie && cstep > 0 && (bend >> 23) == e && (277 - (int)e) > 0 && (277 - (int)e) < 255) {
+                    fast = true;
+                    t_i = __uint_as_float(b + lane * cstep);
+                    t_next = __uint_as_float(bend);
+                }
+            }
         }
+        if (!fast) {
+            float t = t_base;
+            t_i = t;
+#pragma unroll 4
+            for (uint32_t j = 0; j < 32; ++j) {
+                if (j == lane) t_i = t;
+                t = __fadd_rn(t, const_dt ? dt_c : march_dt(c, t));
+            }
+            t_next = t;
+        }
+        // ---- every lane evaluates its point as the serial loop would (raymarching.cu:363-397)
+        const bool valid = t_i < far;
+        float x, y, z, tt = 0.0f;
+        march_pos(c, t_i, x, y, z);
+        const float dt_i = const_dt ? dt_c : march_dt(c, t_i);
+        bool occ = false;
+        if (valid) occ = march_probe(c, grid, t_i, dt_i, x, y, z, tt);
+        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t occ_mask = __ballot_sync(0xffffffffu, valid && occ);
+        if (valid_mask == 0u) break;  // t only grows: nothing further can satisfy t < far
+        // ---- replay the serial control flow on the masks
+        uint32_t cur = 0;
+        if (have_carry) {
+            const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= carry_tt);
+            if (ge) {
+                cur = (uint32_t)__ffs((int)ge) - 1u;
+                have_carry = false;
+            } else {
+                cur = 32;
+            }
+        }
+        uint32_t emit = 0;
+        bool done = false;
+        const uint32_t count0 = count;
+        while (cur < 32) {
+            if (!((valid_mask >> cur) & 1u) || count >= max_steps) {  // loop condition of raymarching.cu:362
+                done = true;
+                break;
+            }
+            if ((occ_mask >> cur) & 1u) {
+                const uint32_t rest = occ_mask >> cur;
+                uint32_t run = (rest == 0xffffffffu) ? 32u : (uint32_t)__ffs((int)~rest) - 1u;
+                run = min(run, max_steps - count);
+                const uint32_t bits = (run >= 32u) ? 0xffffffffu : ((1u << run) - 1u);
+                emit |= bits << cur;
+                count += run;
+                cur += run;
+            } else {
+                const float tt_c = __shfl_sync(0xffffffffu, tt, (int)cur);
+                const uint32_t above = (cur >= 31u) ? 0u : ~((2u << cur) - 1u);
+                const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= tt_c) & above;
+                if (ge) {
+                    cur = (uint32_t)__ffs((int)ge) - 1u;
+                } else {
+                    carry_tt = tt_c;
+                    have_carry = true;
+                    cur = 32;
+                }
+            }
+        }
+        if ((emit >> lane) & 1u) st[count0 + __popc(emit & lt_mask)] = make_float2(t_i, dt_i);
+        if (done) break;
+        t_base = t_next;
     }
-    num_steps_out[n] = (int32_t)num_steps;
-    t0_out[n] = t0;
+    if (lane == 0) {
+        num_steps_out[n] = (int32_t)count;
+        t0_out[n] = t0;
+    }
 }
 
 // Pass 2 (one CTA): exclusive prefix sum of num_steps in ray-id order; rays[n] = (n, offset, count);
@@ -577,7 +673,7 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     float2* stash = reinterpret_cast<float2*>(ws_i32 + head);
     const Pcg32 rng = pcg32_seeded(42u);  // hard-coded seed, raymarching.cu:488
-    k_march_count<<<ceil_div(N, 32), 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+    k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                                   perturb, rng, num_steps, t0, stash);
     PVD_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(num_steps, N, rays, counter);

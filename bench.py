@@ -37,7 +37,7 @@ L2_FLUSH_BYTES = 256 << 20
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index=0, period=0.005):
+    def __init__(self, index=0, period=0.002):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -60,10 +60,9 @@ class ClockSampler:
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
         while not self._stop.is_set():
             try:
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                if util > 0:
-                    self.samples.append(mhz)
+                # NVML's utilisation counter integrates over ~1/6 s, longer than the timed region: keep every sample taken
+                # while the region runs (the sampler is started right before it and stopped right after)
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = get_reasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
