@@ -415,8 +415,9 @@ __device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint
 template <typename T>
 __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                         const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
-                                                        const float* __restrict__ grad_rgbs, uint32_t M,
-                                                        const int32_t* __restrict__ n_valid_p, float* __restrict__ grad_table,
+                                                        const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
+                                                        uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                        float* __restrict__ grad_table,
                                                         float* __restrict__ gw, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -515,9 +516,17 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             float g[16];
             const bool inside = (r.o0_raw >= a.clip_min) && (r.o0_raw <= a.clip_max);  // clamp backward
             // trunc_exp backward: g * exp(clamp(x, -12, 12)) (tools/activation.py:15-21)
-            g[0] = inside ? gsig * a.density_scale * __expf(clampf(r.o0c, -12.0f, 12.0f)) : 0.0f;
+            g[0] = gsig * a.density_scale * __expf(clampf(r.o0c, -12.0f, 12.0f));
 #pragma unroll
             for (int i = 0; i < 15; ++i) g[i + 1] = dc[i];
+            if (grad_feat && live) {  // d(loss)/d(feature_sigma_color): the distillation feature / sigma_l losses
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 gf = __ldg(reinterpret_cast<const float4*>(grad_feat + 16 * (size_t)row) + q);
+                    g[4 * q] += gf.x; g[4 * q + 1] += gf.y; g[4 * q + 2] += gf.z; g[4 * q + 3] += gf.w;
+                }
+            }
+            if (!inside) g[0] = 0.0f;  // clamp backward (network.py:418-420)
             *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
             *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = tc5::pack8(g + 8);
         }
@@ -675,8 +684,8 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
 }
 
 int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
-                            const float* grad_sigmas, const float* grad_rgbs, uint32_t M, const int32_t* n_valid,
-                            float* grad_table, float* gw_ws, int32_t* status, void* stream) {
+                            const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                            const int32_t* n_valid, float* grad_table, float* gw_ws, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
     PVD_REQUIRE(f && f->offsets && f->wblob && xyzs && dirs && enc && grad_sigmas && grad_rgbs && grad_table && gw_ws && status);
     if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
@@ -687,7 +696,7 @@ int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const floa
     // the table is not read in the backward (the encoding was saved); one instantiation serves both table dtypes
     cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return (int)e;
-    k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, M, n_valid,
+    k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
                                                          grad_table, gw_ws, status);
     PVD_LAUNCH_CHECK();
     return PVD_OK;

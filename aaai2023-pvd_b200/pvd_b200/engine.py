@@ -140,7 +140,7 @@ class HashTrainEngine:
                                                          nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(N),
                                                          nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
         nv.check(l.pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), nv.ptr(self.enc),
-                                           nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), _u32(M), nv.ptr(self.counter),
+                                           nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), None, _u32(M), nv.ptr(self.counter),
                                            nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.status), st))
 
     def finish_warmup(self):

@@ -102,14 +102,15 @@ def hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, want_enc=True
 
 
 def hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_table, gw_ws, n_valid=None,
-                            status=None):
+                            status=None, grad_feat=None):
     M = xyzs.shape[0]
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
     f = _cstruct(cfg, table, offsets, wblob)
     with nv.on_device(xyzs):
         nv.check(nv.lib().pvd_hash_field_backward(C.byref(f), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(enc), nv.ptr(grad_sigmas),
-                                                  nv.ptr(grad_rgbs), C.c_uint32(M), nv.ptr(n_valid), nv.ptr(grad_table),
+                                                  nv.ptr(grad_rgbs), nv.ptr(grad_feat), C.c_uint32(M), nv.ptr(n_valid),
+                                                  nv.ptr(grad_table),
                                                   nv.ptr(gw_ws), nv.ptr(status), nv.stream_of(xyzs)))
     return status
 
@@ -129,17 +130,19 @@ class _FusedHashField(Function):
         dirs = dirs.detach().float().contiguous()
         table = staged.table_for(embeddings, cfg.table_fp16)
         wblob = staged.wblob_for((w0, w1, w2, w3, w4), 2 * cfg.num_levels)
-        sigmas, rgbs, enc, feat, status = hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, True, want_feat)
+        need_bwd = any(ctx.needs_input_grad)  # a frozen teacher under no_grad does not save the encoding
+        sigmas, rgbs, enc, feat, status = hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, need_bwd, want_feat)
+        if enc is None:
+            enc = torch.empty(0, dtype=torch.float16, device=xyzs.device)
         ctx.save_for_backward(xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4)
         ctx.cfg = cfg
         ctx.status = status
         if want_feat:
-            ctx.mark_non_differentiable(feat)
             return sigmas, rgbs, feat
         return sigmas, rgbs
 
     @staticmethod
-    def backward(ctx, grad_sigmas, grad_rgbs, *unused):
+    def backward(ctx, grad_sigmas, grad_rgbs, grad_feat=None):
         xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4 = ctx.saved_tensors
         cfg = ctx.cfg
         dev = xyzs.device
@@ -147,7 +150,8 @@ class _FusedHashField(Function):
         gc = (grad_rgbs if grad_rgbs is not None else torch.zeros(xyzs.shape[0], 3, device=dev)).float().contiguous()
         grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)
         gw_ws = torch.zeros(GW_FLOATS, dtype=torch.float32, device=dev)
-        hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status)
+        gf = grad_feat.float().contiguous() if grad_feat is not None else None
+        hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status, gf)
         g = unpack_wgrads(gw_ws, 2 * cfg.num_levels, (w0, w1, w2, w3, w4))
         g = [gi.to(w.dtype) for gi, w in zip(g, (w0, w1, w2, w3, w4))]
         return (None, None, grad_table.to(embeddings.dtype), g[0], g[1], g[2], g[3], g[4], None, None, None, None)
@@ -157,23 +161,30 @@ def fused_hash_field(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, s
     return _FusedHashField.apply(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat)
 
 
-class _Args:  # the few attributes of the reference's argparse namespace that forward() reads (network.py:358,422)
-    def __init__(self, sigma_clip_min=-2.0, sigma_clip_max=7.0, global_step=10 ** 9, stage_iters=None):
+from .renderer import NeRFRenderer  # noqa: E402
+
+
+class _Args:  # the few attributes of the reference's argparse namespace that forward()/run_cuda read (network.py:358,422)
+    def __init__(self, sigma_clip_min=-2.0, sigma_clip_max=7.0, global_step=10 ** 9, stage_iters=None, render_stu_first=True):
         self.sigma_clip_min = sigma_clip_min
         self.sigma_clip_max = sigma_clip_max
         self.global_step = global_step
         self.stage_iters = stage_iters or {"stage1": -1, "stage2": -1}
+        self.render_stu_first = render_stu_first
 
 
-class HashNeRFField(nn.Module):
+class HashNeRFField(NeRFRenderer):
     """`NeRFNetwork(model_type="hash")` of the reference (distill_mutual/network.py:12-182) with a fused forward/backward.
 
-    Same parameter names/shapes: encoder.embeddings [5303704, 2] (L=14), sigma_net.{0,1}.weight, color_net.{0,1,2}.weight.
+    Same parameter names/shapes: encoder.embeddings [5303704, 2] (L=14), sigma_net.{0,1}.weight, color_net.{0,1,2}.weight;
+    same renderer buffers (it IS a NeRFRenderer, like the reference's NeRFNetwork).
     """
 
     def __init__(self, num_levels=14, desired_resolution=2048, bound=1, hidden_dim=64, geo_feat_dim=15, args=None,
-                 density_scale=1.0, table_fp16=True):
-        super().__init__()
+                 density_scale=1.0, table_fp16=True, is_teacher=False, **renderer_kwargs):
+        super().__init__(bound=bound, density_scale=density_scale, **renderer_kwargs)
+        self.is_teacher = is_teacher
+        self.model_type = "hash"
         from gridencoder import GridEncoder
         from shencoder import SHEncoder
         assert hidden_dim == 64 and geo_feat_dim == 15, "the fused kernel is built for PVD's 64-wide / 15-feature heads"
@@ -185,7 +196,6 @@ class HashNeRFField(nn.Module):
         self.sigma_net = nn.ModuleList([nn.Linear(self.in_dim, 64, bias=False), nn.Linear(64, 16, bias=False)])
         self.color_net = nn.ModuleList([nn.Linear(31, 64, bias=False), nn.Linear(64, 64, bias=False),
                                         nn.Linear(64, 3, bias=False)])
-        self.density_scale = density_scale
         self.table_fp16 = table_fp16
         self._staged = StagedParams()
         self.feature_sigma_color = None
@@ -210,3 +220,18 @@ class HashNeRFField(nn.Module):
         self.sigma_l = feat[..., 0]
         self.color_l = color
         return sigma, color
+
+    def density(self, x):
+        """sigma only, for the density-grid upkeep (network.py:439-494; the colour half of the kernel output is discarded)."""
+        x = x.reshape(-1, 3)
+        d = torch.zeros_like(x)
+        with torch.no_grad():
+            sigma, _, _ = fused_hash_field(x, d, self.encoder.embeddings, self.sigma_net[0].weight, self.sigma_net[1].weight,
+                                           self.color_net[0].weight, self.color_net[1].weight, self.color_net[2].weight,
+                                           self.encoder.offsets, self.config(), self._staged, True)
+        return {"sigma": sigma}
+
+    def get_params(self, lr, lr2=1e-3):
+        """Optimizer groups of the reference's hash model (network.py:646-653)."""
+        return [{"params": self.encoder.parameters(), "lr": lr}, {"params": self.sigma_net.parameters(), "lr": lr},
+                {"params": self.encoder_dir.parameters(), "lr": lr}, {"params": self.color_net.parameters(), "lr": lr}]

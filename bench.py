@@ -319,7 +319,7 @@ def time_phases(eng):
                                                      u32(N), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss), st))
     e[3].record()
     nv.check(l.pvd_hash_field_backward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.enc), nv.ptr(eng.grad_sigmas),
-                                       nv.ptr(eng.grad_rgbs), u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),
+                                       nv.ptr(eng.grad_rgbs), None, u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),
                                        nv.ptr(eng.status), st))
     e[4].record()
     torch.cuda.synchronize()
