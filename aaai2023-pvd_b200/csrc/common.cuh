@@ -135,7 +135,7 @@ __device__ __forceinline__ float pcg32_next_float(Pcg32& r) {
 // One evaluation of the loop body of raymarching.cu:362-403 at parameter t.
 struct MarchCtx {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
-    float bound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f;
+    float bound, rbound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f;
     uint32_t C, H, H3;
 };
 
@@ -144,7 +144,7 @@ __device__ __forceinline__ void march_ctx_init(MarchCtx& c, const float* o, cons
     c.ox = o[0]; c.oy = o[1]; c.oz = o[2];
     c.dx = d[0]; c.dy = d[1]; c.dz = d[2];
     c.rdx = __fdiv_rn(1.0f, c.dx); c.rdy = __fdiv_rn(1.0f, c.dy); c.rdz = __fdiv_rn(1.0f, c.dz);
-    c.bound = bound; c.dt_gamma = dt_gamma;
+    c.bound = bound; c.rbound = __fdiv_rn(1.0f, bound); c.dt_gamma = dt_gamma;
     c.Hf = (float)H; c.Hm1f = (float)(H - 1); c.rH = __fdiv_rn(1.0f, c.Hf);
     // dt_min = 2*SQRT3/max_steps ; dt_max = 2*SQRT3*(1<<(C-1))/H   (raymarching.cu:346-347)
     const float two_s3 = __fmul_rn(2.0f, kSqrt3);
@@ -186,9 +186,14 @@ __device__ __forceinline__ float march_exit(int n, float d, float rd, float x, f
 // parameter at which the ray leaves the cell (tt of raymarching.cu:397).
 __device__ __forceinline__ bool march_probe(const MarchCtx& c, const uint8_t* __restrict__ grid, float t,
                                             float dt, float x, float y, float z, float& t_skip) {
-    const int level = max(mip_from_pos(x, y, z, c.C), mip_from_dt(dt, c.Hf, c.C));
-    const float mip_bound = fminf((float)(1u << level), c.bound);
-    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    // level in [0, C-1] (raymarching.cu:371); a single cascade needs no exponent arithmetic at all
+    const int level = (c.C > 1) ? max(mip_from_pos(x, y, z, c.C), mip_from_dt(dt, c.Hf, c.C)) : 0;
+    // mip_bound = min(2^level, bound), mip_rbound = 1 / mip_bound (:373-374).  The IEEE quotient 1 / 2^level is exactly
+    // 2^-level, so the division is only ever needed for 1 / bound, which is hoisted into the context.
+    const float p2 = (float)(1u << level);
+    const bool pow2 = p2 <= c.bound;
+    const float mip_bound = pow2 ? p2 : c.bound;
+    const float mip_rbound = pow2 ? __uint_as_float((uint32_t)(127 - level) << 23) : c.rbound;
     const int nx = march_cell(x, mip_rbound, c.Hf, c.Hm1f);
     const int ny = march_cell(y, mip_rbound, c.Hf, c.Hm1f);
     const int nz = march_cell(z, mip_rbound, c.Hf, c.Hm1f);

@@ -53,14 +53,25 @@ constexpr uint32_t kGW5 = kGW4 + 64 * 64;     // [64][16]  (transposed: [in][out
 constexpr uint32_t kGWTotal = kGW5 + 64 * 16; // 10240
 static_assert(kGWTotal == PVD_FIELD_GW_FLOATS, "workspace size");
 
-struct LevelInfo {
+struct __align__(16) LevelInfo {
     float scale;
     uint32_t res1;    // resolution + 1 (dense stride)
     uint32_t offset;  // first entry
     uint32_t size;    // entries
     uint32_t mode;    // 0 dense (index < size, no modulo), 1 hashed with power-of-two size, 2 generic
     uint32_t mask;
+    uint32_t pad0, pad1;
 };
+
+// explicit ld.shared of one table entry (a generic-pointer access made ptxas insert an S2R + window computation per level)
+__device__ __forceinline__ LevelInfo ld_level(uint32_t lv_saddr, uint32_t l) {
+    LevelInfo v;
+    uint32_t a, b, c, d, e, f;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(lv_saddr + l * 32u));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e), "=r"(f) : "r"(lv_saddr + l * 32u + 16u));
+    v.scale = __uint_as_float(a); v.res1 = b; v.offset = c; v.size = d; v.mode = e; v.mask = f; v.pad0 = 0; v.pad1 = 0;
+    return v;
+}
 
 __device__ __forceinline__ void level_info_init(LevelInfo* lv, const int32_t* offsets, uint32_t L, float S, uint32_t H) {
     const uint32_t l = threadIdx.x;
@@ -76,6 +87,7 @@ __device__ __forceinline__ void level_info_init(LevelInfo* lv, const int32_t* of
         // gridencoder.cu:54-72: the running stride exceeds the level size exactly when the dense grid does not fit
         const bool fits = ((uint64_t)v.res1 <= g.size) && ((uint64_t)v.res1 * v.res1 <= g.size) && (dense <= g.size);
         v.mode = fits ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
+        v.pad0 = v.pad1 = 0;
         lv[l] = v;
     }
 }
@@ -122,27 +134,34 @@ __device__ __forceinline__ void to_unit(const float* __restrict__ p, float bound
     oob = grid_oob<3>(x01);
 }
 
-// interpolate 8 consecutive features (4 levels) of one sample
+// interpolate 8 consecutive features (4 levels) of one sample.  All 32 gathers of the four levels are issued before any
+// of them is consumed (branch-free: a level beyond L re-reads level 0 and is multiplied by zero), because at 9-12 resident
+// warps per SM the gather is latency-bound and memory-level parallelism per thread is what hides it.
 template <typename T>
-__device__ __forceinline__ void encode4(const T* __restrict__ table, const LevelInfo* lv, uint32_t l0, uint32_t L,
+__device__ __forceinline__ void encode4(const T* __restrict__ table, uint32_t lv_saddr, uint32_t l0, uint32_t L,
                                         const float (&x01)[3], bool oob, float (&f)[8]) {
+    float2 fv[4][8];
+    float w[4][8];
 #pragma unroll
     for (uint32_t q = 0; q < 4; ++q) {
-        const uint32_t l = l0 + q;
+        const bool on = (l0 + q < L) && !oob;
+        const LevelInfo v = ld_level(lv_saddr, on ? l0 + q : 0u);
+        Corners c;
+        level_corners(v, x01, c);
+        const T* tab = table + (size_t)v.offset * 2;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+            fv[q][i] = tab_load2(tab, (size_t)c.idx[i] * 2);
+            w[q][i] = on ? c.w[i] : 0.0f;
+        }
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < 4; ++q) {
         float a0 = 0.0f, a1 = 0.0f;
-        if (l < L && !oob) {
-            const LevelInfo v = lv[l];
-            Corners c;
-            level_corners(v, x01, c);
-            const T* tab = table + (size_t)v.offset * 2;
-            float2 fv[8];
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) fv[i] = tab_load2(tab, (size_t)c.idx[i] * 2);
-#pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) {
-                a0 = __fmaf_rn(c.w[i], fv[i].x, a0);
-                a1 = __fmaf_rn(c.w[i], fv[i].y, a1);
-            }
+        for (uint32_t i = 0; i < 8; ++i) {
+            a0 = __fmaf_rn(w[q][i], fv[q][i].x, a0);
+            a1 = __fmaf_rn(w[q][i], fv[q][i].y, a1);
         }
         f[2 * q] = a0;
         f[2 * q + 1] = a1;
@@ -348,6 +367,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
     const T* table = reinterpret_cast<const T*>(a.table);
+    const uint32_t lv_saddr = tc5::smem_u32(lv);
 
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -367,7 +387,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
 #pragma unroll 1
         for (uint32_t j = 0; j < 4; ++j) {
             float f[8];
-            encode4<T>(table, lv, 4 * j, a.L, x01, oob, f);
+            encode4<T>(table, lv_saddr, 4 * j, a.L, x01, oob, f);
             const uint4 u = tc5::pack8(f);
             *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
             if (enc && live) *reinterpret_cast<uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = u;
@@ -447,6 +467,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
     const uint32_t sw = tc5::smem_u32(smw);
     const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+    const uint32_t lv_saddr = tc5::smem_u32(lv);
 
     const uint32_t n_tiles = (n_valid + kTile - 1) / kTile;  // tiles made only of padding rows contribute nothing
     bool first = true;
@@ -560,7 +581,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
 #pragma unroll
                 for (uint32_t l = 0; l < 16; ++l) {
                     if (l < a.L) {
-                        const LevelInfo v = lv[l];
+                        const LevelInfo v = ld_level(lv_saddr, l);
                         Corners c;
                         level_corners(v, x01, c);
                         float* gt = grad_table + (size_t)v.offset * 2;

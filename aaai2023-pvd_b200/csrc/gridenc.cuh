@@ -107,7 +107,8 @@ __device__ __forceinline__ void tab_red(float* t, size_t i, float v) { atomicAdd
 __device__ __forceinline__ void tab_red(__half* t, size_t i, float v) { atomicAdd(t + i, __float2half_rn(v)); }
 __device__ __forceinline__ void tab_red2(float* t, size_t i, float a, float b) {
     // red.global.add.v2.f32 (sm_90+): one 8-byte reduction instead of two 4-byte ones
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t + i), "f"(a), "f"(b) : "memory");
+    // volatile keeps the reduction; no "memory" clobber, so the compiler may overlap the next level's address math with it
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t + i), "f"(a), "f"(b));
 }
 __device__ __forceinline__ void tab_red2(__half* t, size_t i, float a, float b) {
     atomicAdd(reinterpret_cast<__half2*>(t + i), __floats2half2_rn(a, b));
