@@ -21,11 +21,11 @@
 #include "gridenc.cuh"
 #include "shenc.cuh"
 #include "tc5.cuh"
+#include "field_common.cuh"
 #include "../../include/pvd_b200_fused.h"
 
 namespace pvd {
 
-constexpr uint32_t kTile = 128;
 // byte offsets of the weight operand tiles inside the packed blob / shared memory
 constexpr uint32_t kWB1 = 0;      // sigma_net.0 : 64 rows (out) x 32 cols (in, 2L zero padded)
 constexpr uint32_t kWB2 = 4096;   // sigma_net.1 : 16 x 64
@@ -168,83 +168,6 @@ __device__ __forceinline__ void encode4(const T* __restrict__ table, uint32_t lv
     }
 }
 
-struct Pipe {
-    uint64_t* bar;
-    uint32_t phase;
-    uint32_t tmem;
-    int32_t* status;
-};
-
-// Every thread: publish shared-memory operand writes to the async proxy and order prior TMEM reads, then barrier.
-__device__ __forceinline__ void operands_ready() {
-    tc5::fence_async_smem();
-    tc5::fence_before_sync();
-    __syncthreads();
-}
-// Every thread: wait for the MMAs committed by thread 0.
-__device__ __forceinline__ void mma_wait(Pipe& p) {
-    if (!tc5::mbar_wait(p.bar, p.phase)) atomicExch(p.status, 1);
-    p.phase ^= 1u;
-    tc5::fence_after_sync();
-}
-
-// D[128 x N] (=|+=) A[128 x K] * B[N x K]^T, both K-major chunk tiles (forward layer)
-__device__ __forceinline__ void issue_fwd(uint32_t d_tmem, uint32_t a_tile, uint32_t K, uint32_t b_tile, uint32_t b_rows, uint32_t N) {
-    const uint32_t idesc = tc5::instr_desc_f16(128, N, 0, 0);
-    for (uint32_t k0 = 0; k0 < K; k0 += 16)
-        tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, b_rows, k0), idesc, k0 > 0);
-}
-// D[128 x N] = G[128 x K] * W[K x N] with W stored as the forward operand tile [K rows(out) x N cols(in)] (data gradient)
-__device__ __forceinline__ void issue_dgrad(uint32_t d_tmem, uint32_t g_tile, uint32_t K, uint32_t w_tile, uint32_t w_rows, uint32_t N) {
-    const uint32_t idesc = tc5::instr_desc_f16(128, N, 0, 1);
-    for (uint32_t k0 = 0; k0 < K; k0 += 16)
-        tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(g_tile, kTile, k0), tc5::desc_mnmajor(w_tile, w_rows, k0, 0), idesc, k0 > 0);
-}
-// D[64 x N] (+)= P[128 x 64]^T * Q[128 x N]  (weight gradient: reduction over the 128 samples of the tile)
-__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_tile, uint32_t q_tile, uint32_t N, bool first) {
-    const uint32_t idesc = tc5::instr_desc_f16(64, N, 1, 1);
-    for (uint32_t s0 = 0; s0 < kTile; s0 += 16)
-        tc5::mma_f16_ss(d_tmem, tc5::desc_mnmajor(p_tile, kTile, s0, 0), tc5::desc_mnmajor(q_tile, kTile, s0, 0), idesc,
-                        !(first && s0 == 0));
-}
-
-// this thread's row of a [128 x 16*NC16] TMEM accumulator -> ReLU -> fp16 chunk tile
-template <int NC16>
-__device__ __forceinline__ void relu_to_tile(uint32_t tmem_row, uint8_t* tile, uint32_t row) {
-#pragma unroll
-    for (int c = 0; c < NC16; ++c) {
-        float v[16];
-        tc5::tmem_ld16(tmem_row + 16 * c, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        *reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c)) = tc5::pack8(v);
-        *reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c + 1)) = tc5::pack8(v + 8);
-    }
-}
-
-// this thread's row of a 64-wide data gradient, masked by the sign of the saved activation, written IN PLACE over it
-__device__ __forceinline__ void mask_grad_in_place(uint32_t tmem_row, uint8_t* tile, uint32_t row) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float v[16];
-        tc5::tmem_ld16(tmem_row + 16 * c, v);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint4* p = reinterpret_cast<uint4*>(tile + tc5::chunk_off(kTile, row, 2 * c + h));
-            const uint4 a = *p;
-            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-            float g[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 af = __half22float2(ah[i]);
-                g[2 * i] = af.x > 0.0f ? v[8 * h + 2 * i] : 0.0f;
-                g[2 * i + 1] = af.y > 0.0f ? v[8 * h + 2 * i + 1] : 0.0f;
-            }
-            *p = tc5::pack8(g);
-        }
-    }
-}
-
 struct FieldArgs {
     const void* table;
     const int32_t* offsets;
@@ -334,10 +257,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
     for (int i = 0; i < 3; ++i) r.rgb[i] = 1.0f / (1.0f + __expf(-c16[i]));
 }
 
-__device__ __forceinline__ void stage_weights(uint8_t* smw, const uint8_t* __restrict__ blob) {
-    for (uint32_t i = threadIdx.x; i < PVD_FIELD_WBLOB_BYTES / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(smw)[i] = __ldg(reinterpret_cast<const uint4*>(blob) + i);
-}
+__device__ __forceinline__ void stage_weights(uint8_t* smw, const uint8_t* __restrict__ blob) { stage_blob(smw, blob, PVD_FIELD_WBLOB_BYTES); }
 
 // =============================================================================================== forward kernel
 template <typename T>
@@ -348,11 +268,14 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelInfo lv[16];
+    // Forward-only tiles alias: the encoding X is dead once layer 1's MMAs completed, so the colour-net input CIN reuses its
+    // buffer; H1, H3, H4 are each dead when the next one is written (its consumer MMA has been waited for).  44 KB per CTA
+    // instead of 68 KB -> 4 resident CTAs per SM (the TMEM limit) instead of 3, i.e. one tile per CTA at 4096 rays.
     uint8_t* smw = smem;                               // 20480
-    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;         // 8192
-    uint8_t* CIN = X + 8192;                           // 8192
-    uint8_t* HA = CIN + 8192;                          // 16384
-    uint8_t* HB = HA + 16384;                          // 16384
+    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;         // 8192  (X, then CIN)
+    uint8_t* CIN = X;
+    uint8_t* HA = X + 8192;                            // 16384 (H1, then H3, then H4)
+    uint8_t* HB = HA;
     const uint32_t tid = threadIdx.x;
 
     stage_weights(smw, a.wblob);
@@ -414,23 +337,6 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
 }
 
 // =============================================================================================== backward kernel
-__device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint32_t ncols, float* __restrict__ dst) {
-    // M = 64 accumulator: row m lives in TMEM lane (m/16)*32 + m%16 (verified on B200, profiles/r01_tcgen05_probe.log)
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t m = warp * 16 + lane;
-    for (uint32_t c = 0; c < ncols; c += 16) {
-        float v[16];
-        tc5::tmem_ld16(tc5::tmem_addr(tmem_base, warp * 32, col + c), v);
-        if (lane < 16) {
-            float* d = dst + (size_t)m * ncols + c;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
-                             "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                             : "memory");
-        }
-    }
-}
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
@@ -609,16 +515,6 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
 }
 
-// pack one fp32 [out, in] matrix into an fp16 chunk tile of R rows x K cols (zero padded)
-__device__ __forceinline__ void pack_matrix(const float* __restrict__ w, uint32_t out, uint32_t in, uint8_t* tile, uint32_t R,
-                                            uint32_t K) {
-    for (uint32_t e = threadIdx.x; e < R * K; e += blockDim.x) {
-        const uint32_t r = e / K, k = e - r * K;
-        const float v = (r < out && k < in) ? w[(size_t)r * in + k] : 0.0f;
-        *reinterpret_cast<__half*>(tile + tc5::chunk_off(R, r, k >> 3) + (k & 7u) * 2) = __float2half_rn(v);
-    }
-}
-
 __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
                                const float* __restrict__ wc1, const float* __restrict__ wc2, uint32_t in_dim,
                                uint8_t* __restrict__ blob) {
@@ -655,13 +551,9 @@ static FieldArgs to_args(const PvdHashField* f) {
     return a;
 }
 
-static int sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-}
 
-constexpr size_t kFwdSmem = PVD_FIELD_WBLOB_BYTES + 8192 + 8192 + 16384 + 16384;            // 69632
+
+constexpr size_t kFwdSmem = PVD_FIELD_WBLOB_BYTES + 8192 + 16384;                          // 45056
 constexpr size_t kBwdSmem = PVD_FIELD_WBLOB_BYTES + 8192 + 8192 + 16384 * 3 + 4096;         // 90112
 
 }  // namespace pvd
@@ -686,7 +578,7 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
     if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
     const FieldArgs a = to_args(f);
     const uint32_t tiles = (M + kTile - 1) / kTile;
-    const uint32_t grid = min(tiles, (uint32_t)(3 * sm_count()));
+    const uint32_t grid = min(tiles, (uint32_t)(4 * sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (f->table_dtype == PVD_DTYPE_F16) {

@@ -1,0 +1,594 @@
+// field_vm.cu -- fused "vm" (TensoRF vector-matrix) field query for sm_100a, forward and backward.
+//
+// Replaces, for model_type "vm", NeRFNetwork.forward of the reference (distill_mutual/network.py:216-309,344-382):
+// 12 F.grid_sample launches (3 planes + 3 lines, for 16 sigma and 48 colour components each) with ~20 elementwise kernels,
+// basis_mat (144 -> 15), clamps, trunc_exp, SH, color_net and sigmoid -- and the mirror image of all that in autograd.
+//
+// Layout.  The planes/lines are read IN PLACE as channels-last fp32: a parameter of logical shape [1, R, H, W] stored with
+// torch.channels_last strides is [H][W][R] in memory, so one bilinear tap is R contiguous floats (64 B sigma + 192 B colour)
+// instead of R loads H*W*4 bytes apart as in the reference's channel-first storage ("VM layout").  The shapes in
+// the state_dict do not change.
+//
+// Work decomposition.
+//   gather  : ONE WARP PER SAMPLE, lanes = components (lanes 0-7 the 16 sigma components, lanes 8-31 the 48 colour ones,
+//             two per lane) -> every tap is one coalesced 256-byte request; plane x line products go straight into the
+//             fp16 operand tile APP[128 x 144] (colour) and a warp-reduced scalar (sigma).  4608 B/sample algorithmic.
+//   MLP     : thread per sample around tcgen05 GEMMs, exactly as in field_hash.cu: basis_mat (K = 144, 9 MMAs), clamps,
+//             exp, SH concat, color_net (3 layers), sigmoid.
+//   backward: forward recomputed; weight gradients accumulate in TMEM (basis as three M=64 pieces); d(APP) comes back in
+//             three 48-column data-gradient GEMMs; then one warp per sample re-gathers plane/line values and scatters
+//             d(plane) = d(prod) * line, d(line) = d(prod) * plane with red.global.add.v2.f32 into channels-last gradients
+//             (coalesced 256-byte reductions).
+#include "field_common.cuh"
+#include "shenc.cuh"
+#include "../../include/pvd_b200_fused.h"
+
+namespace pvd {
+
+// weight blob (bytes)
+constexpr uint32_t kVB = 0;        // basis_mat : 16 rows (15 out + pad) x 144 cols
+constexpr uint32_t kVB3 = 4608;    // color_net.0 : 64 x 32
+constexpr uint32_t kVB4 = 8704;    // color_net.1 : 64 x 64
+constexpr uint32_t kVB5 = 16896;   // color_net.2 : 16 x 64
+static_assert(kVB5 + 2048 == PVD_VM_WBLOB_BYTES, "vm blob size");
+// TMEM columns
+constexpr uint32_t kVD = 0;        // [0,64)
+constexpr uint32_t kVD16 = 64;     // [64,80)  basis_mat output
+constexpr uint32_t kVD5 = 80;      // [80,96)
+constexpr uint32_t kVAW5 = 96;     // [96,112)   dW5^T [64][16]
+constexpr uint32_t kVAW4 = 112;    // [112,176)  dW4   [64][64]
+constexpr uint32_t kVAW3 = 176;    // [176,208)  dW3   [64][32]
+constexpr uint32_t kVAB = 208;     // [208,256)  dBasis^T as three [64][16] pieces (app channels 0-63, 64-127, 128-143)
+// gradient workspace (floats)
+constexpr uint32_t kVGB = 0;       // [192][16]
+constexpr uint32_t kVG3 = 3072;    // [64][32]
+constexpr uint32_t kVG4 = 5120;    // [64][64]
+constexpr uint32_t kVG5 = 9216;    // [64][16]
+static_assert(kVG5 + 1024 == PVD_FIELD_GW_FLOATS, "vm workspace size");
+
+struct VmArgs {
+    const float* smat[3];
+    const float* svec[3];
+    const float* cmat[3];
+    const float* cvec[3];
+    const uint8_t* wblob;
+    uint32_t res[3];
+    float aabb[6];
+    float clip_min, clip_max, density_scale;
+};
+struct VmGradPtrs {
+    float* smat[3];
+    float* svec[3];
+    float* cmat[3];
+    float* cvec[3];
+};
+
+// bilinear footprint of one sample on plane i and line i (grid_sample, align_corners=True, zeros padding)
+struct Foot {
+    uint32_t pidx[4];  // texel index (y*W + x) of the 4 plane taps
+    float pw[4];       // weights (0 for out-of-range taps)
+    uint32_t lidx[2];
+    float lw[2];
+};
+
+__device__ __forceinline__ void vm_normalise(const float* pos, const float* aabb, float (&xn)[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)  // 2 * (x - lo) / (hi - lo) - 1   (network.py:345-350)
+        xn[d] = __fdiv_rn(2.0f * (pos[d] - aabb[d]), aabb[3 + d] - aabb[d]) - 1.0f;
+}
+
+__device__ __forceinline__ void vm_foot(const float (&xn)[3], const uint32_t (&res)[3], int i, Foot& f) {
+    // mat_ids = [[0,1],[0,2],[1,2]], vec_ids = [2,1,0]  (network.py:76-77)
+    const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2, av = 2 - i;
+    const uint32_t W = res[a0], Hh = res[a1], D = res[av];
+    const float ix = (xn[a0] + 1.0f) * 0.5f * (float)(W - 1);
+    const float iy = (xn[a1] + 1.0f) * 0.5f * (float)(Hh - 1);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    const int x0 = (int)fx, y0 = (int)fy;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+        const bool in = (xx >= 0) && (xx < (int)W) && (yy >= 0) && (yy < (int)Hh);
+        f.pidx[t] = in ? (uint32_t)(yy * (int)W + xx) : 0u;
+        f.pw[t] = in ? ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0) : 0.0f;
+    }
+    const float il = (xn[av] + 1.0f) * 0.5f * (float)(D - 1);
+    const float fl = floorf(il);
+    const float wl1 = il - fl;
+    const int l0 = (int)fl;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int ll = l0 + t;
+        const bool in = (ll >= 0) && (ll < (int)D);
+        f.lidx[t] = in ? (uint32_t)ll : 0u;
+        f.lw[t] = in ? (t ? wl1 : 1.0f - wl1) : 0.0f;
+    }
+}
+
+// plane and line value of this lane's two components
+__device__ __forceinline__ void vm_sample(const float* __restrict__ mat, const float* __restrict__ vec, uint32_t R, uint32_t ch,
+                                          const Foot& f, float2& pv, float2& lv) {
+    pv = make_float2(0.f, 0.f);
+    lv = make_float2(0.f, 0.f);
+    float2 t[4], u[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float2*>(mat + (size_t)f.pidx[k] * R + ch));
+#pragma unroll
+    for (int k = 0; k < 2; ++k) u[k] = __ldg(reinterpret_cast<const float2*>(vec + (size_t)f.lidx[k] * R + ch));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pv.x = __fmaf_rn(f.pw[k], t[k].x, pv.x);
+        pv.y = __fmaf_rn(f.pw[k], t[k].y, pv.y);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        lv.x = __fmaf_rn(f.lw[k], u[k].x, lv.x);
+        lv.y = __fmaf_rn(f.lw[k], u[k].y, lv.y);
+    }
+}
+
+// Gather phase for the 32 samples of this warp: APP tile (colour products, fp16) and sfeat[row] (sigma feature, fp32)
+__device__ __forceinline__ void vm_gather(const VmArgs& a, const float* __restrict__ xyzs, uint32_t tile_row0, uint32_t M,
+                                          uint8_t* APP, float* sfeat) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const bool sig = lane < 8;
+    const uint32_t R = sig ? 16u : 48u;
+    const uint32_t ch = sig ? 2u * lane : 2u * (lane - 8u);
+#pragma unroll 2
+    for (uint32_t s = 0; s < 32; ++s) {
+        const uint32_t r = warp * 32 + s;
+        const uint32_t row = tile_row0 + r;
+        float pos[3] = {0.f, 0.f, 0.f};
+        if (row < M) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+        }
+        float xn[3];
+        vm_normalise(pos, a.aabb, xn);
+        float sacc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Foot f;
+            vm_foot(xn, a.res, i, f);
+            float2 pv, lv;
+            vm_sample(sig ? a.smat[i] : a.cmat[i], sig ? a.svec[i] : a.cvec[i], R, ch, f, pv, lv);
+            const float p0 = pv.x * lv.x, p1 = pv.y * lv.y;
+            if (sig) {
+                sacc += p0 + p1;
+            } else {
+                const uint32_t col = (uint32_t)i * 48u + ch;
+                *reinterpret_cast<__half2*>(APP + tc5::chunk_off(kTile, r, col >> 3) + (col & 7u) * 2u) = __floats2half2_rn(p0, p1);
+            }
+        }
+        sacc = sig ? sacc : 0.0f;
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        if (lane == 0) sfeat[r] = sacc;
+    }
+}
+
+struct VmRegs {
+    float sf_raw, sfc, rgb[3];
+    float cf_raw[15];
+};
+
+// basis_mat + color_net for one tile; APP and sfeat are ready.  CIN may alias APP (forward only).
+__device__ __forceinline__ void vm_mlp_forward(Pipe& p, const VmArgs& a, uint8_t* smw, uint8_t* APP, uint8_t* CIN, uint8_t* H3,
+                                               uint8_t* H4, const float* sfeat, const float* dir, uint32_t row, float& sigma,
+                                               float (&feat)[16], VmRegs& r) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t trow = tc5::tmem_addr(p.tmem, (tid >> 5) * 32, 0);
+    const uint32_t sw = tc5::smem_u32(smw);
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kVD16, tc5::smem_u32(APP), 144, sw + kVB, 16, 16);  // colour features: [128 x 144] x [16 x 144]^T
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    float cf[16];
+    tc5::tmem_ld16(trow + kVD16, cf);
+    r.sf_raw = sfeat[row];
+    r.sfc = clampf(r.sf_raw, a.clip_min, a.clip_max);                         // network.py:353-358
+    feat[0] = r.sfc;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) {
+        r.cf_raw[i] = __half2float(__float2half_rn(cf[i]));                   // basis_mat runs in fp16 under autocast
+        feat[i + 1] = clampf(r.cf_raw[i], a.clip_min, a.clip_max);            // network.py:359-361
+    }
+    sigma = a.density_scale * __expf(r.sfc);
+    {
+        float sh[16], geo[16];
+        sh_basis4(dir[0], dir[1], dir[2], sh);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) geo[i] = feat[i + 1];
+        geo[15] = 0.0f;
+        // CIN may alias APP: every thread has finished reading TMEM, and the basis MMA has completed (waited above)
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 0)) = tc5::pack8(sh);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 1)) = tc5::pack8(sh + 8);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 2)) = tc5::pack8(geo);
+        *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 3)) = tc5::pack8(geo + 8);
+    }
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kVD, tc5::smem_u32(CIN), 32, sw + kVB3, 64, 64);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    relu_to_tile<4>(trow + kVD, H3, row);
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kVD, tc5::smem_u32(H3), 64, sw + kVB4, 64, 64);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    relu_to_tile<4>(trow + kVD, H4, row);
+    operands_ready();
+    if (tid == 0) {
+        tc5::fence_after_sync();
+        issue_fwd(p.tmem + kVD5, tc5::smem_u32(H4), 64, sw + kVB5, 16, 16);
+        tc5::mma_commit(p.bar);
+    }
+    mma_wait(p);
+    float c16[16];
+    tc5::tmem_ld16(trow + kVD5, c16);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.rgb[i] = 1.0f / (1.0f + __expf(-c16[i]));
+}
+
+// =============================================================================================== forward
+__global__ void __launch_bounds__(128) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                      uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
+                                                      float* __restrict__ feat16, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float sfeat[kTile];
+    uint8_t* smw = smem;                          // 18944
+    uint8_t* APP = smem + PVD_VM_WBLOB_BYTES;     // 36864 ; CIN aliases its first 8 KB
+    uint8_t* H = APP + 36864;                     // 16384 ; H3 then H4
+    const uint32_t tid = threadIdx.x;
+    stage_blob(smw, a.wblob, PVD_VM_WBLOB_BYTES);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_fence_init();
+    }
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();  // previous tile's sfeat / APP consumers are done
+        vm_gather(a, xyzs, tile * kTile, M, APP, sfeat);
+        const uint32_t row = tile * kTile + tid;
+        const bool live = row < M;
+        float dir[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+        }
+        float sigma, feat[16];
+        VmRegs r;
+        vm_mlp_forward(p, a, smw, APP, APP, H, H, sfeat, dir, tid, sigma, feat, r);
+        if (live) {
+            sigmas[row] = sigma;
+            rgbs[3 * (size_t)row] = r.rgb[0];
+            rgbs[3 * (size_t)row + 1] = r.rgb[1];
+            rgbs[3 * (size_t)row + 2] = r.rgb[2];
+            if (feat16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(feat16 + 16 * (size_t)row + 4 * q) =
+                        make_float4(feat[4 * q], feat[4 * q + 1], feat[4 * q + 2], feat[4 * q + 3]);
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 128);
+}
+
+// =============================================================================================== backward
+__global__ void __launch_bounds__(128) k_vm_field_bwd(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
+                                                      const float* __restrict__ dirs, const float* __restrict__ grad_sigmas,
+                                                      const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
+                                                      uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ gw,
+                                                      int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float sfeat[kTile];
+    __shared__ float dsf[kTile];
+    uint8_t* smw = smem;                          // 18944
+    uint8_t* APP = smem + PVD_VM_WBLOB_BYTES;     // 36864  (later d(APP))
+    uint8_t* CIN = APP + 36864;                   // 8192
+    uint8_t* H3 = CIN + 8192;                     // 16384
+    uint8_t* H4 = H3 + 16384;                     // 16384
+    uint8_t* G16 = H4 + 16384;                    // 4096
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    stage_blob(smw, a.wblob, PVD_VM_WBLOB_BYTES);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_fence_init();
+    }
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    const uint32_t trow = tc5::tmem_addr(p.tmem, warp * 32, 0);
+    const uint32_t sw = tc5::smem_u32(smw);
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+    const uint32_t n_tiles = (n_valid + kTile - 1) / kTile;
+    bool first = true;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        vm_gather(a, xyzs, tile * kTile, M, APP, sfeat);
+        const uint32_t row = tile * kTile + tid;
+        const bool live = row < n_valid;
+        float dir[3] = {0.f, 0.f, 0.f}, gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
+            }
+            gsig = __ldg(grad_sigmas + row);
+        }
+        float sigma, feat[16];
+        VmRegs r;
+        vm_mlp_forward(p, a, smw, APP, CIN, H3, H4, sfeat, dir, tid, sigma, feat, r);
+        // ---- colour net backward (same sequence as the hash field)
+        {
+            float gq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) gq[i] = grgb[i] * r.rgb[i] * (1.0f - r.rgb[i]);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(gq);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = make_uint4(0, 0, 0, 0);
+        }
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kVAW5, tc5::smem_u32(H4), tc5::smem_u32(G16), 16, first);
+            issue_dgrad(p.tmem + kVD, tc5::smem_u32(G16), 16, sw + kVB5, 16, 64);
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        mask_grad_in_place(trow + kVD, H4, tid);
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kVAW4, tc5::smem_u32(H4), tc5::smem_u32(H3), 64, first);
+            issue_dgrad(p.tmem + kVD, tc5::smem_u32(H4), 64, sw + kVB4, 64, 64);
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        mask_grad_in_place(trow + kVD, H3, tid);
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kVAW3, tc5::smem_u32(H3), tc5::smem_u32(CIN), 32, first);
+            issue_dgrad(p.tmem + kVD, tc5::smem_u32(H3), 64, sw + kVB3, 64, 32);
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        // ---- d(colour features) through the clamp, d(sigma feature) through trunc_exp + clamp
+        {
+            float dc[16], gq[16], gf[16];
+            tc5::tmem_ld16(trow + kVD + 16, dc);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gf[i] = 0.0f;
+            if (grad_feat && live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(grad_feat + 16 * (size_t)row) + q);
+                    gf[4 * q] = v.x; gf[4 * q + 1] = v.y; gf[4 * q + 2] = v.z; gf[4 * q + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 15; ++i) {
+                const bool in = (r.cf_raw[i] >= a.clip_min) && (r.cf_raw[i] <= a.clip_max);
+                gq[i] = in ? dc[i] + gf[i + 1] : 0.0f;
+            }
+            gq[15] = 0.0f;
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(gq);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = tc5::pack8(gq + 8);
+            const bool sin = (r.sf_raw >= a.clip_min) && (r.sf_raw <= a.clip_max);
+            dsf[tid] = (sin && live) ? gsig * a.density_scale * __expf(clampf(r.sfc, -12.0f, 12.0f)) + gf[0] : 0.0f;
+        }
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            // dBasis^T [144 x 16] += APP^T G as three M=64 pieces (the last covers channels 128..191; rows >= 144 are never flushed)
+            const uint32_t idesc = tc5::instr_desc_f16(64, 16, 1, 1);
+            for (uint32_t piece = 0; piece < 3; ++piece)
+                for (uint32_t s0 = 0; s0 < kTile; s0 += 16)
+                    tc5::mma_f16_ss(p.tmem + kVAB + 16 * piece, tc5::desc_mnmajor(tc5::smem_u32(APP), kTile, s0, 64 * piece),
+                                    tc5::desc_mnmajor(tc5::smem_u32(G16), kTile, s0, 0), idesc, !(first && s0 == 0));
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        first = false;
+        // d(APP) = G [128 x 16] x basis [16 x 144], 48 columns at a time, written (fp16) over APP
+        for (uint32_t piece = 0; piece < 3; ++piece) {
+            operands_ready();
+            if (tid == 0) {
+                tc5::fence_after_sync();
+                const uint32_t idesc = tc5::instr_desc_f16(128, 48, 0, 1);
+                tc5::mma_f16_ss(p.tmem + kVD, tc5::desc_kmajor(tc5::smem_u32(G16), kTile, 0),
+                                tc5::desc_mnmajor(sw + kVB, 16, 0, 48 * piece), idesc, 0u);
+                tc5::mma_commit(p.bar);
+            }
+            mma_wait(p);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v[16];
+                tc5::tmem_ld16(trow + kVD + 16 * c, v);
+                *reinterpret_cast<uint4*>(APP + tc5::chunk_off(kTile, tid, 6 * piece + 2 * c)) = tc5::pack8(v);
+                *reinterpret_cast<uint4*>(APP + tc5::chunk_off(kTile, tid, 6 * piece + 2 * c + 1)) = tc5::pack8(v + 8);
+            }
+        }
+        __syncthreads();  // d(APP) and dsf complete in shared memory
+        // ---- scatter: one warp per sample, lanes = components
+        {
+            const bool sig = lane < 8;
+            const uint32_t R = sig ? 16u : 48u;
+            const uint32_t ch = sig ? 2u * lane : 2u * (lane - 8u);
+#pragma unroll 2
+            for (uint32_t s = 0; s < 32; ++s) {
+                const uint32_t rr = warp * 32 + s;
+                const uint32_t grow = tile * kTile + rr;
+                if (grow >= n_valid) break;
+                float pos[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)grow + d);
+                float xn[3];
+                vm_normalise(pos, a.aabb, xn);
+                const float ds = dsf[rr];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Foot f;
+                    vm_foot(xn, a.res, i, f);
+                    float2 pv, lv;
+                    vm_sample(sig ? a.smat[i] : a.cmat[i], sig ? a.svec[i] : a.cvec[i], R, ch, f, pv, lv);
+                    float2 dp;
+                    if (sig) {
+                        dp = make_float2(ds, ds);
+                    } else {
+                        const uint32_t col = (uint32_t)i * 48u + ch;
+                        dp = __half22float2(*reinterpret_cast<const __half2*>(APP + tc5::chunk_off(kTile, rr, col >> 3) + (col & 7u) * 2u));
+                    }
+                    const float2 dpv = make_float2(dp.x * lv.x, dp.y * lv.y), dlv = make_float2(dp.x * pv.x, dp.y * pv.y);
+                    float* gm = sig ? g.smat[i] : g.cmat[i];
+                    float* gv = sig ? g.svec[i] : g.cvec[i];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (f.pw[k] != 0.0f) {
+                            float* dst = gm + (size_t)f.pidx[k] * R + ch;
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(f.pw[k] * dpv.x), "f"(f.pw[k] * dpv.y));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (f.lw[k] != 0.0f) {
+                            float* dst = gv + (size_t)f.lidx[k] * R + ch;
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(f.lw[k] * dlv.x), "f"(f.lw[k] * dlv.y));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    if (!first) {
+        flush_acc(p.tmem, kVAW3, 32, gw + kVG3);
+        flush_acc(p.tmem, kVAW4, 64, gw + kVG4);
+        flush_acc(p.tmem, kVAW5, 16, gw + kVG5);
+        flush_acc(p.tmem, kVAB, 16, gw + kVGB);
+        flush_acc(p.tmem, kVAB + 16, 16, gw + kVGB + 64 * 16);
+        flush_acc(p.tmem, kVAB + 32, 16, gw + kVGB + 128 * 16, 16);
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
+}
+
+__global__ void k_vm_pack_weights(const float* __restrict__ basis, const float* __restrict__ wc0, const float* __restrict__ wc1,
+                                  const float* __restrict__ wc2, uint8_t* __restrict__ blob) {
+    pack_matrix(basis, 15, 144, blob + kVB, 16, 144);
+    pack_matrix(wc0, 64, 31, blob + kVB3, 64, 32);
+    pack_matrix(wc1, 64, 64, blob + kVB4, 64, 64);
+    pack_matrix(wc2, 3, 64, blob + kVB5, 16, 64);
+}
+
+__global__ void k_vm_unpack_wgrads(const float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ g0,
+                                   float* __restrict__ g1, float* __restrict__ g2) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 15 * 144) { const uint32_t o = t / 144, i = t - o * 144; gb[t] += gw[kVGB + i * 16 + o]; }
+    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g0[t] += gw[kVG3 + o * 32 + i]; }
+    if (t < 64 * 64) { g1[t] += gw[kVG4 + t]; }
+    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g2[t] += gw[kVG5 + i * 16 + o]; }
+}
+
+static bool to_vm_args(const PvdVmField* f, VmArgs& a) {
+    for (int i = 0; i < 3; ++i) {
+        a.smat[i] = f->sigma_mat[i]; a.svec[i] = f->sigma_vec[i]; a.cmat[i] = f->color_mat[i]; a.cvec[i] = f->color_vec[i];
+        a.res[i] = f->res[i];
+        if (!a.smat[i] || !a.svec[i] || !a.cmat[i] || !a.cvec[i] || a.res[i] < 2) return false;
+    }
+    for (int i = 0; i < 6; ++i) a.aabb[i] = f->aabb[i];
+    a.wblob = reinterpret_cast<const uint8_t*>(f->wblob);
+    a.clip_min = f->sigma_clip_min; a.clip_max = f->sigma_clip_max; a.density_scale = f->density_scale;
+    return a.wblob != nullptr;
+}
+
+constexpr size_t kVmFwdSmem = PVD_VM_WBLOB_BYTES + 36864 + 16384;                       // 72192
+constexpr size_t kVmBwdSmem = PVD_VM_WBLOB_BYTES + 36864 + 8192 + 16384 + 16384 + 4096; // 100864
+
+}  // namespace pvd
+
+using namespace pvd;
+
+extern "C" {
+
+int pvd_vm_pack_weights(const float* basis_mat, const float* w_color0, const float* w_color1, const float* w_color2, void* wblob,
+                        void* stream) {
+    PVD_REQUIRE(basis_mat && w_color0 && w_color1 && w_color2 && wblob);
+    k_vm_pack_weights<<<1, 256, 0, (cudaStream_t)stream>>>(basis_mat, w_color0, w_color1, w_color2, (uint8_t*)wblob);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_vm_field_forward(const PvdVmField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                         float* feat16, int32_t* status, void* stream) {
+    if (M == 0) return PVD_OK;
+    PVD_REQUIRE(f && xyzs && dirs && sigmas && rgbs && status);
+    VmArgs a;
+    if (!to_vm_args(f, a)) return PVD_EINVAL;
+    const uint32_t tiles = (M + kTile - 1) / kTile;
+    const uint32_t grid = min(tiles, (uint32_t)(3 * sm_count()));
+    cudaError_t e = cudaFuncSetAttribute(k_vm_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmFwdSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_vm_field_fwd<<<grid, 128, kVmFwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_vm_field_backward(const PvdVmField* f, const PvdVmGrads* grads, const float* xyzs, const float* dirs,
+                          const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                          const int32_t* n_valid, float* gw_ws, int32_t* status, void* stream) {
+    if (M == 0) return PVD_OK;
+    PVD_REQUIRE(f && grads && xyzs && dirs && grad_sigmas && grad_rgbs && gw_ws && status);
+    VmArgs a;
+    if (!to_vm_args(f, a)) return PVD_EINVAL;
+    VmGradPtrs g;
+    for (int i = 0; i < 3; ++i) {
+        g.smat[i] = grads->sigma_mat[i]; g.svec[i] = grads->sigma_vec[i]; g.cmat[i] = grads->color_mat[i]; g.cvec[i] = grads->color_vec[i];
+        PVD_REQUIRE(g.smat[i] && g.svec[i] && g.cmat[i] && g.cvec[i]);
+    }
+    const uint32_t tiles = (M + kTile - 1) / kTile;
+    const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
+    cudaError_t e = cudaFuncSetAttribute(k_vm_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmBwdSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_vm_field_bwd<<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
+                                                                   gw_ws, status);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, float* gw_color1, float* gw_color2, void* stream) {
+    PVD_REQUIRE(gw_ws && g_basis && gw_color0 && gw_color1 && gw_color2);
+    k_vm_unpack_wgrads<<<16, 256, 0, (cudaStream_t)stream>>>(gw_ws, g_basis, gw_color0, gw_color1, gw_color2);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -79,6 +79,51 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
 int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,
                             float* gw_color1, float* gw_color2, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * "vm" (TensoRF vector-matrix) field: network.py:72-90 (parameters), :216-309 (plane/line features), :344-382 (forward).
+ * Planes [1,R,H,W] and lines [1,R,D,1] are read in place as CHANNELS-LAST fp32 (torch.channels_last strides: memory order
+ * [H][W][R] / [D][R]); R = 16 for sigma, 48 for colour (network.py:73-74).  res[d] = grid resolution along axis d;
+ * plane i spans axes mat_ids[i] = {0,1},{0,2},{1,2}, line i axis vec_ids[i] = 2,1,0 (network.py:76-77).
+ * ---------------------------------------------------------------------------------------- */
+#define PVD_VM_WBLOB_BYTES 18944u
+
+typedef struct PvdVmField {
+    const float* sigma_mat[3];
+    const float* sigma_vec[3];
+    const float* color_mat[3];
+    const float* color_vec[3];
+    const void* wblob;      /* PVD_VM_WBLOB_BYTES from pvd_vm_pack_weights */
+    uint32_t res[3];
+    float aabb[6];          /* aabb_train: positions are mapped to [-1,1] (network.py:345-350) */
+    float sigma_clip_min;   /* clamp of both sigma_feat and color_feat (network.py:353-361) */
+    float sigma_clip_max;
+    float density_scale;
+} PvdVmField;
+
+typedef struct PvdVmGrads { /* channels-last fp32 gradient buffers, same shapes as the parameters; accumulated into */
+    float* sigma_mat[3];
+    float* sigma_vec[3];
+    float* color_mat[3];
+    float* color_vec[3];
+} PvdVmGrads;
+
+/* basis_mat.weight [15,144], color_net.{0,1,2}.weight [64,31] [64,64] [3,64] (fp32) -> fp16 operand tiles */
+int pvd_vm_pack_weights(const float* basis_mat, const float* w_color0, const float* w_color1, const float* w_color2, void* wblob,
+                        void* stream);
+
+/* Forward: sigmas [M] (x density_scale), rgbs [M,3], optional feat16 [M,16] = [clamped sigma_feat, clamped color_feat(15)]
+ * (`feature_sigma_color`, network.py:362-364). */
+int pvd_vm_field_forward(const PvdVmField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                         float* feat16, int32_t* status, void* stream);
+
+/* Backward: accumulates into the channels-last plane/line gradients of `grads` and into gw_ws (PVD_FIELD_GW_FLOATS floats:
+ * dBasis^T[192][16] | dW3[64][32] | dW4[64][64] | dW5^T[64][16]; pvd_vm_unpack_wgrads adds them onto [out,in] buffers). */
+int pvd_vm_field_backward(const PvdVmField* field, const PvdVmGrads* grads, const float* xyzs, const float* dirs,
+                          const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                          const int32_t* n_valid, float* gw_ws, int32_t* status, void* stream);
+
+int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, float* gw_color1, float* gw_color2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

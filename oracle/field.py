@@ -113,3 +113,48 @@ def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cas
     loss = torch.mean((pred - gt_rgb) ** 2)
     return dict(loss=loss, image=pred, depth=depth_n, weights_sum=ws, xyzs=txyz, dirs=tdir, deltas=tdl, rays=trays,
                 counter=counter, sigma=sigma, rgb=rgb)
+
+
+# ------------------------------------------------------------------------------------------------ VM (TensoRF) field
+MAT_IDS = [[0, 1], [0, 2], [1, 2]]  # network.py:76
+VEC_IDS = [2, 1, 0]                 # network.py:77
+
+
+def vm_plane_line(x, mats, vecs):
+    """Per-component plane and line samples: [3, R, N] each (F.grid_sample, align_corners=True, zero padding;
+    network.py:222-260 for sigma, :269-300 for colour)."""
+    N = x.shape[0]
+    mat_coord = torch.stack([x[..., MAT_IDS[0]], x[..., MAT_IDS[1]], x[..., MAT_IDS[2]]]).detach().view(3, -1, 1, 2)
+    vec_coord = torch.stack([x[..., VEC_IDS[0]], x[..., VEC_IDS[1]], x[..., VEC_IDS[2]]])
+    vec_coord = torch.stack((torch.zeros_like(vec_coord), vec_coord), dim=-1).detach().view(3, -1, 1, 2)
+    pm, pv = [], []
+    for i in range(3):
+        pm.append(F.grid_sample(mats[i], mat_coord[[i]], align_corners=True).view(-1, N))
+        pv.append(F.grid_sample(vecs[i], vec_coord[[i]], align_corners=True).view(-1, N))
+    return pm, pv
+
+
+def vm_field_forward(x, d, sigma_mat, sigma_vec, color_mat, color_vec, basis_w, color_ws, aabb, clip_min=-2.0, clip_max=7.0,
+                     quantize_fp16=False):
+    """`NeRFNetwork.forward` for model_type "vm" (network.py:344-382).  Returns sigma [N], color [N,3], feat [N,16].
+    sigma_mat/color_mat: 3 x [1,R,H,W]; sigma_vec/color_vec: 3 x [1,R,D,1]; basis_w [15,144]; color_ws = (wc0, wc1, wc2)."""
+    q = (lambda t: t.half().float()) if quantize_fp16 else (lambda t: t)
+    xn = 2 * (x - aabb[:3]) / (aabb[3:] - aabb[:3]) - 1
+    sm, sv = vm_plane_line(xn, sigma_mat, sigma_vec)
+    sigma_feat = torch.zeros(x.shape[0])
+    for i in range(3):
+        sigma_feat = sigma_feat + torch.sum(sm[i] * sv[i], dim=0)
+    cm, cv = vm_plane_line(xn, color_mat, color_vec)
+    app = (torch.cat(cm, dim=0) * torch.cat(cv, dim=0)).T  # [N, 144]
+    color_feat = q(F.linear(q(app), q(basis_w)))
+    sigma_feat = torch.clamp(sigma_feat, clip_min, clip_max)
+    color_feat = torch.clamp(color_feat, clip_min, clip_max)
+    feat = torch.cat([sigma_feat.unsqueeze(-1), color_feat], dim=-1)
+    sigma = _TruncExp.apply(sigma_feat)
+    sh = torch.from_numpy(cpu.sh_encode_forward(d.detach().numpy(), 4))
+    wc0, wc1, wc2 = color_ws
+    h = torch.cat([sh, color_feat], dim=-1)
+    h = q(F.relu(F.linear(q(h), q(wc0))))
+    h = q(F.relu(F.linear(h, q(wc1))))
+    color = torch.sigmoid(F.linear(h, q(wc2)))
+    return sigma, color, feat
