@@ -342,7 +342,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                         const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
                                                         const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
-                                                        uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                        uint32_t M, const int32_t* __restrict__ n_valid_p, __half* __restrict__ dx_out,
                                                         float* __restrict__ grad_table,
                                                         float* __restrict__ gw, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -479,7 +479,13 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
         float dx[32];
         tc5::tmem_ld16(trow + kD, *reinterpret_cast<float(*)[16]>(&dx[0]));
         tc5::tmem_ld16(trow + kD + 16, *reinterpret_cast<float(*)[16]>(&dx[16]));
-        if (live) {
+        if (dx_out != nullptr) {  // split mode: hand d(encoding) to the stand-alone, high-occupancy scatter kernel
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(dx_out + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = tc5::pack8(dx + 8 * j);
+            }
+        } else if (live) {
             float x01[3];
             bool oob;
             to_unit(pos, a.bound, x01, oob);
@@ -513,6 +519,44 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     tc5::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
+}
+
+// Stand-alone scatter of d(encoding) [M,32] fp16 into the fp32 table gradient: one thread per (sample, level), 256-thread CTAs,
+// ~40 registers -> full occupancy, so the reductions' issue latency is hidden by other warps instead of stalling a 128-thread
+// MLP CTA that also holds 88 KB of shared memory and 256 TMEM columns (gridencoder.cu:227-314 semantics, fp32 accumulation).
+__global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* __restrict__ xyzs, const __half* __restrict__ dx,
+                                                      uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ grad_table) {
+    __shared__ LevelInfo lvs;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const GridLevel g = grid_level(a.offsets, level, a.S, a.H);
+        LevelInfo v;
+        v.scale = g.scale; v.res1 = g.resolution + 1; v.offset = g.offset; v.size = g.size; v.mask = g.size - 1;
+        const uint64_t dense = (uint64_t)v.res1 * v.res1 * v.res1;
+        const bool fits = ((uint64_t)v.res1 <= g.size) && ((uint64_t)v.res1 * v.res1 <= g.size) && (dense <= g.size);
+        v.mode = fits ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
+        v.pad0 = v.pad1 = 0;
+        lvs = v;
+    }
+    __syncthreads();
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_valid) return;
+    const float2 g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dx + (size_t)b * PVD_FIELD_ENC_STRIDE + 2 * level)));
+    if (g.x == 0.0f && g.y == 0.0f) return;
+    float pos[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)b + d);
+    float x01[3];
+    bool oob;
+    to_unit(pos, a.bound, x01, oob);
+    if (oob) return;
+    const LevelInfo v = lvs;
+    Corners c;
+    level_corners(v, x01, c);
+    float* gt = grad_table + (size_t)v.offset * 2;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g.x, c.w[i] * g.y);
 }
 
 __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
@@ -598,7 +642,7 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
 
 int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
                             const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
-                            const int32_t* n_valid, float* grad_table, float* gw_ws, int32_t* status, void* stream) {
+                            const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
     PVD_REQUIRE(f && f->offsets && f->wblob && xyzs && dirs && enc && grad_sigmas && grad_rgbs && grad_table && gw_ws && status);
     if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
@@ -610,8 +654,13 @@ int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const floa
     cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return (int)e;
     k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                         grad_table, gw_ws, status);
+                                                         (__half*)dx_ws, grad_table, gw_ws, status);
     PVD_LAUNCH_CHECK();
+    if (dx_ws != nullptr) {
+        const dim3 sgrid((M + 255) / 256, f->L, 1);
+        k_hash_scatter<<<sgrid, 256, 0, st>>>(a, xyzs, (const __half*)dx_ws, M, n_valid, grad_table);
+        PVD_LAUNCH_CHECK();
+    }
     return PVD_OK;
 }
 

@@ -116,37 +116,37 @@ __global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thr
 // a coarse block apart... see k_march_count) falls in a masked block cannot produce a sample: every lattice point the marcher
 // could evaluate lies in a cell of an unmasked block's neighbourhood, i.e. in an empty cell.  Output: 4096 bits indexed
 // x + 16 y + 256 z.
-__global__ void __launch_bounds__(1024) k_coarse_mask(const uint8_t* __restrict__ grid, uint32_t H, uint32_t* __restrict__ mask) {
-    __shared__ uint8_t any16[4096];
-    const uint32_t cs = H / 16;                 // cells per coarse block edge (power of two)
-    const uint32_t bytes = cs * cs * cs / 8;    // bytes per coarse block in the Morton-ordered bitfield
-    for (uint32_t m = threadIdx.x; m < 4096; m += blockDim.x) {  // m = Morton index of the coarse block
-        const uint8_t* p = grid + (size_t)m * bytes;
-        uint32_t acc = 0;
-        if (bytes >= 16) {
-            for (uint32_t i = 0; i < bytes; i += 16) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
-                acc |= v.x | v.y | v.z | v.w;
-            }
-        } else {
-            for (uint32_t i = 0; i < bytes; ++i) acc |= __ldg(p + i);
+__global__ void __launch_bounds__(256) k_coarse_any(const uint8_t* __restrict__ grid, uint32_t H, uint8_t* __restrict__ any16) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;  // Morton index of the coarse block
+    if (m >= 4096) return;
+    const uint32_t cs = H / 16;               // cells per coarse block edge (power of two)
+    const uint32_t bytes = cs * cs * cs / 8;  // bytes per coarse block in the Morton-ordered bitfield (>= 1 for H >= 32)
+    const uint8_t* p = grid + (size_t)m * bytes;
+    uint32_t acc = 0;
+    if (bytes >= 16) {
+        for (uint32_t i = 0; i < bytes; i += 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+            acc |= v.x | v.y | v.z | v.w;
         }
-        const uint32_t cx = compact3(m), cy = compact3(m >> 1), cz = compact3(m >> 2);
-        any16[cx + 16 * cy + 256 * cz] = acc ? 1 : 0;
+    } else {
+        for (uint32_t i = 0; i < bytes; ++i) acc |= __ldg(p + i);
     }
-    __syncthreads();
-    for (uint32_t c = threadIdx.x; c < 4096; c += blockDim.x) {
-        const int cx = c & 15, cy = (c >> 4) & 15, cz = c >> 8;
-        uint32_t hit = 0;
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int x = cx + dx, y = cy + dy, z = cz + dz;
-                    if (x >= 0 && x < 16 && y >= 0 && y < 16 && z >= 0 && z < 16) hit |= any16[x + 16 * y + 256 * z];
-                }
-        const uint32_t word = __ballot_sync(0xffffffffu, hit != 0);
-        if ((threadIdx.x & 31u) == 0) mask[c >> 5] = word;
-    }
+    any16[compact3(m) + 16 * compact3(m >> 1) + 256 * compact3(m >> 2)] = acc ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_coarse_dilate(const uint8_t* __restrict__ any16, uint32_t* __restrict__ mask) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 4096) return;
+    const int cx = c & 15, cy = (c >> 4) & 15, cz = c >> 8;
+    uint32_t hit = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                if (x >= 0 && x < 16 && y >= 0 && y < 16 && z >= 0 && z < 16) hit |= __ldg(any16 + x + 16 * y + 256 * z);
+            }
+    const uint32_t word = __ballot_sync(0xffffffffu, hit != 0);
+    if ((threadIdx.x & 31u) == 0) mask[c >> 5] = word;
 }
 
 // Pass 1 -- ONE WARP PER RAY.  The reference walks each ray with one thread (raymarching.cu:357-403): a chain of several
@@ -221,49 +221,16 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
     float carry_tt = 0.0f;
     bool have_carry = false;
     uint32_t count = 0;
-    while (true) {
-        // ---- the 32 lattice points of this window
-        float t_i, t_next;
-        bool fast = false;
-        if (const_dt && t_base > 0.0f) {
-            const uint32_t b = __float_as_uint(t_base);
-            const uint32_t e = b >> 23;
-            const float t1 = __fadd_rn(t_base, dt_c);
-            const uint32_t b1 = __float_as_uint(t1);
-            if (e > 0 && e < 254 && (b1 >> 23) == e) {
-                const uint32_t cstep = b1 - b;
-                // tie check: dt / ulp(t) has fractional part exactly one half -> rounding direction depends on parity
-                const float r = __fmul_rn(dt_c, __uint_as_float((uint32_t)(127 + 150 - (int)e) << 23));  // dt * 2^(23-(e-127))
-                const bool tie = (r - floorf(r)) == 0.5f;
-                const uint32_t bend = b + 32u * cstep;
-                if (!tie && cstep > 0 && (bend >> 23) == e && (277 - (int)e) > 0 && (277 - (int)e) < 255) {
-                    fast = true;
-                    t_i = __uint_as_float(b + lane * cstep);
-                    t_next = __uint_as_float(bend);
-                }
-            }
-        }
-        if (!fast) {
-            float t = t_base;
-            t_i = t;
-#pragma unroll 4
-            for (uint32_t j = 0; j < 32; ++j) {
-                if (j == lane) t_i = t;
-                t = __fadd_rn(t, const_dt ? dt_c : march_dt(c, t));
-            }
-            t_next = t;
-        }
-        // ---- every lane evaluates its point as the serial loop would (raymarching.cu:363-397)
-        const bool valid = t_i < far;
-        float x, y, z, tt = 0.0f;
-        march_pos(c, t_i, x, y, z);
-        const float dt_i = const_dt ? dt_c : march_dt(c, t_i);
-        bool occ = false;
-        if (valid) occ = march_probe(c, grid, t_i, dt_i, x, y, z, tt);
+    bool done = false;
+
+    // Replays the serial control flow of raymarching.cu:362-403 over one window of 32 evaluated lattice points.
+    auto walk = [&](float t_i, float dt_i, float tt, bool valid, bool occ) {
         const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
         const uint32_t occ_mask = __ballot_sync(0xffffffffu, valid && occ);
-        if (valid_mask == 0u) break;  // t only grows: nothing further can satisfy t < far
-        // ---- replay the serial control flow on the masks
+        if (valid_mask == 0u) {  // t only grows: nothing further can satisfy t < far
+            done = true;
+            return;
+        }
         uint32_t cur = 0;
         if (have_carry) {
             const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= carry_tt);
@@ -275,7 +242,6 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
             }
         }
         uint32_t emit = 0;
-        bool done = false;
         const uint32_t count0 = count;
         while (cur < 32) {
             if (!((valid_mask >> cur) & 1u) || count >= max_steps) {  // loop condition of raymarching.cu:362
@@ -304,8 +270,63 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
             }
         }
         if ((emit >> lane) & 1u) st[count0 + __popc(emit & lt_mask)] = make_float2(t_i, dt_i);
-        if (done) break;
-        t_base = t_next;
+    };
+
+    while (!done) {
+        // ---- fast path: constant dt and a group of four windows (128 lattice points) inside one binade.  All four occupancy
+        // probes of a lane are issued before any is consumed, which is what hides the L2 latency of the bitfield loads: the
+        // kernel is bound by the per-ray chain of windows, not by throughput.
+        bool group = false;
+        uint32_t b = 0, cstep = 0;
+        if (const_dt && t_base > 0.0f) {
+            b = __float_as_uint(t_base);
+            const uint32_t e = b >> 23;
+            const uint32_t b1 = __float_as_uint(__fadd_rn(t_base, dt_c));
+            if (e > 22 && e < 254 && (b1 >> 23) == e) {
+                cstep = b1 - b;
+                // tie check: dt / ulp(t) with fractional part exactly one half rounds by the parity of t -> serial path
+                const float r = __fmul_rn(dt_c, __uint_as_float((uint32_t)(277 - (int)e) << 23));  // dt * 2^(150 - e)
+                const bool tie = (r - floorf(r)) == 0.5f;
+                group = !tie && cstep > 0 && ((b + 128u * cstep) >> 23) == e;
+            }
+        }
+        if (group) {
+            float t_i[4], tt[4];
+            bool valid[4], occ[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                t_i[w] = __uint_as_float(b + ((uint32_t)w * 32u + lane) * cstep);
+                valid[w] = t_i[w] < far;
+                tt[w] = 0.0f;
+                occ[w] = false;
+                if (valid[w]) {
+                    float x, y, z;
+                    march_pos(c, t_i[w], x, y, z);
+                    occ[w] = march_probe(c, grid, t_i[w], dt_c, x, y, z, tt[w]);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (!done) walk(t_i[w], dt_c, tt[w], valid[w], occ[w]);
+            }
+            t_base = __uint_as_float(b + 128u * cstep);
+        } else {
+            // ---- general path: one window, lattice by the serial recurrence (every lane runs it and keeps its own element)
+            float t = t_base, t_i = t_base;
+#pragma unroll 4
+            for (uint32_t j = 0; j < 32; ++j) {
+                if (j == lane) t_i = t;
+                t = __fadd_rn(t, const_dt ? dt_c : march_dt(c, t));
+            }
+            const bool valid = t_i < far;
+            float x, y, z, tt = 0.0f;
+            march_pos(c, t_i, x, y, z);
+            const float dt_i = const_dt ? dt_c : march_dt(c, t_i);
+            bool occ = false;
+            if (valid) occ = march_probe(c, grid, t_i, dt_i, x, y, z, tt);
+            walk(t_i, dt_i, tt, valid, occ);
+            t_base = t;
+        }
     }
     if (lane == 0) {
         num_steps_out[n] = (int32_t)count;
@@ -723,10 +744,10 @@ int pvd_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
     return PVD_OK;
 }
 
-constexpr uint64_t kCoarseWords = 128;  // 16^3 bits
+constexpr uint64_t kCoarseWords = 128 + 1024;  // 16^3 mask bits, then 16^3 bytes of per-block occupancy
 
 uint64_t pvd_march_rays_train_workspace_words(uint32_t N, uint32_t max_steps) {
-    // coarse[128] | num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
+    // coarse mask[128] + any16[1024] | num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     return kCoarseWords + head + 2ull * (uint64_t)N * max_steps;
 }
@@ -748,7 +769,10 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
     // coarse rejection needs one cascade and a power-of-two grid of at least 32^3 (Morton-contiguous coarse blocks)
     const bool use_coarse = (C == 1) && (H >= 32) && ((H & (H - 1)) == 0);
     if (use_coarse) {
-        k_coarse_mask<<<1, 1024, 0, st>>>(grid, H, coarse);
+        uint8_t* any16 = reinterpret_cast<uint8_t*>(ws_i32 + 128);
+        k_coarse_any<<<16, 256, 0, st>>>(grid, H, any16);
+        PVD_LAUNCH_CHECK();
+        k_coarse_dilate<<<16, 256, 0, st>>>(any16, coarse);
         PVD_LAUNCH_CHECK();
     }
     k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,

@@ -62,7 +62,7 @@ class HashTrainEngine:
         self.mean_count = 0
         self._counts = []
         self._alloc_samples(N * 32)
-        self.launches_per_step = 10
+        self.launches_per_step = 11 if fused.SPLIT_SCATTER else 10  # kernels of libpvd_b200.so only (torch memsets not counted)
 
     # ------------------------------------------------------------------ buffers sized by M
     def _alloc_samples(self, M: int):
@@ -76,6 +76,7 @@ class HashTrainEngine:
         self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d)
         self.grad_sigmas = torch.zeros(M, device=d)
         self.grad_rgbs = torch.zeros(M, 3, device=d)
+        self.dx_ws = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d) if fused.SPLIT_SCATTER else None
 
     def set_mean_count(self, mean_count: int):
         """M = mean_count rounded up strictly to a multiple of 128 (raymarching.py:235-238)."""
@@ -141,7 +142,7 @@ class HashTrainEngine:
                                                          nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
         nv.check(l.pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), nv.ptr(self.enc),
                                            nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), None, _u32(M), nv.ptr(self.counter),
-                                           nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.status), st))
+                                           nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status), st))
 
     def finish_warmup(self):
         """mean_count = mean of the warm-up sample counts (renderer.py:768-772)."""

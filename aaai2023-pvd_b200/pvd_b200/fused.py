@@ -11,6 +11,7 @@ trainer reads (`feature_sigma_color`, `sigma_l`, `color_l`, distill_mutual/utils
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -23,6 +24,7 @@ from . import _native as nv
 WBLOB_BYTES = 20480
 GW_FLOATS = 10240
 ENC_STRIDE = 32
+SPLIT_SCATTER = os.environ.get("PVD_SPLIT_SCATTER", "1") != "0"  # table-gradient scatter as its own kernel
 
 
 class PvdHashField(C.Structure):
@@ -102,7 +104,7 @@ def hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, want_enc=True
 
 
 def hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_table, gw_ws, n_valid=None,
-                            status=None, grad_feat=None):
+                            status=None, grad_feat=None, dx_ws=None):
     M = xyzs.shape[0]
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=xyzs.device)
@@ -111,7 +113,7 @@ def hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, grad_si
         nv.check(nv.lib().pvd_hash_field_backward(C.byref(f), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(enc), nv.ptr(grad_sigmas),
                                                   nv.ptr(grad_rgbs), nv.ptr(grad_feat), C.c_uint32(M), nv.ptr(n_valid),
                                                   nv.ptr(grad_table),
-                                                  nv.ptr(gw_ws), nv.ptr(status), nv.stream_of(xyzs)))
+                                                  nv.ptr(gw_ws), nv.ptr(dx_ws), nv.ptr(status), nv.stream_of(xyzs)))
     return status
 
 
@@ -151,7 +153,8 @@ class _FusedHashField(Function):
         grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)
         gw_ws = torch.zeros(GW_FLOATS, dtype=torch.float32, device=dev)
         gf = grad_feat.float().contiguous() if grad_feat is not None else None
-        hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status, gf)
+        dx_ws = torch.empty(xyzs.shape[0], ENC_STRIDE, dtype=torch.float16, device=dev) if SPLIT_SCATTER else None
+        hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status, gf, dx_ws)
         g = unpack_wgrads(gw_ws, 2 * cfg.num_levels, (w0, w1, w2, w3, w4))
         g = [gi.to(w.dtype) for gi, w in zip(g, (w0, w1, w2, w3, w4))]
         return (None, None, grad_table.to(embeddings.dtype), g[0], g[1], g[2], g[3], g[4], None, None, None, None)

@@ -320,7 +320,7 @@ def time_phases(eng):
     e[3].record()
     nv.check(l.pvd_hash_field_backward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.enc), nv.ptr(eng.grad_sigmas),
                                        nv.ptr(eng.grad_rgbs), None, u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),
-                                       nv.ptr(eng.status), st))
+                                       nv.ptr(eng.dx_ws), nv.ptr(eng.status), st))
     e[4].record()
     torch.cuda.synchronize()
     return {"march": e[0].elapsed_time(e[1]), "field_fwd": e[1].elapsed_time(e[2]), "composite": e[2].elapsed_time(e[3]),

@@ -58,12 +58,15 @@ int pvd_hash_field_forward(const PvdHashField* field, const float* xyzs, const f
  *   (zero padded; pvd_field_unpack_wgrads adds them onto parameter-shaped [out, in] buffers).
  * grad_feat16 [M,16] (or NULL) is d(loss)/d(feat16): the gradient of the distillation losses that read
  * `feature_sigma_color` / `sigma_l` directly (distill_mutual/utils.py:1046-1108); channel 0 passes the clamp mask.
+ * dx_ws: optional [M, 32] fp16 scratch.  When given, the MLP kernel writes d(encoding) there and a second, full-occupancy
+ * kernel (one thread per sample x level) scatters it into grad_table; when NULL the scatter runs inside the MLP kernel.
  * `enc` is the tensor the forward saved.  Rows >= *n_valid (device pointer, e.g. the march counter; NULL = all M)
  * are padding and contribute nothing. */
 #define PVD_FIELD_GW_FLOATS 10240u
 int pvd_hash_field_backward(const PvdHashField* field, const float* xyzs, const float* dirs, const void* enc,
                             const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
-                            const int32_t* n_valid, float* grad_table, float* gw_ws, int32_t* status, void* stream);
+                            const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status,
+                            void* stream);
 
 /* composite_rays_train_backward (pvd_b200.h) with the upstream gradients derived in the kernel from the photometric loss:
  *   pred = image + (1 - weights_sum) * bg_color   (distill_mutual/renderer.py:445)
