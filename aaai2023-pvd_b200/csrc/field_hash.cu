@@ -524,6 +524,8 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
 // Stand-alone scatter of d(encoding) [M,32] fp16 into the fp32 table gradient: one thread per (sample, level), 256-thread CTAs,
 // ~40 registers -> full occupancy, so the reductions' issue latency is hidden by other warps instead of stalling a 128-thread
 // MLP CTA that also holds 88 KB of shared memory and 256 TMEM columns (gridencoder.cu:227-314 semantics, fp32 accumulation).
+constexpr uint32_t kAggMaxRes1 = 700;  // aggregate runs on levels whose resolution is below this (cell edge > ~0.85 dt at 1024 steps)
+
 __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* __restrict__ xyzs, const __half* __restrict__ dx,
                                                       uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ grad_table) {
     __shared__ LevelInfo lvs;
@@ -541,22 +543,59 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
     __syncthreads();
     const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_valid) return;
-    const float2 g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dx + (size_t)b * PVD_FIELD_ENC_STRIDE + 2 * level)));
-    if (g.x == 0.0f && g.y == 0.0f) return;
-    float pos[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)b + d);
-    float x01[3];
-    bool oob;
-    to_unit(pos, a.bound, x01, oob);
-    if (oob) return;
+    const uint32_t lane = threadIdx.x & 31u;
     const LevelInfo v = lvs;
+    bool active = b < n_valid;
+    float2 g = make_float2(0.f, 0.f);
+    float x01[3] = {0.5f, 0.5f, 0.5f};
+    if (active) {
+        g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dx + (size_t)b * PVD_FIELD_ENC_STRIDE + 2 * level)));
+        float pos[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)b + d);
+        bool oob;
+        to_unit(pos, a.bound, x01, oob);
+        active = !oob && !(g.x == 0.0f && g.y == 0.0f);
+    }
     Corners c;
     level_corners(v, x01, c);
     float* gt = grad_table + (size_t)v.offset * 2;
+    // Coarse levels: consecutive samples of a ray share a cell for many steps (cell edge / dt = 37 samples at level 0), so
+    // most of the 8 x 32 reductions of a warp would hit the same 8 addresses and serialise in the L2 atomic unit.  Lanes of a run
+    // of equal cells are summed with a segmented warp scan first and only the head lane of each run issues reductions.
+    if (v.res1 > kAggMaxRes1) {
+        if (active) {
 #pragma unroll
-    for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g.x, c.w[i] * g.y);
+            for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g.x, c.w[i] * g.y);
+        }
+        return;
+    }
+    // the lower corner identifies the cell exactly (indices of a dense level are unique; for a hashed level compare all 8)
+    uint32_t key0 = active ? c.idx[0] : 0xffffffffu, key7 = active ? c.idx[7] : 0xffffffffu;
+    const uint32_t p0 = __shfl_up_sync(0xffffffffu, key0, 1), p7 = __shfl_up_sync(0xffffffffu, key7, 1);
+    const uint32_t p3 = __shfl_up_sync(0xffffffffu, c.idx[3], 1), p5 = __shfl_up_sync(0xffffffffu, c.idx[5], 1);
+    const bool head = (lane == 0) || !active || (p0 != key0) || (p7 != key7) || (p3 != c.idx[3]) || (p5 != c.idx[5]);
+    const uint32_t head_mask = __ballot_sync(0xffffffffu, head);
+    float val[16];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        val[2 * i] = active ? c.w[i] * g.x : 0.0f;
+        val[2 * i + 1] = active ? c.w[i] * g.y : 0.0f;
+    }
+    const uint32_t after = (lane == 31u) ? 0u : (head_mask >> (lane + 1u));  // head flags of the lanes above this one
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const bool same = (lane + d < 32u) && ((after & ((1u << d) - 1u)) == 0u);  // lanes lane+1 .. lane+d start no new run
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) {
+            const float o = __shfl_down_sync(0xffffffffu, val[i], d);
+            if (same) val[i] += o;
+        }
+    }
+    if (head && active) {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, val[2 * i], val[2 * i + 1]);
+    }
 }
 
 __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
