@@ -171,14 +171,24 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
                                                     const float* __restrict__ nears, const float* __restrict__ fars,
                                                     uint32_t perturb, Pcg32 rng, int32_t* __restrict__ num_steps_out,
                                                     float* __restrict__ t0_out, float2* __restrict__ stash,
-                                                    const uint32_t* __restrict__ coarse) {
+                                                    const uint32_t* __restrict__ coarse, const float* __restrict__ aabb,
+                                                    float min_near, float* __restrict__ nears_out, float* __restrict__ fars_out) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (n >= N) return;
     MarchCtx c;
     march_ctx_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
-    const float far = fars[n];
-    float t0 = nears[n];
+    float far, t0;
+    if (aabb != nullptr) {  // fused near_far_from_aabb (raymarching.cu:94-147): saves a launch and the nears/fars round trip
+        near_far_one(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, aabb, min_near, t0, far);
+        if (lane == 0) {
+            nears_out[n] = t0;
+            fars_out[n] = far;
+        }
+    } else {
+        far = fars[n];
+        t0 = nears[n];
+    }
     if (perturb) {  // raymarching.cu:351-354: the same jitter every call (seed 42, advance(n))
         pcg32_advance(rng, (uint64_t)n);
         t0 = __fmaf_rn(c.dt_min, pcg32_next_float(rng), t0);
@@ -338,15 +348,21 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
 // counter[0] += total, counter[1] += N  (what the reference's two atomics accumulate, raymarching.cu:408-409).
 __global__ void __launch_bounds__(1024) k_march_scan(const int32_t* __restrict__ num_steps, uint32_t N,
                                                     int32_t* __restrict__ rays, int32_t* __restrict__ counter) {
+    // 8 consecutive rays per thread (8192 per pass): serial prefix inside the thread, shuffle scan of the thread totals
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < N; base += blockDim.x) {
-        const uint32_t n = base + threadIdx.x;
-        const int32_t v = (n < N) ? num_steps[n] : 0;
-        int32_t inc = v;
+    for (uint32_t base = 0; base < N; base += 8u * blockDim.x) {
+        const uint32_t n0 = base + 8u * threadIdx.x;
+        int32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (n0 + i < N) ? __ldg(num_steps + n0 + i) : 0;
+        int32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += v[i];
+        int32_t inc = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -365,11 +381,16 @@ __global__ void __launch_bounds__(1024) k_march_scan(const int32_t* __restrict__
         }
         __syncthreads();
         const int32_t carry = carry_s;
-        const int32_t excl = carry + (wid ? warp_tot[wid - 1] : 0) + inc - v;
-        if (n < N) {
-            rays[3 * (size_t)n] = (int32_t)n;
-            rays[3 * (size_t)n + 1] = excl;
-            rays[3 * (size_t)n + 2] = v;
+        int32_t off = carry + (wid ? warp_tot[wid - 1] : 0) + inc - tot;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t n = n0 + i;
+            if (n < N) {
+                rays[3 * (size_t)n] = (int32_t)n;
+                rays[3 * (size_t)n + 1] = off;
+                rays[3 * (size_t)n + 2] = v[i];
+            }
+            off += v[i];
         }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_tot[31];
@@ -464,12 +485,25 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__
     }
     float T = 1.0f, tcarry = 0.0f;           // carried across 32-sample chunks
     float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
-    for (uint32_t base = 0; base < cnt; base += 32) {
+    // software pipeline: the loads of chunk k+1 are in flight while chunk k goes through its two shuffle scans
+    auto fetch = [&](uint32_t base, float& sg, float2& dl, float& c0, float& c1, float& c2) {
         const uint32_t i = base + lane;
         const bool ok = i < cnt;
         const size_t row = (size_t)offset + (ok ? i : 0);
-        const float sigma = ok ? sigmas[row] : 0.0f;
-        const float2 dl = ok ? *reinterpret_cast<const float2*>(deltas + 2 * row) : make_float2(0.f, 0.f);
+        sg = ok ? __ldg(sigmas + row) : 0.0f;
+        dl = ok ? __ldg(reinterpret_cast<const float2*>(deltas + 2 * row)) : make_float2(0.f, 0.f);
+        c0 = ok ? __ldg(rgbs + 3 * row) : 0.f;
+        c1 = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+        c2 = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
+    };
+    float sg_n, c0_n, c1_n, c2_n;
+    float2 dl_n;
+    fetch(0, sg_n, dl_n, c0_n, c1_n, c2_n);
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const float sigma = sg_n, c0 = c0_n, c1 = c1_n, c2 = c2_n;
+        const float2 dl = dl_n;
+        if (base + 32 < cnt) fetch(base + 32, sg_n, dl_n, c0_n, c1_n, c2_n);
+        const bool ok = base + lane < cnt;
         const float alpha = ok ? 1.0f - __expf(-sigma * dl.x) : 0.0f;  // raymarching.cu:546
         const float om = 1.0f - alpha;
         const float incl = warp_scan_mul(om, lane);
@@ -479,9 +513,9 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__
         const float w = alpha * Ti;
         const float tin = tcarry + warp_scan_add(dl.y, lane);
         if (ok) {
-            r += w * rgbs[3 * row];
-            g += w * rgbs[3 * row + 1];
-            b += w * rgbs[3 * row + 2];
+            r += w * c0;
+            g += w * c1;
+            b += w * c2;
             d += w * tin;
             ws += w;
         }
@@ -537,13 +571,24 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
     }
     if (skip) return;
     float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;  // carries (running sums up to the previous chunk)
+    auto fetch = [&](uint32_t base, float& sg, float& d0, float& c0, float& c1, float& c2) {
+        const uint32_t i = base + lane;
+        const bool ok = i < cnt;
+        const size_t row = (size_t)offset + (ok ? i : 0);
+        sg = ok ? __ldg(sigmas + row) : 0.0f;
+        d0 = ok ? __ldg(deltas + 2 * row) : 0.0f;
+        c0 = ok ? __ldg(rgbs + 3 * row) : 0.f;
+        c1 = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+        c2 = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
+    };
+    float sg_n, d0_n, c0_n, c1_n, c2_n;
+    fetch(0, sg_n, d0_n, c0_n, c1_n, c2_n);
     for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t i = base + lane;
         const bool ok = i < cnt;
         const size_t row = (size_t)offset + (ok ? i : 0);
-        const float sigma = ok ? sigmas[row] : 0.0f;
-        const float d0 = ok ? deltas[2 * row] : 0.0f;
-        const float cr = ok ? rgbs[3 * row] : 0.f, cg = ok ? rgbs[3 * row + 1] : 0.f, cb = ok ? rgbs[3 * row + 2] : 0.f;
+        const float sigma = sg_n, d0 = d0_n, cr = c0_n, cg = c1_n, cb = c2_n;
+        if (base + 32 < cnt) fetch(base + 32, sg_n, d0_n, c0_n, c1_n, c2_n);
         const float alpha = ok ? 1.0f - __expf(-sigma * d0) : 0.0f;
         const float om = 1.0f - alpha;
         const float incl = warp_scan_mul(om, lane);
@@ -776,7 +821,39 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
         PVD_LAUNCH_CHECK();
     }
     k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                                  perturb, rng, num_steps, t0, stash, use_coarse ? coarse : nullptr);
+                                                  perturb, rng, num_steps, t0, stash, use_coarse ? coarse : nullptr, nullptr, 0.0f,
+                                                  nullptr, nullptr);
+    PVD_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, st>>>(num_steps, N, rays, counter);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const uint8_t* grid, const float* aabb, float min_near,
+                                    float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                    float* nears, float* fars, int32_t* rays, int32_t* counter, uint32_t perturb,
+                                    uint32_t reuse_coarse, int32_t* ws_i32, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(rays_o && rays_d && grid && aabb && nears && fars && rays && counter && ws_i32);
+    PVD_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(ws_i32) & 7u) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* coarse = reinterpret_cast<uint32_t*>(ws_i32);
+    int32_t* num_steps = ws_i32 + kCoarseWords;
+    float* t0 = reinterpret_cast<float*>(ws_i32 + kCoarseWords + N);
+    const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
+    float2* stash = reinterpret_cast<float2*>(ws_i32 + kCoarseWords + head);
+    const Pcg32 rng = pcg32_seeded(42u);
+    const bool use_coarse = (C == 1) && (H >= 32) && ((H & (H - 1)) == 0);
+    if (use_coarse && !reuse_coarse) {
+        uint8_t* any16 = reinterpret_cast<uint8_t*>(ws_i32 + 128);
+        k_coarse_any<<<16, 256, 0, st>>>(grid, H, any16);
+        PVD_LAUNCH_CHECK();
+        k_coarse_dilate<<<16, 256, 0, st>>>(any16, coarse);
+        PVD_LAUNCH_CHECK();
+    }
+    k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nullptr, nullptr, perturb,
+                                                  rng, num_steps, t0, stash, use_coarse ? coarse : nullptr, aabb, min_near, nears, fars);
     PVD_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(num_steps, N, rays, counter);
     PVD_LAUNCH_CHECK();

@@ -62,7 +62,8 @@ class HashTrainEngine:
         self.mean_count = 0
         self._counts = []
         self._alloc_samples(N * 32)
-        self.launches_per_step = 11 if fused.SPLIT_SCATTER else 10  # kernels of libpvd_b200.so only (torch memsets not counted)
+        self._coarse_valid = False
+        self.launches_per_step = 8 if fused.SPLIT_SCATTER else 7  # kernels of libpvd_b200.so only (torch memsets not counted)
 
     # ------------------------------------------------------------------ buffers sized by M
     def _alloc_samples(self, M: int):
@@ -77,6 +78,11 @@ class HashTrainEngine:
         self.grad_sigmas = torch.zeros(M, device=d)
         self.grad_rgbs = torch.zeros(M, 3, device=d)
         self.dx_ws = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d) if fused.SPLIT_SCATTER else None
+
+    def set_bitfield(self, bitfield: torch.Tensor):
+        """New occupancy bitfield (after a density-grid update): the cached coarse rejection mask is invalid."""
+        self.bitfield = bitfield.to(self.dev).contiguous()
+        self._coarse_valid = False
 
     def set_mean_count(self, mean_count: int):
         """M = mean_count rounded up strictly to a multiple of 128 (raymarching.py:235-238)."""
@@ -98,13 +104,14 @@ class HashTrainEngine:
     # ------------------------------------------------------------------ one step
     def _march_count(self, st):
         l = nv.lib()
-        nv.check(l.pvd_near_far_from_aabb(nv.ptr(self.rays_o), nv.ptr(self.rays_d), nv.ptr(self.aabb), _u32(self.N),
-                                          _f32(self.min_near), nv.ptr(self.nears), nv.ptr(self.fars), st))
         self.counter.zero_()
-        nv.check(l.pvd_march_rays_train_count(nv.ptr(self.rays_o), nv.ptr(self.rays_d), nv.ptr(self.bitfield), _f32(self.bound),
-                                              _f32(self.dt_gamma), _u32(self.max_steps), _u32(self.N), _u32(self.cascade),
-                                              _u32(self.grid_size), nv.ptr(self.nears), nv.ptr(self.fars), nv.ptr(self.rays),
-                                              nv.ptr(self.counter), _u32(1), nv.ptr(self.ws_march), st))
+        # near/far fused into the count kernel; the coarse rejection mask is rebuilt only when the bitfield changed
+        nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(self.rays_o), nv.ptr(self.rays_d), nv.ptr(self.bitfield), nv.ptr(self.aabb),
+                                                   _f32(self.min_near), _f32(self.bound), _f32(self.dt_gamma), _u32(self.max_steps),
+                                                   _u32(self.N), _u32(self.cascade), _u32(self.grid_size), nv.ptr(self.nears),
+                                                   nv.ptr(self.fars), nv.ptr(self.rays), nv.ptr(self.counter), _u32(1),
+                                                   _u32(1 if self._coarse_valid else 0), nv.ptr(self.ws_march), st))
+        self._coarse_valid = True
 
     def step(self, warmup: bool = False):
         """Forward + backward for the rays currently in self.rays_o / rays_d / gt.  Leaves loss in self.loss[0]."""
@@ -143,6 +150,21 @@ class HashTrainEngine:
         nv.check(l.pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), nv.ptr(self.enc),
                                            nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), None, _u32(M), nv.ptr(self.counter),
                                            nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status), st))
+
+    # ------------------------------------------------------------------ CUDA graph of one steady-state step
+    def capture(self):
+        """Capture `step()` (fixed M, static input buffers rays_o / rays_d / gt) into a CUDA graph; `replay()` then costs one
+        launch.  Inputs must be written INTO self.rays_o / self.rays_d / self.gt (copy_), not rebound."""
+        self.step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
 
     def finish_warmup(self):
         """mean_count = mean of the warm-up sample counts (renderer.py:768-772)."""

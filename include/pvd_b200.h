@@ -96,6 +96,12 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
                                float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                const float* nears, const float* fars, int32_t* rays, int32_t* counter,
                                uint32_t perturb, int32_t* ws_i32, void* stream);
+/* count phase with near_far_from_aabb fused in (writes nears/fars) and, when reuse_coarse != 0, re-using the coarse
+ * rejection mask a previous call left in ws_i32 for the SAME grid (a caller whose bitfield is static between density updates). */
+int pvd_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, const uint8_t* grid, const float* aabb,
+                                    float min_near, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                                    uint32_t H, float* nears, float* fars, int32_t* rays, int32_t* counter, uint32_t perturb,
+                                    uint32_t reuse_coarse, int32_t* ws_i32, void* stream);
 int pvd_march_rays_train_write(const float* rays_o, const float* rays_d, float bound, uint32_t max_steps,
                                uint32_t N, uint32_t M, const int32_t* rays, const int32_t* ws_i32, float* xyzs,
                                float* dirs, float* deltas, void* stream);

@@ -1,0 +1,91 @@
+"""The graph-free training-step engine (what bench.py times) against the autograd path built from the drop-in operators, and
+against the CPU oracle's training step; plus CUDA-graph replay equivalence."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _setup(scene, n_rays=1024, seed=0):
+    from pvd_b200.engine import HashTrainEngine
+    from pvd_b200.fused import HashNeRFField
+    torch.manual_seed(seed)
+    net = HashNeRFField(num_levels=14, desired_resolution=2048).cuda()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    eng = HashTrainEngine(net, torch.from_numpy(scene["bitfield"]), n_rays, loss_scale=512.0)
+    eng.stage()
+    ro, rd = scene["batches"][0]
+    ro, rd = ro[:n_rays].contiguous(), rd[:n_rays].contiguous()
+    gt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(3))
+    eng.rays_o.copy_(ro); eng.rays_d.copy_(rd); eng.gt.copy_(gt)
+    return net, eng, ro, rd, gt
+
+
+def test_engine_step_matches_autograd_path_and_oracle(scene):
+    import raymarching
+    from oracle import field
+    net, eng, ro, rd, gt = _setup(scene)
+    eng.step(warmup=True)   # sizes the sample buffers from the counter, like the reference's first iterations
+    eng.finish_warmup()
+    eng.step()              # steady state: M = ceil128(mean_count)
+    torch.cuda.synchronize()
+    assert int(eng.status.item()) == 0
+    loss_e = float(eng.loss[0].item())
+    gw_e = [g.clone() for g in eng.grad_weights()]
+    gt_e = eng.grad_table.clone()
+    pred_e, depth_e = eng.final_image()
+    # the same step through the drop-in operators + autograd, with the same M (mean_count) so the same rays are dropped
+    net.train()
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32, device="cuda")
+    nears, fars = raymarching.near_far_from_aabb(ro.cuda(), rd.cuda(), aabb, 0.2)
+    assert torch.equal(nears, eng.nears) and torch.equal(fars, eng.fars)   # fused near/far is the same arithmetic
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(ro.cuda(), rd.cuda(), 1.0, eng.bitfield, 1, 128, nears, fars, counter,
+                                                            eng.mean_count, True, 128, False, 0.0, 1024)
+    assert xyzs.shape[0] == eng.M and torch.equal(rays, eng.rays)
+    sigma, color = net(xyzs, dirs)
+    ws, depth, image = raymarching.composite_rays_train(sigma, color, deltas, rays)
+    pred = image + (1 - ws).unsqueeze(-1)
+    loss = torch.mean((pred - gt.cuda()) ** 2)
+    (loss * 512.0).backward()
+    assert abs(loss_e - float(loss)) < 1e-5 * max(1.0, float(loss))
+    torch.testing.assert_close(pred_e, pred.detach(), rtol=1e-5, atol=1e-6)
+    assert _rel_l2(gt_e, net.encoder.embeddings.grad) < 1e-3      # same kernels; float atomics reorder
+    for g, m in zip(gw_e, list(net.sigma_net) + list(net.color_net)):
+        assert _rel_l2(g, m.weight.grad) < 1e-3
+    # and the oracle's CPU step (same drop rule through M)
+    e = net.encoder
+    ws_o = [m.weight.detach().cpu() for m in list(net.sigma_net) + list(net.color_net)]
+    fn = lambda x, d: field.hash_field_forward(x, d, e.embeddings.detach().cpu(), e.offsets.cpu().numpy(), float(e.per_level_scale),
+                                               e.base_resolution, ws_o, quantize_fp16=True)[:2]
+    o = field.render_train_step(ro, rd, scene["bitfield"], gt, fn, M=eng.M)
+    assert abs(loss_e - float(o["loss"])) < 1e-2 * float(o["loss"])
+
+
+def test_engine_graph_replay_is_equivalent(scene):
+    net, eng, ro, rd, gt = _setup(scene, n_rays=512, seed=1)
+    eng.step(warmup=True)
+    eng.finish_warmup()
+    eng.step()
+    torch.cuda.synchronize()
+    ref_loss, ref_img = float(eng.loss[0]), eng.image.clone()
+    ref_gt = eng.grad_table.clone()
+    eng.capture()
+    eng.loss.zero_(); eng.image.zero_(); eng.grad_table.zero_()
+    eng.replay()
+    torch.cuda.synchronize()
+    assert abs(float(eng.loss[0]) - ref_loss) < 1e-6 * max(1.0, ref_loss)
+    torch.testing.assert_close(eng.image, ref_img, rtol=1e-6, atol=1e-7)
+    assert _rel_l2(eng.grad_table, ref_gt) < 1e-3
+    # new rays through the same graph
+    ro2, rd2 = scene["batches"][1]
+    eng.rays_o.copy_(ro2[:512]); eng.rays_d.copy_(rd2[:512])
+    eng.replay()
+    torch.cuda.synchronize()
+    assert float(eng.loss[0]) > 0 and int(eng.status.item()) == 0
