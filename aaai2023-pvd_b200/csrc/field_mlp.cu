@@ -1,0 +1,307 @@
+// field_mlp.cu -- fused "mlp" (NeRF) field FORWARD for sm_100a: frequency encoding -> 8 x 256 ReLU MLP with a skip
+// connection -> sigma_net / color_net tail, one kernel.  This is the teacher of BASELINE config 5 (mlp -> hash distillation);
+// it is evaluated under torch.no_grad (distill_mutual/utils.py:1008-1018), so only the forward is fused.
+//
+// Replaces NeRFNetwork.forward for model_type "mlp" (distill_mutual/network.py:56-70,324-333,413-437 and
+// tools/encoding.py:6-49): 21 sin/cos/cat kernels, 8 cuBLAS GEMMs with bias + ReLU + cat kernels between them, then the
+// same 5-GEMM tail as the hash model -- 0.87 MFLOP per sample, the one part of the path where FLOPs dominate.
+//
+// Structure per 128-sample tile (one persistent CTA per SM, 128 threads, thread t owns sample row t):
+//   * PE(10): 63 features (x, then sin/cos(2^k x), k = 0..9) -> fp16 operand tile X0 [128 x 64].
+//   * every 256-wide layer is  D[128 x 256] (TMEM, 256 columns)  +=  A[128 x K] * W[256 x K]^T  streamed in K-chunks of 64:
+//     a chunk of W is a 32 KB fp16 operand tile (pre-packed on the host side), double-buffered in shared memory with
+//     cp.async so that the load of chunk c+1 overlaps the four tcgen05.mma (N = 256, K = 16) of chunk c; an mbarrier per
+//     buffer (tcgen05.commit) says when the tensor core is done reading it.
+//   * the skip layer is two accumulating GEMMs: in_pts (X0, K = 64) and the 256 hidden units -- the concat never exists.
+//   * layer epilogue: each thread pulls its own row from TMEM 16 columns at a time, adds the bias, applies ReLU, and writes
+//     the next layer's A operand (fp16, chunk layout) over the previous one.
+//   * the last layer (256 -> 28) feeds the sigma_net / color_net tail of field_tail.cuh unchanged.
+#include "field_tail.cuh"
+
+namespace pvd {
+
+constexpr uint32_t kMlpChunkBytes = 256 * 64 * 2;   // one K-chunk of a 256-row weight matrix
+constexpr uint32_t kMlpChunks = 26;                 // 1 (L0) + 3*4 (L1-3) + 1+4 (L4: in_pts part, hidden part) + 2*4 (L5-6)
+constexpr uint32_t kMlpL7Bytes = 4 * (32 * 64 * 2); // 256 -> 28 as four [32 x 64] chunks
+constexpr uint32_t kMlpBiasOff = kMlpChunks * kMlpChunkBytes + kMlpL7Bytes;
+constexpr uint32_t kMlpBiasBytes = 8 * 256 * 4;
+static_assert(kMlpBiasOff + kMlpBiasBytes == PVD_MLP_WBLOB_BYTES, "mlp blob size");
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct MlpArgs {
+    const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
+    const uint8_t* tail_blob;  // PVD_FIELD_WBLOB_BYTES (sigma_net / color_net)
+    float clip_min, clip_max, density_scale;
+};
+
+// layer schedule: for each of the 26 streamed chunks, which layer it belongs to and where its A operand comes from
+struct ChunkDesc {
+    uint8_t layer;     // 0..6
+    uint8_t from_x0;   // A = X0 tile (in_pts) instead of the activation tile
+    uint8_t k_chunk;   // which 64-column slice of the activation tile
+    uint8_t last;      // last chunk of its layer
+};
+__constant__ ChunkDesc kSchedule[kMlpChunks] = {
+    {0, 1, 0, 1},
+    {1, 0, 0, 0}, {1, 0, 1, 0}, {1, 0, 2, 0}, {1, 0, 3, 1},
+    {2, 0, 0, 0}, {2, 0, 1, 0}, {2, 0, 2, 0}, {2, 0, 3, 1},
+    {3, 0, 0, 0}, {3, 0, 1, 0}, {3, 0, 2, 0}, {3, 0, 3, 1},
+    {4, 1, 0, 0}, {4, 0, 0, 0}, {4, 0, 1, 0}, {4, 0, 2, 0}, {4, 0, 3, 1},
+    {5, 0, 0, 0}, {5, 0, 1, 0}, {5, 0, 2, 0}, {5, 0, 3, 1},
+    {6, 0, 0, 0}, {6, 0, 1, 0}, {6, 0, 2, 0}, {6, 0, 3, 1},
+};
+
+__global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                          uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
+                                                          float* __restrict__ feat16, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_layer, bar_w[2];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* X0 = smem;                              // 16384 : PE features [128 x 64]
+    uint8_t* A = X0 + 16384;                         // 65536 : activations [128 x 256]; later the tail's tiles
+    uint8_t* WB = A + 65536;                         // 2 x 32768 : streamed weight chunks
+    uint8_t* smw = WB + 2 * kMlpChunkBytes;          // 20480 : tail weights
+    float* bias = reinterpret_cast<float*>(smw + PVD_FIELD_WBLOB_BYTES);  // 8 x 256 floats
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane_base = (tid >> 5) * 32;
+
+    stage_blob(smw, a.tail_blob, PVD_FIELD_WBLOB_BYTES);
+    stage_blob(reinterpret_cast<uint8_t*>(bias), a.wblob + kMlpBiasOff, kMlpBiasBytes);
+    if (tid == 0) {
+        tc5::mbar_init(&bar_layer, 1);
+        tc5::mbar_init(&bar_w[0], 1);
+        tc5::mbar_init(&bar_w[1], 1);
+        tc5::mbar_fence_init();
+    }
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t trow = tc5::tmem_addr(tmem, lane_base, 0);
+    Pipe p{&bar_layer, 0u, tmem, status};
+    uint32_t wphase[2] = {0u, 0u};      // parity each weight buffer's "free" barrier will complete next
+    bool wbusy[2] = {false, false};     // a commit is outstanding on the buffer
+
+    auto load_chunk = [&](uint32_t buf, const uint8_t* src, uint32_t bytes) {
+        const uint32_t dst = tc5::smem_u32(WB + buf * kMlpChunkBytes);
+        for (uint32_t i = tid; i < bytes / 16; i += 128) cp_async16(dst + 16 * i, src + 16 * (size_t)i);
+        cp_async_commit();
+    };
+    auto wait_buffer_free = [&](uint32_t buf) {
+        if (wbusy[buf]) {
+            if (!tc5::mbar_wait(&bar_w[buf], wphase[buf])) atomicExch(status, 1);
+            wphase[buf] ^= 1u;
+            wbusy[buf] = false;
+            tc5::fence_after_sync();
+        }
+    };
+
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTile + tid;
+        const bool live = row < M;
+        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+            }
+        }
+        // first weight chunk in flight while the encoding is computed
+        wait_buffer_free(0);
+        load_chunk(0, a.wblob, kMlpChunkBytes);
+        {   // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9
+            float f[64];
+            f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2];
+            float freq = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float sn, cs;
+                    sincosf(pos[d] * freq, &sn, &cs);
+                    f[3 + 6 * k + d] = sn;
+                    f[3 + 6 * k + 3 + d] = cs;
+                }
+                freq *= 2.0f;
+            }
+            f[63] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(X0 + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(f + 8 * j);
+        }
+        // ---- the 26 streamed chunks of layers 0..6
+        for (uint32_t ci = 0; ci < kMlpChunks; ++ci) {
+            const ChunkDesc cd = kSchedule[ci];
+            const uint32_t buf = ci & 1u;
+            // prefetch the next chunk (or the L7 weights) into the other buffer once the tensor core released it
+            if (ci + 1 < kMlpChunks) {
+                wait_buffer_free(buf ^ 1u);
+                load_chunk(buf ^ 1u, a.wblob + (size_t)(ci + 1) * kMlpChunkBytes, kMlpChunkBytes);
+            } else {
+                wait_buffer_free(buf ^ 1u);
+                load_chunk(buf ^ 1u, a.wblob + (size_t)kMlpChunks * kMlpChunkBytes, kMlpL7Bytes);
+            }
+            // this chunk's weights: everything but the newest cp.async group has landed
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            operands_ready();  // also publishes the activation tile written by the previous layer's epilogue
+            if (tid == 0) {
+                tc5::fence_after_sync();
+                const uint32_t a_tile = cd.from_x0 ? tc5::smem_u32(X0) : tc5::smem_u32(A) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
+                const uint32_t b_tile = tc5::smem_u32(WB + buf * kMlpChunkBytes);
+                const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
+                const bool layer_start = (cd.k_chunk == 0) && (cd.from_x0 || cd.layer != 4);
+#pragma unroll
+                for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                    tc5::mma_f16_ss(tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
+                                    !(layer_start && k0 == 0));
+                tc5::mma_commit(&bar_w[buf]);               // buffer reusable once these MMAs have read it
+                if (cd.last) tc5::mma_commit(&bar_layer);   // layer complete
+            }
+            wbusy[buf] = true;
+            if (cd.last) {
+                mma_wait(p);
+                // epilogue: bias + ReLU -> next layer's A operand (the MMAs that read the old A have all completed)
+                const float* bl = bias + 256 * cd.layer;
+#pragma unroll 1
+                for (int c = 0; c < 16; ++c) {
+                    float v[16];
+                    tc5::tmem_ld16(trow + 16 * c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[16 * c + i], 0.0f);
+                    *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c)) = tc5::pack8(v);
+                    *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c + 1)) = tc5::pack8(v + 8);
+                }
+            }
+        }
+        // ---- layer 7: 256 -> 28 (N = 32), weights are four [32 x 64] chunks sitting in buffer 0 (kMlpChunks is even)
+        cp_async_wait_all();
+        operands_ready();
+        if (tid == 0) {
+            tc5::fence_after_sync();
+            const uint32_t idesc = tc5::instr_desc_f16(128, 32, 0, 0);
+            for (uint32_t c = 0; c < 4; ++c)
+                for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                    tc5::mma_f16_ss(tmem, tc5::desc_kmajor(tc5::smem_u32(A) + c * 8u * (kTile * 16u), kTile, k0),
+                                    tc5::desc_kmajor(tc5::smem_u32(WB) + c * (32u * 64u * 2u), 32, k0), idesc, !(c == 0 && k0 == 0));
+            tc5::mma_commit(&bar_w[0]);
+            tc5::mma_commit(&bar_layer);
+        }
+        wbusy[0] = true;
+        mma_wait(p);
+        // x28 = D[0..27] + bias7 -> the tail's encoding tile (reuses the activation region; its MMAs have completed)
+        uint8_t* X = A;                 // 8192
+        uint8_t* CIN = A;               // aliases X (dead after the first tail layer)
+        uint8_t* H = A + 8192;          // 16384 : H1, H3, H4
+        {
+            float v[32];
+            tc5::tmem_ld16(trow, *reinterpret_cast<float(*)[16]>(&v[0]));
+            tc5::tmem_ld16(trow + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+            const float* b7 = bias + 256 * 7;
+#pragma unroll
+            for (int i = 0; i < 28; ++i) v[i] += b7[i];
+#pragma unroll
+            for (int i = 28; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(v + 8 * j);
+        }
+        FieldArgs fa;
+        fa.clip_min = a.clip_min; fa.clip_max = a.clip_max; fa.density_scale = a.density_scale;
+        float sigma, o16[16];
+        FwdRegs r;
+        mlp_forward(p, fa, smw, X, H, CIN, H, H, dir, tid, sigma, o16, r);
+        if (live) {
+            sigmas[row] = sigma;
+            rgbs[3 * (size_t)row] = r.rgb[0];
+            rgbs[3 * (size_t)row + 1] = r.rgb[1];
+            rgbs[3 * (size_t)row + 2] = r.rgb[2];
+            if (feat16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(feat16 + 16 * (size_t)row + 4 * q) =
+                        make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+            }
+        }
+    }
+    cp_async_wait_all();
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(tmem, 256);
+}
+
+// pack nerf_mlp weights/biases (fp32, nn.Linear layout) into the streamed blob
+__global__ void k_mlp_pack(const float* const* __restrict__ w, const float* const* __restrict__ b, uint8_t* __restrict__ blob) {
+    // chunk index -> (layer, first input column of the slice).  Layer 4's input is cat([in_pts(63), hidden(256)]) (network.py:331-332)
+    const uint32_t ci = blockIdx.x;
+    if (ci < kMlpChunks) {
+        const ChunkDesc cd = kSchedule[ci];
+        const uint32_t in_dim = (cd.layer == 0) ? 63u : (cd.layer == 4 ? 319u : 256u);
+        uint32_t col0, ncols;
+        if (cd.layer == 0) { col0 = 0; ncols = 63; }
+        else if (cd.layer == 4 && cd.from_x0) { col0 = 0; ncols = 63; }
+        else if (cd.layer == 4) { col0 = 63 + 64 * cd.k_chunk; ncols = 64; }
+        else { col0 = 64 * cd.k_chunk; ncols = 64; }
+        uint8_t* tile = blob + (size_t)ci * kMlpChunkBytes;
+        const float* W = w[cd.layer];
+        for (uint32_t e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
+            const uint32_t r = e / 64, k = e - r * 64;
+            const float v = (k < ncols) ? W[(size_t)r * in_dim + col0 + k] : 0.0f;
+            *reinterpret_cast<__half*>(tile + tc5::chunk_off(256, r, k >> 3) + (k & 7u) * 2) = __float2half_rn(v);
+        }
+    } else if (ci < kMlpChunks + 4) {  // layer 7: [28 x 256] as four [32 x 64] chunks
+        const uint32_t c = ci - kMlpChunks;
+        uint8_t* tile = blob + (size_t)kMlpChunks * kMlpChunkBytes + c * (32 * 64 * 2);
+        const float* W = w[7];
+        for (uint32_t e = threadIdx.x; e < 32 * 64; e += blockDim.x) {
+            const uint32_t r = e / 64, k = e - r * 64;
+            const float v = (r < 28) ? W[(size_t)r * 256 + 64 * c + k] : 0.0f;
+            *reinterpret_cast<__half*>(tile + tc5::chunk_off(32, r, k >> 3) + (k & 7u) * 2) = __float2half_rn(v);
+        }
+    } else {  // biases: 8 x 256 floats (layer 7 has 28)
+        float* bb = reinterpret_cast<float*>(blob + kMlpBiasOff);
+        for (uint32_t e = threadIdx.x; e < 8 * 256; e += blockDim.x) {
+            const uint32_t l = e / 256, i = e - l * 256;
+            bb[e] = (l < 7 || i < 28) ? b[l][i] : 0.0f;
+        }
+    }
+}
+
+constexpr size_t kMlpSmem = 16384 + 65536 + 2 * kMlpChunkBytes + PVD_FIELD_WBLOB_BYTES + kMlpBiasBytes;  // 176128
+
+}  // namespace pvd
+
+using namespace pvd;
+
+extern "C" {
+
+int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biases8, void* wblob, void* stream) {
+    PVD_REQUIRE(weights8 && biases8 && wblob);
+    k_mlp_pack<<<kMlpChunks + 5, 256, 0, (cudaStream_t)stream>>>(weights8, biases8, (uint8_t*)wblob);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                          float* feat16, int32_t* status, void* stream) {
+    if (M == 0) return PVD_OK;
+    PVD_REQUIRE(f && f->wblob && f->tail_wblob && xyzs && dirs && sigmas && rgbs && status);
+    MlpArgs a;
+    a.wblob = reinterpret_cast<const uint8_t*>(f->wblob);
+    a.tail_blob = reinterpret_cast<const uint8_t*>(f->tail_wblob);
+    a.clip_min = f->sigma_clip_min; a.clip_max = f->sigma_clip_max; a.density_scale = f->density_scale;
+    const uint32_t tiles = (M + kTile - 1) / kTile;
+    const uint32_t grid = min(tiles, (uint32_t)sm_count());
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_mlp_field_fwd<<<grid, 128, kMlpSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -127,6 +127,28 @@ int pvd_vm_field_backward(const PvdVmField* field, const PvdVmGrads* grads, cons
 
 int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, float* gw_color1, float* gw_color2, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * "mlp" (NeRF) field, FORWARD only -- the frozen teacher of mlp -> hash distillation (BASELINE config 5):
+ * FreqEncoder PE(10) 3 -> 63 (tools/encoding.py:6-49), nerf_mlp = 8 Linear layers with bias, 256 wide, skip concat of the
+ * encoding after the 4th (network.py:56-70,324-333), output 28, then the same sigma_net / color_net tail as the hash model.
+ * ---------------------------------------------------------------------------------------- */
+#define PVD_MLP_WBLOB_BYTES 876544u
+
+typedef struct PvdMlpField {
+    const void* wblob;       /* PVD_MLP_WBLOB_BYTES from pvd_mlp_pack_weights */
+    const void* tail_wblob;  /* PVD_FIELD_WBLOB_BYTES from pvd_field_pack_weights (in_dim = 28) */
+    float sigma_clip_min;
+    float sigma_clip_max;
+    float density_scale;
+} PvdMlpField;
+
+/* weights8 / biases8: DEVICE arrays of 8 device pointers to nerf_mlp.{0..7}.weight ([256,63] [256,256]x3 [256,319] [256,256]x2
+ * [28,256], fp32 row-major) and .bias. */
+int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biases8, void* wblob, void* stream);
+
+int pvd_mlp_field_forward(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                          float* feat16, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,34 @@ def vm_field_forward(x, d, sigma_mat, sigma_vec, color_mat, color_vec, basis_w, 
     h = q(F.relu(F.linear(h, q(wc1))))
     color = torch.sigmoid(F.linear(h, q(wc2)))
     return sigma, color, feat
+
+
+# ------------------------------------------------------------------------------------------------ NeRF MLP field
+def mlp_field_forward(x, d, nerf_w, nerf_b, tail_ws, PE=10, skips=3, clip_min=-2.0, clip_max=7.0, quantize_fp16=False):
+    """`NeRFNetwork.forward` for model_type "mlp": FreqEncoder (tools/encoding.py:36-49) -> nerf_mlp with a skip concat
+    (network.py:324-333) -> the sigma_net / color_net tail (network.py:413-437).  nerf_w / nerf_b: 8 weights / biases."""
+    q = (lambda t: t.half().float()) if quantize_fp16 else (lambda t: t)
+    parts = [x]
+    for k in range(PE):
+        f = 2.0 ** k
+        parts += [torch.sin(x * f), torch.cos(x * f)]
+    h = torch.cat(parts, dim=-1)
+    in_pts = h
+    n = len(nerf_w)
+    for i in range(n):
+        h = F.linear(q(h), q(nerf_w[i])) + nerf_b[i]   # fp16 operands, fp32 accumulate, fp32 bias (as the fused kernel)
+        if i != n - 1:
+            h = F.relu(h)
+        if i == skips:
+            h = torch.cat([in_pts, h], dim=-1)
+    ws0, ws1, wc0, wc1, wc2 = tail_ws
+    h = q(F.relu(F.linear(q(h), q(ws0))))
+    h = q(F.linear(h, q(ws1)))
+    h0 = torch.clamp(h[..., 0], clip_min, clip_max)
+    feat = torch.cat([h0.unsqueeze(-1), h[..., 1:]], dim=-1)
+    sigma = torch.exp(h0)
+    sh = torch.from_numpy(cpu.sh_encode_forward(d.detach().numpy(), 4))
+    c = torch.cat([sh, h[..., 1:]], dim=-1)
+    c = q(F.relu(F.linear(q(c), q(wc0))))
+    c = q(F.relu(F.linear(c, q(wc1))))
+    return sigma, torch.sigmoid(F.linear(c, q(wc2))), feat
