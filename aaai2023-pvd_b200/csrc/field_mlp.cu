@@ -9,9 +9,11 @@
 // Structure per 128-sample tile (one persistent CTA per SM, 128 threads, thread t owns sample row t):
 //   * PE(10): 63 features (x, then sin/cos(2^k x), k = 0..9) -> fp16 operand tile X0 [128 x 64].
 //   * every 256-wide layer is  D[128 x 256] (TMEM, 256 columns)  +=  A[128 x K] * W[256 x K]^T  streamed in K-chunks of 64:
-//     a chunk of W is a 32 KB fp16 operand tile (pre-packed on the host side), double-buffered in shared memory with
-//     cp.async so that the load of chunk c+1 overlaps the four tcgen05.mma (N = 256, K = 16) of chunk c; an mbarrier per
-//     buffer (tcgen05.commit) says when the tensor core is done reading it.
+//     a chunk of W is a 32 KB fp16 operand tile (pre-packed on the host side), double-buffered in shared memory and moved by
+//     the TMA engine: ONE thread arms a "full" mbarrier with the byte count (mbarrier.arrive.expect_tx) and issues one
+//     cp.async.bulk.shared::cluster.global (UBLKCP) per chunk; the same thread waits for it, issues the four tcgen05.mma
+//     (N = 256, K = 16) of the chunk and commits them to the buffer's "empty" mbarrier, so the copy of chunk c+1 overlaps
+//     the MMAs of chunk c and no other thread takes part in weight streaming (no block-wide barrier per chunk).
 //   * the skip layer is two accumulating GEMMs: in_pts (X0, K = 64) and the 256 hidden units -- the concat never exists.
 //   * layer epilogue: each thread pulls its own row from TMEM 16 columns at a time, adds the bias, applies ReLU, and writes
 //     the next layer's A operand (fp16, chunk layout) over the previous one.
@@ -27,11 +29,15 @@ constexpr uint32_t kMlpBiasOff = kMlpChunks * kMlpChunkBytes + kMlpL7Bytes;
 constexpr uint32_t kMlpBiasBytes = 8 * 256 * 4;
 static_assert(kMlpBiasOff + kMlpBiasBytes == PVD_MLP_WBLOB_BYTES, "mlp blob size");
 
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+// TMA bulk copy global -> shared, completion signalled on an mbarrier as transaction bytes
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc5::smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr),
+                 "l"(src), "r"(bytes), "r"(tc5::smem_u32(bar))
+                 : "memory");
+}
 
 struct MlpArgs {
     const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
                                                           uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                           float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_layer, bar_w[2];
+    __shared__ uint64_t bar_layer, bar_full[2], bar_empty[2];
     __shared__ uint32_t tmem_base_s;
     uint8_t* X0 = smem;                              // 16384 : PE features [128 x 64]
     uint8_t* A = X0 + 16384;                         // 65536 : activations [128 x 256]; later the tail's tiles
@@ -74,8 +80,10 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
     stage_blob(reinterpret_cast<uint8_t*>(bias), a.wblob + kMlpBiasOff, kMlpBiasBytes);
     if (tid == 0) {
         tc5::mbar_init(&bar_layer, 1);
-        tc5::mbar_init(&bar_w[0], 1);
-        tc5::mbar_init(&bar_w[1], 1);
+        tc5::mbar_init(&bar_full[0], 1);
+        tc5::mbar_init(&bar_full[1], 1);
+        tc5::mbar_init(&bar_empty[0], 1);
+        tc5::mbar_init(&bar_empty[1], 1);
         tc5::mbar_fence_init();
     }
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
@@ -85,27 +93,31 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
     const uint32_t tmem = tmem_base_s;
     const uint32_t trow = tc5::tmem_addr(tmem, lane_base, 0);
     Pipe p{&bar_layer, 0u, tmem, status};
-    uint32_t wphase[2] = {0u, 0u};      // parity each weight buffer's "free" barrier will complete next
-    bool wbusy[2] = {false, false};     // a commit is outstanding on the buffer
+    // weight pipeline state, meaningful in thread 0 only: running counts of chunk loads issued / chunks consumed
+    uint32_t issued = 0, consumed = 0;
 
-    auto load_chunk = [&](uint32_t buf, const uint8_t* src, uint32_t bytes) {
-        const uint32_t dst = tc5::smem_u32(WB + buf * kMlpChunkBytes);
-        for (uint32_t i = tid; i < bytes / 16; i += 128) cp_async16(dst + 16 * i, src + 16 * (size_t)i);
-        cp_async_commit();
-    };
-    auto wait_buffer_free = [&](uint32_t buf) {
-        if (wbusy[buf]) {
-            if (!tc5::mbar_wait(&bar_w[buf], wphase[buf])) atomicExch(status, 1);
-            wphase[buf] ^= 1u;
-            wbusy[buf] = false;
-            tc5::fence_after_sync();
+    // chunk `c` of a tile: 0..25 = the 32 KB slices of layers 0..6, 26 = the four [32 x 64] slices of layer 7
+    auto issue_load = [&](uint32_t c) {
+        const uint32_t buf = issued & 1u;
+        if (issued >= 2u) {  // the buffer's previous user must have been read by the tensor core
+            if (!tc5::mbar_wait(&bar_empty[buf], ((issued >> 1) - 1u) & 1u)) atomicExch(status, 1);
         }
+        const uint32_t bytes = (c < kMlpChunks) ? kMlpChunkBytes : kMlpL7Bytes;
+        mbar_expect_tx(&bar_full[buf], bytes);
+        bulk_g2s(tc5::smem_u32(WB + buf * kMlpChunkBytes), a.wblob + (size_t)c * kMlpChunkBytes, bytes, &bar_full[buf]);
+        ++issued;
+    };
+    auto wait_full = [&]() -> uint32_t {
+        const uint32_t buf = consumed & 1u;
+        if (!tc5::mbar_wait(&bar_full[buf], (consumed >> 1) & 1u)) atomicExch(status, 1);
+        return buf;
     };
 
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t row = tile * kTile + tid;
         const bool live = row < M;
+        const bool more_tiles = tile + gridDim.x < n_tiles;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         if (live) {
 #pragma unroll
@@ -114,9 +126,7 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
                 dir[d] = __ldg(dirs + 3 * (size_t)row + d);
             }
         }
-        // first weight chunk in flight while the encoding is computed
-        wait_buffer_free(0);
-        load_chunk(0, a.wblob, kMlpChunkBytes);
+        if (tid == 0 && issued == consumed) issue_load(0);  // first tile of this CTA (later tiles were prefetched)
         {   // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9
             float f[64];
             f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2];
@@ -136,64 +146,61 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
 #pragma unroll
             for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(X0 + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(f + 8 * j);
         }
-        // ---- the 26 streamed chunks of layers 0..6
-        for (uint32_t ci = 0; ci < kMlpChunks; ++ci) {
-            const ChunkDesc cd = kSchedule[ci];
-            const uint32_t buf = ci & 1u;
-            // prefetch the next chunk (or the L7 weights) into the other buffer once the tensor core released it
-            if (ci + 1 < kMlpChunks) {
-                wait_buffer_free(buf ^ 1u);
-                load_chunk(buf ^ 1u, a.wblob + (size_t)(ci + 1) * kMlpChunkBytes, kMlpChunkBytes);
-            } else {
-                wait_buffer_free(buf ^ 1u);
-                load_chunk(buf ^ 1u, a.wblob + (size_t)kMlpChunks * kMlpChunkBytes, kMlpL7Bytes);
-            }
-            // this chunk's weights: everything but the newest cp.async group has landed
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            operands_ready();  // also publishes the activation tile written by the previous layer's epilogue
+        // ---- layers 0..6: thread 0 streams the layer's chunks and issues its MMAs; everybody meets at the layer barrier
+        uint32_t ci = 0;
+        for (uint32_t layer = 0; layer < 7; ++layer) {
+            operands_ready();  // publishes X0 / the activation tile written by the previous epilogue, orders the TMEM reads
+            const uint32_t n_chunks = (layer == 0) ? 1u : (layer == 4 ? 5u : 4u);
             if (tid == 0) {
                 tc5::fence_after_sync();
-                const uint32_t a_tile = cd.from_x0 ? tc5::smem_u32(X0) : tc5::smem_u32(A) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
-                const uint32_t b_tile = tc5::smem_u32(WB + buf * kMlpChunkBytes);
                 const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
-                const bool layer_start = (cd.k_chunk == 0) && (cd.from_x0 || cd.layer != 4);
+                for (uint32_t j = 0; j < n_chunks; ++j) {
+                    const ChunkDesc cd = kSchedule[ci + j];
+                    issue_load(ci + j + 1);  // next chunk of the tile (26 = layer 7) into the other buffer
+                    const uint32_t buf = wait_full();
+                    tc5::fence_after_sync();
+                    const uint32_t a_tile = cd.from_x0 ? tc5::smem_u32(X0) : tc5::smem_u32(A) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
+                    const uint32_t b_tile = tc5::smem_u32(WB + buf * kMlpChunkBytes);
 #pragma unroll
-                for (uint32_t k0 = 0; k0 < 64; k0 += 16)
-                    tc5::mma_f16_ss(tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                    !(layer_start && k0 == 0));
-                tc5::mma_commit(&bar_w[buf]);               // buffer reusable once these MMAs have read it
-                if (cd.last) tc5::mma_commit(&bar_layer);   // layer complete
-            }
-            wbusy[buf] = true;
-            if (cd.last) {
-                mma_wait(p);
-                // epilogue: bias + ReLU -> next layer's A operand (the MMAs that read the old A have all completed)
-                const float* bl = bias + 256 * cd.layer;
-#pragma unroll 1
-                for (int c = 0; c < 16; ++c) {
-                    float v[16];
-                    tc5::tmem_ld16(trow + 16 * c, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[16 * c + i], 0.0f);
-                    *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c)) = tc5::pack8(v);
-                    *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c + 1)) = tc5::pack8(v + 8);
+                    for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                        tc5::mma_f16_ss(tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
+                                        !(j == 0 && k0 == 0));
+                    tc5::mma_commit(&bar_empty[buf]);  // buffer reusable once these MMAs have read it
+                    ++consumed;
                 }
+                tc5::mma_commit(&bar_layer);
+            }
+            ci += n_chunks;
+            mma_wait(p);
+            // epilogue: bias + ReLU -> next layer's A operand (the MMAs that read the old A have all completed)
+            const float* bl = bias + 256 * layer;
+#pragma unroll 1
+            for (int c = 0; c < 16; ++c) {
+                float v[16];
+                tc5::tmem_ld16(trow + 16 * c, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[16 * c + i], 0.0f);
+                *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c)) = tc5::pack8(v);
+                *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c + 1)) = tc5::pack8(v + 8);
             }
         }
-        // ---- layer 7: 256 -> 28 (N = 32), weights are four [32 x 64] chunks sitting in buffer 0 (kMlpChunks is even)
-        cp_async_wait_all();
+        // ---- layer 7: 256 -> 28 (N = 32), its four [32 x 64] slices arrived as "chunk 26"
         operands_ready();
         if (tid == 0) {
+            tc5::fence_after_sync();
+            if (more_tiles) issue_load(0);  // next tile's first chunk streams in under the tail
+            const uint32_t buf = wait_full();
             tc5::fence_after_sync();
             const uint32_t idesc = tc5::instr_desc_f16(128, 32, 0, 0);
             for (uint32_t c = 0; c < 4; ++c)
                 for (uint32_t k0 = 0; k0 < 64; k0 += 16)
                     tc5::mma_f16_ss(tmem, tc5::desc_kmajor(tc5::smem_u32(A) + c * 8u * (kTile * 16u), kTile, k0),
-                                    tc5::desc_kmajor(tc5::smem_u32(WB) + c * (32u * 64u * 2u), 32, k0), idesc, !(c == 0 && k0 == 0));
-            tc5::mma_commit(&bar_w[0]);
+                                    tc5::desc_kmajor(tc5::smem_u32(WB + buf * kMlpChunkBytes) + c * (32u * 64u * 2u), 32, k0), idesc,
+                                    !(c == 0 && k0 == 0));
+            tc5::mma_commit(&bar_empty[buf]);
+            ++consumed;
             tc5::mma_commit(&bar_layer);
         }
-        wbusy[0] = true;
         mma_wait(p);
         // x28 = D[0..27] + bias7 -> the tail's encoding tile (reuses the activation region; its MMAs have completed)
         uint8_t* X = A;                 // 8192
@@ -229,7 +236,6 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
             }
         }
     }
-    cp_async_wait_all();
     tc5::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc5::tmem_dealloc(tmem, 256);

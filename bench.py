@@ -180,9 +180,20 @@ def run_ours(args, rank, world, local):
         else:
             eng.step()
 
+    grad_comm = None
+    if world > 1 and args.grad_comm == "fp16":
+        grad_comm = torch.empty(eng.grad_table.shape, dtype=torch.float16, device=dev)
+
     def allreduce():
+        # one gradient exchange per step.  fp16 payload (default for N > 1): the table gradient is cast once (42 MB read, 21 MB
+        # write) and all-reduced in half precision -- the precision the reference ACCUMULATES these gradients in
+        # (gridencoder.cu:299-305) -- which halves the bytes crossing NVLink; the small MLP gradients stay fp32.
         if world > 1:
-            dist.all_reduce(eng.grad_table)
+            if grad_comm is not None:
+                grad_comm.copy_(eng.grad_table)
+                dist.all_reduce(grad_comm)
+            else:
+                dist.all_reduce(eng.grad_table)
             dist.all_reduce(eng.gw_ws)
 
     # ---- 16 sizing steps (the reference's mean_count warm-up), then W untimed steps at the steady-state M
@@ -299,7 +310,8 @@ def run_ours(args, rank, world, local):
                                "synthetic 800x800 Lego-shaped scene, fwd+bwd (MSE), random-init weights",
                    "rays_per_gpu": args.rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
                    "precision": "fp16 table + fp16 tcgen05 MLP, fp32 accumulate / composite / gradients", "loss_scale": 65536,
-                   "parallelism": f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step" if world > 1 else "single GPU",
+                   "parallelism": (f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step "
+                                   f"({args.grad_comm} table-gradient payload)") if world > 1 else "single GPU",
                    "launch": "one CUDA graph per step" if use_graph else "eager (one launch per kernel)",
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write, outside the timed brackets)",
                    "scene_bitfield_sha256": sha[:16]},
@@ -443,6 +455,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-comm", default="fp16", choices=["fp16", "fp32"], help="payload dtype of the table-gradient all-reduce (N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
