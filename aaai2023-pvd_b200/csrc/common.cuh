@@ -24,6 +24,30 @@
         if (!(cond)) return PVD_EINVAL;   \
     } while (0)
 
+// ---- diagnostic timeline (tools/trace build only: -DPVD_TRACE; the shipped library compiles these to nothing) --------------
+#ifdef PVD_TRACE
+#define PVD_TRACE_TU(setter)                                                                   \
+    static __device__ unsigned long long* g_trace_buf;                                         \
+    static __device__ unsigned int g_trace_cap;                                                \
+    extern "C" int setter(unsigned long long* buf, unsigned int records) {                     \
+        cudaError_t e = cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf));                    \
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_cap, &records, sizeof(records));  \
+        return (int)e;                                                                         \
+    }
+#define PVD_T(rec, slot)                                                                       \
+    do {                                                                                       \
+        if (g_trace_buf != nullptr && (unsigned int)(rec) < g_trace_cap) g_trace_buf[(size_t)(rec) * 16 + (slot)] = clock64(); \
+    } while (0)
+#define PVD_TV(rec, slot, val)                                                                 \
+    do {                                                                                       \
+        if (g_trace_buf != nullptr && (unsigned int)(rec) < g_trace_cap) g_trace_buf[(size_t)(rec) * 16 + (slot)] = (unsigned long long)(val); \
+    } while (0)
+#else
+#define PVD_TRACE_TU(setter)
+#define PVD_T(rec, slot) do { } while (0)
+#define PVD_TV(rec, slot, val) do { } while (0)
+#endif
+
 namespace pvd {
 
 constexpr float kSqrt3 = 1.7320508075688772f;  // raymarching.cu:21
@@ -136,6 +160,8 @@ __device__ __forceinline__ float pcg32_next_float(Pcg32& r) {
 struct MarchCtx {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
     float bound, rbound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f;
+    float halfH, rH2;      // 0.5*H and 2/H: exact power-of-two rescalings of H and 1/H
+    int incx, incy, incz;  // 1 where the ray moves towards +axis (sign bit of d clear), else 0
     uint32_t C, H, H3;
 };
 
@@ -150,6 +176,10 @@ __device__ __forceinline__ void march_ctx_init(MarchCtx& c, const float* o, cons
     const float two_s3 = __fmul_rn(2.0f, kSqrt3);
     c.dt_min = __fdiv_rn(two_s3, (float)max_steps);
     c.dt_max = __fdiv_rn(__fmul_rn(two_s3, (float)(1u << (C - 1))), c.Hf);
+    c.halfH = 0.5f * c.Hf; c.rH2 = 2.0f * c.rH;
+    c.incx = (int)((__float_as_uint(c.dx) >> 31) ^ 1u);
+    c.incy = (int)((__float_as_uint(c.dy) >> 31) ^ 1u);
+    c.incz = (int)((__float_as_uint(c.dz) >> 31) ^ 1u);
     c.C = C; c.H = H; c.H3 = H * H * H;
 }
 
@@ -168,43 +198,60 @@ __device__ __forceinline__ void march_pos(const MarchCtx& c, float t, float& x, 
 // The reference evaluates 0.5*(..)*H in double and rounds to float when calling clamp(); with the
 // inner FMA done in float, the double product of a float by 0.5 and by an integer-valued H is exact,
 // so a single correctly-rounded float multiply gives the identical float.
-__device__ __forceinline__ int march_cell(float x, float mip_rbound, float Hf, float Hm1f) {
+// 0.5*a is exact, so fl(fl(0.5*a)*H) = fl(a*(0.5*H)): one multiply by the precomputed 0.5*H.
+__device__ __forceinline__ int march_cell(float x, float mip_rbound, float halfH, float Hm1f) {
     const float a = __fmaf_rn(x, mip_rbound, 1.0f);
-    const float p = __fmul_rn(__fmul_rn(0.5f, a), Hf);
+    const float p = __fmul_rn(a, halfH);
     return (int)clampf(p, 0.0f, Hm1f);
 }
 
 // distance to the exit of the current (empty) cell along one axis (raymarching.cu:393-395)
-__device__ __forceinline__ float march_exit(int n, float d, float rd, float x, float rH, float mip_bound) {
-    const float s = copysignf(1.0f, d);
-    const float a = __fadd_rn(__fadd_rn((float)n, 0.5f), __fmul_rn(0.5f, s));  // exact small numbers
-    const float q = __fadd_rn(__fmul_rn(__fmul_rn(a, rH), 2.0f), -1.0f);      // a*rH*2 - 1
-    return __fmul_rn(__fmaf_rn(q, mip_bound, -x), rd);                          // (q*mb - x) * rd
+// n + 0.5 + 0.5*sign(d) is the exact integer n + inc (inc = 1 for d >= +0, 0 for d <= -0); fl(a*rH)*2 = fl(a*(2*rH)).
+__device__ __forceinline__ float march_exit(int n, int inc, float rd, float x, float rH2, float mip_bound) {
+    const float a = (float)(n + inc);
+    const float q = __fadd_rn(__fmul_rn(a, rH2), -1.0f);        // a*rH*2 - 1
+    return __fmul_rn(__fmaf_rn(q, mip_bound, -x), rd);          // (q*mb - x) * rd
 }
 
-// Returns true if the sample at t is in an occupied cell. When it is not, `t_skip` receives the
-// parameter at which the ray leaves the cell (tt of raymarching.cu:397).
-__device__ __forceinline__ bool march_probe(const MarchCtx& c, const uint8_t* __restrict__ grid, float t,
-                                            float dt, float x, float y, float z, float& t_skip) {
+// The occupancy cell of a sample, split from the load of its bit so that callers can put several loads in flight.
+struct MarchCell {
+    int nx, ny, nz;
+    float mip_bound;
+    uint32_t index;  // bit index into the density bitfield (level * H^3 + morton)
+};
+
+__device__ __forceinline__ MarchCell march_locate(const MarchCtx& c, float dt, float x, float y, float z) {
+    MarchCell m;
     // level in [0, C-1] (raymarching.cu:371); a single cascade needs no exponent arithmetic at all
     const int level = (c.C > 1) ? max(mip_from_pos(x, y, z, c.C), mip_from_dt(dt, c.Hf, c.C)) : 0;
     // mip_bound = min(2^level, bound), mip_rbound = 1 / mip_bound (:373-374).  The IEEE quotient 1 / 2^level is exactly
     // 2^-level, so the division is only ever needed for 1 / bound, which is hoisted into the context.
     const float p2 = (float)(1u << level);
     const bool pow2 = p2 <= c.bound;
-    const float mip_bound = pow2 ? p2 : c.bound;
+    m.mip_bound = pow2 ? p2 : c.bound;
     const float mip_rbound = pow2 ? __uint_as_float((uint32_t)(127 - level) << 23) : c.rbound;
-    const int nx = march_cell(x, mip_rbound, c.Hf, c.Hm1f);
-    const int ny = march_cell(y, mip_rbound, c.Hf, c.Hm1f);
-    const int nz = march_cell(z, mip_rbound, c.Hf, c.Hm1f);
-    const uint32_t index = (uint32_t)level * c.H3 + morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
-    const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
-    if (!occ) {
-        const float tx = march_exit(nx, c.dx, c.rdx, x, c.rH, mip_bound);
-        const float ty = march_exit(ny, c.dy, c.rdy, y, c.rH, mip_bound);
-        const float tz = march_exit(nz, c.dz, c.rdz, z, c.rH, mip_bound);
-        t_skip = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    }
+    m.nx = march_cell(x, mip_rbound, c.halfH, c.Hm1f);
+    m.ny = march_cell(y, mip_rbound, c.halfH, c.Hm1f);
+    m.nz = march_cell(z, mip_rbound, c.halfH, c.Hm1f);
+    m.index = (uint32_t)level * c.H3 + morton3((uint32_t)m.nx, (uint32_t)m.ny, (uint32_t)m.nz);
+    return m;
+}
+
+// parameter at which the ray leaves the cell (tt of raymarching.cu:397)
+__device__ __forceinline__ float march_leave(const MarchCtx& c, const MarchCell& m, float t, float x, float y, float z) {
+    const float tx = march_exit(m.nx, c.incx, c.rdx, x, c.rH2, m.mip_bound);
+    const float ty = march_exit(m.ny, c.incy, c.rdy, y, c.rH2, m.mip_bound);
+    const float tz = march_exit(m.nz, c.incz, c.rdz, z, c.rH2, m.mip_bound);
+    return __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+}
+
+// Returns true if the sample at t is in an occupied cell. When it is not, `t_skip` receives the
+// parameter at which the ray leaves the cell.
+__device__ __forceinline__ bool march_probe(const MarchCtx& c, const uint8_t* __restrict__ grid, float t,
+                                            float dt, float x, float y, float z, float& t_skip) {
+    const MarchCell m = march_locate(c, dt, x, y, z);
+    const bool occ = (__ldg(grid + (m.index >> 3)) >> (m.index & 7u)) & 1u;
+    if (!occ) t_skip = march_leave(c, m, t, x, y, z);
     return occ;
 }
 

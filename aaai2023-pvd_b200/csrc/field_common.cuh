@@ -13,6 +13,7 @@ struct Pipe {
     uint32_t phase;
     uint32_t tmem;
     int32_t* status;
+    uint32_t trec = 0;  // timeline record of this CTA (PVD_TRACE builds only)
 };
 
 // Every thread: publish shared-memory operand writes to the async proxy and order prior TMEM reads, then barrier.

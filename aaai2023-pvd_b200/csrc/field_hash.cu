@@ -18,6 +18,8 @@
 //     transposed weight copy exists); the encoding gradient is scattered with red.global.add.v2.f32.
 // CTAs are persistent (grid = min(#tiles, 2 x #SMs)) so weights are staged and TMEM is allocated once per CTA and
 // weight gradients leave the SM once.
+#include "common.cuh"
+PVD_TRACE_TU(pvd_debug_trace_field_hash)
 #include "gridenc.cuh"
 #include "shenc.cuh"
 #include "tc5.cuh"
@@ -172,6 +174,16 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     uint8_t* HB = HA;
     const uint32_t tid = threadIdx.x;
 
+    if (tid == 0) {
+        PVD_T(blockIdx.x, 0);
+#ifdef PVD_TRACE
+        unsigned long long gt; unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        PVD_TV(blockIdx.x, 12, gt);
+        PVD_TV(blockIdx.x, 13, smid);
+#endif
+    }
     stage_weights(smw, a.wblob);
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
@@ -183,6 +195,8 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     __syncthreads();
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
+    p.trec = blockIdx.x;
+    if (tid == 0) PVD_T(blockIdx.x, 1);
     const T* table = reinterpret_cast<const T*>(a.table);
     const uint32_t lv_saddr = tc5::smem_u32(lv);
 
@@ -208,6 +222,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
             const uint4 u = tc5::pack8(f);
             *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
             if (enc && live) *reinterpret_cast<uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = u;
+            if (tid == 0) PVD_T(blockIdx.x, 2 + j);
         }
         float sigma, o16[16];
         FwdRegs r;
@@ -225,9 +240,17 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
             }
         }
     }
+    if (tid == 0) PVD_T(blockIdx.x, 11);
     tc5::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 128);
+#ifdef PVD_TRACE
+    if (tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        PVD_TV(blockIdx.x, 14, gt);
+    }
+#endif
 }
 
 // =============================================================================================== backward kernel
@@ -264,6 +287,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     __syncthreads();
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
+    p.trec = ~0u;  // the backward is not on the PVD_TRACE timeline
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
     const uint32_t sw = tc5::smem_u32(smw);
     const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;

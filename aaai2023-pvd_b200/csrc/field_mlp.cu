@@ -18,6 +18,8 @@
 //   * layer epilogue: each thread pulls its own row from TMEM 16 columns at a time, adds the bias, applies ReLU, and writes
 //     the next layer's A operand (fp16, chunk layout) over the previous one.
 //   * the last layer (256 -> 28) feeds the sigma_net / color_net tail of field_tail.cuh unchanged.
+#include "common.cuh"
+PVD_TRACE_TU(pvd_debug_trace_field_mlp)
 #include "field_tail.cuh"
 
 namespace pvd {

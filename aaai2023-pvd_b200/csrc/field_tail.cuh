@@ -55,6 +55,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
+    if (tid == 0) PVD_T(p.trec, 6);
     relu_to_tile<4>(trow + kD, H1, row);
     // ---- sigma_net.1 : [128 x 64] x [16 x 64]^T
     operands_ready();
@@ -64,6 +65,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
+    if (tid == 0) PVD_T(p.trec, 7);
     tc5::tmem_ld16(trow + kD16, o16);
 #pragma unroll
     for (int i = 0; i < 16; ++i) o16[i] = __half2float(__float2half_rn(o16[i]));  // the reference's fp16 activations
@@ -91,6 +93,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
+    if (tid == 0) PVD_T(p.trec, 8);
     relu_to_tile<4>(trow + kD, H3, row);
     // ---- color_net.1 : [128 x 64] x [64 x 64]^T
     operands_ready();
@@ -100,6 +103,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
+    if (tid == 0) PVD_T(p.trec, 9);
     relu_to_tile<4>(trow + kD, H4, row);
     // ---- color_net.2 : [128 x 64] x [16 x 64]^T , sigmoid
     operands_ready();
@@ -109,6 +113,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
+    if (tid == 0) PVD_T(p.trec, 10);
     float c16[16];
     tc5::tmem_ld16(trow + kD5, c16);
 #pragma unroll

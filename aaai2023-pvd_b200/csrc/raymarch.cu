@@ -10,7 +10,10 @@
 //     colour / depth sums are warp shuffle scans over 32 samples at a time instead of a serial loop
 //     per thread, so sample reads are coalesced across the warp.
 //   * every launch goes to the caller's stream and reports launch errors.
+#include <type_traits>
+
 #include "common.cuh"
+PVD_TRACE_TU(pvd_debug_trace_raymarch)
 
 namespace pvd {
 
@@ -110,43 +113,40 @@ __global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thr
 // training march: count+stash -> scan -> expand
 // =============================================================================================
 
-// Coarse rejection mask (single cascade only).  The H^3 occupancy bitfield is Morton ordered, so an aligned block of
-// (H/16)^3 cells is one contiguous run of bits; any16[c] = "some cell of coarse block c is occupied", and the mask bit of a
-// coarse block is the OR of any16 over the block and its 26 neighbours.  A ray none of whose probe points (spaced a quarter of
-// a coarse block apart... see k_march_count) falls in a masked block cannot produce a sample: every lattice point the marcher
-// could evaluate lies in a cell of an unmasked block's neighbourhood, i.e. in an empty cell.  Output: 4096 bits indexed
-// x + 16 y + 256 z.
-__global__ void __launch_bounds__(256) k_coarse_any(const uint8_t* __restrict__ grid, uint32_t H, uint8_t* __restrict__ any16) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;  // Morton index of the coarse block
-    if (m >= 4096) return;
-    const uint32_t cs = H / 16;               // cells per coarse block edge (power of two)
-    const uint32_t bytes = cs * cs * cs / 8;  // bytes per coarse block in the Morton-ordered bitfield (>= 1 for H >= 32)
-    const uint8_t* p = grid + (size_t)m * bytes;
-    uint32_t acc = 0;
-    if (bytes >= 16) {
-        for (uint32_t i = 0; i < bytes; i += 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
-            acc |= v.x | v.y | v.z | v.w;
-        }
-    } else {
-        for (uint32_t i = 0; i < bytes; ++i) acc |= __ldg(p + i);
-    }
-    any16[compact3(m) + 16 * compact3(m >> 1) + 256 * compact3(m >> 2)] = acc ? 1 : 0;
+// Coarse rejection mask (single cascade, H = 128 -- the reference's only grid size, renderer.py:36).  The H^3 occupancy
+// bitfield is Morton ordered, so an aligned block of 2x2x2 cells is exactly one BYTE of it; any[b] = "some cell of block b is
+// occupied" on the 64^3 block lattice, and the mask bit of a block is the OR of any[] over the block and its 26 neighbours
+// (dilation by one block).  A lattice point of a ray lying within 0.9 block (Euclidean) of a probe point whose block is NOT
+// masked sits in a cell of that probe's 3x3x3 block neighbourhood, i.e. in an empty cell (see k_march_count).
+// Both arrays: 64^3 bits indexed x + 64 y + 4096 z, 8192 words.
+constexpr uint32_t kCoarseB = 64;                 // blocks per axis
+constexpr uint32_t kCoarseMaskWords = 64 * 64 * 64 / 32;
+
+__global__ void __launch_bounds__(256) k_coarse_any(const uint8_t* __restrict__ grid, uint32_t* __restrict__ any) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // output word: 32 consecutive x at fixed (y, z)
+    if (w >= kCoarseMaskWords) return;
+    const uint32_t x0 = (w & 1u) * 32u, y = (w >> 1) & 63u, z = w >> 7;
+    const uint32_t myz = (spread3(y) << 1) | (spread3(z) << 2);
+    uint32_t word = 0;
+#pragma unroll 8
+    for (uint32_t i = 0; i < 32; ++i) word |= (__ldg(grid + (spread3(x0 + i) | myz)) ? 1u : 0u) << i;
+    any[w] = word;
 }
 
-__global__ void __launch_bounds__(256) k_coarse_dilate(const uint8_t* __restrict__ any16, uint32_t* __restrict__ mask) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 4096) return;
-    const int cx = c & 15, cy = (c >> 4) & 15, cz = c >> 8;
-    uint32_t hit = 0;
+__global__ void __launch_bounds__(256) k_coarse_dilate(const uint32_t* __restrict__ any, uint32_t* __restrict__ mask) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= kCoarseMaskWords) return;
+    const int half = (int)(w & 1u), y = (int)((w >> 1) & 63u), z = (int)(w >> 7);
+    uint64_t acc = 0;
     for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx, y = cy + dy, z = cz + dz;
-                if (x >= 0 && x < 16 && y >= 0 && y < 16 && z >= 0 && z < 16) hit |= __ldg(any16 + x + 16 * y + 256 * z);
-            }
-    const uint32_t word = __ballot_sync(0xffffffffu, hit != 0);
-    if ((threadIdx.x & 31u) == 0) mask[c >> 5] = word;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy, zz = z + dz;
+            if (yy < 0 || yy > 63 || zz < 0 || zz > 63) continue;
+            const uint32_t r = (uint32_t)(yy * 2 + zz * 128);
+            const uint64_t row = (uint64_t)__ldg(any + r) | ((uint64_t)__ldg(any + r + 1) << 32);
+            acc |= row | (row << 1) | (row >> 1);
+        }
+    mask[w] = half ? (uint32_t)(acc >> 32) : (uint32_t)acc;
 }
 
 // Pass 1 -- ONE WARP PER RAY.  The reference walks each ray with one thread (raymarching.cu:357-403): a chain of several
@@ -159,13 +159,15 @@ __global__ void __launch_bounds__(256) k_coarse_dilate(const uint8_t* __restrict
 // t_0 = t0, t_{k+1} = fl(t_k + dtf(t_k)) that does not depend on the grid.  A lattice point is "landed" if the serial loop
 // evaluates it: point 0 is; after an occupied landed point k, k+1 is; after an empty landed point k with cell exit tt_k,
 // the first j > k with t_j >= tt_k is.  Each lane evaluates its lattice point exactly as the serial loop would
-// (same position, cell, level, exit expressions), and the landed set is then resolved with ballots.  Lattice values are
+// (same position, cell, level, exit expressions), and the landed set is then resolved by pointer doubling over the successor
+// map (see `close_chains` / `resolve` below).  One warp per CTA makes every branch provably warp-uniform for the compiler
+// (no WARPSYNC / re-convergence code around the shuffles).  Lattice values are
 // produced either by the 32-step serial recurrence (every lane runs it redundantly and keeps its own element) or, when
 // dt is constant and the window stays inside one binade, from the observation that fl(t + dt) advances the bit pattern of
 // t by a constant number of ulps c (round-to-nearest of dt/ulp; ties are detected and sent to the serial path), so
 // bits(t_{k0+i}) = bits(t_{k0}) + i*c.
 // The accepted (t, dt) pairs go to the stash in march order; num_steps[n] and t0[n] to the workspace.
-__global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+__global__ void __launch_bounds__(32) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma,
                                                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                                     const float* __restrict__ nears, const float* __restrict__ fars,
@@ -173,9 +175,19 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
                                                     float* __restrict__ t0_out, float2* __restrict__ stash,
                                                     const uint32_t* __restrict__ coarse, const float* __restrict__ aabb,
                                                     float min_near, float* __restrict__ nears_out, float* __restrict__ fars_out) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x;  // one warp per CTA: the ray index, and with it all control flow below, is warp-uniform
+    const uint32_t lane = threadIdx.x;
     if (n >= N) return;
+#ifdef PVD_TRACE
+    unsigned int tr_groups = 0, tr_general = 0, tr_iters = 0;
+    long long tr_c0 = 0, tr_probe = 0, tr_prep = 0, tr_res = 0, tr_gen = 0, tr_head = 0;
+    if (lane == 0) {
+        unsigned long long gt; unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        PVD_T(n, 0); PVD_TV(n, 8, gt); PVD_TV(n, 7, smid);
+    }
+#endif
     MarchCtx c;
     march_ctx_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
     float far, t0;
@@ -193,35 +205,44 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
         pcg32_advance(rng, (uint64_t)n);
         t0 = __fmaf_rn(c.dt_min, pcg32_next_float(rng), t0);
     }
-    // ---- exact early-out: probe the dilated coarse mask every quarter of a coarse block along [t0, far].  Every parameter the
-    // marcher can evaluate is within an eighth of a block of a probe, so its cell lies in the probe's 3x3x3 block neighbourhood;
-    // if no probe is masked, no evaluated cell is occupied and the ray has zero samples (80 % of the rays of a typical batch).
-    if (coarse != nullptr && t0 < far) {
+    // ---- exact pruning with the dilated 64^3 block mask: probe [t0, far] every 0.9 block.  Every parameter t the marcher can
+    // evaluate is within half a probe spacing of a probe, and a point within 0.9 block of a probe has its cell in the probe's
+    // 3x3x3 block neighbourhood (clamping to the cube moves both the same way), so around an UNMASKED probe every cell is empty.
+    //   * no probe masked  -> no evaluated cell is occupied: zero samples (most rays of a batch);
+    //   * beyond the last masked probe (+ 3/4 spacing) nothing can be emitted any more, so the march may stop there: `far` is
+    //     pulled in.  (The part BEFORE the first masked probe cannot be skipped: which lattice points are evaluated later
+    //     depends on the chain of cell exits from t0 on.)
+    if (coarse != nullptr && t0 > 0.0f && t0 < far) {
         const float dlen = sqrtf(c.dx * c.dx + c.dy * c.dy + c.dz * c.dz);
-        const float step = 0.25f * (2.0f * bound / 16.0f) / dlen;
+        const float step = 0.9f * (2.0f * bound / (float)kCoarseB) / dlen;
         const float span = far - t0;
-        if (dlen > 0.0f && step > 0.0f && span < 1024.0f * step) {  // finite, sane ray; otherwise fall through to the marcher
+        if (dlen > 0.0f && step > 0.0f && span < 2048.0f * step) {  // finite, sane ray; otherwise fall through to the marcher
             const uint32_t probes = (uint32_t)(span / step) + 2u;
-            bool hit = false;
+            uint32_t t_hit = 0;  // bit pattern of the largest masked probe parameter (t > 0, so bit order = float order)
+            const float bscale = 0.5f * (float)kCoarseB;
             for (uint32_t k = lane; k < probes; k += 32) {
                 const float t = fminf(t0 + (float)k * step, far);
                 float x, y, z;
                 march_pos(c, t, x, y, z);
-                const int cx = min(15, max(0, (int)((x * c.rbound + 1.0f) * 8.0f)));
-                const int cy = min(15, max(0, (int)((y * c.rbound + 1.0f) * 8.0f)));
-                const int cz = min(15, max(0, (int)((z * c.rbound + 1.0f) * 8.0f)));
-                const uint32_t ci = (uint32_t)(cx + 16 * cy + 256 * cz);
-                hit |= (__ldg(coarse + (ci >> 5)) >> (ci & 31u)) & 1u;
+                const int cx = min((int)kCoarseB - 1, max(0, (int)((x * c.rbound + 1.0f) * bscale)));
+                const int cy = min((int)kCoarseB - 1, max(0, (int)((y * c.rbound + 1.0f) * bscale)));
+                const int cz = min((int)kCoarseB - 1, max(0, (int)((z * c.rbound + 1.0f) * bscale)));
+                const uint32_t ci = (uint32_t)(cx + 64 * cy + 4096 * cz);
+                if ((__ldg(coarse + (ci >> 5)) >> (ci & 31u)) & 1u) t_hit = max(t_hit, __float_as_uint(t));  // t >= t0 > 0
             }
-            if (!__any_sync(0xffffffffu, hit)) {
+            t_hit = __reduce_max_sync(0xffffffffu, t_hit);
+            if (t_hit == 0u) {
                 if (lane == 0) {
                     num_steps_out[n] = 0;
                     t0_out[n] = t0;
+                    PVD_T(n, 1); PVD_T(n, 2);
                 }
                 return;
             }
+            far = fminf(far, __uint_as_float(t_hit) + 0.75f * step);
         }
     }
+    if (lane == 0) PVD_T(n, 1);
     float2* st = stash + (size_t)n * max_steps;
     const bool const_dt = (dt_gamma == 0.0f);
     const float dt_c = march_dt(c, 0.0f);
@@ -233,59 +254,128 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
     uint32_t count = 0;
     bool done = false;
 
-    // Replays the serial control flow of raymarching.cu:362-403 over one window of 32 evaluated lattice points.
-    auto walk = [&](float t_i, float dt_i, float tt, bool valid, bool occ) {
-        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-        const uint32_t occ_mask = __ballot_sync(0xffffffffu, valid && occ);
-        if (valid_mask == 0u) {  // t only grows: nothing further can satisfy t < far
-            done = true;
-            return;
+    // Replays the serial control flow of raymarching.cu:362-403 over one window of 32 evaluated lattice points WITHOUT a serial
+    // loop.  Every point i has a successor nxt(i): i+1 after an occupied point (:389), the first j > i with t_j >= tt_i after an
+    // empty one (the do-while of :398-402), 32 when that lies beyond the window.  The points the serial loop evaluates are the
+    // chain start -> nxt(start) -> ...; nxt is found for all 32 points at once (integer arithmetic on the lattice, or a
+    // 6-shuffle lower bound over the lanes' ascending t) and the chains are closed by pointer doubling (5 rounds: V =
+    // points on the chain from i, as a bit mask; `close_chains`), all of it independent of where the chain enters the window -- so the four
+    // windows of a group are prepared with full instruction-level parallelism and only `resolve` (a dozen instructions) is
+    // serial from window to window.
+    struct Prep {
+        uint32_t V, valid_mask, occ_mask;
+    };
+    // first window index j with t_j >= tt, by a 6-shuffle binary search over the lanes' ascending t (any lattice)
+    auto lower_bound_shfl = [&](float t_i, float tt) -> uint32_t {
+        uint32_t pos = 0;
+#pragma unroll
+        for (uint32_t sft = 16; sft >= 1; sft >>= 1) {
+            const float v = __shfl_sync(0xffffffffu, t_i, (int)(pos + sft - 1u));
+            if (v < tt) pos += sft;
         }
-        uint32_t cur = 0;
-        if (have_carry) {
-            const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= carry_tt);
-            if (ge) {
-                cur = (uint32_t)__ffs((int)ge) - 1u;
-                have_carry = false;
-            } else {
-                cur = 32;
+        const float v31 = __shfl_sync(0xffffffffu, t_i, 31);
+        if (pos == 31u && v31 < tt) pos = 32u;
+        return pos;
+    };
+    // the same on the uniform lattice bits(t_j) = bw + j*cstep (positive floats: bit order = value order), no shuffles:
+    // j = ceil((bits(tt) - bw) / cstep) clamped to [0, 32]; the quotient is estimated in float and corrected exactly.
+    auto lower_bound_lattice = [&](uint32_t bw, uint32_t cstep, float rcstep, float tt) -> uint32_t {
+        const uint32_t ttb = __float_as_uint(tt);
+        const uint32_t diff = ttb - bw;                         // meaningful when ttb > bw
+        uint32_t q = (uint32_t)((float)min(diff, 32u * cstep) * rcstep);  // cstep < 2^16 (group condition): exact float, |error| <= 1
+        if (q * cstep > diff) --q;
+        if ((q + 1u) * cstep <= diff) ++q;
+        q += (q * cstep < diff) ? 1u : 0u;
+        if (diff > 31u * cstep) q = 32u;                        // beyond t_31
+        if (ttb <= bw) q = 0u;
+        return q;
+    };
+    // successor of every point, then the chains closed by pointer doubling; W windows side by side so that their shuffle
+    // chains interleave (the rounds are the outer loop).
+    auto successors = [&](uint32_t pos, bool valid, bool occ) -> uint32_t {
+        uint32_t P = (valid && occ) ? lane + 1u : max(pos, lane + 1u);
+        if (!valid) P = 32u;  // landing on a point with t >= far ends the loop (:362)
+        return P;
+    };
+    auto close_chains = [&](auto& pr, auto& P, auto W) {
+        constexpr int kW = decltype(W)::value;
+        uint32_t any_occ = 0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) any_occ |= pr[w].occ_mask;
+        if (any_occ == 0u) {
+            // nothing to emit in these windows (the common case): only each chain's last point matters, for the pending exit.
+            // Q = successor with a self-loop at the end of the chain; five squarings reach the end from every start.
+            uint32_t Q[kW];
+#pragma unroll
+            for (int w = 0; w < kW; ++w) Q[w] = (P[w] < 32u) ? P[w] : lane;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                for (int w = 0; w < kW; ++w) Q[w] = __shfl_sync(0xffffffffu, Q[w], (int)Q[w]);
             }
-        }
-        uint32_t emit = 0;
-        const uint32_t count0 = count;
-        while (cur < 32) {
-            if (!((valid_mask >> cur) & 1u) || count >= max_steps) {  // loop condition of raymarching.cu:362
-                done = true;
-                break;
-            }
-            if ((occ_mask >> cur) & 1u) {
-                const uint32_t rest = occ_mask >> cur;
-                uint32_t run = (rest == 0xffffffffu) ? 32u : (uint32_t)__ffs((int)~rest) - 1u;
-                run = min(run, max_steps - count);
-                const uint32_t bits = (run >= 32u) ? 0xffffffffu : ((1u << run) - 1u);
-                emit |= bits << cur;
-                count += run;
-                cur += run;
-            } else {
-                const float tt_c = __shfl_sync(0xffffffffu, tt, (int)cur);
-                const uint32_t above = (cur >= 31u) ? 0u : ~((2u << cur) - 1u);
-                const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= tt_c) & above;
-                if (ge) {
-                    cur = (uint32_t)__ffs((int)ge) - 1u;
-                } else {
-                    carry_tt = tt_c;
-                    have_carry = true;
-                    cur = 32;
+#pragma unroll
+            for (int w = 0; w < kW; ++w) pr[w].V = (1u << lane) | (1u << Q[w]);
+        } else {
+            uint32_t V[kW];
+#pragma unroll
+            for (int w = 0; w < kW; ++w) V[w] = 1u << lane;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                for (int w = 0; w < kW; ++w) {
+                    const uint32_t Pv = __shfl_sync(0xffffffffu, P[w], (int)(P[w] & 31u));
+                    const uint32_t Vv = __shfl_sync(0xffffffffu, V[w], (int)(P[w] & 31u));
+                    const bool in = P[w] < 32u;
+                    V[w] |= in ? Vv : 0u;
+                    P[w] = in ? Pv : P[w];
                 }
             }
+#pragma unroll
+            for (int w = 0; w < kW; ++w) pr[w].V = V[w];
         }
-        if ((emit >> lane) & 1u) st[count0 + __popc(emit & lt_mask)] = make_float2(t_i, dt_i);
+    };
+    // Straight-line on purpose: every shuffle / ballot is executed by the whole warp on every call and the (warp-uniform) state
+    // is updated under predicates, so the compiler needs no re-convergence points between the windows of a group.
+    auto resolve = [&](const Prep& r, float t_i, float dt_i, float tt) {
+        const uint32_t ge = __ballot_sync(0xffffffffu, t_i >= carry_tt);
+        const uint32_t cur = (have_carry && ge != 0u) ? (uint32_t)__ffs((int)ge) - 1u : 0u;
+        uint32_t L = __shfl_sync(0xffffffffu, r.V, (int)cur);  // the evaluated points of this window, in chain order = bit order
+        bool act = !done;
+        if (act && r.valid_mask == 0u) {  // t only grows: nothing further can satisfy t < far
+            done = true;
+            act = false;
+        }
+        if (have_carry && ge == 0u) act = false;  // the pending skip passes over the whole window; it stays pending
+        if (!act) L = 0u;
+#ifdef PVD_TRACE
+        if (act) ++tr_iters;
+#endif
+        const bool hit_far = (L & ~r.valid_mask) != 0u;  // the chain reaches a point with t >= far (its last point)
+        L &= r.valid_mask;
+        const uint32_t want = L & r.occ_mask;
+        const uint32_t room = max_steps - count;
+        const uint32_t rank = __popc(want & lt_mask);
+        const bool full = (uint32_t)__popc(want) >= room;  // num_steps reaches max_steps inside this window (:362)
+        const uint32_t emit = __ballot_sync(0xffffffffu, ((want >> lane) & 1u) && rank < room);
+        if ((emit >> lane) & 1u) st[count + rank] = make_float2(t_i, dt_i);
+        count += (uint32_t)__popc(emit);
+        const uint32_t last = L ? 31u - (uint32_t)__clz((int)L) : 0u;
+        const float tt_last = __shfl_sync(0xffffffffu, tt, (int)last);
+        if (act) {
+            if (hit_far || full) done = true;
+            // the chain left the window through an empty cell: its exit is still pending
+            have_carry = (L != 0u) && !((r.occ_mask >> last) & 1u);
+            if (have_carry) carry_tt = tt_last;
+        }
     };
 
+#ifdef PVD_TRACE
+    tr_c0 = clock64();
+#endif
     while (!done) {
         // ---- fast path: constant dt and a group of four windows (128 lattice points) inside one binade.  All four occupancy
-        // probes of a lane are issued before any is consumed, which is what hides the L2 latency of the bitfield loads: the
-        // kernel is bound by the per-ray chain of windows, not by throughput.
+        // probes of a lane are issued before any is consumed, which hides the L2 latency of the bitfield loads, and the four
+        // chain preparations interleave.
         bool group = false;
         uint32_t b = 0, cstep = 0;
         if (const_dt && t_base > 0.0f) {
@@ -300,25 +390,56 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
                 group = !tie && cstep > 0 && ((b + 128u * cstep) >> 23) == e;
             }
         }
+#ifdef PVD_TRACE
+        if (group) ++tr_groups; else ++tr_general;
+        tr_head += clock64() - tr_c0;
+        tr_c0 = clock64();
+#endif
         if (group) {
+            // branch-free: a clamped position always has a cell, so points beyond `far` are located and loaded too (and
+            // ignored) -- no divergent region, the four bitfield loads are in flight together while the exits are computed.
             float t_i[4], tt[4];
             bool valid[4], occ[4];
+            uint32_t bits[4], sh[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 t_i[w] = __uint_as_float(b + ((uint32_t)w * 32u + lane) * cstep);
                 valid[w] = t_i[w] < far;
-                tt[w] = 0.0f;
-                occ[w] = false;
-                if (valid[w]) {
-                    float x, y, z;
-                    march_pos(c, t_i[w], x, y, z);
-                    occ[w] = march_probe(c, grid, t_i[w], dt_c, x, y, z, tt[w]);
-                }
+                float x, y, z;
+                march_pos(c, t_i[w], x, y, z);
+                const MarchCell m = march_locate(c, dt_c, x, y, z);
+                bits[w] = __ldg(grid + (m.index >> 3));
+                sh[w] = m.index & 7u;
+                tt[w] = march_leave(c, m, t_i[w], x, y, z);
             }
 #pragma unroll
+            for (int w = 0; w < 4; ++w) occ[w] = (bits[w] >> sh[w]) & 1u;
+#ifdef PVD_TRACE
+            if (__ballot_sync(0xffffffffu, occ[0] | occ[1] | occ[2] | occ[3]) == 0xdeadbeefu) ++tr_iters;  // consume the loads
+            tr_probe += clock64() - tr_c0;
+            tr_c0 = clock64();
+#endif
+            Prep pr[4];
+            uint32_t P[4];
+            const float rcstep = 1.0f / (float)cstep;
+#pragma unroll
             for (int w = 0; w < 4; ++w) {
-                if (!done) walk(t_i[w], dt_c, tt[w], valid[w], occ[w]);
+                pr[w].valid_mask = __ballot_sync(0xffffffffu, valid[w]);
+                pr[w].occ_mask = __ballot_sync(0xffffffffu, valid[w] && occ[w]);
+                P[w] = successors(lower_bound_lattice(b + (uint32_t)w * 32u * cstep, cstep, rcstep, tt[w]), valid[w], occ[w]);
             }
+            close_chains(pr, P, std::integral_constant<int, 4>{});
+#ifdef PVD_TRACE
+            if ((pr[0].V ^ pr[1].V ^ pr[2].V ^ pr[3].V) == 0xdeadbeefu) ++tr_iters;
+            tr_prep += clock64() - tr_c0;
+            tr_c0 = clock64();
+#endif
+#pragma unroll
+            for (int w = 0; w < 4; ++w) resolve(pr[w], t_i[w], dt_c, tt[w]);
+#ifdef PVD_TRACE
+            tr_res += clock64() - tr_c0;
+            tr_c0 = clock64();
+#endif
             t_base = __uint_as_float(b + 128u * cstep);
         } else {
             // ---- general path: one window, lattice by the serial recurrence (every lane runs it and keeps its own element)
@@ -334,13 +455,29 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
             const float dt_i = const_dt ? dt_c : march_dt(c, t_i);
             bool occ = false;
             if (valid) occ = march_probe(c, grid, t_i, dt_i, x, y, z, tt);
-            walk(t_i, dt_i, tt, valid, occ);
+            Prep pr[1];
+            uint32_t P[1];
+            pr[0].valid_mask = __ballot_sync(0xffffffffu, valid);
+            pr[0].occ_mask = __ballot_sync(0xffffffffu, valid && occ);
+            P[0] = successors(lower_bound_shfl(t_i, tt), valid, occ);
+            close_chains(pr, P, std::integral_constant<int, 1>{});
+            resolve(pr[0], t_i, dt_i, tt);
             t_base = t;
+#ifdef PVD_TRACE
+            tr_gen += clock64() - tr_c0;
+            tr_c0 = clock64();
+#endif
         }
     }
     if (lane == 0) {
         num_steps_out[n] = (int32_t)count;
         t0_out[n] = t0;
+#ifdef PVD_TRACE
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        PVD_T(n, 2); PVD_TV(n, 3, tr_groups); PVD_TV(n, 4, tr_general); PVD_TV(n, 5, tr_iters); PVD_TV(n, 6, count); PVD_TV(n, 9, gt);
+        PVD_TV(n, 10, tr_probe); PVD_TV(n, 11, tr_prep); PVD_TV(n, 12, tr_res); PVD_TV(n, 13, tr_gen); PVD_TV(n, 14, tr_head);
+#endif
     }
 }
 
@@ -789,10 +926,10 @@ int pvd_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
     return PVD_OK;
 }
 
-constexpr uint64_t kCoarseWords = 128 + 1024;  // 16^3 mask bits, then 16^3 bytes of per-block occupancy
+constexpr uint64_t kCoarseWords = 2ull * kCoarseMaskWords;  // dilated 64^3 block mask, then the undilated one
 
 uint64_t pvd_march_rays_train_workspace_words(uint32_t N, uint32_t max_steps) {
-    // coarse mask[128] + any16[1024] | num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
+    // coarse mask[8192] + any[8192] | num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     return kCoarseWords + head + 2ull * (uint64_t)N * max_steps;
 }
@@ -811,16 +948,16 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     float2* stash = reinterpret_cast<float2*>(ws_i32 + kCoarseWords + head);
     const Pcg32 rng = pcg32_seeded(42u);  // hard-coded seed, raymarching.cu:488
-    // coarse rejection needs one cascade and a power-of-two grid of at least 32^3 (Morton-contiguous coarse blocks)
-    const bool use_coarse = (C == 1) && (H >= 32) && ((H & (H - 1)) == 0);
+    // coarse pruning: one cascade, the reference's 128^3 grid (a 2x2x2 block of cells = one byte of the Morton bitfield)
+    const bool use_coarse = (C == 1) && (H == 2 * kCoarseB);
     if (use_coarse) {
-        uint8_t* any16 = reinterpret_cast<uint8_t*>(ws_i32 + 128);
-        k_coarse_any<<<16, 256, 0, st>>>(grid, H, any16);
+        uint32_t* any = reinterpret_cast<uint32_t*>(ws_i32) + kCoarseMaskWords;
+        k_coarse_any<<<kCoarseMaskWords / 256, 256, 0, st>>>(grid, any);
         PVD_LAUNCH_CHECK();
-        k_coarse_dilate<<<16, 256, 0, st>>>(any16, coarse);
+        k_coarse_dilate<<<kCoarseMaskWords / 256, 256, 0, st>>>(any, coarse);
         PVD_LAUNCH_CHECK();
     }
-    k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+    k_march_count<<<N, 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                                   perturb, rng, num_steps, t0, stash, use_coarse ? coarse : nullptr, nullptr, 0.0f,
                                                   nullptr, nullptr);
     PVD_LAUNCH_CHECK();
@@ -844,15 +981,15 @@ int pvd_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, co
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     float2* stash = reinterpret_cast<float2*>(ws_i32 + kCoarseWords + head);
     const Pcg32 rng = pcg32_seeded(42u);
-    const bool use_coarse = (C == 1) && (H >= 32) && ((H & (H - 1)) == 0);
+    const bool use_coarse = (C == 1) && (H == 2 * kCoarseB);
     if (use_coarse && !reuse_coarse) {
-        uint8_t* any16 = reinterpret_cast<uint8_t*>(ws_i32 + 128);
-        k_coarse_any<<<16, 256, 0, st>>>(grid, H, any16);
+        uint32_t* any = reinterpret_cast<uint32_t*>(ws_i32) + kCoarseMaskWords;
+        k_coarse_any<<<kCoarseMaskWords / 256, 256, 0, st>>>(grid, any);
         PVD_LAUNCH_CHECK();
-        k_coarse_dilate<<<16, 256, 0, st>>>(any16, coarse);
+        k_coarse_dilate<<<kCoarseMaskWords / 256, 256, 0, st>>>(any, coarse);
         PVD_LAUNCH_CHECK();
     }
-    k_march_count<<<ceil_div(N, 4), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nullptr, nullptr, perturb,
+    k_march_count<<<N, 32, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nullptr, nullptr, perturb,
                                                   rng, num_steps, t0, stash, use_coarse ? coarse : nullptr, aabb, min_near, nears, fars);
     PVD_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(num_steps, N, rays, counter);

@@ -15,14 +15,15 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(PKG_DIR, "..", "csrc"))
 INCLUDE = os.path.normpath(os.path.join(PKG_DIR, "..", "..", "include"))
-BUILD_DIR = os.path.join(CSRC, "build")
-LIB_PATH = os.path.join(PKG_DIR, "libpvd_b200.so")
+TRACE = os.environ.get("PVD_TRACE", "0") == "1"   # diagnostic timeline build (tools/trace_kernels.py), never the default
+BUILD_DIR = os.path.join(CSRC, "build_trace" if TRACE else "build")
+LIB_PATH = os.path.join(PKG_DIR, "libpvd_b200_trace.so" if TRACE else "libpvd_b200.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC",
     "-DPVD_BUILDING",
-]
+] + (["-DPVD_TRACE"] if TRACE else [])
 
 
 def sources():

@@ -11,7 +11,8 @@ import os
 
 import torch
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpvd_b200.so")
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        "libpvd_b200_trace.so" if os.environ.get("PVD_TRACE", "0") == "1" else "libpvd_b200.so")
 ABI_VERSION = 1
 
 _lib = None

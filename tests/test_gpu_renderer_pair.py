@@ -97,6 +97,69 @@ def test_distillation_pair_at_shared_samples(scene):
     assert _rel_l2(stu.encoder.embeddings.grad.cpu(), es.grad) < 3e-2
 
 
+def test_hash_to_vm_distillation_pair(scene):
+    """BASELINE config 3 (hash teacher -> vm student, main_distill_mutual.py): the student marches, the frozen teacher is
+    queried at the SAME samples, the losses of distill_mutual/utils.py:1110-1176 drive the student only.  Checked against
+    the torch-CPU oracle of both fields on the oracle's own march of the same rays."""
+    from oracle import field
+    from pvd_b200.fused import _Args
+    from pvd_b200.fused_vm import VMNeRFField
+    tea = _net(5, scene, is_teacher=True, args=_Args())
+    torch.manual_seed(6)
+    stu = VMNeRFField(resolution0=48, scale=0.4, args=_Args()).cuda()
+    for m in list(stu.color_net) + [stu.basis_mat]:
+        m.weight.data.mul_(1.5)
+    stu.density_bitfield.copy_(torch.from_numpy(scene["bitfield"]))
+    stu.train(); tea.train()
+    for p_ in tea.parameters():
+        p_.requires_grad_(False)
+    ro, rd = scene["batches"][2]
+    ro, rd = ro[:640].contiguous(), rd[:640].contiguous()
+    o_s = stu.render(ro.cuda().unsqueeze(0), rd.cuda().unsqueeze(0), bg_color=1, perturb=True)
+    with torch.no_grad():
+        o_t = tea.render(ro.cuda().unsqueeze(0), rd.cuda().unsqueeze(0), bg_color=1, perturb=True,
+                         inherited_params=o_s["inherited_params"])
+    assert o_t["inherited_params"][0].data_ptr() == o_s["inherited_params"][0].data_ptr()
+    rates = dict(rgb=1.0, fea=0.002, color=0.002, sigma=0.002)
+    loss = (rates["rgb"] * torch.norm(o_t["image"] - o_s["image"]) + rates["fea"] * torch.norm(stu.feature_sigma_color - tea.feature_sigma_color)
+            + rates["color"] * torch.norm(stu.color_l - tea.color_l) + rates["sigma"] * torch.norm(stu.sigma_l - tea.sigma_l))
+    (loss * 128.0).backward()
+    assert all(p_.grad is None for p_ in tea.parameters())
+
+    c = lambda p_: p_.detach().cpu().contiguous().clone().requires_grad_(True)
+    P = dict(sm=[c(p_) for p_ in stu.sigma_mat], sv=[c(p_) for p_ in stu.sigma_vec], cm=[c(p_) for p_ in stu.color_mat],
+             cv=[c(p_) for p_ in stu.color_vec], bw=c(stu.basis_mat.weight), cw=[c(m.weight) for m in stu.color_net])
+    et, offsets, pls, H, ws_t = _oracle_params(tea)
+    aabb = stu.aabb_train.cpu()
+    feats = {}
+
+    def f_s(x, d):
+        s_, c_, f_ = field.vm_field_forward(x, d, P["sm"], P["sv"], P["cm"], P["cv"], P["bw"], P["cw"], aabb, quantize_fp16=True)
+        feats["s"] = (s_, c_, f_)
+        return s_, c_
+
+    o = field.render_train_step(ro, rd, scene["bitfield"], torch.zeros(640, 3), f_s)
+    with torch.no_grad():
+        st, ct, ft = field.hash_field_forward(o["xyzs"], o["dirs"], et, offsets, pls, H, ws_t, quantize_fp16=True)
+        wt, _, it = field.composite(st, ct, o["deltas"], o["rays"])
+        img_t = it + (1 - wt).unsqueeze(-1)
+    s_s, c_s, f_s_ = feats["s"]
+    loss_o = (rates["rgb"] * torch.norm(img_t - o["image"]) + rates["fea"] * torch.norm(f_s_ - ft) + rates["color"] * torch.norm(c_s - ct)
+              + rates["sigma"] * torch.norm(f_s_[:, 0] - ft[:, 0]))
+    (loss_o * 128.0).backward()
+    assert abs(float(loss.detach()) - float(loss_o.detach())) < 2e-2 * float(loss_o.detach())
+    torch.testing.assert_close(o_s["image"].detach().cpu()[0], o["image"].detach(), rtol=1e-2, atol=5e-3)
+    torch.testing.assert_close(o_t["image"].cpu()[0], img_t, rtol=1e-2, atol=5e-3)
+    for i in range(3):
+        assert _rel_l2(stu.sigma_mat[i].grad.cpu(), P["sm"][i].grad) < 3e-2, f"sigma_mat {i}"
+        assert _rel_l2(stu.sigma_vec[i].grad.cpu(), P["sv"][i].grad) < 3e-2, f"sigma_vec {i}"
+        assert _rel_l2(stu.color_mat[i].grad.cpu(), P["cm"][i].grad) < 3e-2, f"color_mat {i}"
+        assert _rel_l2(stu.color_vec[i].grad.cpu(), P["cv"][i].grad) < 3e-2, f"color_vec {i}"
+    assert _rel_l2(stu.basis_mat.weight.grad.cpu(), P["bw"].grad) < 3e-2
+    for i, (m, w) in enumerate(zip(stu.color_net, P["cw"])):
+        assert _rel_l2(m.weight.grad.cpu(), w.grad) < 3e-2, f"color_net {i}"
+
+
 def test_density_grid_upkeep_and_inference(scene):
     net = _net(3, scene)
     net.density_grid.zero_()
