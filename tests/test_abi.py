@@ -31,7 +31,7 @@ def test_abi_version_and_error_strings():
     assert l.pvd_abi_version() == _native.ABI_VERSION
     assert b"invalid argument" in l.pvd_error_string(-1)
     assert b"unsupported" in l.pvd_error_string(-2)
-    assert l.pvd_march_rays_train_workspace_words(4096, 1024) == 1152 + 2 * 4096 + 2 * 4096 * 1024
+    assert l.pvd_march_rays_train_workspace_words(4096, 1024) == 16384 + 2 * 4096 + 2 * 4096 * 1024
 
 
 def test_argument_validation_needs_no_gpu():
