@@ -184,13 +184,15 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
         PVD_TV(blockIdx.x, 13, smid);
 #endif
     }
+    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
+    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     stage_weights(smw, a.wblob);
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_fence_init();
     }
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
         float x01[3];
         bool oob;
         to_unit(pos, a.bound, x01, oob);
+        if (oob) x01[0] = x01[1] = x01[2] = 0.0f;  // keeps the (ignored) gathers of an out-of-range sample inside the table
 #pragma unroll 1
         for (uint32_t j = 0; j < 4; ++j) {
             float f[8];
@@ -276,13 +279,15 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     const uint32_t tid = threadIdx.x;
     const uint32_t lane_base = (tid >> 5) * 32;
 
+    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
+    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
     stage_weights(smw, a.wblob);
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_fence_init();
     }
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();

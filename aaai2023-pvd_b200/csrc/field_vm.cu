@@ -252,12 +252,14 @@ __global__ void __launch_bounds__(128) k_vm_field_fwd(VmArgs a, const float* __r
     uint8_t* APP = smem + PVD_VM_WBLOB_BYTES;     // 36864 ; CIN aliases its first 8 KB
     uint8_t* H = APP + 36864;                     // 16384 ; H3 then H4
     const uint32_t tid = threadIdx.x;
+    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
+    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     stage_blob(smw, a.wblob, PVD_VM_WBLOB_BYTES);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_fence_init();
     }
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
@@ -312,12 +314,14 @@ __global__ void __launch_bounds__(128) k_vm_field_bwd(VmArgs a, VmGradPtrs g, co
     uint8_t* H4 = H3 + 16384;                     // 16384
     uint8_t* G16 = H4 + 16384;                    // 4096
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
+    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
     stage_blob(smw, a.wblob, PVD_VM_WBLOB_BYTES);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_fence_init();
     }
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();

@@ -112,6 +112,14 @@ def main():
     for i, nm in enumerate(names):
         d = us(f[:, i + 1] - f[:, i])
         print(f"   {nm:34s}: median {pct(d, 50):6.2f} us  p90 {pct(d, 90):6.2f}  max {d.max():6.2f}")
+    sm = f[:, 13]
+    for sid in (0, 1, 73, 147):
+        sel = np.where(sm == sid)[0]
+        st = np.sort((f[sel, 12] - g0) / 1e3)
+        en = np.sort((f[sel, 14] - g0) / 1e3)
+        print(f"   SM {sid}: CTA starts {np.round(st, 2).tolist()} ends {np.round(en, 2).tolist()}")
+    starts = np.sort((f[:, 12] - g0) / 1e3)
+    print(f"   CTA start time percentiles: 25% {pct(starts, 25):.2f}  50% {pct(starts, 50):.2f}  75% {pct(starts, 75):.2f}  100% {starts.max():.2f} us")
     tot = us(f[:, 11] - f[:, 0])
     print(f"   total per CTA: median {pct(tot, 50):.2f} us, max {tot.max():.2f}")
 
