@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
     // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) PVD_T(2048u + blockIdx.x, 0);
     stage_weights(smw, a.wblob);
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     __syncthreads();
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
-    p.trec = ~0u;  // the backward is not on the PVD_TRACE timeline
+    p.trec = 2048u + blockIdx.x;  // PVD_TRACE timeline record of this CTA (the last tile it processes wins)
+    if (tid == 0) PVD_T(p.trec, 1);
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
     const uint32_t sw = tc5::smem_u32(smw);
     const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             if (live) u = __ldg(reinterpret_cast<const uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j));
             *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
         }
+        if (tid == 0) PVD_T(p.trec, 2);
         float sigma, o16[16];
         FwdRegs r;
         mlp_forward(p, a, smw, X, H1, CIN, H3, H4, dir, tid, sigma, o16, r);
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             tc5::mma_commit(p.bar);
         }
         mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 3);
         mask_grad_in_place(trow + kD, H4, tid);                                              // G4 (over H4)
         operands_ready();
         if (tid == 0) {
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             tc5::mma_commit(p.bar);
         }
         mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 4);
         mask_grad_in_place(trow + kD, H3, tid);                                              // G3 (over H3)
         operands_ready();
         if (tid == 0) {
@@ -359,6 +364,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             tc5::mma_commit(p.bar);
         }
         mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 5);
         // ---- d(sigma_net.1 output): channel 0 through trunc_exp + clamp, channels 1..15 = geo part of dCIN
         {
             float dc[16];
@@ -388,6 +394,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             tc5::mma_commit(p.bar);
         }
         mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 11);
         mask_grad_in_place(trow + kD, H1, tid);                                              // G1 (over H1)
         operands_ready();
         if (tid == 0) {
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             tc5::mma_commit(p.bar);
         }
         mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 12);
         first = false;
         // ---- scatter d(encoding) into the table gradient (gridencoder.cu:227-314 semantics, fp32 accumulation)
         float dx[32];
@@ -428,10 +436,12 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
             }
         }
     }
+    if (tid == 0) PVD_T(p.trec, 13);
     // ---- weight gradients leave the SM once per CTA
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
+    gw += (size_t)(blockIdx.x % PVD_FIELD_GW_COPIES) * PVD_FIELD_GW_FLOATS;
     if (!first) {
         flush_acc(p.tmem, kAW1, 32, gw + kGW1);
         flush_acc(p.tmem, kAW2, 16, gw + kGW2);
@@ -439,6 +449,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
         flush_acc(p.tmem, kAW4, 64, gw + kGW4);
         flush_acc(p.tmem, kAW5, 16, gw + kGW5);
     }
+    if (tid == 0) PVD_T(p.trec, 14);
     tc5::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
@@ -535,11 +546,17 @@ __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __res
 __global__ void k_unpack_wgrads(const float* __restrict__ gw, uint32_t in_dim, float* __restrict__ g0, float* __restrict__ g1,
                                 float* __restrict__ g2, float* __restrict__ g3, float* __restrict__ g4) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 64 * in_dim) { const uint32_t o = t / in_dim, i = t - o * in_dim; g0[t] += gw[kGW1 + o * 32 + i]; }
-    if (t < 16 * 64) { const uint32_t o = t / 64, i = t - o * 64; g1[t] += gw[kGW2 + i * 16 + o]; }
-    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g2[t] += gw[kGW3 + o * 32 + i]; }
-    if (t < 64 * 64) { g3[t] += gw[kGW4 + t]; }
-    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g4[t] += gw[kGW5 + i * 16 + o]; }
+    auto sum = [&](uint32_t i) {
+        float acc = 0.0f;
+#pragma unroll
+        for (uint32_t c = 0; c < PVD_FIELD_GW_COPIES; ++c) acc += gw[(size_t)c * PVD_FIELD_GW_FLOATS + i];
+        return acc;
+    };
+    if (t < 64 * in_dim) { const uint32_t o = t / in_dim, i = t - o * in_dim; g0[t] += sum(kGW1 + o * 32 + i); }
+    if (t < 16 * 64) { const uint32_t o = t / 64, i = t - o * 64; g1[t] += sum(kGW2 + i * 16 + o); }
+    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g2[t] += sum(kGW3 + o * 32 + i); }
+    if (t < 64 * 64) { g3[t] += sum(kGW4 + t); }
+    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g4[t] += sum(kGW5 + i * 16 + o); }
 }
 
 static FieldArgs to_args(const PvdHashField* f) {

@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(128) k_vm_field_bwd(VmArgs a, VmGradPtrs g, co
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
+    gw += (size_t)(blockIdx.x % PVD_FIELD_GW_COPIES) * PVD_FIELD_GW_FLOATS;
     if (!first) {
         flush_acc(p.tmem, kVAW3, 32, gw + kVG3);
         flush_acc(p.tmem, kVAW4, 64, gw + kVG4);
@@ -516,10 +517,16 @@ __global__ void k_vm_pack_weights(const float* __restrict__ basis, const float* 
 __global__ void k_vm_unpack_wgrads(const float* __restrict__ gw, float* __restrict__ gb, float* __restrict__ g0,
                                    float* __restrict__ g1, float* __restrict__ g2) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 15 * 144) { const uint32_t o = t / 144, i = t - o * 144; gb[t] += gw[kVGB + i * 16 + o]; }
-    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g0[t] += gw[kVG3 + o * 32 + i]; }
-    if (t < 64 * 64) { g1[t] += gw[kVG4 + t]; }
-    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g2[t] += gw[kVG5 + i * 16 + o]; }
+    auto sum = [&](uint32_t i) {
+        float acc = 0.0f;
+#pragma unroll
+        for (uint32_t c = 0; c < PVD_FIELD_GW_COPIES; ++c) acc += gw[(size_t)c * PVD_FIELD_GW_FLOATS + i];
+        return acc;
+    };
+    if (t < 15 * 144) { const uint32_t o = t / 144, i = t - o * 144; gb[t] += sum(kVGB + i * 16 + o); }
+    if (t < 64 * 31) { const uint32_t o = t / 31, i = t - o * 31; g0[t] += sum(kVG3 + o * 32 + i); }
+    if (t < 64 * 64) { g1[t] += sum(kVG4 + t); }
+    if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g2[t] += sum(kVG5 + i * 16 + o); }
 }
 
 static bool to_vm_args(const PvdVmField* f, VmArgs& a) {

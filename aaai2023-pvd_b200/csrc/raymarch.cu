@@ -706,7 +706,17 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
         gws = grad_ws[index];
         gr = grad_img[3 * (size_t)index]; gg = grad_img[3 * (size_t)index + 1]; gb = grad_img[3 * (size_t)index + 2];
     }
-    if (skip) return;
+    if (skip) {
+        // a ray that does not fit the sample buffer contributes nothing (raymarching.cu:629), but its rows below M are still read by
+        // the field backward: zero them here, so that the caller need not clear the whole gradient buffers every step
+        for (uint32_t i = offset + lane; i < min(offset + cnt, M); i += 32) {
+            grad_sigmas[i] = 0.0f;
+            grad_rgbs[3 * (size_t)i] = 0.0f;
+            grad_rgbs[3 * (size_t)i + 1] = 0.0f;
+            grad_rgbs[3 * (size_t)i + 2] = 0.0f;
+        }
+        return;
+    }
     float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;  // carries (running sums up to the previous chunk)
     auto fetch = [&](uint32_t base, float& sg, float& d0, float& c0, float& c1, float& c2) {
         const uint32_t i = base + lane;

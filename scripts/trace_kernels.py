@@ -103,7 +103,8 @@ def main():
         print(f"   marching rays per SM: min {per_sm.min()} median {np.median(per_sm):.0f} max {per_sm.max()}")
 
     # ---------------- hash field forward
-    f = bufs["field_hash"].cpu().numpy().astype(np.int64)
+    fall = bufs["field_hash"].cpu().numpy().astype(np.int64)
+    f = fall[:2048]
     f = f[f[:, 0] > 0]
     g0 = f[:, 12].min()
     print(f"== k_hash_field_fwd: {len(f)} CTAs; span {(f[:, 14].max() - g0) / 1e3:.2f} us; last CTA start {(f[:, 12].max() - g0) / 1e3:.2f} us")
@@ -122,7 +123,24 @@ def main():
     print(f"   CTA start time percentiles: 25% {pct(starts, 25):.2f}  50% {pct(starts, 50):.2f}  75% {pct(starts, 75):.2f}  100% {starts.max():.2f} us")
     tot = us(f[:, 11] - f[:, 0])
     print(f"   total per CTA: median {pct(tot, 50):.2f} us, max {tot.max():.2f}")
+    report_bwd(fall, us, pct)
+
+
+def report_bwd(fall, us, pct):
+    b = fall[2048:4096]
+    b = b[b[:, 0] > 0]
+    print(f"== k_hash_field_bwd: {len(b)} CTAs (timeline of the LAST tile of each CTA; start/setup/end are per CTA)")
+    seq = [("setup (tmem alloc, weights)", 0, 1), ("[all earlier tiles]", 1, 2), ("fwd: sigma_net.0", 2, 6), ("fwd: sigma_net.1", 6, 7), ("fwd: color_net.0", 7, 8),
+           ("fwd: color_net.1", 8, 9), ("fwd: color_net.2", 9, 10), ("bwd: color_net.2 (wgrad+dgrad)", 10, 3), ("bwd: color_net.1", 3, 4),
+           ("bwd: color_net.0", 4, 5), ("bwd: sigma_net.1", 5, 11), ("bwd: sigma_net.0", 11, 12), ("dx store", 12, 13), ("wgrad flush", 13, 14)]
+    for nm, i0, i1 in seq:
+        d = us(b[:, i1] - b[:, i0])
+        print(f"   {nm:34s}: median {pct(d, 50):6.2f} us  p90 {pct(d, 90):6.2f}  max {d.max():6.2f}")
+    tot = us(b[:, 14] - b[:, 0])
+    print(f"   total per CTA: median {pct(tot, 50):.2f} us, max {tot.max():.2f}")
 
 
 if __name__ == "__main__":
     main()
+
+
