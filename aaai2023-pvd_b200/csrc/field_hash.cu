@@ -262,8 +262,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                         const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
                                                         const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
-                                                        uint32_t M, const int32_t* __restrict__ n_valid_p, __half* __restrict__ dx_out,
-                                                        float* __restrict__ grad_table,
+                                                        uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                        __half* __restrict__ dx_out, float* __restrict__ grad_table,
                                                         float* __restrict__ gw, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -297,13 +297,15 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     if (tid == 0) PVD_T(p.trec, 1);
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
     const uint32_t sw = tc5::smem_u32(smw);
-    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+    // this launch covers rows [row0, row0 + M) of the sample buffers, cut at n_valid (rows of padding contribute nothing)
+    const uint32_t row_end = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
+    const uint32_t n_valid = row_end;
     const uint32_t lv_saddr = tc5::smem_u32(lv);
 
-    const uint32_t n_tiles = (n_valid + kTile - 1) / kTile;  // tiles made only of padding rows contribute nothing
+    const uint32_t n_tiles = (row_end > row0) ? (row_end - row0 + kTile - 1) / kTile : 0u;
     bool first = true;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kTile + tid;
+        const uint32_t row = row0 + tile * kTile + tid;
         const bool live = row < n_valid;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         float gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
@@ -461,7 +463,8 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
 constexpr uint32_t kAggMaxRes1 = 700;  // aggregate runs on levels whose resolution is below this (cell edge > ~0.85 dt at 1024 steps)
 
 __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* __restrict__ xyzs, const __half* __restrict__ dx,
-                                                      uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ grad_table) {
+                                                      uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                      float* __restrict__ grad_table) {
     __shared__ LevelInfo lvs;
     const uint32_t level = blockIdx.y;
     if (threadIdx.x == 0) {
@@ -475,8 +478,8 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
         lvs = v;
     }
     __syncthreads();
-    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
+    const uint32_t b = row0 + blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
     const LevelInfo v = lvs;
     bool active = b < n_valid;
@@ -619,28 +622,46 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
     return PVD_OK;
 }
 
-int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
-                            const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
-                            const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status, void* stream) {
-    if (M == 0) return PVD_OK;
+static int hash_backward_rows(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc, const float* grad_sigmas,
+                              const float* grad_rgbs, const float* grad_feat16, uint32_t row0, uint32_t rows, const int32_t* n_valid,
+                              float* grad_table, float* gw_ws, void* dx_ws, int32_t* status, uint32_t phases, void* stream) {
+    if (rows == 0) return PVD_OK;
     PVD_REQUIRE(f && f->offsets && f->wblob && xyzs && dirs && enc && grad_sigmas && grad_rgbs && grad_table && gw_ws && status);
     if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
     const FieldArgs a = to_args(f);
-    const uint32_t tiles = (M + kTile - 1) / kTile;
-    const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
-    // the table is not read in the backward (the encoding was saved); one instantiation serves both table dtypes
-    cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    if (e != cudaSuccess) return (int)e;
-    k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                         (__half*)dx_ws, grad_table, gw_ws, status);
-    PVD_LAUNCH_CHECK();
-    if (dx_ws != nullptr) {
-        const dim3 sgrid((M + 255) / 256, f->L, 1);
-        k_hash_scatter<<<sgrid, 256, 0, st>>>(a, xyzs, (const __half*)dx_ws, M, n_valid, grad_table);
+    if (phases & PVD_BWD_MLP) {
+        const uint32_t tiles = (rows + kTile - 1) / kTile;
+        const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
+        // the table is not read in the backward (the encoding was saved); one instantiation serves both table dtypes
+        cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, row0,
+                                                             rows, n_valid, (__half*)dx_ws, grad_table, gw_ws, status);
+        PVD_LAUNCH_CHECK();
+    }
+    if ((phases & PVD_BWD_SCATTER) && dx_ws != nullptr) {
+        const dim3 sgrid((rows + 255) / 256, f->L, 1);
+        k_hash_scatter<<<sgrid, 256, 0, st>>>(a, xyzs, (const __half*)dx_ws, row0, rows, n_valid, grad_table);
         PVD_LAUNCH_CHECK();
     }
     return PVD_OK;
+}
+
+int pvd_hash_field_backward(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
+                            const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                            const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status, void* stream) {
+    return hash_backward_rows(f, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_feat16, 0u, M, n_valid, grad_table, gw_ws, dx_ws, status,
+                              PVD_BWD_MLP | PVD_BWD_SCATTER, stream);
+}
+
+int pvd_hash_field_backward_rows(const PvdHashField* f, const float* xyzs, const float* dirs, const void* enc,
+                                 const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t row0,
+                                 uint32_t rows, const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status,
+                                 uint32_t phases, void* stream) {
+    PVD_REQUIRE(dx_ws != nullptr && (phases & (PVD_BWD_MLP | PVD_BWD_SCATTER)) != 0);
+    return hash_backward_rows(f, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_feat16, row0, rows, n_valid, grad_table, gw_ws, dx_ws,
+                              status, phases, stream);
 }
 
 int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,

@@ -8,6 +8,10 @@ launches on one stream:
     near_far | march count | offset scan | sample expand | field fwd | composite fwd | composite bwd (+MSE) | field bwd
     (+ two memsets of the gradient accumulators)
 
+Two ray sets (inputs + march outputs) are kept so that the march of batch i+1 -- a latency-bound kernel chain that depends on
+nothing the model computes -- can run BESIDE the field backward of batch i (`capture_pipelined` / `replay_pipelined`: the
+prefetch a training loop's data loader would do, expressed as a second branch of the step's CUDA graph).
+
 Sample-buffer sizing follows the reference: the first `warmup` steps read the sample counter back (raymarching.py:277) and
 their mean becomes `mean_count`; afterwards M = mean_count rounded up strictly to 128 and rays that do not fit are dropped
 (raymarching.cu:419).  Gradients are left in `grad_table` / `grad_weights()`; an optimizer step is the caller's business
@@ -16,6 +20,7 @@ their mean becomes `mean_count`; afterwards M = mean_count rounded up strictly t
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -24,9 +29,45 @@ from . import _native as nv
 from . import fused
 
 _u32, _f32 = C.c_uint32, C.c_float
+# opt-in experiment (measured SLOWER on B200, 0.129 vs 0.120 ms/step: the full-occupancy scatter CTAs crowd out the MLP CTAs of the
+# other half instead of overlapping with them); the default issues MLP backward and scatter back to back on one stream
+SPLIT_HALVES = os.environ.get("PVD_SPLIT_HALVES", "0") == "1"
+
+
+class _RaySet:
+    """What belongs to one batch of rays: the inputs and everything the march produces from them."""
+
+    def __init__(self, N, dev):
+        self.rays_o = torch.empty(N, 3, device=dev)
+        self.rays_d = torch.empty(N, 3, device=dev)
+        self.gt = torch.empty(N, 3, device=dev)
+        self.nears = torch.empty(N, device=dev)
+        self.fars = torch.empty(N, device=dev)
+        self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.xyzs = self.dirs = self.deltas = None
+
+    def alloc_samples(self, M, dev):
+        self.xyzs = torch.zeros(M, 3, device=dev)
+        self.dirs = torch.zeros(M, 3, device=dev)
+        self.deltas = torch.zeros(M, 2, device=dev)
+
+
+def _set_attr(name):
+    def get(self):
+        return getattr(self.sets[self.cur], name)
+
+    def put(self, v):
+        setattr(self.sets[self.cur], name, v)
+    return property(get, put)
 
 
 class HashTrainEngine:
+    # the "current" ray set is what step() and every single-set accessor works on
+    rays_o, rays_d, gt = _set_attr("rays_o"), _set_attr("rays_d"), _set_attr("gt")
+    nears, fars, rays, counter = _set_attr("nears"), _set_attr("fars"), _set_attr("rays"), _set_attr("counter")
+    xyzs, dirs, deltas = _set_attr("xyzs"), _set_attr("dirs"), _set_attr("deltas")
+
     def __init__(self, field: "fused.HashNeRFField", bitfield: torch.Tensor, n_rays: int, bound: float = 1.0, cascade: int = 1,
                  grid_size: int = 128, min_near: float = 0.2, max_steps: int = 1024, dt_gamma: float = 0.0, bg_color=(1.0, 1.0, 1.0),
                  loss_scale: float = 1.0, density_scale: float = 1.0, device="cuda"):
@@ -42,19 +83,15 @@ class HashTrainEngine:
         N = self.N
         self.aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=d)
         self.bg = torch.tensor(list(bg_color), dtype=torch.float32, device=d)
-        self.rays_o = torch.empty(N, 3, device=d)
-        self.rays_d = torch.empty(N, 3, device=d)
-        self.gt = torch.empty(N, 3, device=d)
-        self.nears = torch.empty(N, device=d)
-        self.fars = torch.empty(N, device=d)
-        self.rays = torch.empty(N, 3, dtype=torch.int32, device=d)
-        # everything that must be zero at the start of a step lives in ONE buffer (one memset node instead of four):
-        # counter[2] int32 | loss[2] f32 | gw_ws
+        self.sets = [_RaySet(N, d), _RaySet(N, d)]
+        self.cur = 0
+        # what must be zero before a backward lives in ONE buffer (one memset node): loss[2] f32 | pad[2] | gw_ws
         self._zeros = torch.zeros(4 + fused.GW_WS_FLOATS, dtype=torch.float32, device=d)
-        self.counter = self._zeros[0:2].view(torch.int32)
-        self.loss = self._zeros[2:4]
+        self.loss = self._zeros[0:2]
         self.gw_ws = self._zeros[4:]
-        self._side = torch.cuda.Stream(device=d)
+        self._side = torch.cuda.Stream(device=d)    # table-gradient memset
+        self._side2 = torch.cuda.Stream(device=d)   # march of the next batch (pipelined mode)
+        self._side3 = torch.cuda.Stream(device=d)   # table-gradient scatter beside the MLP backward of the other half
         self.ws_march = torch.empty(int(nv.lib().pvd_march_rays_train_workspace_words(N, self.max_steps)), dtype=torch.int32, device=d)
         self.weights_sum = torch.empty(N, device=d)
         self.depth = torch.empty(N, device=d)
@@ -67,15 +104,15 @@ class HashTrainEngine:
         self._counts = []
         self._alloc_samples(N * 32)
         self._coarse_valid = False
-        self.launches_per_step = 8 if fused.SPLIT_SCATTER else 7  # kernels of libpvd_b200.so only (torch memsets not counted)
+        # kernels of libpvd_b200.so only (torch memsets not counted): count, scan, expand, fwd, composite fwd/bwd, MLP bwd, scatter
+        self.launches_per_step = (10 if SPLIT_HALVES else 8) if fused.SPLIT_SCATTER else 7
 
     # ------------------------------------------------------------------ buffers sized by M
     def _alloc_samples(self, M: int):
         d = self.dev
         self.M = int(M)
-        self.xyzs = torch.zeros(M, 3, device=d)
-        self.dirs = torch.zeros(M, 3, device=d)
-        self.deltas = torch.zeros(M, 2, device=d)
+        for rs in self.sets:
+            rs.alloc_samples(M, d)
         self.sigmas = torch.empty(M, device=d)
         self.rgbs = torch.empty(M, 3, device=d)
         self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d)
@@ -106,28 +143,73 @@ class HashTrainEngine:
         self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
 
     # ------------------------------------------------------------------ one step
-    def _march_count(self, st):
+    def _march_count(self, st, rs=None):
+        rs = rs or self.sets[self.cur]
         l = nv.lib()
+        rs.counter.zero_()
         # near/far fused into the count kernel; the coarse rejection mask is rebuilt only when the bitfield changed
-        nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(self.rays_o), nv.ptr(self.rays_d), nv.ptr(self.bitfield), nv.ptr(self.aabb),
+        nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(rs.rays_o), nv.ptr(rs.rays_d), nv.ptr(self.bitfield), nv.ptr(self.aabb),
                                                    _f32(self.min_near), _f32(self.bound), _f32(self.dt_gamma), _u32(self.max_steps),
-                                                   _u32(self.N), _u32(self.cascade), _u32(self.grid_size), nv.ptr(self.nears),
-                                                   nv.ptr(self.fars), nv.ptr(self.rays), nv.ptr(self.counter), _u32(1),
+                                                   _u32(self.N), _u32(self.cascade), _u32(self.grid_size), nv.ptr(rs.nears),
+                                                   nv.ptr(rs.fars), nv.ptr(rs.rays), nv.ptr(rs.counter), _u32(1),
                                                    _u32(1 if self._coarse_valid else 0), nv.ptr(self.ws_march), st))
         self._coarse_valid = True
 
-    def step(self, warmup: bool = False):
-        """Forward + backward for the rays currently in self.rays_o / rays_d / gt.  Leaves loss in self.loss[0]."""
+    def _march_write(self, st, rs, M_drop):
+        nv.check(nv.lib().pvd_march_rays_train_write(nv.ptr(rs.rays_o), nv.ptr(rs.rays_d), _f32(self.bound), _u32(self.max_steps),
+                                                     _u32(self.N), _u32(M_drop), nv.ptr(rs.rays), nv.ptr(self.ws_march),
+                                                     nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(rs.deltas), st))
+
+    def _forward(self, st, rs, M, M_drop):
         l = nv.lib()
-        st = nv.stream_of(self.rays_o)
+        nv.check(l.pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), _u32(M), nv.ptr(self.sigmas),
+                                          nv.ptr(self.rgbs), nv.ptr(self.enc), None, nv.ptr(self.status), st))
+        nv.check(l.pvd_composite_rays_train_forward(nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(rs.deltas), nv.ptr(rs.rays),
+                                                    _u32(M_drop), _u32(self.N), nv.ptr(self.weights_sum), nv.ptr(self.depth),
+                                                    nv.ptr(self.image), st))
+
+    def _loss_backward(self, st, rs, M_drop):
+        # grad_sigmas / grad_rgbs need no clearing: every row below n_valid is written by the composite backward
+        nv.check(nv.lib().pvd_composite_rays_train_backward_mse(
+            nv.ptr(rs.gt), nv.ptr(self.bg), _f32(self.loss_scale), nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(rs.deltas),
+            nv.ptr(rs.rays), nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(self.N), nv.ptr(self.grad_sigmas),
+            nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
+
+    def _field_backward(self, st, rs, M, cur=None):
+        """MLP backward + table-gradient scatter.  With a stream handle for the main branch (`cur`), the rows are cut in two
+        halves: MLP(A), MLP(B) run on the main branch and scatter(A), scatter(B) on a side branch, so that the atomic-bound scatter
+        of one half overlaps the latency-bound tcgen05 chain of the other."""
+        l = nv.lib()
+        args = (C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(self.enc), nv.ptr(self.grad_sigmas),
+                nv.ptr(self.grad_rgbs), None)
+        tail = (nv.ptr(rs.counter), nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status))
+        Mh = (M // 256) * 128
+        if cur is None or self.dx_ws is None or Mh == 0 or not SPLIT_HALVES:
+            nv.check(l.pvd_hash_field_backward(*args, _u32(M), *tail, st))
+            return
+        st3 = C.c_void_p(self._side3.cuda_stream)
+        nv.check(l.pvd_hash_field_backward_rows(*args, _u32(0), _u32(Mh), *tail, _u32(1), st))
+        self._side3.wait_stream(cur)
+        with torch.cuda.stream(self._side3):
+            nv.check(l.pvd_hash_field_backward_rows(*args, _u32(0), _u32(Mh), *tail, _u32(2), st3))
+        nv.check(l.pvd_hash_field_backward_rows(*args, _u32(Mh), _u32(M - Mh), *tail, _u32(1), st))
+        self._side3.wait_stream(cur)
+        with torch.cuda.stream(self._side3):
+            nv.check(l.pvd_hash_field_backward_rows(*args, _u32(Mh), _u32(M - Mh), *tail, _u32(2), st3))
+        cur.wait_stream(self._side3)
+
+    def step(self, warmup: bool = False):
+        """Forward + backward for the rays of the current set (self.rays_o / rays_d / gt).  Leaves the loss in self.loss[0]."""
+        rs = self.sets[self.cur]
         cur = torch.cuda.current_stream(self.dev)
-        self._zeros.zero_()                    # counter, loss, weight-gradient workspace
+        st = C.c_void_p(cur.cuda_stream)
+        self._zeros.zero_()                    # loss, weight-gradient workspace
         self._side.wait_stream(cur)            # fork: the 42 MB table-gradient memset runs beside the march (HBM vs. latency bound)
         with torch.cuda.stream(self._side):
             self.grad_table.zero_()
-        self._march_count(st)
+        self._march_count(st, rs)
         if warmup:  # size the sample buffers from this step's count (one D2H read, raymarching.py:277)
-            total = int(self.counter[0].item())
+            total = int(rs.counter[0].item())
             self._counts.append(total)
             need = total + (128 - total % 128)
             if need > self.M:
@@ -136,24 +218,11 @@ class HashTrainEngine:
             M = need
         else:
             M = M_drop = self.M
-        N = self.N
-        nv.check(l.pvd_march_rays_train_write(nv.ptr(self.rays_o), nv.ptr(self.rays_d), _f32(self.bound), _u32(self.max_steps),
-                                              _u32(N), _u32(M_drop), nv.ptr(self.rays), nv.ptr(self.ws_march), nv.ptr(self.xyzs),
-                                              nv.ptr(self.dirs), nv.ptr(self.deltas), st))
-        nv.check(l.pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), _u32(M), nv.ptr(self.sigmas),
-                                          nv.ptr(self.rgbs), nv.ptr(self.enc), None, nv.ptr(self.status), st))
-        nv.check(l.pvd_composite_rays_train_forward(nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(self.deltas), nv.ptr(self.rays),
-                                                    _u32(M_drop), _u32(N), nv.ptr(self.weights_sum), nv.ptr(self.depth),
-                                                    nv.ptr(self.image), st))
-        # backward (grad_sigmas / grad_rgbs need no clearing: every row below n_valid is written by the composite backward)
-        nv.check(l.pvd_composite_rays_train_backward_mse(nv.ptr(self.gt), nv.ptr(self.bg), _f32(self.loss_scale), nv.ptr(self.sigmas),
-                                                         nv.ptr(self.rgbs), nv.ptr(self.deltas), nv.ptr(self.rays),
-                                                         nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(N),
-                                                         nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
+        self._march_write(st, rs, M_drop)
+        self._forward(st, rs, M, M_drop)
+        self._loss_backward(st, rs, M_drop)
         cur.wait_stream(self._side)            # join: the table gradient is clear before the first reduction into it
-        nv.check(l.pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(self.xyzs), nv.ptr(self.dirs), nv.ptr(self.enc),
-                                           nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), None, _u32(M), nv.ptr(self.counter),
-                                           nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status), st))
+        self._field_backward(st, rs, M, cur)
 
     # ------------------------------------------------------------------ CUDA graph of one steady-state step
     def capture(self):
@@ -169,6 +238,63 @@ class HashTrainEngine:
 
     def replay(self):
         self.graph.replay()
+
+    # ------------------------------------------------------------------ pipelined steady state: march(i+1) beside backward(i)
+    def march(self, k: int):
+        """Eagerly march ray set k (priming the pipeline: the first batch has no previous step to hide behind)."""
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        self._march_count(st, self.sets[k])
+        self._march_write(st, self.sets[k], self.M)
+
+    def _pipelined_step(self, k: int):
+        """Field forward/backward of set k (already marched) with the march of set 1-k on a parallel branch.  The branch forks
+        after the composite backward: from there on the main branch runs k_hash_field_bwd (2 CTAs of 128 threads per SM) and the
+        scatter, which leave the thread slots the one-warp march CTAs need."""
+        rs, nxt = self.sets[k], self.sets[1 - k]
+        cur = torch.cuda.current_stream(self.dev)
+        st = C.c_void_p(cur.cuda_stream)
+        M = self.M
+        self._zeros.zero_()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.grad_table.zero_()
+        fork_early = os.environ.get("PVD_PIPE_FORK", "early") == "early"
+        if fork_early:
+            self._side2.wait_stream(cur)
+            with torch.cuda.stream(self._side2):
+                st2 = C.c_void_p(self._side2.cuda_stream)
+                self._march_count(st2, nxt)
+                self._march_write(st2, nxt, M)
+        self._forward(st, rs, M, M)
+        self._loss_backward(st, rs, M)
+        if not fork_early:
+            self._side2.wait_stream(cur)
+            with torch.cuda.stream(self._side2):
+                st2 = C.c_void_p(self._side2.cuda_stream)
+                self._march_count(st2, nxt)
+                self._march_write(st2, nxt, M)
+        cur.wait_stream(self._side)
+        self._field_backward(st, rs, M, cur)
+        cur.wait_stream(self._side2)
+
+    def capture_pipelined(self):
+        """Two graphs (even / odd steps).  Protocol: write batch 0 into sets[0], call march(0); then for step i write batch i+1
+        into sets[(i+1) % 2] (rays_o, rays_d, gt) and replay_pipelined(i)."""
+        self.graphs = []
+        for k in (0, 1):
+            self.march(k)
+            self._pipelined_step(k)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._pipelined_step(k)
+            self.graphs.append(g)
+        torch.cuda.synchronize()
+        return self.graphs
+
+    def replay_pipelined(self, i: int):
+        self.cur = i & 1
+        self.graphs[i & 1].replay()
 
     def finish_warmup(self):
         """mean_count = mean of the warm-up sample counts (renderer.py:768-772)."""

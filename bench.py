@@ -166,16 +166,26 @@ def run_ours(args, rank, world, local):
     devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
 
     use_graph = False
+    pipelined = False
+    pipe = {"i": 0}   # pipelined mode: index of the next replay (its parity selects the ray set that is computed on)
 
-    def load(i):
-        ro, rd, gt = devb[i % len(devb)]
-        if use_graph:  # the captured graph reads the engine's static input buffers
-            eng.rays_o.copy_(ro); eng.rays_d.copy_(rd); eng.gt.copy_(gt)
+    def load(i, from_host=False):
+        """Make batch i the input of the next step.  Pipelined: batch i goes into the set the NEXT replay marches (it is computed
+        on one replay later), which is exactly one batch of look-ahead; the caller passes consecutive i."""
+        ro, rd, gt = (host if from_host else devb)[i % len(devb)]
+        if pipelined:
+            rs = eng.sets[(pipe["i"] + 1) & 1]
+            rs.rays_o.copy_(ro, non_blocking=True); rs.rays_d.copy_(rd, non_blocking=True); rs.gt.copy_(gt, non_blocking=True)
+        elif use_graph or from_host:  # the captured graph reads the engine's static input buffers
+            eng.rays_o.copy_(ro, non_blocking=True); eng.rays_d.copy_(rd, non_blocking=True); eng.gt.copy_(gt, non_blocking=True)
         else:
             eng.rays_o, eng.rays_d, eng.gt = ro, rd, gt
 
     def run_step():
-        if use_graph:
+        if pipelined:
+            eng.replay_pipelined(pipe["i"])
+            pipe["i"] += 1
+        elif use_graph:
             eng.replay()
         else:
             eng.step()
@@ -202,17 +212,37 @@ def run_ours(args, rank, world, local):
         eng.step(warmup=True)
     eng.finish_warmup()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    serial_ms = None
     if not args.no_graph:
-        try:  # one CUDA graph for the whole step (8 kernels + 5 memsets): removes launch gaps and host work from the loop
-            eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
+        try:  # CUDA graphs for the whole step: removes launch gaps and host work from the loop
+            for rs in eng.sets:
+                rs.rays_o, rs.rays_d, rs.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
+            use_graph = True
             load(16)
             eng.capture()
-            use_graph = True
+            if not args.no_pipeline:
+                # reference point: the serial single-graph step, timed the same way (reported as serial_ms_per_step)
+                for i in range(args.warmup):
+                    load(16 + i); run_step()
+                sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+                for i, (a, b) in enumerate(sev):
+                    load(16 + i); flush.fill_(i & 0xFF); a.record(); run_step(); b.record()
+                torch.cuda.synchronize()
+                serial_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
+                # steady state: the march of batch i+1 runs beside the field backward of batch i (two graphs, two ray sets)
+                eng.capture_pipelined()
+                pipelined = True
+                pipe["i"] = 0
+                rs = eng.sets[0]   # prime: batch 16 is marched eagerly, its compute is replay 0
+                ro, rd, gt = devb[16 % len(devb)]
+                rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
+                eng.march(0)
         except Exception as ex:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed ({ex!r}); running eagerly", file=sys.stderr)
-            use_graph = False
+            use_graph = pipelined = False
+    nb = 17   # next batch to feed (pipelined: one ahead of the batch being computed)
     for i in range(args.warmup):
-        load(16 + i)
+        load(nb); nb += 1
         run_step()
         allreduce()
     torch.cuda.synchronize()
@@ -228,7 +258,7 @@ def run_ours(args, rank, world, local):
         dist.barrier()
     torch.cuda.synchronize()
     for i in range(args.steps):
-        load(16 + args.warmup + i)
+        load(nb); nb += 1
         flush.fill_(i & 0xFF)
         ev[i][0].record()
         run_step()
@@ -247,6 +277,8 @@ def run_ours(args, rank, world, local):
     kt = {"march": 0.0, "field_fwd": 0.0, "composite": 0.0, "field_bwd": 0.0}
     S_total = 0
     reps = min(args.steps, 50)
+    was_pipelined, pipelined = pipelined, False
+    eng.cur = 0
     for i in range(reps):
         load(16 + args.warmup + i)
         flush.fill_(i & 0xFF)
@@ -257,25 +289,27 @@ def run_ours(args, rank, world, local):
     for k in kt:
         kt[k] /= reps
     S_mean = S_total / reps
+    pipelined = was_pipelined
+    if pipelined:  # re-prime the pipeline for the end-to-end pass
+        pipe["i"] = 0
+        rs = eng.sets[0]
+        ro, rd, gt = devb[nb % len(devb)]
+        rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
+        eng.march(0)
+        nb += 1
 
     # ---- end-to-end through the public API with HOST buffers: H2D of rays + gt, step, D2H of the loss
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
-    if use_graph:
-        ro_d, rd_d, gt_d = eng.rays_o, eng.rays_d, eng.gt
-    else:
-        ro_d, rd_d, gt_d = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
-        eng.rays_o, eng.rays_d, eng.gt = ro_d, rd_d, gt_d
+    if not use_graph:
+        eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     for i in range(args.steps):
-        ro, rd, gt = host[(16 + args.warmup + i) % len(host)]
         flush.fill_(i & 0xFF)
         e2e_ev[i][0].record()
-        ro_d.copy_(ro, non_blocking=True)
-        rd_d.copy_(rd, non_blocking=True)
-        gt_d.copy_(gt, non_blocking=True)
+        load(nb, from_host=True); nb += 1   # pinned host rays + gt -> device (pipelined: the batch that is marched in this step)
         run_step()
         allreduce()
         loss_host.copy_(eng.loss, non_blocking=True)
@@ -312,9 +346,12 @@ def run_ours(args, rank, world, local):
                    "precision": "fp16 table + fp16 tcgen05 MLP, fp32 accumulate / composite / gradients", "loss_scale": 65536,
                    "parallelism": (f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step "
                                    f"({args.grad_comm} table-gradient payload)") if world > 1 else "single GPU",
-                   "launch": "one CUDA graph per step" if use_graph else "eager (one launch per kernel)",
+                   "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch beside the field "
+                              "backward of batch i (one batch of look-ahead, double-buffered ray sets)") if pipelined else
+                             ("one CUDA graph per step" if use_graph else "eager (one launch per kernel)"),
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write, outside the timed brackets)",
                    "scene_bitfield_sha256": sha[:16]},
+        "serial_ms_per_step": serial_ms,
         "kernel_ms": kt,
         "roofline": {"bound": "hbm", "kernel": "k_hash_field_bwd" if dom == "field_bwd" else "k_hash_field_fwd", "achieved": ach,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
@@ -457,6 +494,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grad-comm", default="fp16", choices=["fp16", "fp32"], help="payload dtype of the table-gradient all-reduce (N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--no-pipeline", action="store_true", help="serial step graph: do not overlap the next batch's march with the backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()

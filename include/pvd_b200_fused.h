@@ -82,6 +82,18 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
                                           const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                           float* grad_sigmas, float* grad_rgbs, float* loss_out, void* stream);
 
+/* The same backward restricted to rows [row0, row0 + rows) of the sample buffers (all pointers are the buffers' bases), and split
+ * in its two kernels so that a caller can run them on different streams: PVD_BWD_MLP = tcgen05 MLP backward, leaves d(encoding) in
+ * dx_ws (required here); PVD_BWD_SCATTER = reductions of dx_ws into grad_table.  Halving the rows and issuing
+ * MLP(A) ; MLP(B) on one stream and SCATTER(A) ; SCATTER(B) on another overlaps the atomic-bound scatter of one half with the
+ * latency-bound MLP chain of the other.  n_valid counts rows from the start of the buffers, as above. */
+#define PVD_BWD_MLP 1u
+#define PVD_BWD_SCATTER 2u
+int pvd_hash_field_backward_rows(const PvdHashField* field, const float* xyzs, const float* dirs, const void* enc,
+                                 const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t row0,
+                                 uint32_t rows, const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status,
+                                 uint32_t phases, void* stream);
+
 /* gw_* += un-padded / transposed views of gw_ws; shapes [64,in_dim], [16,64], [64,31], [64,64], [3,64]. */
 int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,
                             float* gw_color1, float* gw_color2, void* stream);

@@ -89,3 +89,43 @@ def test_engine_graph_replay_is_equivalent(scene):
     eng.replay()
     torch.cuda.synchronize()
     assert float(eng.loss[0]) > 0 and int(eng.status.item()) == 0
+
+
+def test_pipelined_graphs_match_the_serial_step(scene):
+    """Two-graph pipelined steady state (march of batch i+1 beside the backward of batch i) gives, batch by batch, what the
+    serial step gives: same rays / offsets, same loss, same gradients up to atomic ordering."""
+    net, eng, ro0, rd0, gt0 = _setup(scene, n_rays=1024)
+    eng.step(warmup=True)
+    eng.finish_warmup()
+    batches = []
+    for b in range(4):
+        ro, rd = scene["batches"][b % 3]
+        sl = slice(1024 * (b // 3), 1024 * (b // 3) + 1024)
+        gt = torch.rand(1024, 3, generator=torch.Generator().manual_seed(10 + b))
+        batches.append((ro[sl].contiguous().cuda(), rd[sl].contiguous().cuda(), gt.cuda()))
+    # serial reference
+    ref = []
+    eng.cur = 0
+    for ro, rd, gt in batches:
+        eng.rays_o.copy_(ro); eng.rays_d.copy_(rd); eng.gt.copy_(gt)
+        eng.step()
+        torch.cuda.synchronize()
+        ref.append((eng.loss.clone(), eng.grad_table.clone(), eng.gw_ws.clone().view(16, -1).sum(0), eng.rays.clone(), eng.image.clone()))
+    # pipelined
+    eng.capture_pipelined()
+    s0 = eng.sets[0]
+    s0.rays_o.copy_(batches[0][0]); s0.rays_d.copy_(batches[0][1]); s0.gt.copy_(batches[0][2])
+    eng.march(0)
+    for i in range(4):
+        nxt = eng.sets[(i + 1) & 1]
+        ro, rd, gt = batches[(i + 1) % 4]
+        nxt.rays_o.copy_(ro); nxt.rays_d.copy_(rd); nxt.gt.copy_(gt)
+        eng.replay_pipelined(i)
+        torch.cuda.synchronize()
+        loss_r, gt_r, gw_r, rays_r, img_r = ref[i]
+        assert torch.equal(eng.rays, rays_r), f"step {i}: ray offsets"
+        torch.testing.assert_close(eng.image, img_r, rtol=0, atol=0)
+        torch.testing.assert_close(eng.loss, loss_r, rtol=1e-5, atol=1e-7)
+        assert _rel_l2(eng.grad_table, gt_r) < 1e-4
+        assert _rel_l2(eng.gw_ws.view(16, -1).sum(0), gw_r) < 1e-4
+    assert int(eng.status.item()) == 0
