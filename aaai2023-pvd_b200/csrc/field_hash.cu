@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
     if (v.res1 > kAggMaxRes1) {
         if (active) {
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g.x, c.w[i] * g.y);
+            for (uint32_t i = 0; i < 8; i += 2)
+                tab_red_pair(gt, c.idx[i], c.idx[i + 1], c.w[i] * g.x, c.w[i] * g.y, c.w[i + 1] * g.x, c.w[i + 1] * g.y);
         }
         return;
     }
@@ -531,7 +532,8 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
     }
     if (head && active) {
 #pragma unroll
-        for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, val[2 * i], val[2 * i + 1]);
+        for (uint32_t i = 0; i < 8; i += 2)
+            tab_red_pair(gt, c.idx[i], c.idx[i + 1], val[2 * i], val[2 * i + 1], val[2 * i + 2], val[2 * i + 3]);
     }
 }
 

@@ -110,6 +110,20 @@ __device__ __forceinline__ void tab_red2(float* t, size_t i, float a, float b) {
     // volatile keeps the reduction; no "memory" clobber, so the compiler may overlap the next level's address math with it
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(t + i), "f"(a), "f"(b));
 }
+// the x-neighbour pair of one (y, z) corner: entries e0, e1 with values (a0, b0), (a1, b1).  When the two entries are the two
+// halves of one 16-byte slot (e0 ^ e1 == 1: always on hashed levels when x is even, on dense ones when e0 is even) a single
+// red.global.add.v4.f32 replaces two v2 reductions -- the scatter is bound by reduction lane-operations per SM.
+__device__ __forceinline__ void tab_red_pair(float* t, uint32_t e0, uint32_t e1, float a0, float b0, float a1, float b1) {
+    if ((e0 ^ e1) == 1u) {
+        const bool lo = (e0 & 1u) == 0u;  // e0 is the lower entry of the slot
+        float* p = t + (size_t)(e0 & ~1u) * 2;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(lo ? a0 : a1), "f"(lo ? b0 : b1), "f"(lo ? a1 : a0),
+                     "f"(lo ? b1 : b0));
+    } else {
+        tab_red2(t, (size_t)e0 * 2, a0, b0);
+        tab_red2(t, (size_t)e1 * 2, a1, b1);
+    }
+}
 __device__ __forceinline__ void tab_red2(__half* t, size_t i, float a, float b) {
     atomicAdd(reinterpret_cast<__half2*>(t + i), __floats2half2_rn(a, b));
 }

@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "../../include/pvd_b200_fused.h"
 PVD_TRACE_TU(pvd_debug_trace_raymarch)
 
 namespace pvd {
@@ -600,12 +601,12 @@ __device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+__global__ void __launch_bounds__(32) k_composite_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                       const float* __restrict__ deltas, const int32_t* __restrict__ rays,
                                                       uint32_t M, uint32_t N, float* __restrict__ weights_sum,
                                                       float* __restrict__ depth, float* __restrict__ image) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x;  // one warp per CTA: n, and every branch below, is provably warp-uniform (no WARPSYNC around the scans)
+    const uint32_t lane = threadIdx.x;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n];
     const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
@@ -622,42 +623,45 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__
     }
     float T = 1.0f, tcarry = 0.0f;           // carried across 32-sample chunks
     float r = 0, g = 0, b = 0, ws = 0, d = 0;  // per-lane partial sums
-    // software pipeline: the loads of chunk k+1 are in flight while chunk k goes through its two shuffle scans
-    auto fetch = [&](uint32_t base, float& sg, float2& dl, float& c0, float& c1, float& c2) {
-        const uint32_t i = base + lane;
-        const bool ok = i < cnt;
-        const size_t row = (size_t)offset + (ok ? i : 0);
-        sg = ok ? __ldg(sigmas + row) : 0.0f;
-        dl = ok ? __ldg(reinterpret_cast<const float2*>(deltas + 2 * row)) : make_float2(0.f, 0.f);
-        c0 = ok ? __ldg(rgbs + 3 * row) : 0.f;
-        c1 = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
-        c2 = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
-    };
-    float sg_n, c0_n, c1_n, c2_n;
-    float2 dl_n;
-    fetch(0, sg_n, dl_n, c0_n, c1_n, c2_n);
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        const float sigma = sg_n, c0 = c0_n, c1 = c1_n, c2 = c2_n;
-        const float2 dl = dl_n;
-        if (base + 32 < cnt) fetch(base + 32, sg_n, dl_n, c0_n, c1_n, c2_n);
-        const bool ok = base + lane < cnt;
-        const float alpha = ok ? 1.0f - __expf(-sigma * dl.x) : 0.0f;  // raymarching.cu:546
-        const float om = 1.0f - alpha;
-        const float incl = warp_scan_mul(om, lane);
-        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 1.0f;
-        const float Ti = T * excl;
-        const float w = alpha * Ti;
-        const float tin = tcarry + warp_scan_add(dl.y, lane);
-        if (ok) {
-            r += w * c0;
-            g += w * c1;
-            b += w * c2;
-            d += w * tin;
-            ws += w;
+    // blocks of 4 chunks (128 samples): the loads of all four chunks are issued before the first one goes through its two shuffle
+    // scans, so a ray costs one memory latency per 128 samples instead of one per 32 (most rays: one latency in all)
+    for (uint32_t base0 = 0; base0 < cnt; base0 += 128) {
+        float sg[4], c0[4], c1[4], c2[4];
+        float2 dl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = base0 + 32u * q + lane;
+            const bool ok = i < cnt;
+            const size_t row = (size_t)offset + (ok ? i : 0);
+            sg[q] = ok ? __ldg(sigmas + row) : 0.0f;
+            dl[q] = ok ? __ldg(reinterpret_cast<const float2*>(deltas + 2 * row)) : make_float2(0.f, 0.f);
+            c0[q] = ok ? __ldg(rgbs + 3 * row) : 0.f;
+            c1[q] = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+            c2[q] = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
         }
-        T *= __shfl_sync(0xffffffffu, incl, 31);
-        tcarry = __shfl_sync(0xffffffffu, tin, 31);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t base = base0 + 32u * q;
+            if (base >= cnt) break;  // warp-uniform
+            const bool ok = base + lane < cnt;
+            const float alpha = ok ? 1.0f - __expf(-sg[q] * dl[q].x) : 0.0f;  // raymarching.cu:546
+            const float om = 1.0f - alpha;
+            const float incl = warp_scan_mul(om, lane);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const float Ti = T * excl;
+            const float w = alpha * Ti;
+            const float tin = tcarry + warp_scan_add(dl[q].y, lane);
+            if (ok) {
+                r += w * c0[q];
+                g += w * c1[q];
+                b += w * c2[q];
+                d += w * tin;
+                ws += w;
+            }
+            T *= __shfl_sync(0xffffffffu, incl, 31);
+            tcarry = __shfl_sync(0xffffffffu, tin, 31);
+        }
     }
     r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
     if (lane == 0) {
@@ -674,15 +678,23 @@ __global__ void __launch_bounds__(128) k_composite_fwd(const float* __restrict__
 // grad_ws then points to gt [N,3], grad_img to bg [3]; `loss_scale` multiplies the gradients (GradScaler) and
 // loss_out[0] accumulates the UNSCALED loss, loss_out[1] the number of rays that contributed.
 template <bool FUSED_MSE>
-__global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_img,
+__global__ void __launch_bounds__(32) k_composite_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_img,
                                                       const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                       const float* __restrict__ deltas, const int32_t* __restrict__ rays,
                                                       const float* __restrict__ weights_sum, const float* __restrict__ image,
                                                       uint32_t M, uint32_t N, float* __restrict__ grad_sigmas,
                                                       float* __restrict__ grad_rgbs, float loss_scale, float* __restrict__ loss_out) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = blockIdx.x;  // one warp per CTA: n, and every branch below, is provably warp-uniform (no WARPSYNC around the scans)
+    const uint32_t lane = threadIdx.x;
     if (n >= N) return;
+#ifdef PVD_TRACE
+    if (lane == 0) {
+        unsigned long long gt_; unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        PVD_T(4096u + n, 0); PVD_TV(4096u + n, 8, gt_); PVD_TV(4096u + n, 7, smid);
+    }
+#endif
     const uint32_t index = (uint32_t)rays[3 * (size_t)n];
     const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
     const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
@@ -697,8 +709,9 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
         const float dr = r_final + om * bgr - gt[0], dg = g_final + om * bgg - gt[1], db = b_final + om * bgb - gt[2];
         const float k = 2.0f / (3.0f * (float)N);
         if (lane == 0) {
-            atomicAdd(loss_out, (dr * dr + dg * dg + db * db) / (3.0f * (float)N));
-            if (!skip) atomicAdd(loss_out + 1, 1.0f);
+            float* slot = loss_out + 2u * (n % PVD_LOSS_SLOTS);
+            atomicAdd(slot, (dr * dr + dg * dg + db * db) / (3.0f * (float)N));
+            if (!skip) atomicAdd(slot + 1, 1.0f);
         }
         gr = k * dr * loss_scale; gg = k * dg * loss_scale; gb = k * db * loss_scale;
         gws = -(gr * bgr + gg * bgg + gb * bgb);
@@ -706,6 +719,7 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
         gws = grad_ws[index];
         gr = grad_img[3 * (size_t)index]; gg = grad_img[3 * (size_t)index + 1]; gb = grad_img[3 * (size_t)index + 2];
     }
+    if (lane == 0) { PVD_T(4096u + n, 1); PVD_TV(4096u + n, 6, cnt); }
     if (skip) {
         // a ray that does not fit the sample buffer contributes nothing (raymarching.cu:629), but its rows below M are still read by
         // the field backward: zero them here, so that the caller need not clear the whole gradient buffers every step
@@ -718,24 +732,27 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
         return;
     }
     float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;  // carries (running sums up to the previous chunk)
-    auto fetch = [&](uint32_t base, float& sg, float& d0, float& c0, float& c1, float& c2) {
+    for (uint32_t base0 = 0; base0 < cnt; base0 += 128) {  // 4 chunks of loads in flight at once, as in the forward
+        float sgv[4], d0v[4], c0v[4], c1v[4], c2v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = base0 + 32u * q + lane;
+            const bool ok = i < cnt;
+            const size_t row = (size_t)offset + (ok ? i : 0);
+            sgv[q] = ok ? __ldg(sigmas + row) : 0.0f;
+            d0v[q] = ok ? __ldg(deltas + 2 * row) : 0.0f;
+            c0v[q] = ok ? __ldg(rgbs + 3 * row) : 0.f;
+            c1v[q] = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+            c2v[q] = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+        const uint32_t base = base0 + 32u * q;
+        if (base >= cnt) break;  // warp-uniform
         const uint32_t i = base + lane;
         const bool ok = i < cnt;
         const size_t row = (size_t)offset + (ok ? i : 0);
-        sg = ok ? __ldg(sigmas + row) : 0.0f;
-        d0 = ok ? __ldg(deltas + 2 * row) : 0.0f;
-        c0 = ok ? __ldg(rgbs + 3 * row) : 0.f;
-        c1 = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
-        c2 = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
-    };
-    float sg_n, d0_n, c0_n, c1_n, c2_n;
-    fetch(0, sg_n, d0_n, c0_n, c1_n, c2_n);
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        const uint32_t i = base + lane;
-        const bool ok = i < cnt;
-        const size_t row = (size_t)offset + (ok ? i : 0);
-        const float sigma = sg_n, d0 = d0_n, cr = c0_n, cg = c1_n, cb = c2_n;
-        if (base + 32 < cnt) fetch(base + 32, sg_n, d0_n, c0_n, c1_n, c2_n);
+        const float sigma = sgv[q], d0 = d0v[q], cr = c0v[q], cg = c1v[q], cb = c2v[q];
         const float alpha = ok ? 1.0f - __expf(-sigma * d0) : 0.0f;
         const float om = 1.0f - alpha;
         const float incl = warp_scan_mul(om, lane);
@@ -759,7 +776,15 @@ __global__ void __launch_bounds__(128) k_composite_bwd(const float* __restrict__
         gc = __shfl_sync(0xffffffffu, g_run, 31);
         bc = __shfl_sync(0xffffffffu, b_run, 31);
         wc = __shfl_sync(0xffffffffu, w_run, 31);
+        }
     }
+#ifdef PVD_TRACE
+    if (lane == 0) {
+        unsigned long long gt_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
+        PVD_T(4096u + n, 2); PVD_TV(4096u + n, 9, gt_);
+    }
+#endif
 }
 
 // =============================================================================================
@@ -1037,7 +1062,7 @@ int pvd_composite_rays_train_forward(const float* sigmas, const float* rgbs, con
                                      void* stream) {
     if (N == 0) return PVD_OK;
     PVD_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image);
-    k_composite_fwd<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, weights_sum,
+    k_composite_fwd<<<N, 32, 0, (cudaStream_t)stream>>>(sigmas, rgbs, deltas, rays, M, N, weights_sum,
                                                                       depth, image);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
@@ -1050,7 +1075,7 @@ int pvd_composite_rays_train_backward(const float* grad_weights_sum, const float
     if (N == 0) return PVD_OK;
     PVD_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image &&
                 grad_sigmas && grad_rgbs);
-    k_composite_bwd<false><<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
+    k_composite_bwd<false><<<N, 32, 0, (cudaStream_t)stream>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas,
                                                                              rays, weights_sum, image, M, N, grad_sigmas,
                                                                              grad_rgbs, 1.0f, nullptr);
     PVD_LAUNCH_CHECK();
@@ -1064,7 +1089,7 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
     if (N == 0) return PVD_OK;
     PVD_REQUIRE(gt_rgb && bg_color && sigmas && rgbs && deltas && rays && weights_sum && image && grad_sigmas && grad_rgbs &&
                 loss_out);
-    k_composite_bwd<true><<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, sigmas, rgbs, deltas, rays,
+    k_composite_bwd<true><<<N, 32, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, sigmas, rgbs, deltas, rays,
                                                                             weights_sum, image, M, N, grad_sigmas, grad_rgbs,
                                                                             loss_scale, loss_out);
     PVD_LAUNCH_CHECK();

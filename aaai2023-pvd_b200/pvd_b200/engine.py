@@ -85,10 +85,10 @@ class HashTrainEngine:
         self.bg = torch.tensor(list(bg_color), dtype=torch.float32, device=d)
         self.sets = [_RaySet(N, d), _RaySet(N, d)]
         self.cur = 0
-        # what must be zero before a backward lives in ONE buffer (one memset node): loss[2] f32 | pad[2] | gw_ws
-        self._zeros = torch.zeros(4 + fused.GW_WS_FLOATS, dtype=torch.float32, device=d)
-        self.loss = self._zeros[0:2]
-        self.gw_ws = self._zeros[4:]
+        # what must be zero before a backward lives in ONE buffer (one memset node): loss slots [64][2] f32 | gw_ws
+        self._zeros = torch.zeros(2 * fused.LOSS_SLOTS + fused.GW_WS_FLOATS, dtype=torch.float32, device=d)
+        self.loss_slots = self._zeros[0:2 * fused.LOSS_SLOTS]   # PVD_LOSS_SLOTS pairs (loss, rays); see `loss`
+        self.gw_ws = self._zeros[2 * fused.LOSS_SLOTS:]
         self._side = torch.cuda.Stream(device=d)    # table-gradient memset
         self._side2 = torch.cuda.Stream(device=d)   # march of the next batch (pipelined mode)
         self._side3 = torch.cuda.Stream(device=d)   # table-gradient scatter beside the MLP backward of the other half
@@ -173,7 +173,7 @@ class HashTrainEngine:
         nv.check(nv.lib().pvd_composite_rays_train_backward_mse(
             nv.ptr(rs.gt), nv.ptr(self.bg), _f32(self.loss_scale), nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(rs.deltas),
             nv.ptr(rs.rays), nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(self.N), nv.ptr(self.grad_sigmas),
-            nv.ptr(self.grad_rgbs), nv.ptr(self.loss), st))
+            nv.ptr(self.grad_rgbs), nv.ptr(self.loss_slots), st))
 
     def _field_backward(self, st, rs, M, cur=None):
         """MLP backward + table-gradient scatter.  With a stream handle for the main branch (`cur`), the rows are cut in two
@@ -295,6 +295,11 @@ class HashTrainEngine:
     def replay_pipelined(self, i: int):
         self.cur = i & 1
         self.graphs[i & 1].replay()
+
+    @property
+    def loss(self):
+        """[unscaled MSE loss, rays that contributed] of the last step (the kernel spreads them over PVD_LOSS_SLOTS slots)."""
+        return self.loss_slots.view(fused.LOSS_SLOTS, 2).sum(0)
 
     def finish_warmup(self):
         """mean_count = mean of the warm-up sample counts (renderer.py:768-772)."""

@@ -25,6 +25,7 @@ WBLOB_BYTES = 20480
 GW_FLOATS = 10240
 GW_COPIES = 16                   # PVD_FIELD_GW_COPIES: replicas of the weight-gradient workspace
 GW_WS_FLOATS = GW_FLOATS * GW_COPIES
+LOSS_SLOTS = 64                  # PVD_LOSS_SLOTS
 ENC_STRIDE = 32
 SPLIT_SCATTER = os.environ.get("PVD_SPLIT_SCATTER", "1") != "0"  # table-gradient scatter as its own kernel
 

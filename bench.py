@@ -300,7 +300,7 @@ def run_ours(args, rank, world, local):
 
     # ---- end-to-end through the public API with HOST buffers: H2D of rays + gt, step, D2H of the loss
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_host = torch.empty(eng.loss_slots.numel(), dtype=torch.float32).pin_memory()   # 64 (loss, rays) slots, summed on the host
     if not use_graph:
         eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
     if world > 1:
@@ -312,7 +312,7 @@ def run_ours(args, rank, world, local):
         load(nb, from_host=True); nb += 1   # pinned host rays + gt -> device (pipelined: the batch that is marched in this step)
         run_step()
         allreduce()
-        loss_host.copy_(eng.loss, non_blocking=True)
+        loss_host.copy_(eng.loss_slots, non_blocking=True)
         e2e_ev[i][1].record()
     torch.cuda.synchronize()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
@@ -356,7 +356,7 @@ def run_ours(args, rank, world, local):
         "roofline": {"bound": "hbm", "kernel": "k_hash_field_bwd" if dom == "field_bwd" else "k_hash_field_fwd", "achieved": ach,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_sample": bytes_fwd if dom == "field_fwd" else bytes_bwd},
-        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * 9 * 4, "d2h_bytes_per_step": 8},
+        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * 9 * 4, "d2h_bytes_per_step": 4 * eng.loss_slots.numel()},
         "gpu_launches": eng.launches_per_step * args.steps,
         "clocks": clocks,
     }
@@ -389,7 +389,7 @@ def time_phases(eng):
                                                 nv.ptr(eng.weights_sum), nv.ptr(eng.depth), nv.ptr(eng.image), st))
     nv.check(l.pvd_composite_rays_train_backward_mse(nv.ptr(eng.gt), nv.ptr(eng.bg), f32(eng.loss_scale), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
                                                      nv.ptr(eng.deltas), nv.ptr(eng.rays), nv.ptr(eng.weights_sum), nv.ptr(eng.image), u32(M),
-                                                     u32(N), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss), st))
+                                                     u32(N), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss_slots), st))
     e[3].record()
     nv.check(l.pvd_hash_field_backward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.enc), nv.ptr(eng.grad_sigmas),
                                        nv.ptr(eng.grad_rgbs), None, u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),

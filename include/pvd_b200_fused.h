@@ -75,7 +75,9 @@ int pvd_hash_field_backward(const PvdHashField* field, const float* xyzs, const 
 /* composite_rays_train_backward (pvd_b200.h) with the upstream gradients derived in the kernel from the photometric loss:
  *   pred = image + (1 - weights_sum) * bg_color   (distill_mutual/renderer.py:445)
  *   loss = mean((pred - gt_rgb)^2) over the N x 3 values (just_train_tea/utils.py:841-846, MSELoss)
- * gradients are multiplied by loss_scale (GradScaler); loss_out[0] += unscaled loss, loss_out[1] += rays that carried
+ * gradients are multiplied by loss_scale (GradScaler).  loss_out is PVD_LOSS_SLOTS pairs of floats: ray n adds into pair
+ * n % PVD_LOSS_SLOTS (4096 same-address atomics would serialise in L2 and stall the SMs' memory pipes), and the step's values are the
+ * sums over the slots: sum loss_out[2s] = unscaled loss, sum loss_out[2s+1] = rays that carried
  * samples.  gt_rgb [N,3], bg_color [3]. */
 int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_color, float loss_scale, const float* sigmas,
                                           const float* rgbs, const float* deltas, const int32_t* rays,
@@ -87,6 +89,7 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
  * dx_ws (required here); PVD_BWD_SCATTER = reductions of dx_ws into grad_table.  Halving the rows and issuing
  * MLP(A) ; MLP(B) on one stream and SCATTER(A) ; SCATTER(B) on another overlaps the atomic-bound scatter of one half with the
  * latency-bound MLP chain of the other.  n_valid counts rows from the start of the buffers, as above. */
+#define PVD_LOSS_SLOTS 64u
 #define PVD_BWD_MLP 1u
 #define PVD_BWD_SCATTER 2u
 int pvd_hash_field_backward_rows(const PvdHashField* field, const float* xyzs, const float* dirs, const void* enc,

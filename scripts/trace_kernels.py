@@ -102,6 +102,24 @@ def main():
         per_sm = np.bincount(smid[heavy], minlength=148)
         print(f"   marching rays per SM: min {per_sm.min()} median {np.median(per_sm):.0f} max {per_sm.max()}")
 
+    # ---------------- composite backward
+    cb = bufs["raymarch"].cpu().numpy().astype(np.int64)[4096:4096 + args.rays]
+    cb = cb[cb[:, 0] > 0]
+    if len(cb):
+        g0 = cb[:, 8].min()
+        act = cb[cb[:, 9] > 0]
+        print(f"== k_composite_bwd: {len(cb)} rays traced, {len(act)} composited; first start -> last end {(act[:, 9].max() - g0) / 1e3:.2f} us; "
+              f"last warp START {(cb[:, 8].max() - g0) / 1e3:.2f} us")
+        hd = us(act[:, 1] - act[:, 0]); lp = us(act[:, 2] - act[:, 1])
+        print(f"   header loads: median {pct(hd, 50):.2f} us p99 {pct(hd, 99):.2f}; sample loop: median {pct(lp, 50):.2f} us p99 {pct(lp, 99):.2f} max {lp.max():.2f}; "
+              f"samples/ray median {pct(act[:, 6], 50):.0f} max {act[:, 6].max()}")
+        for lo, hi in ((1, 32), (33, 64), (65, 96), (97, 128), (129, 160), (161, 192), (193, 256), (257, 1024)):
+            sel = (act[:, 6] >= lo) & (act[:, 6] <= hi)
+            if sel.any():
+                print(f"     {lo:4d}-{hi:4d} samples: n={int(sel.sum()):4d} loop median {pct(lp[sel], 50):.2f} us max {lp[sel].max():.2f}")
+        late = np.argsort(-act[:, 9])[:3]
+        for i in late:
+            print(f"     late: start {(act[i, 8] - g0) / 1e3:.2f} end {(act[i, 9] - g0) / 1e3:.2f} us cnt {act[i, 6]} header {us(act[i, 1] - act[i, 0]):.2f} loop {us(act[i, 2] - act[i, 1]):.2f}")
     # ---------------- hash field forward
     fall = bufs["field_hash"].cpu().numpy().astype(np.int64)
     f = fall[:2048]

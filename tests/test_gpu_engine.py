@@ -77,7 +77,7 @@ def test_engine_graph_replay_is_equivalent(scene):
     ref_loss, ref_img = float(eng.loss[0]), eng.image.clone()
     ref_gt = eng.grad_table.clone()
     eng.capture()
-    eng.loss.zero_(); eng.image.zero_(); eng.grad_table.zero_()
+    eng.loss_slots.zero_(); eng.image.zero_(); eng.grad_table.zero_()
     eng.replay()
     torch.cuda.synchronize()
     assert abs(float(eng.loss[0]) - ref_loss) < 1e-6 * max(1.0, ref_loss)
