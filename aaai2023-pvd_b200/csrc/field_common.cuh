@@ -14,6 +14,7 @@ struct Pipe {
     uint32_t tmem;
     int32_t* status;
     uint32_t trec = 0;  // timeline record of this CTA (PVD_TRACE builds only)
+    uint64_t* wbar = nullptr;  // non-null while the TMA copy of the weight blob may still be in flight (thread 0 waits once)
 };
 
 // Every thread: publish shared-memory operand writes to the async proxy and order prior TMEM reads, then barrier.
@@ -102,6 +103,21 @@ __device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint
                              : "memory");
         }
     }
+}
+
+// Thread 0, before its first MMA that reads the weight tiles: wait for the bulk copy started by stage_blob_async.  The tensor
+// core reads shared memory through the async proxy, the same proxy TMA wrote it through: no proxy fence is needed.
+__device__ __forceinline__ void weights_ready(Pipe& p) {
+    if (p.wbar != nullptr) {
+        if (!tc5::mbar_wait(p.wbar, 0)) atomicExch(p.status, 1);
+        p.wbar = nullptr;
+    }
+}
+// Thread 0: start ONE TMA bulk copy of the packed weight tiles into shared memory (mbarrier `wbar`, initialised with count 1,
+// completes when the bytes have landed).  Nothing waits here: the copy overlaps the gather / the first tile's loads.
+__device__ __forceinline__ void stage_blob_async(uint8_t* smw, const uint8_t* __restrict__ blob, uint32_t bytes, uint64_t* wbar) {
+    tc5::mbar_expect_tx(wbar, bytes);
+    tc5::bulk_g2s(tc5::smem_u32(smw), blob, bytes, wbar);
 }
 
 // copy `bytes` (multiple of 16) of packed weight tiles from global to shared memory

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
                                                         uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                         __half* __restrict__ enc, float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, wbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelInfo lv[16];
     // Forward-only tiles alias: the encoding X is dead once layer 1's MMAs completed, so the colour-net input CIN reuses its
@@ -187,16 +187,18 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
     // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
-    stage_weights(smw, a.wblob);
-    level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
+        tc5::mbar_init(&wbar, 1);
         tc5::mbar_fence_init();
+        stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile is gathered
     }
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
+    p.wbar = &wbar;
     p.trec = blockIdx.x;
     if (tid == 0) PVD_T(blockIdx.x, 1);
     const T* table = reinterpret_cast<const T*>(a.table);
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
         }
     }
     if (tid == 0) PVD_T(blockIdx.x, 11);
+    if (tid == 0) weights_ready(p);  // a CTA without tiles must not exit under its own in-flight bulk copy
     tc5::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 128);
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
                                                         __half* __restrict__ dx_out, float* __restrict__ grad_table,
                                                         float* __restrict__ gw, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, wbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelInfo lv[16];
     uint8_t* smw = smem;                        // 20480
@@ -283,16 +286,18 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
     // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
     if (tid == 0) PVD_T(2048u + blockIdx.x, 0);
-    stage_weights(smw, a.wblob);
-    level_info_init(lv, a.offsets, a.L, a.S, a.H);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
+        tc5::mbar_init(&wbar, 1);
         tc5::mbar_fence_init();
+        stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile's rows are loaded
     }
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
     tc5::fence_before_sync();
     __syncthreads();
     tc5::fence_after_sync();
     Pipe p{&bar, 0u, tmem_base_s, status};
+    p.wbar = &wbar;
     p.trec = 2048u + blockIdx.x;  // PVD_TRACE timeline record of this CTA (the last tile it processes wins)
     if (tid == 0) PVD_T(p.trec, 1);
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float
         }
     }
     if (tid == 0) PVD_T(p.trec, 13);
+    if (tid == 0) weights_ready(p);  // a CTA without tiles must not exit under its own in-flight bulk copy
     // ---- weight gradients leave the SM once per CTA
     tc5::fence_before_sync();
     __syncthreads();

@@ -31,16 +31,6 @@ constexpr uint32_t kMlpBiasOff = kMlpChunks * kMlpChunkBytes + kMlpL7Bytes;
 constexpr uint32_t kMlpBiasBytes = 8 * 256 * 4;
 static_assert(kMlpBiasOff + kMlpBiasBytes == PVD_MLP_WBLOB_BYTES, "mlp blob size");
 
-// TMA bulk copy global -> shared, completion signalled on an mbarrier as transaction bytes
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc5::smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr),
-                 "l"(src), "r"(bytes), "r"(tc5::smem_u32(bar))
-                 : "memory");
-}
-
 struct MlpArgs {
     const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
     const uint8_t* tail_blob;  // PVD_FIELD_WBLOB_BYTES (sigma_net / color_net)
@@ -105,8 +95,8 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
             if (!tc5::mbar_wait(&bar_empty[buf], ((issued >> 1) - 1u) & 1u)) atomicExch(status, 1);
         }
         const uint32_t bytes = (c < kMlpChunks) ? kMlpChunkBytes : kMlpL7Bytes;
-        mbar_expect_tx(&bar_full[buf], bytes);
-        bulk_g2s(tc5::smem_u32(WB + buf * kMlpChunkBytes), a.wblob + (size_t)c * kMlpChunkBytes, bytes, &bar_full[buf]);
+        tc5::mbar_expect_tx(&bar_full[buf], bytes);
+        tc5::bulk_g2s(tc5::smem_u32(WB + buf * kMlpChunkBytes), a.wblob + (size_t)c * kMlpChunkBytes, bytes, &bar_full[buf]);
         ++issued;
     };
     auto wait_full = [&]() -> uint32_t {

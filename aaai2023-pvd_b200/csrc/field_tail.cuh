@@ -51,6 +51,7 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
     operands_ready();
     if (tid == 0) {
         tc5::fence_after_sync();
+        weights_ready(p);
         issue_fwd(p.tmem + kD, tc5::smem_u32(X), 32, sw + kWB1, 64, 64);
         tc5::mma_commit(p.bar);
     }

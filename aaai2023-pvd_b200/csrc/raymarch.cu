@@ -787,6 +787,145 @@ __global__ void __launch_bounds__(32) k_composite_bwd(const float* __restrict__ 
 #endif
 }
 
+// Training composite, forward AND backward in one launch, for the MSE criterion (the engine's path): the warp that owns a ray runs
+// the forward sweep (raymarching.cu:505-579), derives d(loss)/d(image, weights_sum) from the finished pixel exactly as
+// k_composite_bwd<true> does, and sweeps the ray again for the sample gradients (raymarching.cu:597-697) -- the second sweep hits
+// L1/L2, and one launch, one set of header loads and one kernel tail disappear from the step's critical path.
+__global__ void __launch_bounds__(32) k_composite_train_mse(const float* __restrict__ gt_rgb, const float* __restrict__ bg,
+                                                           float loss_scale, const float* __restrict__ sigmas,
+                                                           const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                                           const int32_t* __restrict__ rays, uint32_t M, uint32_t N,
+                                                           float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                           float* __restrict__ image, float* __restrict__ grad_sigmas,
+                                                           float* __restrict__ grad_rgbs, float* __restrict__ loss_out) {
+    const uint32_t n = blockIdx.x;
+    const uint32_t lane = threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n];
+    const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    const bool skip = (cnt == 0 || offset + cnt >= M);  // raymarching.cu:525-532, :629
+    const float gt0 = gt_rgb[3 * (size_t)index], gt1 = gt_rgb[3 * (size_t)index + 1], gt2 = gt_rgb[3 * (size_t)index + 2];
+    const float bgr = bg[0], bgg = bg[1], bgb = bg[2];
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (!skip) {
+        float T = 1.0f, tcarry = 0.0f;
+        for (uint32_t base0 = 0; base0 < cnt; base0 += 128) {
+            float sg[4], c0[4], c1[4], c2[4];
+            float2 dl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = base0 + 32u * q + lane;
+                const bool ok = i < cnt;
+                const size_t row = (size_t)offset + (ok ? i : 0);
+                sg[q] = ok ? __ldg(sigmas + row) : 0.0f;
+                dl[q] = ok ? __ldg(reinterpret_cast<const float2*>(deltas + 2 * row)) : make_float2(0.f, 0.f);
+                c0[q] = ok ? __ldg(rgbs + 3 * row) : 0.f;
+                c1[q] = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+                c2[q] = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t base = base0 + 32u * q;
+                if (base >= cnt) break;  // warp-uniform
+                const bool ok = base + lane < cnt;
+                const float alpha = ok ? 1.0f - __expf(-sg[q] * dl[q].x) : 0.0f;
+                const float om = 1.0f - alpha;
+                const float incl = warp_scan_mul(om, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                const float w = alpha * (T * excl);
+                const float tin = tcarry + warp_scan_add(dl[q].y, lane);
+                if (ok) {
+                    r += w * c0[q];
+                    g += w * c1[q];
+                    b += w * c2[q];
+                    d += w * tin;
+                    ws += w;
+                }
+                T *= __shfl_sync(0xffffffffu, incl, 31);
+                tcarry = __shfl_sync(0xffffffffu, tin, 31);
+            }
+        }
+        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    }
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[3 * (size_t)index] = r;
+        image[3 * (size_t)index + 1] = g;
+        image[3 * (size_t)index + 2] = b;
+    }
+    // ---- loss and its gradient w.r.t. the pixel (renderer.py:445 background mix, MSELoss over N x 3 values)
+    const float r_final = r, g_final = g, b_final = b, ws_final = ws;
+    const float om_f = 1.0f - ws_final;
+    const float dr = r_final + om_f * bgr - gt0, dg = g_final + om_f * bgg - gt1, db = b_final + om_f * bgb - gt2;
+    const float k = 2.0f / (3.0f * (float)N);
+    if (lane == 0) {
+        float* slot = loss_out + 2u * (n % PVD_LOSS_SLOTS);
+        atomicAdd(slot, (dr * dr + dg * dg + db * db) / (3.0f * (float)N));
+        if (!skip) atomicAdd(slot + 1, 1.0f);
+    }
+    const float gr = k * dr * loss_scale, gg = k * dg * loss_scale, gb = k * db * loss_scale;
+    const float gws = -(gr * bgr + gg * bgg + gb * bgb);
+    if (skip) {  // rows below M of a ray that does not fit are still read by the field backward: clear them
+        for (uint32_t i = offset + lane; i < min(offset + cnt, M); i += 32) {
+            grad_sigmas[i] = 0.0f;
+            grad_rgbs[3 * (size_t)i] = 0.0f;
+            grad_rgbs[3 * (size_t)i + 1] = 0.0f;
+            grad_rgbs[3 * (size_t)i + 2] = 0.0f;
+        }
+        return;
+    }
+    float T = 1.0f, rc = 0, gc = 0, bc = 0, wc = 0;
+    for (uint32_t base0 = 0; base0 < cnt; base0 += 128) {
+        float sgv[4], d0v[4], c0v[4], c1v[4], c2v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = base0 + 32u * q + lane;
+            const bool ok = i < cnt;
+            const size_t row = (size_t)offset + (ok ? i : 0);
+            sgv[q] = ok ? __ldg(sigmas + row) : 0.0f;
+            d0v[q] = ok ? __ldg(deltas + 2 * row) : 0.0f;
+            c0v[q] = ok ? __ldg(rgbs + 3 * row) : 0.f;
+            c1v[q] = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
+            c2v[q] = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t base = base0 + 32u * q;
+            if (base >= cnt) break;  // warp-uniform
+            const uint32_t i = base + lane;
+            const bool ok = i < cnt;
+            const size_t row = (size_t)offset + (ok ? i : 0);
+            const float sigma = sgv[q], d0 = d0v[q], cr = c0v[q], cg = c1v[q], cb = c2v[q];
+            const float alpha = ok ? 1.0f - __expf(-sigma * d0) : 0.0f;
+            const float om = 1.0f - alpha;
+            const float incl = warp_scan_mul(om, lane);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const float w = alpha * (T * excl);
+            const float T_after = T * incl;
+            const float r_run = rc + warp_scan_add(w * cr, lane);
+            const float g_run = gc + warp_scan_add(w * cg, lane);
+            const float b_run = bc + warp_scan_add(w * cb, lane);
+            const float w_run = wc + warp_scan_add(w, lane);
+            if (ok) {
+                grad_rgbs[3 * row] = gr * w;
+                grad_rgbs[3 * row + 1] = gg * w;
+                grad_rgbs[3 * row + 2] = gb * w;
+                grad_sigmas[row] = d0 * (gr * (T_after * cr - (r_final - r_run)) + gg * (T_after * cg - (g_final - g_run)) +
+                                         gb * (T_after * cb - (b_final - b_run)) + gws * (T_after - (ws_final - w_run)));
+            }
+            T *= __shfl_sync(0xffffffffu, incl, 31);
+            rc = __shfl_sync(0xffffffffu, r_run, 31);
+            gc = __shfl_sync(0xffffffffu, g_run, 31);
+            bc = __shfl_sync(0xffffffffu, b_run, 31);
+            wc = __shfl_sync(0xffffffffu, w_run, 31);
+        }
+    }
+}
+
 // =============================================================================================
 // inference kernels: one thread per alive ray, n_step <= 8 samples per call
 // =============================================================================================
@@ -1092,6 +1231,19 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
     k_composite_bwd<true><<<N, 32, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, sigmas, rgbs, deltas, rays,
                                                                             weights_sum, image, M, N, grad_sigmas, grad_rgbs,
                                                                             loss_scale, loss_out);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_composite_rays_train_mse(const float* gt_rgb, const float* bg_color, float loss_scale, const float* sigmas,
+                                 const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                 float* weights_sum, float* depth, float* image, float* grad_sigmas, float* grad_rgbs,
+                                 float* loss_out, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(gt_rgb && bg_color && sigmas && rgbs && deltas && rays && weights_sum && depth && image && grad_sigmas &&
+                grad_rgbs && loss_out);
+    k_composite_train_mse<<<N, 32, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, loss_scale, sigmas, rgbs, deltas, rays, M, N,
+                                                              weights_sum, depth, image, grad_sigmas, grad_rgbs, loss_out);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

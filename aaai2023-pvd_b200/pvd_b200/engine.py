@@ -104,8 +104,8 @@ class HashTrainEngine:
         self._counts = []
         self._alloc_samples(N * 32)
         self._coarse_valid = False
-        # kernels of libpvd_b200.so only (torch memsets not counted): count, scan, expand, fwd, composite fwd/bwd, MLP bwd, scatter
-        self.launches_per_step = (10 if SPLIT_HALVES else 8) if fused.SPLIT_SCATTER else 7
+        # kernels of libpvd_b200.so only (torch memsets not counted): count, scan, expand, fwd, composite (fwd+bwd), MLP bwd, scatter
+        self.launches_per_step = (9 if SPLIT_HALVES else 7) if fused.SPLIT_SCATTER else 6
 
     # ------------------------------------------------------------------ buffers sized by M
     def _alloc_samples(self, M: int):
@@ -161,19 +161,16 @@ class HashTrainEngine:
                                                      nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(rs.deltas), st))
 
     def _forward(self, st, rs, M, M_drop):
-        l = nv.lib()
-        nv.check(l.pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), _u32(M), nv.ptr(self.sigmas),
-                                          nv.ptr(self.rgbs), nv.ptr(self.enc), None, nv.ptr(self.status), st))
-        nv.check(l.pvd_composite_rays_train_forward(nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(rs.deltas), nv.ptr(rs.rays),
-                                                    _u32(M_drop), _u32(self.N), nv.ptr(self.weights_sum), nv.ptr(self.depth),
-                                                    nv.ptr(self.image), st))
+        nv.check(nv.lib().pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), _u32(M), nv.ptr(self.sigmas),
+                                                 nv.ptr(self.rgbs), nv.ptr(self.enc), None, nv.ptr(self.status), st))
 
     def _loss_backward(self, st, rs, M_drop):
-        # grad_sigmas / grad_rgbs need no clearing: every row below n_valid is written by the composite backward
-        nv.check(nv.lib().pvd_composite_rays_train_backward_mse(
+        """composite forward + MSE + composite backward in one launch.  grad_sigmas / grad_rgbs need no clearing: every row below
+        n_valid is written here."""
+        nv.check(nv.lib().pvd_composite_rays_train_mse(
             nv.ptr(rs.gt), nv.ptr(self.bg), _f32(self.loss_scale), nv.ptr(self.sigmas), nv.ptr(self.rgbs), nv.ptr(rs.deltas),
-            nv.ptr(rs.rays), nv.ptr(self.weights_sum), nv.ptr(self.image), _u32(M_drop), _u32(self.N), nv.ptr(self.grad_sigmas),
-            nv.ptr(self.grad_rgbs), nv.ptr(self.loss_slots), st))
+            nv.ptr(rs.rays), _u32(M_drop), _u32(self.N), nv.ptr(self.weights_sum), nv.ptr(self.depth), nv.ptr(self.image),
+            nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss_slots), st))
 
     def _field_backward(self, st, rs, M, cur=None):
         """MLP backward + table-gradient scatter.  With a stream handle for the main branch (`cur`), the rows are cut in two

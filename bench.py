@@ -385,11 +385,9 @@ def time_phases(eng):
     nv.check(l.pvd_hash_field_forward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), u32(M), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
                                       nv.ptr(eng.enc), None, nv.ptr(eng.status), st))
     e[2].record()
-    nv.check(l.pvd_composite_rays_train_forward(nv.ptr(eng.sigmas), nv.ptr(eng.rgbs), nv.ptr(eng.deltas), nv.ptr(eng.rays), u32(M), u32(N),
-                                                nv.ptr(eng.weights_sum), nv.ptr(eng.depth), nv.ptr(eng.image), st))
-    nv.check(l.pvd_composite_rays_train_backward_mse(nv.ptr(eng.gt), nv.ptr(eng.bg), f32(eng.loss_scale), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
-                                                     nv.ptr(eng.deltas), nv.ptr(eng.rays), nv.ptr(eng.weights_sum), nv.ptr(eng.image), u32(M),
-                                                     u32(N), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss_slots), st))
+    nv.check(l.pvd_composite_rays_train_mse(nv.ptr(eng.gt), nv.ptr(eng.bg), f32(eng.loss_scale), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
+                                            nv.ptr(eng.deltas), nv.ptr(eng.rays), u32(M), u32(N), nv.ptr(eng.weights_sum), nv.ptr(eng.depth),
+                                            nv.ptr(eng.image), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss_slots), st))
     e[3].record()
     nv.check(l.pvd_hash_field_backward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.enc), nv.ptr(eng.grad_sigmas),
                                        nv.ptr(eng.grad_rgbs), None, u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),

@@ -84,6 +84,13 @@ int pvd_composite_rays_train_backward_mse(const float* gt_rgb, const float* bg_c
                                           const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                           float* grad_sigmas, float* grad_rgbs, float* loss_out, void* stream);
 
+/* composite_rays_train_forward + _backward_mse in ONE launch (same arithmetic, same outputs): the warp that owns a ray sweeps it
+ * forward, forms the pixel's loss gradient, and sweeps it again for the sample gradients. */
+int pvd_composite_rays_train_mse(const float* gt_rgb, const float* bg_color, float loss_scale, const float* sigmas,
+                                 const float* rgbs, const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                 float* weights_sum, float* depth, float* image, float* grad_sigmas, float* grad_rgbs,
+                                 float* loss_out, void* stream);
+
 /* The same backward restricted to rows [row0, row0 + rows) of the sample buffers (all pointers are the buffers' bases), and split
  * in its two kernels so that a caller can run them on different streams: PVD_BWD_MLP = tcgen05 MLP backward, leaves d(encoding) in
  * dx_ws (required here); PVD_BWD_SCATTER = reductions of dx_ws into grad_table.  Halving the rows and issuing
