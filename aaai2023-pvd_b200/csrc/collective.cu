@@ -1,0 +1,85 @@
+// collective.cu -- the one exchange step of the multi-GPU path: sum of the table gradient over the ranks.
+//
+// Rays shard across GPUs, parameters are replicated, so the only collective of a training step is the all-reduce of the hash
+// table's gradient (42 MB fp32, 21 MB as the fp16 payload the reference accumulates these gradients in, gridencoder.cu:299-305).
+// NCCL needs 67 us for those 21 MB on two B200 (scripts/micro/allreduce_probe.py) -- of the order of the whole compute step.
+// On an NVSwitch system the reduction can be done BY THE SWITCH: the payload lives in a symmetric buffer that is also mapped
+// through a multicast address; rank r owns 1/W of it, pulls the sum of all ranks' copies of its shard with
+// multimem.ld_reduce (fp16 operands, fp32 accumulation in the switch) and pushes the result back to every rank with
+// multimem.st.  Each link carries the shard once in and (W-1)/W... once out: two passes over 1/W of the data per GPU instead of
+// NCCL's ring/tree steps.  MEASURED on 2 x B200 (scripts/micro/exchange_probe.py): this kernel 68 us for a 10.6 MB shard + two
+// 13 us barriers + 11 us cast = 106 us, NCCL (cast + all-reduce) 89 us -- so NCCL stays the default and this path is opt-in
+// (bench.py --grad-comm multimem) until it is tuned on more than two GPUs.  The barriers before (all payloads written) and after (all results visible) are the caller's
+// (torch symmetric-memory signal pads: pvd_b200/dist.py).
+#include "common.cuh"
+#include "../../include/pvd_b200_fused.h"
+
+namespace pvd {
+
+__global__ void __launch_bounds__(256) k_multimem_allreduce_f16(__half* __restrict__ mc, uint64_t first_vec, uint64_t n_vec) {
+    // four 16-byte switch reductions in flight per thread: the round trip through the NVSwitch is several microseconds
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += 4 * stride) {
+        uint32_t v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < n_vec) {
+                __half* p = mc + (first_vec + i) * 8;  // 8 halves = 16 bytes per lane
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                             : "l"(p)
+                             : "memory");
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < n_vec) {
+                __half* p = mc + (first_vec + i) * 8;
+                asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v[u][0]), "r"(v[u][1]),
+                             "r"(v[u][2]), "r"(v[u][3])
+                             : "memory");
+            }
+        }
+    }
+}
+
+// fp32 gradient -> fp16 payload, and the inverse
+__global__ void __launch_bounds__(256) k_f32_to_f16(const float4* __restrict__ src, uint2* __restrict__ dst, uint64_t n_vec4) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+}
+
+}  // namespace pvd
+
+using namespace pvd;
+
+extern "C" {
+
+int pvd_multimem_allreduce_f16(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, void* stream) {
+    if (elem_count == 0) return PVD_OK;
+    PVD_REQUIRE(multicast_ptr != nullptr && (elem_offset % 8u) == 0 && (elem_count % 8u) == 0);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(multicast_ptr) & 15u) == 0);
+    const uint64_t n_vec = elem_count / 8u;
+    const uint32_t grid = (uint32_t)min((unsigned long long)((n_vec + 1023u) / 1024u), 148ull * 8ull);
+    k_multimem_allreduce_f16<<<grid, 256, 0, (cudaStream_t)stream>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream) {
+    if (elem_count == 0) return PVD_OK;
+    PVD_REQUIRE(src && dst && (elem_count % 4u) == 0);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0);
+    const uint64_t n = elem_count / 4u;
+    const uint32_t grid = (uint32_t)min((unsigned long long)((n + 255u) / 256u), 148ull * 16ull);
+    k_f32_to_f16<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint2*)dst, n);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+}  // extern "C"

@@ -79,3 +79,66 @@ class ShardedNormL2(torch.autograd.Function):
 
 def sharded_norm_l2(x, group=None):
     return ShardedNormL2.apply(x, group)
+
+
+class TableGradExchange:
+    """The per-step gradient exchange of the ray-sharded training path: sum over ranks of the hash table's gradient (fp16
+    payload) and of the small MLP-gradient workspace (fp32).
+
+    Fast path (NVSwitch, CUDA ranks): the payload lives in a torch symmetric-memory buffer that is also mapped through a
+    multicast address; after the cast each rank reduces ITS 1/W of the buffer in the switch with `pvd_multimem_allreduce_f16`
+    (multimem.ld_reduce / multimem.st, csrc/collective.cu) between two signal-pad barriers.  The small fp32 workspace goes
+    through NCCL on a side stream at the same time.  Anything that does not set up (no NVLS, an older torch, one GPU) falls back
+    to NCCL for both, with the same result layout: `self.payload` holds the reduced fp16 table gradient.
+    """
+
+    def __init__(self, grad_table: torch.Tensor, small: torch.Tensor, mode: str = "auto", group=None):
+        import ctypes as C
+        self._C = C
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = grad_table.numel()
+        self.small = small
+        self.grad_table = grad_table
+        self.kind = "nccl"
+        self.why = ""
+        self._side = torch.cuda.Stream(device=grad_table.device)
+        self.payload = None
+        if mode in ("auto", "multimem") and self.world > 1 and self.n % 8 == 0:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(self.n, dtype=torch.float16, device=grad_table.device)
+                hdl = symm.rendezvous(buf, self.group.group_name)
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                if mc == 0:
+                    raise RuntimeError("no multicast mapping (NVLS unavailable)")
+                self.payload, self._hdl, self._mc = buf, hdl, mc
+                vecs = self.n // 8
+                lo = (vecs * self.rank) // self.world
+                hi = (vecs * (self.rank + 1)) // self.world
+                self._off, self._cnt = 8 * lo, 8 * (hi - lo)
+                self.kind = "multimem"
+            except Exception as ex:  # noqa: BLE001  (any failure: NCCL carries the exchange)
+                self.why = repr(ex)[:160]
+                if mode == "multimem":
+                    raise
+        if self.payload is None:
+            self.payload = torch.empty(self.n, dtype=torch.float16, device=grad_table.device)
+
+    def __call__(self):
+        from . import _native as nv
+        C = self._C
+        cur = torch.cuda.current_stream(self.grad_table.device)
+        st = C.c_void_p(cur.cuda_stream)
+        # the small fp32 workspace: NCCL on a side stream, concurrent with the table exchange
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.small, group=self.group)
+        nv.check(nv.lib().pvd_cast_f32_to_f16(nv.ptr(self.grad_table), nv.ptr(self.payload), C.c_uint64(self.n), st))
+        if self.kind == "multimem":
+            self._hdl.barrier(channel=0)     # every rank's payload is written
+            nv.check(nv.lib().pvd_multimem_allreduce_f16(C.c_void_p(self._mc), C.c_uint64(self._off), C.c_uint64(self._cnt), st))
+            self._hdl.barrier(channel=1)     # every rank's shard of sums is visible everywhere
+        else:
+            dist.all_reduce(self.payload, group=self.group)
+        cur.wait_stream(self._side)

@@ -190,27 +190,43 @@ def run_ours(args, rank, world, local):
         else:
             eng.step()
 
-    grad_comm = None
-    if world > 1 and args.grad_comm == "fp16":
-        grad_comm = torch.empty(eng.grad_table.shape, dtype=torch.float16, device=dev)
+    exchange = None
+    if world > 1 and args.grad_comm != "fp32":
+        from pvd_b200.dist import TableGradExchange
+        exchange = TableGradExchange(eng.grad_table.view(-1), eng.gw_ws, mode={"fp16": "nccl", "multimem": "auto"}[args.grad_comm])
+        if rank == 0:
+            print(f"[bench] gradient exchange: {exchange.kind} {exchange.why}", file=sys.stderr)
 
     def allreduce():
-        # one gradient exchange per step.  fp16 payload (default for N > 1): the table gradient is cast once (42 MB read, 21 MB
-        # write) and all-reduced in half precision -- the precision the reference ACCUMULATES these gradients in
-        # (gridencoder.cu:299-305) -- which halves the bytes crossing NVLink; the small MLP gradients stay fp32.
+        # one gradient exchange per step.  fp16 payload (default for N > 1): the table gradient is cast once and summed in half
+        # precision -- the precision the reference ACCUMULATES these gradients in (gridencoder.cu:299-305); on NVSwitch the sum is
+        # done by the switch (multimem, csrc/collective.cu), else by NCCL.  The small MLP gradients stay fp32 (NCCL, side stream).
         if world > 1:
-            if grad_comm is not None:
-                grad_comm.copy_(eng.grad_table)
-                dist.all_reduce(grad_comm)
+            if exchange is not None:
+                exchange()
             else:
                 dist.all_reduce(eng.grad_table)
-            dist.all_reduce(eng.gw_ws)
+                dist.all_reduce(eng.gw_ws)
 
     # ---- 16 sizing steps (the reference's mean_count warm-up), then W untimed steps at the steady-state M
     for i in range(16):
         load(i)
         eng.step(warmup=True)
     eng.finish_warmup()
+    if exchange is not None and exchange.kind == "multimem":
+        # self-check of the in-switch reduction against NCCL on this step's real gradients; any rank's mismatch -> all fall back
+        ref = eng.grad_table.view(-1).to(torch.float16)
+        dist.all_reduce(ref)
+        exchange()
+        torch.cuda.synchronize()
+        err = (exchange.payload.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-20)
+        bad = torch.tensor([0.0 if float(err) < 2e-2 else 1.0], device=dev)
+        dist.all_reduce(bad)
+        if float(bad.item()) > 0:
+            exchange.kind, exchange.why = "nccl", f"multimem self-check failed (rel err {float(err):.3g})"
+        if rank == 0:
+            print(f"[bench] multimem exchange self-check: max rel err {float(err):.3g} -> using {exchange.kind}", file=sys.stderr)
+        del ref
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     serial_ms = None
     if not args.no_graph:
@@ -345,7 +361,7 @@ def run_ours(args, rank, world, local):
                    "rays_per_gpu": args.rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
                    "precision": "fp16 table + fp16 tcgen05 MLP, fp32 accumulate / composite / gradients", "loss_scale": 65536,
                    "parallelism": (f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step "
-                                   f"({args.grad_comm} table-gradient payload)") if world > 1 else "single GPU",
+                                   f"({'fp32 NCCL' if exchange is None else 'fp16 payload, ' + ('in-switch multimem reduction' if exchange.kind == 'multimem' else 'NCCL')})") if world > 1 else "single GPU",
                    "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch beside the field "
                               "backward of batch i (one batch of look-ahead, double-buffered ray sets)") if pipelined else
                              ("one CUDA graph per step" if use_graph else "eager (one launch per kernel)"),
@@ -490,7 +506,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-comm", default="fp16", choices=["fp16", "fp32"], help="payload dtype of the table-gradient all-reduce (N > 1)")
+    ap.add_argument("--grad-comm", default="fp16", choices=["multimem", "fp16", "fp32"], help="table-gradient exchange for N > 1: fp16 payload over NCCL (default), fp16 payload reduced in the NVSwitch (multimem; measured slower on 2 GPUs: 106 vs 89 us), or fp32 over NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="serial step graph: do not overlap the next batch's march with the backward")
     args = ap.parse_args()

@@ -175,6 +175,15 @@ int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biase
 int pvd_mlp_field_forward(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
                           float* feat16, int32_t* status, void* stream);
 
+/* ---- multi-GPU: the one exchange step (rays shard, parameters replicate) ------------------------------------------
+ * Sum over all ranks of elements [elem_offset, elem_offset + elem_count) of a symmetric fp16 buffer, done in the NVSwitch:
+ * `multicast_ptr` is the multicast mapping of the buffer (torch symmetric memory: handle.multicast_ptr); the range is read with
+ * multimem.ld_reduce (fp32 accumulation) and written back to every rank with multimem.st.  Rank r calls it on its own 1/W of the
+ * buffer, between two all-rank barriers supplied by the caller.  Offsets and counts in elements, multiples of 8. */
+int pvd_multimem_allreduce_f16(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, void* stream);
+/* fp32 gradient -> fp16 exchange payload (elem_count multiple of 4, 16-byte aligned source) */
+int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
