@@ -262,4 +262,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// inclusive scans over the warp
+__device__ __forceinline__ float warp_scan_mul(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += u;
+    }
+    return v;
+}
+
 }  // namespace pvd

@@ -583,24 +583,6 @@ struct Chunk {
     float w, T_after, r, g, b, tsum;
 };
 
-// inclusive scans over the warp
-__device__ __forceinline__ float warp_scan_mul(float v, uint32_t lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float u = __shfl_up_sync(0xffffffffu, v, o);
-        if ((int)lane >= o) v *= u;
-    }
-    return v;
-}
-__device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float u = __shfl_up_sync(0xffffffffu, v, o);
-        if ((int)lane >= o) v += u;
-    }
-    return v;
-}
-
 __global__ void __launch_bounds__(32) k_composite_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                       const float* __restrict__ deltas, const int32_t* __restrict__ rays,
                                                       uint32_t M, uint32_t N, float* __restrict__ weights_sum,

@@ -2,11 +2,13 @@
 on caller-provided parameters, with pre-allocated device buffers, no host synchronisation and no autograd graph.
 
 This is what `NeRFRenderer.run_cuda` (training branch, distill_mutual/renderer.py:359-448) + `Trainer.train_step`'s
-criterion (just_train_tea/utils.py:841-846) + `loss.backward()` amount to for a "hash" model, expressed as 10 kernel
-launches on one stream:
+criterion (just_train_tea/utils.py:841-846) + `loss.backward()` amount to for a "hash" or "vm" model, expressed as 6-7 kernel
+launches on one stream (+ two memsets of the gradient accumulators on a side branch):
 
-    near_far | march count | offset scan | sample expand | field fwd | composite fwd | composite bwd (+MSE) | field bwd
-    (+ two memsets of the gradient accumulators)
+    march count (+ near/far) | offset scan | sample expand | field fwd | composite fwd + MSE + composite bwd | field bwd (| scatter)
+
+`FieldTrainEngine` is that step for one model (HashTrainEngine / VMTrainEngine); `PairDistillEngine` is the distillation step of
+`main_distill_mutual.py` for a (teacher, student) pair evaluated at the SAME samples (distill_mutual/utils.py:954-1189).
 
 Two ray sets (inputs + march outputs) are kept so that the march of batch i+1 -- a latency-bound kernel chain that depends on
 nothing the model computes -- can run BESIDE the field backward of batch i (`capture_pipelined` / `replay_pipelined`: the
@@ -26,7 +28,7 @@ import numpy as np
 import torch
 
 from . import _native as nv
-from . import fused
+from . import field_ops, fused
 
 _u32, _f32 = C.c_uint32, C.c_float
 # opt-in experiment (measured SLOWER on B200, 0.129 vs 0.120 ms/step: the full-occupancy scatter CTAs crowd out the MLP CTAs of the
@@ -62,15 +64,17 @@ def _set_attr(name):
     return property(get, put)
 
 
-class HashTrainEngine:
+class FieldTrainEngine:
+    """Training from images of ONE model of type hash or vm (`main_just_train_tea.py`; BASELINE configs 2 and 3): MSE against
+    gt_rgb (just_train_tea/utils.py:841-846), plus l1_reg_weight * density_loss() for vm models (:843-844)."""
     # the "current" ray set is what step() and every single-set accessor works on
     rays_o, rays_d, gt = _set_attr("rays_o"), _set_attr("rays_d"), _set_attr("gt")
     nears, fars, rays, counter = _set_attr("nears"), _set_attr("fars"), _set_attr("rays"), _set_attr("counter")
     xyzs, dirs, deltas = _set_attr("xyzs"), _set_attr("dirs"), _set_attr("deltas")
 
-    def __init__(self, field: "fused.HashNeRFField", bitfield: torch.Tensor, n_rays: int, bound: float = 1.0, cascade: int = 1,
+    def __init__(self, field, bitfield: torch.Tensor, n_rays: int, bound: float = 1.0, cascade: int = 1,
                  grid_size: int = 128, min_near: float = 0.2, max_steps: int = 1024, dt_gamma: float = 0.0, bg_color=(1.0, 1.0, 1.0),
-                 loss_scale: float = 1.0, density_scale: float = 1.0, device="cuda"):
+                 loss_scale: float = 1.0, density_scale: float = 1.0, l1_reg_weight: float = 0.0, device="cuda"):
         self.field = field
         self.dev = torch.device(device)
         self.N = int(n_rays)
@@ -78,6 +82,7 @@ class HashTrainEngine:
         self.min_near, self.max_steps, self.dt_gamma = float(min_near), int(max_steps), float(dt_gamma)
         self.loss_scale = float(loss_scale)
         self.density_scale = float(density_scale)
+        self.l1_reg_weight = float(l1_reg_weight)
         self.bitfield = bitfield.to(self.dev).contiguous()
         d = self.dev
         N = self.N
@@ -85,11 +90,8 @@ class HashTrainEngine:
         self.bg = torch.tensor(list(bg_color), dtype=torch.float32, device=d)
         self.sets = [_RaySet(N, d), _RaySet(N, d)]
         self.cur = 0
-        # what must be zero before a backward lives in ONE buffer (one memset node): loss slots [64][2] f32 | gw_ws
-        self._zeros = torch.zeros(2 * fused.LOSS_SLOTS + fused.GW_WS_FLOATS, dtype=torch.float32, device=d)
-        self.loss_slots = self._zeros[0:2 * fused.LOSS_SLOTS]   # PVD_LOSS_SLOTS pairs (loss, rays); see `loss`
-        self.gw_ws = self._zeros[2 * fused.LOSS_SLOTS:]
-        self._side = torch.cuda.Stream(device=d)    # table-gradient memset
+        self._init_small_buffers()
+        self._side = torch.cuda.Stream(device=d)    # parameter-gradient memset
         self._side2 = torch.cuda.Stream(device=d)   # march of the next batch (pipelined mode)
         self._side3 = torch.cuda.Stream(device=d)   # table-gradient scatter beside the MLP backward of the other half
         self.ws_march = torch.empty(int(nv.lib().pvd_march_rays_train_workspace_words(N, self.max_steps)), dtype=torch.int32, device=d)
@@ -97,15 +99,45 @@ class HashTrainEngine:
         self.depth = torch.empty(N, device=d)
         self.image = torch.empty(N, 3, device=d)
         self.status = torch.zeros(1, dtype=torch.int32, device=d)
-        emb = field.encoder.embeddings
-        self.grad_table = torch.zeros(emb.shape, dtype=torch.float32, device=d)
+        self._init_fields()
         self.M = 0
         self.mean_count = 0
         self._counts = []
         self._alloc_samples(N * 32)
         self._coarse_valid = False
-        # kernels of libpvd_b200.so only (torch memsets not counted): count, scan, expand, fwd, composite (fwd+bwd), MLP bwd, scatter
-        self.launches_per_step = (9 if SPLIT_HALVES else 7) if fused.SPLIT_SCATTER else 6
+
+    def _init_small_buffers(self):
+        # what must be zero before a backward lives in ONE buffer (one memset node): loss slots [64][2] f32 | gw_ws
+        self._zeros = torch.zeros(2 * fused.LOSS_SLOTS + fused.GW_WS_FLOATS, dtype=torch.float32, device=self.dev)
+        self.loss_slots = self._zeros[0:2 * fused.LOSS_SLOTS]   # PVD_LOSS_SLOTS pairs (loss, rays); see `loss`
+        self.gw_ws = self._zeros[2 * fused.LOSS_SLOTS:]
+
+    def _init_fields(self):
+        self.ops = field_ops.make_ops(self.field, self.dev, trainable=True)
+        # kernels of libpvd_b200.so only (torch memsets not counted): count, scan, expand, fwd, composite (fwd+bwd), field backward
+        self.launches_per_step = 3 + self.ops.kernels_fwd + 1 + self.ops.kernels_bwd
+        if self.ops.kind == "vm" and self.l1_reg_weight:
+            self.launches_per_step += 6
+
+    @property
+    def grad_table(self):   # hash models: the table gradient [entries, 2] fp32
+        return self.ops.grad_table
+
+    @property
+    def enc(self):
+        return self.ops.enc
+
+    @property
+    def dx_ws(self):
+        return self.ops.dx_ws
+
+    @property
+    def cfield(self):
+        return self.ops.cfield
+
+    @property
+    def cfg(self):
+        return self.ops.cfg
 
     # ------------------------------------------------------------------ buffers sized by M
     def _alloc_samples(self, M: int):
@@ -115,10 +147,12 @@ class HashTrainEngine:
             rs.alloc_samples(M, d)
         self.sigmas = torch.empty(M, device=d)
         self.rgbs = torch.empty(M, 3, device=d)
-        self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d)
         self.grad_sigmas = torch.zeros(M, device=d)
         self.grad_rgbs = torch.zeros(M, 3, device=d)
-        self.dx_ws = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=d) if fused.SPLIT_SCATTER else None
+        self._alloc_field_samples(M)
+
+    def _alloc_field_samples(self, M: int):
+        self.ops.alloc(M)
 
     def set_bitfield(self, bitfield: torch.Tensor):
         """New occupancy bitfield (after a density-grid update): the cached coarse rejection mask is invalid."""
@@ -132,15 +166,8 @@ class HashTrainEngine:
         self._alloc_samples(M)
 
     def stage(self):
-        """Refresh the fp16 table shadow and the packed weight tiles if the parameters changed."""
-        f = self.field
-        cfg = f.config()
-        cfg.density_scale = self.density_scale
-        self.cfg = cfg
-        self.table = f._staged.table_for(f.encoder.embeddings, cfg.table_fp16)
-        self.wblob = f._staged.wblob_for((f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight,
-                                          f.color_net[1].weight, f.color_net[2].weight), 2 * cfg.num_levels)
-        self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
+        """Refresh the staged parameters (fp16 table shadow, packed weight tiles) if the parameters changed."""
+        self.ops.stage(self.density_scale)
 
     # ------------------------------------------------------------------ one step
     def _march_count(self, st, rs=None):
@@ -161,10 +188,9 @@ class HashTrainEngine:
                                                      nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(rs.deltas), st))
 
     def _forward(self, st, rs, M, M_drop):
-        nv.check(nv.lib().pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), _u32(M), nv.ptr(self.sigmas),
-                                                 nv.ptr(self.rgbs), nv.ptr(self.enc), None, nv.ptr(self.status), st))
+        self.ops.forward(st, rs.xyzs, rs.dirs, M, self.sigmas, self.rgbs, None, self.status)
 
-    def _loss_backward(self, st, rs, M_drop):
+    def _loss_backward(self, st, rs, M, M_drop):
         """composite forward + MSE + composite backward in one launch.  grad_sigmas / grad_rgbs need no clearing: every row below
         n_valid is written here."""
         nv.check(nv.lib().pvd_composite_rays_train_mse(
@@ -173,17 +199,18 @@ class HashTrainEngine:
             nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.loss_slots), st))
 
     def _field_backward(self, st, rs, M, cur=None):
-        """MLP backward + table-gradient scatter.  With a stream handle for the main branch (`cur`), the rows are cut in two
-        halves: MLP(A), MLP(B) run on the main branch and scatter(A), scatter(B) on a side branch, so that the atomic-bound scatter
-        of one half overlaps the latency-bound tcgen05 chain of the other."""
-        l = nv.lib()
-        args = (C.byref(self.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(self.enc), nv.ptr(self.grad_sigmas),
-                nv.ptr(self.grad_rgbs), None)
-        tail = (nv.ptr(rs.counter), nv.ptr(self.grad_table), nv.ptr(self.gw_ws), nv.ptr(self.dx_ws), nv.ptr(self.status))
+        """Field backward (hash: MLP backward + table-gradient scatter).  With a stream handle for the main branch (`cur`) and
+        PVD_SPLIT_HALVES=1, the rows of a hash model are cut in two halves: MLP(A), MLP(B) run on the main branch and scatter(A),
+        scatter(B) on a side branch, so that the atomic-bound scatter of one half overlaps the latency-bound tcgen05 chain of the other."""
+        ops = self.ops
         Mh = (M // 256) * 128
-        if cur is None or self.dx_ws is None or Mh == 0 or not SPLIT_HALVES:
-            nv.check(l.pvd_hash_field_backward(*args, _u32(M), *tail, st))
+        if ops.kind != "hash" or cur is None or ops.dx_ws is None or Mh == 0 or not SPLIT_HALVES:
+            ops.backward(st, rs.xyzs, rs.dirs, self.grad_sigmas, self.grad_rgbs, None, M, rs.counter, self.gw_ws, self.status)
             return
+        l = nv.lib()
+        args = (C.byref(ops.cfield), nv.ptr(rs.xyzs), nv.ptr(rs.dirs), nv.ptr(ops.enc), nv.ptr(self.grad_sigmas),
+                nv.ptr(self.grad_rgbs), None)
+        tail = (nv.ptr(rs.counter), nv.ptr(ops.grad_table), nv.ptr(self.gw_ws), nv.ptr(ops.dx_ws), nv.ptr(self.status))
         st3 = C.c_void_p(self._side3.cuda_stream)
         nv.check(l.pvd_hash_field_backward_rows(*args, _u32(0), _u32(Mh), *tail, _u32(1), st))
         self._side3.wait_stream(cur)
@@ -195,15 +222,22 @@ class HashTrainEngine:
             nv.check(l.pvd_hash_field_backward_rows(*args, _u32(Mh), _u32(M - Mh), *tail, _u32(2), st3))
         cur.wait_stream(self._side3)
 
+    def _clear_big(self, cur):
+        """fork: the parameter-gradient memset (42 MB hash table / 69 MB vm planes) runs beside the march and the forward (HBM- vs.
+        latency-bound); parameter-only loss terms (the vm L1 penalty) follow it on the same branch."""
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.ops.clear_grads()
+            if self.l1_reg_weight:
+                self.ops.regularise(C.c_void_p(self._side.cuda_stream), self.loss_scale, self.loss_slots, self.l1_reg_weight)
+
     def step(self, warmup: bool = False):
         """Forward + backward for the rays of the current set (self.rays_o / rays_d / gt).  Leaves the loss in self.loss[0]."""
         rs = self.sets[self.cur]
         cur = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(cur.cuda_stream)
         self._zeros.zero_()                    # loss, weight-gradient workspace
-        self._side.wait_stream(cur)            # fork: the 42 MB table-gradient memset runs beside the march (HBM vs. latency bound)
-        with torch.cuda.stream(self._side):
-            self.grad_table.zero_()
+        self._clear_big(cur)
         self._march_count(st, rs)
         if warmup:  # size the sample buffers from this step's count (one D2H read, raymarching.py:277)
             total = int(rs.counter[0].item())
@@ -217,7 +251,7 @@ class HashTrainEngine:
             M = M_drop = self.M
         self._march_write(st, rs, M_drop)
         self._forward(st, rs, M, M_drop)
-        self._loss_backward(st, rs, M_drop)
+        self._loss_backward(st, rs, M, M_drop)
         cur.wait_stream(self._side)            # join: the table gradient is clear before the first reduction into it
         self._field_backward(st, rs, M, cur)
 
@@ -252,9 +286,7 @@ class HashTrainEngine:
         st = C.c_void_p(cur.cuda_stream)
         M = self.M
         self._zeros.zero_()
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
-            self.grad_table.zero_()
+        self._clear_big(cur)
         fork_early = os.environ.get("PVD_PIPE_FORK", "early") == "early"
         if fork_early:
             self._side2.wait_stream(cur)
@@ -263,7 +295,7 @@ class HashTrainEngine:
                 self._march_count(st2, nxt)
                 self._march_write(st2, nxt, M)
         self._forward(st, rs, M, M)
-        self._loss_backward(st, rs, M)
+        self._loss_backward(st, rs, M, M)
         if not fork_early:
             self._side2.wait_stream(cur)
             with torch.cuda.stream(self._side2):
@@ -305,12 +337,144 @@ class HashTrainEngine:
         self._counts = []
 
     def grad_weights(self):
-        f = self.field
-        like = (f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
-        return fused.unpack_wgrads(self.gw_ws, 2 * self.cfg.num_levels, like)
+        """The MLP weight gradients in parameter shapes, reference order (hash: sigma_net.{0,1}, color_net.{0,1,2};
+        vm: basis_mat, color_net.{0,1,2})."""
+        return list(self.ops.weight_grads(self.gw_ws).values())
+
+    def grads(self):
+        """{reference parameter name: gradient} for every trainable parameter of the model."""
+        return self.ops.grads(self.gw_ws)
 
     def final_image(self):
         """pred rgb [N,3] and normalised depth [N] as run_cuda returns them (renderer.py:445-446)."""
         pred = self.image + (1 - self.weights_sum).unsqueeze(-1) * self.bg
         depth = torch.clamp(self.depth - self.nears, min=0) / (self.fars - self.nears + 1e-6)
         return pred, depth
+
+
+class HashTrainEngine(FieldTrainEngine):
+    """hash (INGP) teacher training -- BASELINE configs[1], the configuration bench.py times by default."""
+
+    def __init__(self, field: "fused.HashNeRFField", *a, **k):
+        assert getattr(field, "model_type", None) == "hash"
+        super().__init__(field, *a, **k)
+
+
+class VMTrainEngine(FieldTrainEngine):
+    """vm (TensoRF VM-48) teacher training -- BASELINE configs[2]; `l1_reg_weight` defaults to the reference's 1e-4
+    (main_just_train_tea.py:170)."""
+
+    def __init__(self, field, *a, l1_reg_weight: float = 1e-4, **k):
+        assert getattr(field, "model_type", None) == "vm"
+        super().__init__(field, *a, l1_reg_weight=l1_reg_weight, **k)
+
+
+
+PAIR_SUM_STRIDE = 4   # PVD_PAIR_SUM_STRIDE
+
+
+class PvdPairRates(C.Structure):
+    _fields_ = [("rgb", C.c_float), ("fea", C.c_float), ("color", C.c_float), ("sigma", C.c_float)]
+
+
+class PairDistillEngine(FieldTrainEngine):
+    """The distillation step of `main_distill_mutual.py` (Trainer.train_step, distill_mutual/utils.py:954-1189) for one
+    (teacher, student) pair: the student's rays are marched ONCE, the frozen teacher (hash | mlp | vm) and the student (hash | vm)
+    are queried at the SAME samples back to back (renderer.py:374-394: `inherited_params`), and the normL2 losses
+
+        rate_rgb ||pred_tea - pred_stu|| + rate_fea ||feat_stu - feat_tea|| + rate_color ||color_l|| + rate_sigma ||sigma_l||
+
+    (+ l1_reg_weight * density_loss() for a vm student, :1135-1136) drive the student's backward -- 10 launches, no Python between
+    them, no [M,16] activation ever leaves the device-side buffers.  `stage` follows the reference's schedule: 1 = feature loss
+    only, 2 = + colour and sigma (neither composites, :1046-1108), 3 = everything.  Defaults are the reference's
+    (main_distill_mutual.py:174-178).  BASELINE configs 4 (hash -> vm) and 5 (mlp -> hash).
+    """
+
+    def __init__(self, teacher, student, bitfield: torch.Tensor, n_rays: int, rates=(1.0, 0.002, 0.002, 0.002), stage: int = 3,
+                 l1_reg_weight: float = 1e-4, **kw):
+        self.teacher_field = teacher
+        self.distill_stage = int(stage)
+        r = [float(v) for v in rates]
+        if self.distill_stage == 1:
+            r = [0.0, r[1], 0.0, 0.0]
+        elif self.distill_stage == 2:
+            r[0] = 0.0
+        self.rates = PvdPairRates(*r)
+        if getattr(student, "model_type", None) != "vm" or self.distill_stage != 3:
+            l1_reg_weight = 0.0
+        super().__init__(student, bitfield, n_rays, l1_reg_weight=l1_reg_weight, **kw)
+
+    def _init_small_buffers(self):
+        n_sum = PAIR_SUM_STRIDE * fused.LOSS_SLOTS
+        self._zeros = torch.zeros(n_sum + 2 * fused.LOSS_SLOTS + fused.GW_WS_FLOATS, dtype=torch.float32, device=self.dev)
+        self.pair_sums = self._zeros[0:n_sum]                                  # [64][4]: rgb, feature, colour, sigma sums of squares
+        self.loss_slots = self._zeros[n_sum:n_sum + 2 * fused.LOSS_SLOTS]      # parameter-only terms (vm L1 penalty)
+        self.gw_ws = self._zeros[n_sum + 2 * fused.LOSS_SLOTS:]
+        self.loss_out = torch.zeros(5, dtype=torch.float32, device=self.dev)   # total, ||rgb||, ||fea||, ||color||, ||sigma||
+        self.pred_tea = torch.empty(self.N, 3, device=self.dev)
+
+    def _init_fields(self):
+        self.ops = field_ops.make_ops(self.field, self.dev, trainable=True)
+        self.tea = field_ops.make_ops(self.teacher_field, self.dev, trainable=False)
+        # count, scan, expand, tail | teacher fwd, student fwd | sample_sq, (composite), combine | student bwd
+        self.launches_per_step = 4 + self.tea.kernels_fwd + self.ops.kernels_fwd + (3 if self.distill_stage == 3 else 2) + self.ops.kernels_bwd
+        if self.l1_reg_weight:
+            self.launches_per_step += 6
+
+    def _alloc_field_samples(self, M: int):
+        d = self.dev
+        self.ops.alloc(M)
+        self.tea.alloc(M)
+        self.sigmas_tea = torch.empty(M, device=d)
+        self.rgbs_tea = torch.empty(M, 3, device=d)
+        self.feat_tea = torch.empty(M, 16, device=d)
+        self.feat = torch.empty(M, 16, device=d)
+        self.grad_feat = torch.zeros(M, 16, device=d)
+
+    def stage(self):
+        self.ops.stage(self.density_scale)
+        self.tea.stage(self.density_scale)
+
+    def _march_write(self, st, rs, M_drop):
+        super()._march_write(st, rs, M_drop)
+        # rows no surviving ray owns are zeros in the reference (fresh torch.zeros every call) and both networks see them
+        M = rs.xyzs.shape[0]
+        nv.check(nv.lib().pvd_zero_sample_tail(nv.ptr(rs.rays), nv.ptr(rs.counter), _u32(self.N), _u32(min(M, M_drop)), nv.ptr(rs.xyzs),
+                                               nv.ptr(rs.dirs), nv.ptr(rs.deltas), st))
+
+    def _forward(self, st, rs, M, M_drop):
+        self.tea.forward(st, rs.xyzs, rs.dirs, M, self.sigmas_tea, self.rgbs_tea, self.feat_tea, self.status)
+        self.ops.forward(st, rs.xyzs, rs.dirs, M, self.sigmas, self.rgbs, self.feat, self.status)
+
+    def _loss_backward(self, st, rs, M, M_drop):
+        l = nv.lib()
+        nv.check(l.pvd_pair_sample_sq(nv.ptr(self.feat_tea), nv.ptr(self.feat), nv.ptr(self.rgbs_tea), nv.ptr(self.rgbs), _u32(M),
+                                      nv.ptr(self.pair_sums), st))
+        if self.distill_stage == 3:
+            nv.check(l.pvd_pair_composite(nv.ptr(self.bg), nv.ptr(self.sigmas_tea), nv.ptr(self.rgbs_tea), nv.ptr(self.sigmas),
+                                          nv.ptr(self.rgbs), nv.ptr(rs.deltas), nv.ptr(rs.rays), _u32(M_drop), _u32(self.N),
+                                          nv.ptr(self.pred_tea), nv.ptr(self.weights_sum), nv.ptr(self.depth), nv.ptr(self.image),
+                                          nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.pair_sums), st))
+        nv.check(l.pvd_pair_combine(nv.ptr(self.feat_tea), nv.ptr(self.feat), nv.ptr(self.rgbs_tea), nv.ptr(self.rgbs),
+                                    nv.ptr(self.pair_sums), C.byref(self.rates), _f32(self.loss_scale), _u32(M),
+                                    nv.ptr(rs.counter) if self.distill_stage == 3 else None, nv.ptr(self.grad_sigmas),
+                                    nv.ptr(self.grad_rgbs), nv.ptr(self.grad_feat), nv.ptr(self.loss_out), st))
+
+    def _field_backward(self, st, rs, M, cur=None):
+        # all M rows: the per-sample losses cover the padding rows too
+        self.ops.backward(st, rs.xyzs, rs.dirs, self.grad_sigmas, self.grad_rgbs, self.grad_feat, M, None, self.gw_ws, self.status)
+
+    @property
+    def loss(self):
+        """[total loss (un-scaled, L1 penalty included), rays] -- same shape of answer as FieldTrainEngine.loss."""
+        reg = self.loss_slots.view(fused.LOSS_SLOTS, 2).sum(0)[0]
+        return torch.stack([self.loss_out[0] + reg, torch.tensor(float(self.N), device=self.dev)])
+
+    def loss_terms(self):
+        """The un-weighted norms the reference's trainer logs: rgb, feature, colour, sigma (utils.py:1177-1187)."""
+        return {k: float(v) for k, v in zip(("rgb", "fea", "color", "sigma"), self.loss_out[1:5].tolist())}
+
+    def final_images(self):
+        """(student pred [N,3], teacher pred [N,3]) with the background mixed in (renderer.py:445)."""
+        pred = self.image + (1 - self.weights_sum).unsqueeze(-1) * self.bg
+        return pred, self.pred_tea

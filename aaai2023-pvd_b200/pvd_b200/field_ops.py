@@ -1,0 +1,203 @@
+"""Per-field-type launchers the training engines are built from: what `NeRFNetwork.forward` / its autograd backward amount to for
+one model type (distill_mutual/network.py:335-437), on pre-allocated buffers, no autograd, no allocation, CUDA-graph safe.
+
+    HashOps  model_type "hash"  (fused.HashNeRFField)     forward + backward   csrc/field_hash.cu
+    VmOps    model_type "vm"    (fused_vm.VMNeRFField)    forward + backward   csrc/field_vm.cu
+    MlpOps   model_type "mlp"   (fused_mlp.MLPNeRFField)  forward only (the frozen teacher of mlp -> hash distillation)
+
+Common protocol (all sample tensors are the engine's): `stage(density_scale)` refreshes staged parameters (fp16 table shadow,
+packed weight tiles); `alloc(M)` sizes per-sample scratch; `forward(st, xyzs, dirs, M, sigmas, rgbs, feat, status)`;
+`backward(st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status)`; `clear_grads()` zeroes the big
+parameter-gradient buffers (the engines run it on a side stream); `grads()` returns {reference parameter name: gradient}.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as nv
+from . import fused
+
+_u32, _f32 = C.c_uint32, C.c_float
+
+
+class HashOps:
+    kind = "hash"
+    kernels_fwd = 1
+
+    def __init__(self, field: "fused.HashNeRFField", dev, trainable: bool = True):
+        self.field, self.dev, self.trainable = field, torch.device(dev), trainable
+        self.grad_table = torch.zeros(field.encoder.embeddings.shape, dtype=torch.float32, device=self.dev) if trainable else None
+        self.enc = self.dx_ws = None
+        self.kernels_bwd = 2 if fused.SPLIT_SCATTER else 1
+
+    def stage(self, density_scale=1.0):
+        f = self.field
+        cfg = f.config()
+        cfg.density_scale = density_scale
+        self.cfg = cfg
+        self.table = f._staged.table_for(f.encoder.embeddings, cfg.table_fp16)
+        self.wblob = f._staged.wblob_for((f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight,
+                                          f.color_net[1].weight, f.color_net[2].weight), 2 * cfg.num_levels)
+        self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
+
+    def alloc(self, M):
+        if self.trainable:
+            self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev)
+            self.dx_ws = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev) if fused.SPLIT_SCATTER else None
+
+    def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
+        nv.check(nv.lib().pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
+                                                 nv.ptr(self.enc), nv.ptr(feat), nv.ptr(status), st))
+
+    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status):
+        nv.check(nv.lib().pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc), nv.ptr(grad_sigmas),
+                                                  nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid), nv.ptr(self.grad_table),
+                                                  nv.ptr(gw_ws), nv.ptr(self.dx_ws), nv.ptr(status), st))
+
+    def clear_grads(self):
+        self.grad_table.zero_()
+
+    def regularise(self, st, loss_scale, loss_slots, weight):
+        pass
+
+    def weight_grads(self, gw_ws):
+        f = self.field
+        like = (f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
+        g = fused.unpack_wgrads(gw_ws, 2 * self.cfg.num_levels, like)
+        return dict(zip(("sigma_net.0.weight", "sigma_net.1.weight", "color_net.0.weight", "color_net.1.weight", "color_net.2.weight"), g))
+
+    def grads(self, gw_ws):
+        out = {"encoder.embeddings": self.grad_table}
+        out.update(self.weight_grads(gw_ws))
+        return out
+
+    def algorithmic_bytes(self):
+        """(forward, backward) bytes per sample: L x 8 corners x 2 features x 2 B gathered; fp32 reductions + the saved encoding."""
+        L = self.cfg.num_levels
+        return L * 8 * 2 * 2, (L * 8 * 2 * 4 + 64) if self.trainable else 0
+
+
+class VmOps:
+    kind = "vm"
+    kernels_fwd = 1
+    kernels_bwd = 1
+
+    def __init__(self, field, dev, trainable: bool = True):
+        from . import fused_vm
+        self._vm = fused_vm
+        self.field, self.dev, self.trainable = field, torch.device(dev), trainable
+        self.groups = [list(field.sigma_mat), list(field.sigma_vec), list(field.color_mat), list(field.color_vec)]
+        for grp in self.groups:
+            for p in grp:
+                assert p.is_contiguous(memory_format=torch.channels_last), "vm planes/lines must be torch.channels_last"
+        self._flat = None
+        if trainable:
+            # every plane/line gradient lives in ONE flat buffer (one memset per step); each view has its parameter's shape and
+            # channels-last strides ([H][W][R] in memory), sigma planes and lines first (the L1 penalty covers exactly that prefix)
+            total = sum(p.numel() for grp in self.groups for p in grp)
+            self._flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+            off, self.grad_groups = 0, []
+            for grp in (self.groups[0], self.groups[1], self.groups[2], self.groups[3]):
+                views = []
+                for p in grp:
+                    _, R, H, W = p.shape
+                    views.append(self._flat[off:off + p.numel()].view(1, H, W, R).permute(0, 3, 1, 2))
+                    off += p.numel()
+                self.grad_groups.append(views)
+            self._cgrads = fused_vm.PvdVmGrads(sigma_mat=fused_vm._ptrs3(self.grad_groups[0]), sigma_vec=fused_vm._ptrs3(self.grad_groups[1]),
+                                               color_mat=fused_vm._ptrs3(self.grad_groups[2]), color_vec=fused_vm._ptrs3(self.grad_groups[3]))
+
+    def stage(self, density_scale=1.0):
+        f = self.field
+        self.wblob = f._staged.get((f.basis_mat.weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight))
+        aabb = [float(v) for v in f.aabb_train.tolist()]
+        planes = [[p.detach() for p in grp] for grp in self.groups]
+        self.cfield = self._vm._vm_struct(planes, self.wblob, f.resolution, aabb, float(f.args.sigma_clip_min), float(f.args.sigma_clip_max),
+                                          float(density_scale))
+
+    def alloc(self, M):
+        pass
+
+    def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
+        nv.check(nv.lib().pvd_vm_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
+                                               nv.ptr(feat), nv.ptr(status), st))
+
+    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status):
+        nv.check(nv.lib().pvd_vm_field_backward(C.byref(self.cfield), C.byref(self._cgrads), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(grad_sigmas),
+                                                nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid), nv.ptr(gw_ws),
+                                                nv.ptr(status), st))
+
+    def clear_grads(self):
+        self._flat.zero_()
+
+    def regularise(self, st, loss_scale, loss_slots, weight):
+        """l1_reg_weight * density_loss() (network.py:549-557; added to the loss for vm models, utils.py:1135-1136): its gradient
+        goes onto the sigma plane / line gradients, its value into the step's loss slots."""
+        if not weight:
+            return
+        for p, g in zip(self.groups[0] + self.groups[1], self.grad_groups[0] + self.grad_groups[1]):
+            nv.check(nv.lib().pvd_l1_mean_reg(nv.ptr(p), C.c_uint64(p.numel()), _f32(weight), _f32(loss_scale), nv.ptr(g), nv.ptr(loss_slots), st))
+
+    def weight_grads(self, gw_ws):
+        f = self.field
+        ws = (f.basis_mat.weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
+        wg = [torch.zeros_like(w, dtype=torch.float32) for w in ws]
+        with nv.on_device(gw_ws):
+            nv.check(nv.lib().pvd_vm_unpack_wgrads(nv.ptr(gw_ws), nv.ptr(wg[0]), nv.ptr(wg[1]), nv.ptr(wg[2]), nv.ptr(wg[3]), nv.stream_of(gw_ws)))
+        return dict(zip(("basis_mat.weight", "color_net.0.weight", "color_net.1.weight", "color_net.2.weight"), wg))
+
+    def grads(self, gw_ws):
+        out = {}
+        for name, views in zip(("sigma_mat", "sigma_vec", "color_mat", "color_vec"), self.grad_groups):
+            for i, v in enumerate(views):
+                out[f"{name}.{i}"] = v
+        out.update(self.weight_grads(gw_ws))
+        return out
+
+    def algorithmic_bytes(self):
+        """3 (plane, line) pairs x (4 + 2) taps x (16 + 48) components x 4 B, forward; the same again as reductions backward."""
+        b = 3 * (4 + 2) * (16 + 48) * 4
+        return b, (b if self.trainable else 0)
+
+
+class MlpOps:
+    kind = "mlp"
+    kernels_fwd = 1
+    kernels_bwd = 0
+    trainable = False
+
+    def __init__(self, field, dev, trainable: bool = False):
+        assert not trainable, "the fused NeRF-MLP field is forward only (it is the frozen teacher, distill_mutual/utils.py:1008-1018)"
+        self.field, self.dev = field, torch.device(dev)
+
+    def stage(self, density_scale=1.0):
+        from .fused_mlp import PvdMlpField
+        f = self.field
+        self.tail = f._staged.wblob_for((f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight,
+                                         f.color_net[2].weight), f.in_dim)
+        self.blob = f._blob()
+        self.cfield = PvdMlpField(wblob=self.blob.data_ptr(), tail_wblob=self.tail.data_ptr(), sigma_clip_min=float(f.args.sigma_clip_min),
+                                  sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
+
+    def alloc(self, M):
+        pass
+
+    def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
+        nv.check(nv.lib().pvd_mlp_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
+                                                nv.ptr(feat), nv.ptr(status), st))
+
+    def algorithmic_bytes(self):
+        return 0, 0   # FLOP-bound: 865 280 FLOP/sample forward
+
+
+def make_ops(field, dev, trainable):
+    mt = getattr(field, "model_type", None)
+    if mt == "hash":
+        return HashOps(field, dev, trainable)
+    if mt == "vm":
+        return VmOps(field, dev, trainable)
+    if mt == "mlp":
+        return MlpOps(field, dev, trainable)
+    raise ValueError(f"no fused field for model_type {mt!r} (hash | vm | mlp)")

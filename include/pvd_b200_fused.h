@@ -175,6 +175,47 @@ int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biase
 int pvd_mlp_field_forward(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
                           float* feat16, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (teacher, student) distillation at SHARED samples: the loss side of Trainer.train_step, distill_mutual/utils.py:954-1189,
+ * loss_type "normL2" (get_loss :940-951):
+ *   loss = rgb * ||pred_tea - pred_stu|| + fea * ||feat_stu - feat_tea|| + color * ||rgbs_stu - rgbs_tea|| + sigma * ||feat_stu[:,0] - feat_tea[:,0]||
+ * with pred = image + (1 - weights_sum) * bg_color (renderer.py:445), feat = `feature_sigma_color` [M,16], rgbs = `color_l` [M,3].
+ * Both fields are first evaluated on the same xyzs/dirs (pvd_*_field_forward with feat16); then, on one stream:
+ *   pvd_pair_sample_sq -> pvd_pair_composite -> pvd_pair_combine -> the student's pvd_*_field_backward(grad_sigmas, grad_rgbs, grad_feat16).
+ * `sums` is PVD_LOSS_SLOTS x PVD_PAIR_SUM_STRIDE floats, zeroed by the caller before pvd_pair_sample_sq:
+ *   slot[0] sum (pred_stu - pred_tea)^2, slot[1] feature, slot[2] colour, slot[3] sigma; the step's values are the sums over slots.
+ * Stages 1 and 2 of the reference (no compositing, :1046-1108) skip pvd_pair_composite and pass n_composite = NULL.
+ * ---------------------------------------------------------------------------------------- */
+#define PVD_PAIR_SUM_STRIDE 4u
+typedef struct PvdPairRates { /* loss_rate_rgb / loss_rate_fea_sc / loss_rate_color / loss_rate_sigma (main_distill_mutual.py) */
+    float rgb, fea, color, sigma;
+} PvdPairRates;
+
+/* per-sample sums of squares over ALL M rows (padding rows included, as in the reference: raymarching.py:240-242) */
+int pvd_pair_sample_sq(const float* feat_tea, const float* feat_stu, const float* rgbs_tea, const float* rgbs_stu, uint32_t M,
+                       float* sums, void* stream);
+/* composite_rays_train_forward of teacher AND student on the same rays (raymarching.cu:505-582) + sum of squared pixel differences
+ * + composite_rays_train_backward of the student (:607-686) with the UN-normalised upstream (pred_stu - pred_tea).
+ * Outputs: pred_tea [N,3] (background mixed in), the student's weights_sum [N], depth [N], image [N,3] (raw, as the op returns them),
+ * grad_sigmas [M], grad_rgbs [M,3] (un-normalised; rows of rays that own samples), sums slot[0]. */
+int pvd_pair_composite(const float* bg_color, const float* sigmas_tea, const float* rgbs_tea, const float* sigmas_stu,
+                       const float* rgbs_stu, const float* deltas, const int32_t* rays, uint32_t M, uint32_t N, float* pred_tea,
+                       float* weights_sum, float* depth, float* image, float* grad_sigmas, float* grad_rgbs, float* sums,
+                       void* stream);
+/* final gradients, in place over grad_sigmas / grad_rgbs (rows >= *n_composite carry no composite gradient), and
+ * grad_feat16 [M,16]; all multiplied by loss_scale.  loss_out [5] = total loss, then the four un-weighted norms (rgb, fea, color, sigma). */
+int pvd_pair_combine(const float* feat_tea, const float* feat_stu, const float* rgbs_tea, const float* rgbs_stu, const float* sums,
+                     const PvdPairRates* rates, float loss_scale, uint32_t M, const int32_t* n_composite, float* grad_sigmas,
+                     float* grad_rgbs, float* grad_feat16, float* loss_out, void* stream);
+/* zero the rows of xyzs / dirs / deltas [M,*] that no surviving ray owns (past counter[0], or owned by a ray that was dropped because
+ * it does not fit): what torch.zeros gives the reference every call (raymarching.py:240-242) for persistent buffers. */
+int pvd_zero_sample_tail(const int32_t* rays, const int32_t* counter, uint32_t N, uint32_t M, float* xyzs, float* dirs,
+                         float* deltas, void* stream);
+
+/* grad[i] += loss_scale * weight / n * sign(param[i]);  loss_slots[2*s] += weight / n * sum|param|  -- the gradient and value of
+ * weight * mean|param|, one term of NeRFNetwork.density_loss (network.py:549-557; vm models, l1_reg_weight, utils.py:1135-1136). */
+int pvd_l1_mean_reg(const float* param, uint64_t n, float weight, float loss_scale, float* grad, float* loss_slots, void* stream);
+
 /* ---- multi-GPU: the one exchange step (rays shard, parameters replicate) ------------------------------------------
  * Sum over all ranks of elements [elem_offset, elem_offset + elem_count) of a symmetric fp16 buffer, done in the NVSwitch:
  * `multicast_ptr` is the multicast mapping of the buffer (torch symmetric memory: handle.multicast_ptr); the range is read with

@@ -89,23 +89,32 @@ def composite(sigmas, rgbs, deltas, rays):
     return _Composite.apply(sigmas, rgbs, deltas, rays)
 
 
-def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cascade=1, grid_size=128, min_near=0.2, bg_color=1.0,
-                      density_scale=1.0, M=None, perturb=True, dt_gamma=0.0, max_steps=1024, aabb=None):
-    """One reference training step on the CPU: near/far -> march -> field -> composite -> bg mix -> MSE.
-
-    Returns dict(loss, image, depth, weights_sum, xyzs, dirs, deltas, rays, counter).  `field_fn(xyzs, dirs) -> (sigma, rgb)`.
-    """
+def march_samples(rays_o, rays_d, bitfield, bound=1.0, cascade=1, grid_size=128, min_near=0.2, M=None, perturb=True, dt_gamma=0.0,
+                  max_steps=1024, aabb=None):
+    """near/far + march_rays_train on the CPU (renderer.py:342-391): torch tensors xyzs, dirs, deltas, rays + counter, nears, fars.
+    M=None is the warm-up sizing: the total rounded up strictly to 128 (raymarching.py:276-282); padding rows are zeros."""
     ro, rd = rays_o.numpy(), rays_d.numpy()
     if aabb is None:
         aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
     nears, fars = cpu.near_far_from_aabb(ro, rd, aabb, min_near)
     xyzs, dirs, deltas, rays, counter = cpu.march_rays_train(ro, rd, bound, bitfield, cascade, grid_size, nears, fars, M=M,
                                                             perturb=perturb, dt_gamma=dt_gamma, max_steps=max_steps)
-    if M is None:  # warm-up sizing: total rounded up strictly to 128 (raymarching.py:276-282)
+    if M is None:
         m = int(counter[0])
         m += 128 - m % 128
         xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
     txyz, tdir, tdl, trays = (torch.from_numpy(np.ascontiguousarray(a)) for a in (xyzs, dirs, deltas, rays))
+    return txyz, tdir, tdl, trays, counter, nears, fars
+
+
+def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cascade=1, grid_size=128, min_near=0.2, bg_color=1.0,
+                      density_scale=1.0, M=None, perturb=True, dt_gamma=0.0, max_steps=1024, aabb=None):
+    """One reference training step on the CPU: near/far -> march -> field -> composite -> bg mix -> MSE.
+
+    Returns dict(loss, image, depth, weights_sum, xyzs, dirs, deltas, rays, counter).  `field_fn(xyzs, dirs) -> (sigma, rgb)`.
+    """
+    txyz, tdir, tdl, trays, counter, nears, fars = march_samples(rays_o, rays_d, bitfield, bound, cascade, grid_size, min_near, M,
+                                                                 perturb, dt_gamma, max_steps, aabb)
     sigma, rgb = field_fn(txyz, tdir)
     ws, depth, image = composite(density_scale * sigma, rgb, tdl, trays)
     pred = image + (1 - ws).unsqueeze(-1) * bg_color  # renderer.py:445
@@ -113,6 +122,53 @@ def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cas
     loss = torch.mean((pred - gt_rgb) ** 2)
     return dict(loss=loss, image=pred, depth=depth_n, weights_sum=ws, xyzs=txyz, dirs=tdir, deltas=tdl, rays=trays,
                 counter=counter, sigma=sigma, rgb=rgb)
+
+
+def pair_distill_step(rays_o, rays_d, bitfield, student_fn, teacher_fn, rates=(1.0, 0.002, 0.002, 0.002), stage=3, l1_reg=None,
+                      bg_color=1.0, density_scale=1.0, M=None, **march_kw):
+    """One distillation step of `Trainer.train_step` (distill_mutual/utils.py:954-1189, loss_type normL2) on the CPU.
+
+    The student marches, the teacher is evaluated under no_grad at the SAME samples (renderer.py:374-394), both see all M rows
+    (padding rows are zeros).  student_fn / teacher_fn: (xyzs, dirs) -> (sigma [M], rgb [M,3], feat [M,16]).
+    rates = (rgb, fea_sc, color, sigma) (main_distill_mutual.py:174-177); stage 1 = feature term only (:1046-1060), 2 = + colour and
+    sigma without compositing (:1061-1108), 3 = all four (:1110-1176); l1_reg = weight * density_loss() of a vm student, a scalar
+    tensor (:1135-1136, stage 3 only).  Returns dict(loss, terms, image, image_tea, rays, xyzs, ...); loss.backward() gives the
+    student's reference gradients."""
+    txyz, tdir, tdl, trays, counter, nears, fars = march_samples(rays_o, rays_d, bitfield, M=M, **march_kw)
+    s_s, c_s, f_s = student_fn(txyz, tdir)
+    with torch.no_grad():
+        s_t, c_t, f_t = teacher_fn(txyz, tdir)
+    r_rgb, r_fea, r_col, r_sig = rates
+    terms = {"fea": torch.norm(f_s - f_t)}
+    out = dict(xyzs=txyz, dirs=tdir, deltas=tdl, rays=trays, counter=counter, feat=f_s, feat_tea=f_t)
+    if stage == 1:
+        out.update(loss=r_fea * terms["fea"], terms=terms)
+        return out
+    terms["color"] = torch.norm(c_s - c_t)
+    terms["sigma"] = torch.norm(f_s[:, 0] - f_t[:, 0])
+    loss = r_fea * terms["fea"] + r_col * terms["color"] + r_sig * terms["sigma"]
+    if stage == 2:
+        out.update(loss=loss, terms=terms)
+        return out
+    ws, depth, image = composite(density_scale * s_s, c_s, tdl, trays)
+    pred = image + (1 - ws).unsqueeze(-1) * bg_color
+    with torch.no_grad():
+        wt, _, it = composite(density_scale * s_t, c_t, tdl, trays)
+        pred_t = it + (1 - wt).unsqueeze(-1) * bg_color
+    terms["rgb"] = torch.norm(pred_t - pred)
+    loss = loss + r_rgb * terms["rgb"]
+    if l1_reg is not None:
+        loss = loss + l1_reg
+    out.update(loss=loss, terms=terms, image=pred, image_tea=pred_t, weights_sum=ws)
+    return out
+
+
+def vm_density_loss(sigma_mat, sigma_vec):
+    """NeRFNetwork.density_loss (network.py:549-557): sum of mean |.| over the sigma planes and lines."""
+    loss = 0
+    for m, v in zip(sigma_mat, sigma_vec):
+        loss = loss + torch.mean(torch.abs(m)) + torch.mean(torch.abs(v))
+    return loss
 
 
 # ------------------------------------------------------------------------------------------------ VM (TensoRF) field
