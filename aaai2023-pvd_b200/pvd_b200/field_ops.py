@@ -51,13 +51,24 @@ class HashOps:
         nv.check(nv.lib().pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
                                                  nv.ptr(self.enc), nv.ptr(feat), nv.ptr(status), st))
 
-    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status):
-        nv.check(nv.lib().pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc), nv.ptr(grad_sigmas),
-                                                  nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid), nv.ptr(self.grad_table),
-                                                  nv.ptr(gw_ws), nv.ptr(self.dx_ws), nv.ptr(status), st))
+    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status, phases=None):
+        """phases: None = the whole backward; PVD_BWD_MLP (1) / PVD_BWD_SCATTER (2) = one of its two kernels (needs dx_ws)."""
+        if phases is None:
+            nv.check(nv.lib().pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc),
+                                                      nv.ptr(grad_sigmas), nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid),
+                                                      nv.ptr(self.grad_table), nv.ptr(gw_ws), nv.ptr(self.dx_ws), nv.ptr(status), st))
+        else:
+            nv.check(nv.lib().pvd_hash_field_backward_rows(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc),
+                                                           nv.ptr(grad_sigmas), nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(0), _u32(M),
+                                                           nv.ptr(n_valid), nv.ptr(self.grad_table), nv.ptr(gw_ws), nv.ptr(self.dx_ws),
+                                                           nv.ptr(status), _u32(phases), st))
 
     def clear_grads(self):
         self.grad_table.zero_()
+
+    def big_grad(self):
+        """The flat fp32 buffer that dominates the multi-GPU gradient exchange."""
+        return self.grad_table.view(-1)
 
     def regularise(self, st, loss_scale, loss_slots, weight):
         pass
@@ -131,6 +142,9 @@ class VmOps:
 
     def clear_grads(self):
         self._flat.zero_()
+
+    def big_grad(self):
+        return self._flat
 
     def regularise(self, st, loss_scale, loss_slots, weight):
         """l1_reg_weight * density_loss() (network.py:549-557; added to the loss for vm models, utils.py:1135-1136): its gradient

@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- training rays/s (forward + backward) of the PVD volume-rendering hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--levels 14] [--rays 4096]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload hash|vm|hash-vm|mlp-hash] [--levels 14] [--rays R]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): "hash" teacher training, 4096 rays per GPU per step x 1024 max steps, synthetic
-800x800 Lego-shaped scene (pvd_b200/synthetic.py), random-init weights, fp16 tables + fp16 tensor-core MLP with fp32
-accumulation (the reference's own autocast precision), MSE loss, loss scale 65536 (GradScaler's default).
+Default workload (BASELINE.json configs[1], the one `metric` is quoted on): "hash" teacher training, 4096 rays per GPU per step x
+1024 max steps, synthetic 800x800 Lego-shaped scene (pvd_b200/synthetic.py), random-init weights, fp16 tables + fp16 tensor-core MLP
+with fp32 accumulation (the reference's own autocast precision), MSE loss, loss scale 65536 (GradScaler's default).
+The other BASELINE configurations run through the same harness with --workload: vm (configs[2], TensoRF VM-48 teacher training),
+hash-vm (configs[3], hash teacher -> vm student distillation at shared samples), mlp-hash (configs[4], NeRF-MLP teacher -> hash
+student, 8192 rays).
 A step = near/far -> march -> field query -> composite -> loss -> backward of all of it (and, for N > 1, one NCCL all-reduce
 of the gradients); the optimizer step, data loading and density-grid upkeep are outside, as in SURVEY.md 8d.
 
@@ -113,53 +116,198 @@ def make_workload(n_rays, n_batches, seed, rank):
     return out
 
 
+WORKLOADS = {
+    "hash": "hash (INGP L={L} T=2^19 F=2) teacher training, {R} rays/GPU x 1024 max steps, cuda_ray, synthetic 800x800 Lego-shaped scene, "
+            "fwd+bwd (MSE), random-init weights",
+    "vm": "vm (TensoRF VM-48: sigma 16 + colour 48 components, 300^3) teacher training, {R} rays/GPU x 1024 max steps, cuda_ray, synthetic "
+          "800x800 Lego-shaped scene, fwd+bwd (MSE + L1 on the sigma planes), random-init weights",
+    "hash-vm": "hash (L={L}) teacher -> vm (VM-48, 300^3) student distillation (main_distill_mutual stage 3: normL2 rgb + feature + colour + sigma "
+               "losses), both networks queried at the SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
+    "mlp-hash": "mlp (NeRF 8x256, PE 10) teacher -> hash (L={L}) student distillation (main_distill_mutual stage 3), both networks queried at the "
+                "SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
+}
+DEFAULT_RAYS = {"hash": 4096, "vm": 4096, "hash-vm": 4096, "mlp-hash": 8192}
+PAIR_RATES = (1.0, 0.002, 0.002, 0.002)   # main_distill_mutual.py:174-177
+L1_REG = 1e-4                             # main_distill_mutual.py:178 / main_just_train_tea.py:170
+MLP_FLOPS_PER_SAMPLE = 865280             # 2 * (63*256 + 5*256^2 + 319*256 + 256*28)
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline(levels, n_rays, budget_s=20.0):
-    """The oracle's CPU training step (C kernels + torch CPU MLP, fp32) on a bounded sample of the same workload."""
+def cpu_baseline(workload, levels, n_rays, budget_s=15.0):
+    """The oracle's CPU training step (C kernels + torch-CPU networks, fp32) on a bounded sample of the same workload: whole steps
+    of n_rays rays until `budget_s` seconds are spent (at least one)."""
     from oracle import cpu, field
     from pvd_b200 import synthetic as syn
     torch.set_num_threads(os.cpu_count() or 1)
     _, bitfield, _ = syn.lego_bitfield()
-    offsets, pls = cpu.grid_offsets(3, levels, 16, 19, desired_resolution=2048)
     torch.manual_seed(0)
-    emb = torch.empty(int(offsets[-1]), 2).uniform_(-1e-4, 1e-4).requires_grad_(True)
-    lin = [torch.nn.Linear(i, o, bias=False) for i, o in ((2 * levels, 64), (64, 16), (31, 64), (64, 64), (64, 3))]
-    ws = [l.weight for l in lin]
+    lin = lambda dims: [torch.nn.Linear(i, o, bias=False).weight for i, o in dims]
+    TAIL = ((2 * levels, 64), (64, 16), (31, 64), (64, 64), (64, 3))
+
+    def hash_model(train):
+        offsets, pls = cpu.grid_offsets(3, levels, 16, 19, desired_resolution=2048)
+        emb = torch.empty(int(offsets[-1]), 2).uniform_(-1e-4, 1e-4).requires_grad_(train)
+        ws = lin(TAIL)
+        return (lambda x, d: field.hash_field_forward(x, d, emb, offsets, pls, 16, ws)), [emb] + ws
+
+    def vm_model():
+        mk = lambda r, w: [(0.1 * torch.randn(1, r, 300, w)).requires_grad_(True) for _ in range(3)]
+        sm, sv, cm, cv = mk(16, 300), mk(16, 1), mk(48, 300), mk(48, 1)
+        bw, cw = lin(((144, 15),))[0], lin(((31, 64), (64, 64), (64, 3)))
+        aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+        fn = lambda x, d: field.vm_field_forward(x, d, sm, sv, cm, cv, bw, cw, aabb)
+        return fn, sm + sv + cm + cv + [bw] + cw, (sm, sv)
+
+    def mlp_model():
+        dims = [(63, 256)] + [(256, 256)] * 3 + [(319, 256)] + [(256, 256)] * 2 + [(256, 28)]
+        ls = [torch.nn.Linear(i, o) for i, o in dims]
+        nw, nb, tw = [l.weight.detach() for l in ls], [l.bias.detach() for l in ls], [w.detach() for w in lin(((28, 64),) + TAIL[1:])]
+        return lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw)
+
+    if workload == "hash":
+        f_s, params = hash_model(True)
+        one = lambda ro, rd, gt: field.render_train_step(ro, rd, bitfield, gt, lambda x, d: f_s(x, d)[:2])["loss"]
+    elif workload == "vm":
+        f_s, params, (sm, sv) = vm_model()
+        one = lambda ro, rd, gt: field.render_train_step(ro, rd, bitfield, gt, lambda x, d: f_s(x, d)[:2])["loss"] + L1_REG * field.vm_density_loss(sm, sv)
+    elif workload == "hash-vm":
+        f_t, _ = hash_model(False)
+        f_s, params, (sm, sv) = vm_model()
+        one = lambda ro, rd, gt: field.pair_distill_step(ro, rd, bitfield, f_s, f_t, PAIR_RATES, l1_reg=L1_REG * field.vm_density_loss(sm, sv))["loss"]
+    else:
+        f_t = mlp_model()
+        f_s, params = hash_model(True)
+        one = lambda ro, rd, gt: field.pair_distill_step(ro, rd, bitfield, f_s, f_t, PAIR_RATES)["loss"]
     batches = syn.make_ray_batches(8, n_rays, seed=123)
     g = torch.Generator().manual_seed(5)
-    done, t0 = 0, time.perf_counter()
-    for ro, rd in batches:
+    done, i, t0 = 0, 0, time.perf_counter()
+    while True:
+        ro, rd = batches[i % len(batches)]
+        i += 1
         gt = torch.rand(n_rays, 3, generator=g)
-        fn = lambda x, d: field.hash_field_forward(x, d, emb, offsets, pls, 16, ws)[:2]
-        o = field.render_train_step(ro, rd, bitfield, gt, fn)
-        emb.grad = None
-        for w in ws:
-            w.grad = None
-        o["loss"].backward()
+        for p_ in params:
+            p_.grad = None
+        one(ro, rd, gt).backward()
         done += n_rays
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{done} rays ({done // n_rays} steps of {n_rays}) of the same workload, fp32, oracle C kernels + torch-CPU MLP, "
-                      f"{dt:.1f} s"}
+            "sample": f"{done} rays ({done // n_rays} steps of {n_rays}) of the same workload, fp32, oracle C kernels (1 thread) + torch-CPU "
+                      f"networks ({torch.get_num_threads()} threads), {dt:.1f} s"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def build_engine(args, dev, bitfield):
+    """The engine of the chosen workload, module-default random init under seed 0."""
+    from pvd_b200.engine import HashTrainEngine, PairDistillEngine, VMTrainEngine
+    from pvd_b200.fused import HashNeRFField
+    torch.manual_seed(0)
+    bf = torch.from_numpy(bitfield)
+    kw = dict(loss_scale=65536.0, device=dev)
+    w = args.workload
+    if w == "hash":
+        return HashTrainEngine(HashNeRFField(num_levels=args.levels, desired_resolution=2048).to(dev), bf, args.rays, **kw)
+    if w == "vm":
+        from pvd_b200.fused_vm import VMNeRFField
+        return VMTrainEngine(VMNeRFField(resolution0=300).to(dev), bf, args.rays, l1_reg_weight=L1_REG, **kw)
+    if w == "hash-vm":
+        from pvd_b200.fused_vm import VMNeRFField
+        tea = HashNeRFField(num_levels=args.levels, desired_resolution=2048, is_teacher=True).to(dev)
+        return PairDistillEngine(tea, VMNeRFField(resolution0=300).to(dev), bf, args.rays, rates=PAIR_RATES, stage=3, l1_reg_weight=L1_REG, **kw)
+    from pvd_b200.fused_mlp import MLPNeRFField
+    tea = MLPNeRFField().to(dev)
+    return PairDistillEngine(tea, HashNeRFField(num_levels=args.levels, desired_resolution=2048).to(dev), bf, args.rays, rates=PAIR_RATES,
+                             stage=3, **kw)
+
+
+def phase_plan(eng):
+    """[(phase name, launcher)] of one eager step, for per-kernel event timing (roofline pass only)."""
+    import ctypes as C
+    st = lambda: C.c_void_p(torch.cuda.current_stream(eng.dev).cuda_stream)
+    rs = lambda: eng.sets[eng.cur]
+    pair = hasattr(eng, "tea")
+    plan = [("march", lambda: (eng._march_count(st(), rs()), eng._march_write(st(), rs(), eng.M)))]
+    if pair:
+        plan.append(("teacher_fwd", lambda: eng.tea.forward(st(), rs().xyzs, rs().dirs, eng.M, eng.sigmas_tea, eng.rgbs_tea, eng.feat_tea, eng.status)))
+        plan.append(("field_fwd", lambda: eng.ops.forward(st(), rs().xyzs, rs().dirs, eng.M, eng.sigmas, eng.rgbs, eng.feat, eng.status)))
+    else:
+        plan.append(("field_fwd", lambda: eng._forward(st(), rs(), eng.M, eng.M)))
+    plan.append(("composite", lambda: eng._loss_backward(st(), rs(), eng.M, eng.M)))
+    gfeat = eng.grad_feat if pair else None
+    nval = (lambda: None) if pair else (lambda: rs().counter)
+    if eng.ops.kind == "hash" and eng.ops.dx_ws is not None:
+        for name, ph in (("mlp_bwd", 1), ("scatter", 2)):
+            plan.append((name, lambda ph=ph: eng.ops.backward(st(), rs().xyzs, rs().dirs, eng.grad_sigmas, eng.grad_rgbs, gfeat, eng.M, nval(),
+                                                              eng.gw_ws, eng.status, phases=ph)))
+    else:
+        plan.append(("field_bwd", lambda: eng._field_backward(st(), rs(), eng.M, None)))
+    return plan
+
+
+def time_phases(eng, plan):
+    """One step with events between phases (perturbs the step by a few event records)."""
+    cur = torch.cuda.current_stream(eng.dev)
+    eng._zeros.zero_()
+    eng._clear_big(cur)
+    cur.wait_stream(eng._side)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan) + 1)]
+    e[0].record()
+    for i, (_, fn) in enumerate(plan):
+        fn()
+        e[i + 1].record()
+    torch.cuda.synchronize()
+    return {name: e[i].elapsed_time(e[i + 1]) for i, (name, _) in enumerate(plan)}
+
+
+def roofline_kernels(eng):
+    """(kernel, phase, bound, algorithmic bytes or FLOPs per sample) for the field kernels of the step."""
+    out = []
+    pair = hasattr(eng, "tea")
+    if pair:
+        t = eng.tea
+        if t.kind == "hash":
+            out.append(("k_hash_field_fwd(teacher)", "teacher_fwd", "hbm", t.algorithmic_bytes()[0]))
+        elif t.kind == "vm":
+            out.append(("k_vm_field_fwd(teacher)", "teacher_fwd", "hbm", t.algorithmic_bytes()[0]))
+        else:
+            out.append(("k_mlp_field_fwd", "teacher_fwd", "tensor", MLP_FLOPS_PER_SAMPLE))
+    o = eng.ops
+    fb, bb = o.algorithmic_bytes()
+    if o.kind == "hash":
+        out.append(("k_hash_field_fwd", "field_fwd", "hbm", fb))
+        if o.dx_ws is not None:
+            out.append(("k_hash_field_bwd", "mlp_bwd", "hbm", 64 + 64 + 16))   # saved encoding in, d(encoding) out, sample gradients in
+            out.append(("k_hash_scatter", "scatter", "hbm", bb))               # fp32 reductions + d(encoding) in
+        else:
+            out.append(("k_hash_field_bwd", "field_bwd", "hbm", bb))
+    else:
+        out.append(("k_vm_field_fwd", "field_fwd", "hbm", fb))
+        out.append(("k_vm_field_bwd", "field_bwd", "hbm", fb + bb))             # the backward re-gathers the taps, then reduces into them
+    return out
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        k = t["kernels"].get(kernel.split("(")[0])
+        return (k["dram_bytes"], t.get("source")) if k else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_ours(args, rank, world, local):
     import torch.distributed as dist
     from pvd_b200 import synthetic as syn
-    from pvd_b200.engine import HashTrainEngine
-    from pvd_b200.fused import HashNeRFField
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)
-    field = HashNeRFField(num_levels=args.levels, desired_resolution=2048).to(dev)
     _, bitfield, sha = syn.lego_bitfield()
-    eng = HashTrainEngine(field, torch.from_numpy(bitfield), args.rays, loss_scale=65536.0, device=dev)
+    eng = build_engine(args, dev, bitfield)
+    pair = hasattr(eng, "tea")
     eng.stage()
     n_b = 16 + args.warmup + args.steps
     host = make_workload(args.rays, min(n_b, 64), seed=0, rank=rank)
@@ -171,15 +319,19 @@ def run_ours(args, rank, world, local):
 
     def load(i, from_host=False):
         """Make batch i the input of the next step.  Pipelined: batch i goes into the set the NEXT replay marches (it is computed
-        on one replay later), which is exactly one batch of look-ahead; the caller passes consecutive i."""
+        on one replay later), which is exactly one batch of look-ahead; the caller passes consecutive i.  A distillation step has
+        no ground-truth colours (the teacher's rendering is the target): only the rays are copied."""
         ro, rd, gt = (host if from_host else devb)[i % len(devb)]
         if pipelined:
             rs = eng.sets[(pipe["i"] + 1) & 1]
-            rs.rays_o.copy_(ro, non_blocking=True); rs.rays_d.copy_(rd, non_blocking=True); rs.gt.copy_(gt, non_blocking=True)
         elif use_graph or from_host:  # the captured graph reads the engine's static input buffers
-            eng.rays_o.copy_(ro, non_blocking=True); eng.rays_d.copy_(rd, non_blocking=True); eng.gt.copy_(gt, non_blocking=True)
+            rs = eng.sets[eng.cur]
         else:
             eng.rays_o, eng.rays_d, eng.gt = ro, rd, gt
+            return
+        rs.rays_o.copy_(ro, non_blocking=True); rs.rays_d.copy_(rd, non_blocking=True)
+        if not pair:
+            rs.gt.copy_(gt, non_blocking=True)
 
     def run_step():
         if pipelined:
@@ -191,21 +343,22 @@ def run_ours(args, rank, world, local):
             eng.step()
 
     exchange = None
+    big = eng.ops.big_grad()
     if world > 1 and args.grad_comm != "fp32":
         from pvd_b200.dist import TableGradExchange
-        exchange = TableGradExchange(eng.grad_table.view(-1), eng.gw_ws, mode={"fp16": "nccl", "multimem": "auto"}[args.grad_comm])
+        exchange = TableGradExchange(big, eng.gw_ws, mode={"fp16": "nccl", "multimem": "auto"}[args.grad_comm])
         if rank == 0:
             print(f"[bench] gradient exchange: {exchange.kind} {exchange.why}", file=sys.stderr)
 
     def allreduce():
-        # one gradient exchange per step.  fp16 payload (default for N > 1): the table gradient is cast once and summed in half
-        # precision -- the precision the reference ACCUMULATES these gradients in (gridencoder.cu:299-305); on NVSwitch the sum is
-        # done by the switch (multimem, csrc/collective.cu), else by NCCL.  The small MLP gradients stay fp32 (NCCL, side stream).
+        # one gradient exchange per step.  fp16 payload (default for N > 1): the big parameter gradient (hash table / vm planes) is cast
+        # once and summed in half precision -- the precision the reference ACCUMULATES table gradients in (gridencoder.cu:299-305); on
+        # NVSwitch the sum can be done by the switch (multimem, csrc/collective.cu), else by NCCL.  The small MLP gradients stay fp32.
         if world > 1:
             if exchange is not None:
                 exchange()
             else:
-                dist.all_reduce(eng.grad_table)
+                dist.all_reduce(big)
                 dist.all_reduce(eng.gw_ws)
 
     # ---- 16 sizing steps (the reference's mean_count warm-up), then W untimed steps at the steady-state M
@@ -215,7 +368,7 @@ def run_ours(args, rank, world, local):
     eng.finish_warmup()
     if exchange is not None and exchange.kind == "multimem":
         # self-check of the in-switch reduction against NCCL on this step's real gradients; any rank's mismatch -> all fall back
-        ref = eng.grad_table.view(-1).to(torch.float16)
+        ref = big.to(torch.float16)
         dist.all_reduce(ref)
         exchange()
         torch.cuda.synchronize()
@@ -268,8 +421,6 @@ def run_ours(args, rank, world, local):
     sampler.start()
     # ---- timed region: K steps, each bracketed by events, L2 flushed between steps (outside the brackets)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    samples = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -290,7 +441,8 @@ def run_ours(args, rank, world, local):
     t_ms = float(tt.item())
 
     # ---- per-kernel pass (same steps again, events around the field kernels; used for the roofline only)
-    kt = {"march": 0.0, "field_fwd": 0.0, "composite": 0.0, "field_bwd": 0.0}
+    plan = phase_plan(eng)
+    kt = {name: 0.0 for name, _ in plan}
     S_total = 0
     reps = min(args.steps, 50)
     was_pipelined, pipelined = pipelined, False
@@ -298,7 +450,7 @@ def run_ours(args, rank, world, local):
     for i in range(reps):
         load(16 + args.warmup + i)
         flush.fill_(i & 0xFF)
-        t = time_phases(eng)
+        t = time_phases(eng, plan)
         for k in kt:
             kt[k] += t[k]
         S_total += min(int(eng.counter[0].item()), eng.M)
@@ -314,9 +466,10 @@ def run_ours(args, rank, world, local):
         eng.march(0)
         nb += 1
 
-    # ---- end-to-end through the public API with HOST buffers: H2D of rays + gt, step, D2H of the loss
+    # ---- end-to-end through the public API with HOST buffers: H2D of rays (+ gt), step, D2H of the loss
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    loss_host = torch.empty(eng.loss_slots.numel(), dtype=torch.float32).pin_memory()   # 64 (loss, rays) slots, summed on the host
+    loss_dev = eng.loss_out if pair else eng.loss_slots   # pair: [total, 4 norms]; single model: 64 (loss, rays) slots, summed on the host
+    loss_host = torch.empty(loss_dev.numel(), dtype=torch.float32).pin_memory()
     if not use_graph:
         eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
     if world > 1:
@@ -325,10 +478,10 @@ def run_ours(args, rank, world, local):
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         e2e_ev[i][0].record()
-        load(nb, from_host=True); nb += 1   # pinned host rays + gt -> device (pipelined: the batch that is marched in this step)
+        load(nb, from_host=True); nb += 1   # pinned host rays (+ gt) -> device (pipelined: the batch that is marched in this step)
         run_step()
         allreduce()
-        loss_host.copy_(eng.loss_slots, non_blocking=True)
+        loss_host.copy_(loss_dev, non_blocking=True)
         e2e_ev[i][1].record()
     torch.cuda.synchronize()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
@@ -347,19 +500,26 @@ def run_ours(args, rank, world, local):
     rays_total = args.rays * world * args.steps
     value = rays_total / (t_ms * 1e-3)
     L = args.levels
-    bytes_fwd = L * 8 * 2 * 2            # 8 corners x 2 features x fp16
-    bytes_bwd = L * 8 * 2 * 4 + 64       # fp32 reductions + the saved fp16 encoding
-    dom = max(("field_fwd", "field_bwd"), key=lambda k: kt[k])
-    alg = S_mean * (bytes_fwd if dom == "field_fwd" else bytes_bwd)
-    ach = alg / (kt[dom] * 1e-3) / 1e9
+    # roofline of every field kernel; the headline object is the dominant one (longest average launch)
+    roofs = []
+    for kernel, phase, bound, per_sample in roofline_kernels(eng):
+        ms = kt[phase]
+        if bound == "hbm":
+            ach, peak, unit = S_mean * per_sample / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = S_mean * per_sample / (ms * 1e-3) / 1e12, peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "TFLOP/s"
+        traffic, src = ncu_traffic(kernel)
+        roofs.append({"bound": bound, "kernel": kernel, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                      "traffic": traffic, "traffic_source": src, "peak_kind": peak_kind,
+                      ("algorithmic_bytes_per_sample" if bound == "hbm" else "algorithmic_flops_per_sample"): per_sample})
+    dom = max(roofs, key=lambda r: r["ms"])
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": f"hash (INGP L={L} T=2^19 F=2) teacher training, {args.rays} rays/GPU x 1024 max steps, cuda_ray, "
-                               "synthetic 800x800 Lego-shaped scene, fwd+bwd (MSE), random-init weights",
+        "config": {"workload": WORKLOADS[args.workload].format(L=L, R=args.rays), "workload_key": args.workload,
                    "rays_per_gpu": args.rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
-                   "precision": "fp16 table + fp16 tcgen05 MLP, fp32 accumulate / composite / gradients", "loss_scale": 65536,
+                   "precision": "fp16 table + fp16 tcgen05 MLP, fp32 planes / accumulate / composite / gradients", "loss_scale": 65536,
                    "parallelism": (f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step "
                                    f"({'fp32 NCCL' if exchange is None else 'fp16 payload, ' + ('in-switch multimem reduction' if exchange.kind == 'multimem' else 'NCCL')})") if world > 1 else "single GPU",
                    "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch beside the field "
@@ -369,52 +529,40 @@ def run_ours(args, rank, world, local):
                    "scene_bitfield_sha256": sha[:16]},
         "serial_ms_per_step": serial_ms,
         "kernel_ms": kt,
-        "roofline": {"bound": "hbm", "kernel": "k_hash_field_bwd" if dom == "field_bwd" else "k_hash_field_fwd", "achieved": ach,
-                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
-                     "algorithmic_bytes_per_sample": bytes_fwd if dom == "field_fwd" else bytes_bwd},
-        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * 9 * 4, "d2h_bytes_per_step": 4 * eng.loss_slots.numel()},
+        "roofline": dom,
+        "roofline_all": roofs,
+        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * (6 if pair else 9) * 4,
+                "d2h_bytes_per_step": 4 * loss_dev.numel()},
         "gpu_launches": eng.launches_per_step * args.steps,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.levels, args.rays, budget_s=args.cpu_budget)
+        out["cpu_baseline"] = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def time_phases(eng):
-    """One step with events between phases (roofline pass only; perturbs the step by a few event records)."""
-    import ctypes as C
-    from pvd_b200 import _native as nv
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    l = nv.lib()
-    st = nv.stream_of(eng.rays_o)
-    u32, f32 = C.c_uint32, C.c_float
-    M, N = eng.M, eng.N
-    eng._zeros.zero_(); eng.grad_table.zero_()
-    e[0].record()
-    eng._march_count(st)
-    nv.check(l.pvd_march_rays_train_write(nv.ptr(eng.rays_o), nv.ptr(eng.rays_d), f32(eng.bound), u32(eng.max_steps), u32(N), u32(M),
-                                          nv.ptr(eng.rays), nv.ptr(eng.ws_march), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.deltas), st))
-    e[1].record()
-    nv.check(l.pvd_hash_field_forward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), u32(M), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
-                                      nv.ptr(eng.enc), None, nv.ptr(eng.status), st))
-    e[2].record()
-    nv.check(l.pvd_composite_rays_train_mse(nv.ptr(eng.gt), nv.ptr(eng.bg), f32(eng.loss_scale), nv.ptr(eng.sigmas), nv.ptr(eng.rgbs),
-                                            nv.ptr(eng.deltas), nv.ptr(eng.rays), u32(M), u32(N), nv.ptr(eng.weights_sum), nv.ptr(eng.depth),
-                                            nv.ptr(eng.image), nv.ptr(eng.grad_sigmas), nv.ptr(eng.grad_rgbs), nv.ptr(eng.loss_slots), st))
-    e[3].record()
-    nv.check(l.pvd_hash_field_backward(C.byref(eng.cfield), nv.ptr(eng.xyzs), nv.ptr(eng.dirs), nv.ptr(eng.enc), nv.ptr(eng.grad_sigmas),
-                                       nv.ptr(eng.grad_rgbs), None, u32(M), nv.ptr(eng.counter), nv.ptr(eng.grad_table), nv.ptr(eng.gw_ws),
-                                       nv.ptr(eng.dx_ws), nv.ptr(eng.status), st))
-    e[4].record()
-    torch.cuda.synchronize()
-    return {"march": e[0].elapsed_time(e[1]), "field_fwd": e[1].elapsed_time(e[2]), "composite": e[2].elapsed_time(e[3]),
-            "field_bwd": e[3].elapsed_time(e[4])}
-
-
 # ------------------------------------------------------------------------------------------------ reference arm
+def build_reference(args, dev, ext, bitfield):
+    from oracle import cpu, ref_pipeline as rp
+    torch.manual_seed(0)
+    bf = torch.from_numpy(bitfield).to(dev)
+
+    def hash_net():
+        offsets, pls = cpu.grid_offsets(3, args.levels, 16, 19, desired_resolution=2048)
+        return rp.RefHashNetwork(ext, offsets, pls).to(dev)
+
+    w = args.workload
+    if w == "hash":
+        return rp.RefTrainer(ext, hash_net(), bf)
+    if w == "vm":
+        return rp.RefTrainer(ext, rp.RefVmNetwork(ext).to(dev), bf, l1_reg_weight=L1_REG)
+    if w == "hash-vm":
+        return rp.RefPairTrainer(ext, rp.RefVmNetwork(ext).to(dev), hash_net(), bf, rates=PAIR_RATES, l1_reg_weight=L1_REG)
+    return rp.RefPairTrainer(ext, hash_net(), rp.RefMlpNetwork(ext).to(dev), bf, rates=PAIR_RATES, l1_reg_weight=0.0)
+
+
 def run_reference(args, rank, world, local):
     """The reference's own CUDA extensions + its Python flow (oracle/ref_pipeline.py) on ONE GPU; if oracle/_ref cannot be
     loaded, the CPU oracle port on the host cores instead."""
@@ -423,17 +571,16 @@ def run_reference(args, rank, world, local):
     from pvd_b200 import synthetic as syn
     why = "no CUDA device"
     try:
-        from oracle import cpu, ref_pipeline
+        from oracle import ref_pipeline
         ext = ref_pipeline.load_ext()
         have_ref = torch.cuda.is_available()
     except Exception as ex:  # noqa: BLE001
         ext, have_ref = None, False
         why = repr(ex)
-    cfg = {"workload": f"hash (INGP L={args.levels} T=2^19 F=2) teacher training, {args.rays} rays x 1024 max steps, cuda_ray, "
-                       "synthetic 800x800 Lego-shaped scene, fwd+bwd (MSE), random-init weights",
+    cfg = {"workload": WORKLOADS[args.workload].format(L=args.levels, R=args.rays), "workload_key": args.workload,
            "rays_per_gpu": args.rays, "levels": args.levels}
     if not have_ref:
-        cb = cpu_baseline(args.levels, args.rays, budget_s=max(20.0, args.cpu_budget))
+        cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=max(20.0, args.cpu_budget))
         out = {"metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * args.rays / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": cb,
@@ -444,10 +591,8 @@ def run_reference(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _, bitfield, sha = syn.lego_bitfield()
-    offsets, pls = cpu.grid_offsets(3, args.levels, 16, 19, desired_resolution=2048)
-    torch.manual_seed(0)
-    net = ref_pipeline.RefHashNetwork(ext, offsets, pls).to(dev)
-    tr = ref_pipeline.RefTrainer(ext, net, torch.from_numpy(bitfield).to(dev))
+    tr = build_reference(args, dev, ext, bitfield)
+    pair = args.workload in ("hash-vm", "mlp-hash")
     host = make_workload(args.rays, min(16 + args.warmup + args.steps, 64), seed=0, rank=0)
     devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
     for i in range(16):  # the reference's 16 warm-up iterations with a D2H sync each, then mean_count
@@ -474,22 +619,22 @@ def run_reference(args, rank, world, local):
         ro, rd, gt = host[(16 + args.warmup + i) % len(host)]
         flush.fill_(i & 0xFF)
         e2[i][0].record()
-        loss = tr.step(ro.to(dev, non_blocking=True), rd.to(dev, non_blocking=True), gt.to(dev, non_blocking=True))
+        loss = tr.step(ro.to(dev, non_blocking=True), rd.to(dev, non_blocking=True), None if pair else gt.to(dev, non_blocking=True))
         _ = loss.detach().to("cpu", non_blocking=True)
         e2[i][1].record()
     torch.cuda.synchronize()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2)
     clocks = sampler.stop()
     rays_total = args.rays * args.steps
-    cb = cpu_baseline(args.levels, args.rays, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
+    cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
     cfg.update({"M_rows": tr.mean_count + (128 - tr.mean_count % 128), "precision": "torch autocast fp16 (the reference's -O default), GradScaler-style loss scale 65536",
                 "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)", "scene_bitfield_sha256": sha[:16],
-                "what": "unmodified reference CUDA extensions (oracle/_ref, sm_100a rebuild) + cuBLAS GEMMs via F.linear + torch autograd, "
-                        "Python flow restated in oracle/ref_pipeline.py"})
+                "what": "unmodified reference CUDA extensions (oracle/_ref, sm_100a rebuild) + cuBLAS GEMMs via F.linear + F.grid_sample + torch "
+                        "autograd, Python flow restated in oracle/ref_pipeline.py"})
     out = {"metric": METRIC, "value": rays_total / (t_ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
            "data": "synthetic", "impl": "reference", "config": cfg,
-           "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * 9 * 4, "d2h_bytes_per_step": 4},
+           "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * (6 if pair else 9) * 4, "d2h_bytes_per_step": 4},
            "clocks": clocks}
     if cb:
         out["cpu_baseline"] = cb
@@ -502,15 +647,19 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hash", choices=sorted(WORKLOADS), help="hash = BASELINE configs[1] (the headline); vm = configs[2]; "
+                    "hash-vm = configs[3] (distillation, teacher and student at shared samples); mlp-hash = configs[4]")
     ap.add_argument("--levels", type=int, default=14, help="hash levels: 14 = what PVD builds (network.py:47-51), 16 = BASELINE.json's text")
-    ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
+    ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (default 4096; 8192 for mlp-hash)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-comm", default="fp16", choices=["multimem", "fp16", "fp32"], help="table-gradient exchange for N > 1: fp16 payload over NCCL (default), fp16 payload reduced in the NVSwitch (multimem; measured slower on 2 GPUs: 106 vs 89 us), or fp32 over NCCL")
+    ap.add_argument("--grad-comm", default="fp16", choices=["multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (default), fp16 payload reduced in the NVSwitch (multimem; measured slower on 2 GPUs: 106 vs 89 us), or fp32 over NCCL")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="serial step graph: do not overlap the next batch's march with the backward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.rays is None:
+        args.rays = DEFAULT_RAYS[args.workload]
     rank, world, local = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world, local)

@@ -148,12 +148,16 @@ def _run_engine(eng, ro, rd, gt=None):
     assert int(eng.status.item()) == 0, "tensor-core pipeline reported a timeout"
 
 
-def _check_grads(eng, named, scale, tol=3e-2):
+def _check_grads(eng, named, tol=3e-2):
+    """engine gradients vs the oracle's.  The oracle's loss is multiplied by the SAME loss scale before backward(): its
+    quantize_fp16 casts round the gradient to fp16 on the way back, exactly like autocast, so an unscaled oracle underflows."""
     got = eng.grads()
     assert set(got) == set(named), (sorted(got), sorted(named))
     for k, ref in named.items():
-        assert ref.grad is not None, k
-        e = _rel_l2(got[k] / scale, ref.grad)
+        if ref.grad is None:   # a parameter the stage's loss does not reach (stage 1: the colour head)
+            assert float(got[k].abs().max()) == 0.0, k
+            continue
+        e = _rel_l2(got[k], ref.grad)
         assert e < tol, f"{k}: rel-L2 {e}"
 
 
@@ -170,7 +174,7 @@ def test_pair_engine_hash_to_vm_stage3(scene):
     f_s, named, P = _vm_oracle(stu)
     o = field.pair_distill_step(ro, rd, scene["bitfield"], f_s, f_t, RATES, stage=3, M=eng.M,
                                 l1_reg=1e-2 * field.vm_density_loss(P["sm"], P["sv"]))
-    o["loss"].backward()
+    (o["loss"] * 128.0).backward()
     assert torch.equal(eng.rays.cpu(), o["rays"])
     assert torch.equal(eng.xyzs.cpu(), o["xyzs"]), "sample rows (padding included) differ from the oracle"
     terms = eng.loss_terms()
@@ -180,7 +184,7 @@ def test_pair_engine_hash_to_vm_stage3(scene):
     pred_s, pred_t = eng.final_images()
     torch.testing.assert_close(pred_s.cpu(), o["image"].detach(), rtol=1e-2, atol=5e-3)
     torch.testing.assert_close(pred_t.cpu(), o["image_tea"], rtol=1e-2, atol=5e-3)
-    _check_grads(eng, named, 128.0)
+    _check_grads(eng, named)
 
 
 @pytest.mark.parametrize("stage", [1, 2, 3])
@@ -195,9 +199,9 @@ def test_pair_engine_hash_to_hash_stages(scene, stage):
     f_t, _ = _hash_oracle(tea, False)
     f_s, named = _hash_oracle(stu, True)
     o = field.pair_distill_step(ro, rd, scene["bitfield"], f_s, f_t, RATES, stage=stage, M=eng.M)
-    o["loss"].backward()
+    (o["loss"] * 64.0).backward()
     assert abs(float(eng.loss[0]) - float(o["loss"])) < 2e-2 * float(o["loss"])
-    _check_grads(eng, named, 64.0)
+    _check_grads(eng, named)
 
 
 def test_pair_engine_mlp_to_hash(scene):
@@ -219,9 +223,9 @@ def test_pair_engine_mlp_to_hash(scene):
     f_t = lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw, quantize_fp16=True)
     f_s, named = _hash_oracle(stu, True)
     o = field.pair_distill_step(ro, rd, scene["bitfield"], f_s, f_t, RATES, stage=3, M=eng.M)
-    o["loss"].backward()
+    (o["loss"] * 64.0).backward()
     assert abs(float(eng.loss[0]) - float(o["loss"])) < 2e-2 * float(o["loss"])
-    _check_grads(eng, named, 64.0)
+    _check_grads(eng, named)
 
 
 def test_vm_train_engine(scene):
@@ -232,17 +236,18 @@ def test_vm_train_engine(scene):
     ro, rd = scene["batches"][0]
     ro, rd = ro[:640].contiguous(), rd[:640].contiguous()
     gt = torch.rand(640, 3, generator=torch.Generator().manual_seed(3))
-    eng = VMTrainEngine(net, torch.from_numpy(scene["bitfield"]), 640, loss_scale=256.0, l1_reg_weight=1e-2)
+    LS = 65536.0   # GradScaler's initial scale (the reference trains under torch.cuda.amp.GradScaler)
+    eng = VMTrainEngine(net, torch.from_numpy(scene["bitfield"]), 640, loss_scale=LS, l1_reg_weight=1e-2)
     _run_engine(eng, ro.cuda(), rd.cuda(), gt.cuda())
     f_s, named, P = _vm_oracle(net)
     o = field.render_train_step(ro, rd, scene["bitfield"], gt, lambda x, d: f_s(x, d)[:2], M=eng.M, aabb=None)
     loss = o["loss"] + 1e-2 * field.vm_density_loss(P["sm"], P["sv"])
-    loss.backward()
+    (loss * LS).backward()
     assert torch.equal(eng.rays.cpu(), o["rays"])
     assert abs(float(eng.loss[0]) - float(loss)) < 2e-2 * float(loss)
     pred, _ = eng.final_image()
     torch.testing.assert_close(pred.cpu(), o["image"].detach(), rtol=1e-2, atol=5e-3)
-    _check_grads(eng, named, 256.0)
+    _check_grads(eng, named)
 
 
 def test_pair_engine_graph_and_pipeline_equal_eager(scene):
