@@ -15,13 +15,25 @@ struct Pipe {
     int32_t* status;
     uint32_t trec = 0;  // timeline record of this CTA (PVD_TRACE builds only)
     uint64_t* wbar = nullptr;  // non-null while the TMA copy of the weight blob may still be in flight (thread 0 waits once)
+    uint32_t wphase = 0;       // parity of `wbar` to wait for
+    uint32_t team = 0;         // 0: the whole CTA works on one tile (barrier 0, leader = thread 0); n > 0: a 128-thread warpgroup
+                               // works on its own tile (named barrier n, leader = the warpgroup's first thread)
 };
+
+__device__ __forceinline__ bool team_leader(const Pipe& p) { return p.team ? ((threadIdx.x & 127u) == 0u) : (threadIdx.x == 0u); }
 
 // Every thread: publish shared-memory operand writes to the async proxy and order prior TMEM reads, then barrier.
 __device__ __forceinline__ void operands_ready() {
     tc5::fence_async_smem();
     tc5::fence_before_sync();
     __syncthreads();
+}
+// The same for the team of `p` (see Pipe::team).
+__device__ __forceinline__ void operands_ready(const Pipe& p) {
+    tc5::fence_async_smem();
+    tc5::fence_before_sync();
+    if (p.team == 0u) __syncthreads();
+    else asm volatile("bar.sync %0, 128;" ::"r"(p.team) : "memory");
 }
 // Every thread: wait for the MMAs committed by thread 0.
 __device__ __forceinline__ void mma_wait(Pipe& p) {
@@ -109,7 +121,7 @@ __device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint
 // core reads shared memory through the async proxy, the same proxy TMA wrote it through: no proxy fence is needed.
 __device__ __forceinline__ void weights_ready(Pipe& p) {
     if (p.wbar != nullptr) {
-        if (!tc5::mbar_wait(p.wbar, 0)) atomicExch(p.status, 1);
+        if (!tc5::mbar_wait(p.wbar, p.wphase)) atomicExch(p.status, 1);
         p.wbar = nullptr;
     }
 }

@@ -18,6 +18,7 @@
 //   * layer epilogue: each thread pulls its own row from TMEM 16 columns at a time, adds the bias, applies ReLU, and writes
 //     the next layer's A operand (fp16, chunk layout) over the previous one.
 //   * the last layer (256 -> 28) feeds the sigma_net / color_net tail of field_tail.cuh unchanged.
+#include <stdlib.h>
 #include "common.cuh"
 PVD_TRACE_TU(pvd_debug_trace_field_mlp)
 #include "field_tail.cuh"
@@ -54,7 +55,7 @@ __constant__ ChunkDesc kSchedule[kMlpChunks] = {
     {6, 0, 0, 0}, {6, 0, 1, 0}, {6, 0, 2, 0}, {6, 0, 3, 1},
 };
 
-__global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+__global__ void __launch_bounds__(128, 1) k_mlp_field_fwd_v1(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                           uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                           float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -233,6 +234,260 @@ __global__ void __launch_bounds__(128, 1) k_mlp_field_fwd(MlpArgs a, const float
     if (tid < 32) tc5::tmem_dealloc(tmem, 256);
 }
 
+
+// =============================================================================================== v2: warp-specialised, two tiles per CTA
+// One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream:
+//   warps 0-3 (warpgroup 0) own the rows of tile 0, warps 4-7 (warpgroup 1) the rows of tile 1: PE, layer epilogues (TMEM -> bias ->
+//     ReLU -> fp16 operand tile, in place), the sigma/colour tail and the outputs of their tile;
+//   warp 8, one lane: TMA producer.  The packed weights are streamed in 16 KB pieces ([256 x 32] fp16 = half of a v1 chunk, same
+//     blob) through a FOUR-stage ring; loads run up to four pieces ahead of the tensor core, across layers, tiles pairs and the
+//     tail, so their latency (the bound of v1: a two-stage ring serialised copy -> MMA -> copy) is off the critical path;
+//   warp 9, one lane: MMA issuer.  Every piece feeds 2 + 2 tcgen05.mma (tile 0, tile 1; N = 256, K = 16), so L2 -> shared weight
+//     traffic per sample is halved; accumulators: tile t in TMEM columns [256 t, 256 t + 256) -- all 512 columns of the SM.
+// Hand-offs are mbarriers only (no CTA-wide barrier in the steady state):
+//   ring_full[s] (TMA bytes) / ring_empty[s] (tcgen05.commit)        producer <-> issuer
+//   acc_full[t]  (tcgen05.commit after a layer's last MMA)           issuer   ->  warpgroup t: accumulator complete, operand tile dead
+//   act_ready[t] (128 arrivals)                                      warpgroup t -> issuer: next operand tile written, TMEM drained
+// Shared memory: 2 x 64 KB operand tiles + 2 x 16 KB PE tiles + 4 x 16 KB ring = 224 KB.  The 20 KB tail weights are copied (TMA)
+// into the dead upper half of a tile's own operand buffer when its layer 7 has completed; biases are read through the constant-
+// like __ldg path (all threads of a warp read the same address).
+constexpr uint32_t kPiece = 16384;                    // bytes per streamed piece
+constexpr uint32_t kPieces = 2 * kMlpChunks + 1;      // 52 half-chunks of layers 0-6 + layer 7
+constexpr uint32_t kStages = 4;
+constexpr uint32_t kV2Threads = 320;
+constexpr uint32_t kTailWOff = 32768;                 // tail weights inside a tile's operand buffer
+
+struct V2Wait {  // bounded waits that stop costing time after the first failure (a wrong barrier must not hang the GPU)
+    int32_t* status;
+    bool dead = false;
+    __device__ __forceinline__ void operator()(uint64_t* bar, uint32_t parity) {
+        if (!tc5::mbar_wait(bar, parity, dead ? 1u : (1u << 22))) {
+            dead = true;
+            atomicExch(status, 2);
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                                uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
+                                                                float* __restrict__ feat16, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t ring_full[kStages], ring_empty[kStages], acc_full[2], act_ready[2], tail_bar[2], tail_w[2];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* const ring = smem + 2 * 65536 + 2 * 16384;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < kStages; ++s) {
+            tc5::mbar_init(&ring_full[s], 1);
+            tc5::mbar_init(&ring_empty[s], 1);
+        }
+        for (uint32_t t = 0; t < 2; ++t) {
+            tc5::mbar_init(&acc_full[t], 1);
+            tc5::mbar_init(&act_ready[t], 128);
+            tc5::mbar_init(&tail_bar[t], 1);
+            tc5::mbar_init(&tail_w[t], 1);
+        }
+        tc5::mbar_fence_init();
+    }
+    if (warp == 0) tc5::tmem_alloc(&tmem_base_s, 512);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    const uint32_t n_pairs = (n_tiles + 1) / 2;
+    V2Wait wait{status};
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t pc = 0;  // pieces issued so far (ring position)
+            for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (uint32_t q = 0; q < kPieces; ++q, ++pc) {
+                    const uint32_t s = pc % kStages;
+                    if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
+                    tc5::mbar_expect_tx(&ring_full[s], kPiece);
+                    tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), a.wblob + (size_t)q * kPiece, kPiece, &ring_full[s]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t pc = 0, acts = 0;  // pieces consumed; act_ready phases consumed (same count for both tiles)
+            const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
+            const uint32_t idesc7 = tc5::instr_desc_f16(128, 32, 0, 0);
+            for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                uint32_t q = 0;
+                for (uint32_t layer = 0; layer < 7; ++layer) {
+                    const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : 8u);
+                    for (uint32_t j = 0; j < n_pieces; ++j, ++q, ++pc) {
+                        const ChunkDesc cd = kSchedule[q >> 1];
+                        const uint32_t s = pc % kStages;
+                        wait(&ring_full[s], (pc / kStages) & 1u);
+                        const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                        for (uint32_t t = 0; t < 2; ++t) {
+                            if (j == 0) wait(&act_ready[t], acts & 1u);  // operand tile of this layer written, accumulator drained
+                            tc5::fence_after_sync();
+                            const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
+                                                               : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
+                            const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);   // which 32-column half of the 64-column slice
+#pragma unroll
+                            for (uint32_t k0 = 0; k0 < 32; k0 += 16)
+                                tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
+                                                !(j == 0 && k0 == 0));
+                            if (j + 1 == n_pieces) tc5::mma_commit(&acc_full[t]);
+                        }
+                        tc5::mma_commit(&ring_empty[s]);
+                    }
+                    ++acts;
+                }
+                {   // layer 7: 256 -> 28 (N = 32); the piece holds four [32 x 64] operand tiles
+                    const uint32_t s = pc % kStages;
+                    wait(&ring_full[s], (pc / kStages) & 1u);
+                    const uint32_t b_base = tc5::smem_u32(ring + s * kPiece);
+                    for (uint32_t t = 0; t < 2; ++t) {
+                        wait(&act_ready[t], acts & 1u);
+                        tc5::fence_after_sync();
+                        for (uint32_t c = 0; c < 4; ++c)
+#pragma unroll
+                            for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                                tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(tc5::smem_u32(smem + t * 65536) + c * 8u * (kTile * 16u), kTile, k0),
+                                                tc5::desc_kmajor(b_base + c * (32u * 64u * 2u), 32, k0), idesc7, !(c == 0 && k0 == 0));
+                        tc5::mma_commit(&acc_full[t]);
+                    }
+                    tc5::mma_commit(&ring_empty[s]);
+                    ++pc;
+                    ++acts;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ the two warpgroups: one tile each
+        const uint32_t t = warp >> 2;          // tile of the pair / warpgroup
+        const uint32_t r = tid & 127u;         // row inside the tile
+        uint8_t* const A = smem + t * 65536;
+        uint8_t* const X0 = smem + 2 * 65536 + t * 16384;
+        const uint32_t trow = tc5::tmem_addr(tmem + 256u * t, (warp & 3u) * 32u, 0);
+        const float* __restrict__ bias = reinterpret_cast<const float*>(a.wblob + kMlpBiasOff);
+        Pipe p{&tail_bar[t], 0u, tmem + 256u * t, status};
+        p.team = 1u + t;
+        uint32_t accs = 0, pairs_done = 0;
+        for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pairs_done) {
+            const uint32_t row = (2u * pair + t) * kTile + r;
+            const bool live = row < M;
+            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+                    dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+                }
+            }
+            {   // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9
+                float f[64];
+                f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2];
+                float freq = 1.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        float sn, cs;
+                        sincosf(pos[d] * freq, &sn, &cs);
+                        f[3 + 6 * k + d] = sn;
+                        f[3 + 6 * k + 3 + d] = cs;
+                    }
+                    freq *= 2.0f;
+                }
+                f[63] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(X0 + tc5::chunk_off(kTile, r, j)) = tc5::pack8(f + 8 * j);
+            }
+            tc5::fence_async_smem();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive(&act_ready[t]);
+            // ---- layers 0..6: wait for the accumulator, bias + ReLU, rewrite the operand tile in place
+            for (uint32_t layer = 0; layer < 7; ++layer, ++accs) {
+                wait(&acc_full[t], accs & 1u);
+                tc5::fence_after_sync();
+                const float4* __restrict__ bl = reinterpret_cast<const float4*>(bias + 256 * layer);
+                uint32_t buf[2][32];
+                tc5::tmem_ld32_issue(trow, buf[0]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    tc5::tmem_ld_wait();
+                    if (c + 1 < 8) tc5::tmem_ld32_issue(trow + 32 * (c + 1), buf[(c + 1) & 1]);
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(bl + 8 * c + i);
+                        v[4 * i + 0] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 0]) + b4.x, 0.0f);
+                        v[4 * i + 1] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 1]) + b4.y, 0.0f);
+                        v[4 * i + 2] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 2]) + b4.z, 0.0f);
+                        v[4 * i + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 3]) + b4.w, 0.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, r, 4 * c + i)) = tc5::pack8(v + 8 * i);
+                }
+                tc5::fence_async_smem();
+                tc5::fence_before_sync();
+                tc5::mbar_arrive(&act_ready[t]);
+            }
+            // ---- layer 7 -> x28; then the sigma / colour tail on this warpgroup's tile
+            wait(&acc_full[t], accs & 1u);
+            ++accs;
+            tc5::fence_after_sync();
+            if (r == 0) {  // the operand tile is dead: fetch the tail weights into its upper half while x28 is formed
+                tc5::mbar_expect_tx(&tail_w[t], PVD_FIELD_WBLOB_BYTES);
+                tc5::bulk_g2s(tc5::smem_u32(A + kTailWOff), a.tail_blob, PVD_FIELD_WBLOB_BYTES, &tail_w[t]);
+            }
+            uint8_t* X = A;                 // 8192
+            uint8_t* CIN = A;               // aliases X (dead after the first tail layer)
+            uint8_t* H = A + 8192;          // 16384 : H1, H3, H4
+            {
+                float v[32];
+                tc5::tmem_ld16(trow, *reinterpret_cast<float(*)[16]>(&v[0]));
+                tc5::tmem_ld16(trow + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                const float* b7 = bias + 256 * 7;
+#pragma unroll
+                for (int i = 0; i < 28; ++i) v[i] += __ldg(b7 + i);
+#pragma unroll
+                for (int i = 28; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, r, j)) = tc5::pack8(v + 8 * j);
+            }
+            FieldArgs fa;
+            fa.clip_min = a.clip_min; fa.clip_max = a.clip_max; fa.density_scale = a.density_scale;
+            float sigma, o16[16];
+            FwdRegs fr;
+            p.wbar = &tail_w[t];
+            p.wphase = pairs_done & 1u;
+            mlp_forward(p, fa, A + kTailWOff, X, H, CIN, H, H, dir, r, sigma, o16, fr);
+            if (live) {
+                sigmas[row] = sigma;
+                rgbs[3 * (size_t)row] = fr.rgb[0];
+                rgbs[3 * (size_t)row + 1] = fr.rgb[1];
+                rgbs[3 * (size_t)row + 2] = fr.rgb[2];
+                if (feat16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(feat16 + 16 * (size_t)row + 4 * q) =
+                            make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
+                }
+            }
+            // the tail's last TMEM read / its tiles must be done before the next pair's PE arrival lets layer 0 overwrite them
+            tc5::fence_before_sync();
+            asm volatile("bar.sync %0, 128;" ::"r"(1u + t) : "memory");
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc5::tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t kMlpSmemV2 = 2 * 65536 + 2 * 16384 + kStages * kPiece;  // 229376
+
 // pack nerf_mlp weights/biases (fp32, nn.Linear layout) into the streamed blob
 __global__ void k_mlp_pack(const float* const* __restrict__ w, const float* const* __restrict__ b, uint8_t* __restrict__ blob) {
     // chunk index -> (layer, first input column of the slice).  Layer 4's input is cat([in_pts(63), hidden(256)]) (network.py:331-332)
@@ -294,10 +549,20 @@ int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* 
     a.tail_blob = reinterpret_cast<const uint8_t*>(f->tail_wblob);
     a.clip_min = f->sigma_clip_min; a.clip_max = f->sigma_clip_max; a.density_scale = f->density_scale;
     const uint32_t tiles = (M + kTile - 1) / kTile;
+    static const bool use_v1 = []() { const char* v = getenv("PVD_MLP_V1"); return v != nullptr && v[0] == '1'; }();
+    if (!use_v1) {
+        const uint32_t pairs = (tiles + 1) / 2;
+        const uint32_t grid2 = min(pairs, (uint32_t)sm_count());
+        cudaError_t e2 = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
+        if (e2 != cudaSuccess) return (int)e2;
+        k_mlp_field_fwd<<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+        PVD_LAUNCH_CHECK();
+        return PVD_OK;
+    }
     const uint32_t grid = min(tiles, (uint32_t)sm_count());
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_field_fwd_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem);
     if (e != cudaSuccess) return (int)e;
-    k_mlp_field_fwd<<<grid, 128, kMlpSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    k_mlp_field_fwd_v1<<<grid, 128, kMlpSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

@@ -39,34 +39,36 @@ struct FwdRegs {  // what the backward needs from the recomputed forward of this
 };
 
 // Layers 1..5 for one tile.  X tile must already hold the encoding.  Tiles: X, H1, CIN, H3, H4 (H3/H4 may alias X-independent
-// buffers in the forward-only kernel).  Returns sigma (scaled) and rgb for this thread's row.
+// buffers in the forward-only kernel).  Returns sigma (scaled) and rgb for this thread's row.  `row` is the thread's row inside the
+// tile (0..127); the cooperating threads are the team of `p` (the whole CTA, or one 128-thread warpgroup of a larger CTA).
 __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t* smw, uint8_t* X, uint8_t* H1, uint8_t* CIN,
                                             uint8_t* H3, uint8_t* H4, const float* __restrict__ dir, uint32_t row, float& sigma,
                                             float (&o16)[16], FwdRegs& r) {
     const uint32_t tid = threadIdx.x;
-    const uint32_t lane_base = (tid >> 5) * 32;
+    const uint32_t lane_base = ((tid >> 5) & 3u) * 32;  // TMEM lanes a warp may touch: 32 * (warp % 4)
+    const bool leader = team_leader(p);
     const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
     const uint32_t sw = tc5::smem_u32(smw);
     // ---- sigma_net.0 : [128 x 32] x [64 x 32]^T
-    operands_ready();
-    if (tid == 0) {
+    operands_ready(p);
+    if (leader) {
         tc5::fence_after_sync();
         weights_ready(p);
         issue_fwd(p.tmem + kD, tc5::smem_u32(X), 32, sw + kWB1, 64, 64);
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
-    if (tid == 0) PVD_T(p.trec, 6);
+    if (leader) PVD_T(p.trec, 6);
     relu_to_tile<4>(trow + kD, H1, row);
     // ---- sigma_net.1 : [128 x 64] x [16 x 64]^T
-    operands_ready();
-    if (tid == 0) {
+    operands_ready(p);
+    if (leader) {
         tc5::fence_after_sync();
         issue_fwd(p.tmem + kD16, tc5::smem_u32(H1), 64, sw + kWB2, 16, 16);
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
-    if (tid == 0) PVD_T(p.trec, 7);
+    if (leader) PVD_T(p.trec, 7);
     tc5::tmem_ld16(trow + kD16, o16);
 #pragma unroll
     for (int i = 0; i < 16; ++i) o16[i] = __half2float(__float2half_rn(o16[i]));  // the reference's fp16 activations
@@ -87,34 +89,34 @@ __device__ __forceinline__ void mlp_forward(Pipe& p, const FieldArgs& a, uint8_t
         *reinterpret_cast<uint4*>(CIN + tc5::chunk_off(kTile, row, 3)) = tc5::pack8(geo + 8);
     }
     // ---- color_net.0 : [128 x 32] x [64 x 32]^T
-    operands_ready();
-    if (tid == 0) {
+    operands_ready(p);
+    if (leader) {
         tc5::fence_after_sync();
         issue_fwd(p.tmem + kD, tc5::smem_u32(CIN), 32, sw + kWB3, 64, 64);
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
-    if (tid == 0) PVD_T(p.trec, 8);
+    if (leader) PVD_T(p.trec, 8);
     relu_to_tile<4>(trow + kD, H3, row);
     // ---- color_net.1 : [128 x 64] x [64 x 64]^T
-    operands_ready();
-    if (tid == 0) {
+    operands_ready(p);
+    if (leader) {
         tc5::fence_after_sync();
         issue_fwd(p.tmem + kD, tc5::smem_u32(H3), 64, sw + kWB4, 64, 64);
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
-    if (tid == 0) PVD_T(p.trec, 9);
+    if (leader) PVD_T(p.trec, 9);
     relu_to_tile<4>(trow + kD, H4, row);
     // ---- color_net.2 : [128 x 64] x [16 x 64]^T , sigmoid
-    operands_ready();
-    if (tid == 0) {
+    operands_ready(p);
+    if (leader) {
         tc5::fence_after_sync();
         issue_fwd(p.tmem + kD5, tc5::smem_u32(H4), 64, sw + kWB5, 16, 16);
         tc5::mma_commit(p.bar);
     }
     mma_wait(p);
-    if (tid == 0) PVD_T(p.trec, 10);
+    if (leader) PVD_T(p.trec, 10);
     float c16[16];
     tc5::tmem_ld16(trow + kD5, c16);
 #pragma unroll
