@@ -10,14 +10,14 @@
 // the state_dict do not change.
 //
 // Work decomposition.
-//   gather  : ONE WARP PER SAMPLE, lanes = components (lanes 0-7 the 16 sigma components, lanes 8-31 the 48 colour ones,
-//             two per lane) -> every tap is one coalesced 256-byte request; plane x line products go straight into the
-//             fp16 operand tile APP[128 x 144] (colour) and a warp-reduced scalar (sigma).  4608 B/sample algorithmic.
+//   gather  : HALF A WARP PER SAMPLE, lanes = components (lanes 0-3 the 16 sigma components, lanes 4-15 the 48 colour ones,
+//             four per lane) -> every tap is one coalesced 256-byte request of 128-bit loads; plane x line products go straight
+//             into the fp16 operand tile APP[128 x 144] (colour) and a group-reduced scalar (sigma).  4608 B/sample algorithmic.
 //   MLP     : thread per sample around tcgen05 GEMMs, exactly as in field_hash.cu: basis_mat (K = 144, 9 MMAs), clamps,
 //             exp, SH concat, color_net (3 layers), sigmoid.
 //   backward: forward recomputed; weight gradients accumulate in TMEM (basis as three M=64 pieces); d(APP) comes back in
-//             three 48-column data-gradient GEMMs; then one warp per sample re-gathers plane/line values and scatters
-//             d(plane) = d(prod) * line, d(line) = d(prod) * plane with red.global.add.v2.f32 into channels-last gradients
+//             three 48-column data-gradient GEMMs; then half a warp per sample re-gathers plane/line values and scatters
+//             d(plane) = d(prod) * line, d(line) = d(prod) * plane with red.global.add.v4.f32 into channels-last gradients
 //             (coalesced 256-byte reductions).
 #include "field_common.cuh"
 #include "shenc.cuh"
@@ -106,66 +106,128 @@ __device__ __forceinline__ void vm_foot(const float (&xn)[3], const uint32_t (&r
     }
 }
 
-// plane and line value of this lane's two components
-__device__ __forceinline__ void vm_sample(const float* __restrict__ mat, const float* __restrict__ vec, uint32_t R, uint32_t ch,
-                                          const Foot& f, float2& pv, float2& lv) {
-    pv = make_float2(0.f, 0.f);
-    lv = make_float2(0.f, 0.f);
-    float2 t[4], u[2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float2*>(mat + (size_t)f.pidx[k] * R + ch));
-#pragma unroll
-    for (int k = 0; k < 2; ++k) u[k] = __ldg(reinterpret_cast<const float2*>(vec + (size_t)f.lidx[k] * R + ch));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        pv.x = __fmaf_rn(f.pw[k], t[k].x, pv.x);
-        pv.y = __fmaf_rn(f.pw[k], t[k].y, pv.y);
+// Lane mapping of the gather / scatter: HALF a warp per sample, four consecutive components per lane.  Lane L works on sample
+// (L >> 4) of the current pair; its 16-lane group covers the 64 components of a tap: lanes 0-3 the 16 sigma components, lanes 4-15
+// the 48 colour ones.  A tap of one sample is then 16 lanes x 16 B = the same contiguous 256 bytes as before, but every load is a
+// 128-bit load and every reduction a red.global.add.v4.f32: half the instructions and -- what bounds the backward -- half the
+// reduction lane-operations (the SM retires roughly one reduction lane-operation per 1.3 cycles whatever its width).
+struct LaneMap {
+    bool sig;        // this lane holds sigma components
+    uint32_t R;      // components per texel of its tensors (16 / 48)
+    uint32_t ch;     // first of its four components
+    uint32_t half;   // which sample of the pair
+    __device__ __forceinline__ LaneMap() {
+        const uint32_t lane = threadIdx.x & 31u, l16 = lane & 15u;
+        sig = l16 < 4u;
+        R = sig ? 16u : 48u;
+        ch = sig ? 4u * l16 : 4u * (l16 - 4u);
+        half = lane >> 4;
     }
+};
+
+// All 18 taps (3 planes x 4 + 3 lines x 2) of one sample for this lane's four components, and their bilinear weights.  The loads
+// are ISSUED here and consumed later: the gather is latency-bound (ncu: 62% of the stall samples of a one-sample-at-a-time loop
+// were long-scoreboard waits on these loads), so a warp keeps the taps of two samples (9 KB) in flight.
+// 128-bit read-only load that stays where it is written (volatile): all 18 loads of a sample are issued back to back before the
+// first one is consumed; left to itself the compiler sinks each plane's loads next to their use (three serial latencies per sample)
+__device__ __forceinline__ float4 ldg_v4_issue(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+struct SampleTaps {
+    float4 t[3][4], u[3][2];
+    float pw[3][4], lw[3][2];
+};
+
+__device__ __forceinline__ void vm_issue(const VmArgs& a, const float (&pos)[3], const LaneMap& m, SampleTaps& T) {
+    float xn[3];
+    vm_normalise(pos, a.aabb, xn);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        lv.x = __fmaf_rn(f.lw[k], u[k].x, lv.x);
-        lv.y = __fmaf_rn(f.lw[k], u[k].y, lv.y);
+    for (int i = 0; i < 3; ++i) {
+        Foot f;
+        vm_foot(xn, a.res, i, f);
+        const float* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
+        const float* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            T.t[i][k] = ldg_v4_issue(mat + (size_t)f.pidx[k] * m.R + m.ch);
+            T.pw[i][k] = f.pw[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            T.u[i][k] = ldg_v4_issue(vec + (size_t)f.lidx[k] * m.R + m.ch);
+            T.lw[i][k] = f.lw[k];
+        }
     }
 }
 
-// Gather phase for the 32 samples of this warp: APP tile (colour products, fp16) and sfeat[row] (sigma feature, fp32)
+// interpolated plane and line value of pair i (grid_sample's bilinear sum, tap order 00, 01, 10, 11)
+__device__ __forceinline__ void vm_interp(const SampleTaps& T, int i, float4& pv, float4& lv) {
+    pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    lv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pv.x = __fmaf_rn(T.pw[i][k], T.t[i][k].x, pv.x);
+        pv.y = __fmaf_rn(T.pw[i][k], T.t[i][k].y, pv.y);
+        pv.z = __fmaf_rn(T.pw[i][k], T.t[i][k].z, pv.z);
+        pv.w = __fmaf_rn(T.pw[i][k], T.t[i][k].w, pv.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        lv.x = __fmaf_rn(T.lw[i][k], T.u[i][k].x, lv.x);
+        lv.y = __fmaf_rn(T.lw[i][k], T.u[i][k].y, lv.y);
+        lv.z = __fmaf_rn(T.lw[i][k], T.u[i][k].z, lv.z);
+        lv.w = __fmaf_rn(T.lw[i][k], T.u[i][k].w, lv.w);
+    }
+}
+
+// products -> APP tile row r (colour, fp16) and sfeat[r] (sigma, summed over the four sigma lanes of the half-warp)
+__device__ __forceinline__ void vm_finish(const SampleTaps& T, const LaneMap& m, uint32_t r, uint8_t* APP, float* sfeat) {
+    float sacc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float4 pv, lv;
+        vm_interp(T, i, pv, lv);
+        const float p0 = pv.x * lv.x, p1 = pv.y * lv.y, p2 = pv.z * lv.z, p3 = pv.w * lv.w;
+        if (m.sig) {
+            sacc += (p0 + p1) + (p2 + p3);
+        } else {
+            const uint32_t col = (uint32_t)i * 48u + m.ch;
+            const __half2 lo = __floats2half2_rn(p0, p1), hi = __floats2half2_rn(p2, p3);
+            *reinterpret_cast<uint2*>(APP + tc5::chunk_off(kTile, r, col >> 3) + (col & 7u) * 2u) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+    }
+    sacc = m.sig ? sacc : 0.0f;
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    if ((threadIdx.x & 15u) == 0u) sfeat[r] = sacc;
+}
+
+// Gather phase for the 32 samples of this warp, two at a time: APP tile (colour products, fp16) and sfeat[row] (sigma feature,
+// fp32).  Lane l first fetches the position of the warp's sample l; a sample's position is then a shuffle away.
 __device__ __forceinline__ void vm_gather(const VmArgs& a, const float* __restrict__ xyzs, uint32_t tile_row0, uint32_t M,
                                           uint8_t* APP, float* sfeat) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const bool sig = lane < 8;
-    const uint32_t R = sig ? 16u : 48u;
-    const uint32_t ch = sig ? 2u * lane : 2u * (lane - 8u);
-#pragma unroll 2
-    for (uint32_t s = 0; s < 32; ++s) {
-        const uint32_t r = warp * 32 + s;
-        const uint32_t row = tile_row0 + r;
-        float pos[3] = {0.f, 0.f, 0.f};
+    const LaneMap m;
+    float mine[3] = {0.f, 0.f, 0.f};
+    {
+        const uint32_t row = tile_row0 + warp * 32 + lane;
         if (row < M) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+            for (int d = 0; d < 3; ++d) mine[d] = __ldg(xyzs + 3 * (size_t)row + d);
         }
-        float xn[3];
-        vm_normalise(pos, a.aabb, xn);
-        float sacc = 0.0f;
+    }
+#pragma unroll 1
+    for (uint32_t s = 0; s < 32; s += 2) {
+        float pos[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            Foot f;
-            vm_foot(xn, a.res, i, f);
-            float2 pv, lv;
-            vm_sample(sig ? a.smat[i] : a.cmat[i], sig ? a.svec[i] : a.cvec[i], R, ch, f, pv, lv);
-            const float p0 = pv.x * lv.x, p1 = pv.y * lv.y;
-            if (sig) {
-                sacc += p0 + p1;
-            } else {
-                const uint32_t col = (uint32_t)i * 48u + ch;
-                *reinterpret_cast<__half2*>(APP + tc5::chunk_off(kTile, r, col >> 3) + (col & 7u) * 2u) = __floats2half2_rn(p0, p1);
-            }
-        }
-        sacc = sig ? sacc : 0.0f;
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        if (lane == 0) sfeat[r] = sacc;
+        for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)(s + m.half));
+        SampleTaps T;
+        vm_issue(a, pos, m, T);
+        vm_finish(T, m, warp * 32 + s + m.half, APP, sfeat);
     }
 }
 
@@ -241,7 +303,7 @@ __device__ __forceinline__ void vm_mlp_forward(Pipe& p, const VmArgs& a, uint8_t
 }
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(128) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+__global__ void __launch_bounds__(128, 3) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                       uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                       float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -297,7 +359,7 @@ __global__ void __launch_bounds__(128) k_vm_field_fwd(VmArgs a, const float* __r
 }
 
 // =============================================================================================== backward
-__global__ void __launch_bounds__(128) k_vm_field_bwd(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
+__global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
                                                       const float* __restrict__ dirs, const float* __restrict__ grad_sigmas,
                                                       const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
                                                       uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ gw,
@@ -439,53 +501,85 @@ __global__ void __launch_bounds__(128) k_vm_field_bwd(VmArgs a, VmGradPtrs g, co
             }
         }
         __syncthreads();  // d(APP) and dsf complete in shared memory
-        // ---- scatter: one warp per sample, lanes = components
+        // ---- scatter: half a warp per sample, four components per lane (LaneMap); the re-gather of the next pair of samples is
+        //      in flight under the reductions of this pair
         {
-            const bool sig = lane < 8;
-            const uint32_t R = sig ? 16u : 48u;
-            const uint32_t ch = sig ? 2u * lane : 2u * (lane - 8u);
-#pragma unroll 2
-            for (uint32_t s = 0; s < 32; ++s) {
-                const uint32_t rr = warp * 32 + s;
-                const uint32_t grow = tile * kTile + rr;
-                if (grow >= n_valid) break;
-                float pos[3];
+            const LaneMap m;
+            const uint32_t row0 = tile * kTile + warp * 32;
+            const uint32_t n_s = (row0 < n_valid) ? min(32u, n_valid - row0) : 0u;
+            float mine[3] = {0.f, 0.f, 0.f};
+            if (lane < n_s) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)grow + d);
+                for (int d = 0; d < 3; ++d) mine[d] = __ldg(xyzs + 3 * (size_t)(row0 + lane) + d);
+            }
+            auto pos_of = [&](uint32_t s2, float (&pos)[3]) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)((s2 + m.half) & 31u));
+            };
+            auto reduce = [&](const SampleTaps& T, const float (&pos)[3], uint32_t s2) {
+                if (s2 + m.half >= n_s) return;   // the odd sample of the last pair
+                const uint32_t rr = warp * 32 + s2 + m.half;
                 float xn[3];
                 vm_normalise(pos, a.aabb, xn);
                 const float ds = dsf[rr];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     Foot f;
-                    vm_foot(xn, a.res, i, f);
-                    float2 pv, lv;
-                    vm_sample(sig ? a.smat[i] : a.cmat[i], sig ? a.svec[i] : a.cvec[i], R, ch, f, pv, lv);
-                    float2 dp;
-                    if (sig) {
-                        dp = make_float2(ds, ds);
+                    vm_foot(xn, a.res, i, f);   // indices again (cheap ALU; keeps 18 registers out of the in-flight state)
+                    float4 pv, lv;
+                    vm_interp(T, i, pv, lv);
+                    float4 dp;
+                    if (m.sig) {
+                        dp = make_float4(ds, ds, ds, ds);
                     } else {
-                        const uint32_t col = (uint32_t)i * 48u + ch;
-                        dp = __half22float2(*reinterpret_cast<const __half2*>(APP + tc5::chunk_off(kTile, rr, col >> 3) + (col & 7u) * 2u));
+                        const uint32_t col = (uint32_t)i * 48u + m.ch;
+                        const uint2 raw = *reinterpret_cast<const uint2*>(APP + tc5::chunk_off(kTile, rr, col >> 3) + (col & 7u) * 2u);
+                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                        dp = make_float4(lo.x, lo.y, hi.x, hi.y);
                     }
-                    const float2 dpv = make_float2(dp.x * lv.x, dp.y * lv.y), dlv = make_float2(dp.x * pv.x, dp.y * pv.y);
-                    float* gm = sig ? g.smat[i] : g.cmat[i];
-                    float* gv = sig ? g.svec[i] : g.cvec[i];
+                    const float4 dpv = make_float4(dp.x * lv.x, dp.y * lv.y, dp.z * lv.z, dp.w * lv.w);
+                    const float4 dlv = make_float4(dp.x * pv.x, dp.y * pv.y, dp.z * pv.z, dp.w * pv.w);
+                    float* gm = m.sig ? g.smat[i] : g.cmat[i];
+                    float* gv = m.sig ? g.svec[i] : g.cvec[i];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (f.pw[k] != 0.0f) {
-                            float* dst = gm + (size_t)f.pidx[k] * R + ch;
-                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(f.pw[k] * dpv.x), "f"(f.pw[k] * dpv.y));
+                            float* dst = gm + (size_t)f.pidx[k] * m.R + m.ch;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.pw[k] * dpv.x), "f"(f.pw[k] * dpv.y),
+                                         "f"(f.pw[k] * dpv.z), "f"(f.pw[k] * dpv.w)
+                                         : "memory");
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (f.lw[k] != 0.0f) {
-                            float* dst = gv + (size_t)f.lidx[k] * R + ch;
-                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(f.lw[k] * dlv.x), "f"(f.lw[k] * dlv.y));
+                            float* dst = gv + (size_t)f.lidx[k] * m.R + m.ch;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.lw[k] * dlv.x), "f"(f.lw[k] * dlv.y),
+                                         "f"(f.lw[k] * dlv.z), "f"(f.lw[k] * dlv.w)
+                                         : "memory");
                         }
                     }
                 }
+            };
+            SampleTaps T0, T1;
+            float p0[3], p1[3];
+            if (n_s > 0) {
+                pos_of(0, p0);
+                vm_issue(a, p0, m, T0);
+            }
+#pragma unroll 1
+            for (uint32_t s = 0; s < n_s; s += 4) {
+                if (s + 2 < n_s) {
+                    pos_of(s + 2, p1);
+                    vm_issue(a, p1, m, T1);
+                }
+                reduce(T0, p0, s);
+                if (s + 4 < n_s) {
+                    pos_of(s + 4, p0);
+                    vm_issue(a, p0, m, T0);
+                }
+                if (s + 2 < n_s) reduce(T1, p1, s + 2);
             }
         }
     }
