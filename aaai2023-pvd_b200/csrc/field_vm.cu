@@ -19,6 +19,7 @@
 //             three 48-column data-gradient GEMMs; then half a warp per sample re-gathers plane/line values and scatters
 //             d(plane) = d(prod) * line, d(line) = d(prod) * plane with red.global.add.v4.f32 into channels-last gradients
 //             (coalesced 256-byte reductions).
+#include <stdlib.h>
 #include "field_common.cuh"
 #include "shenc.cuh"
 #include "../../include/pvd_b200_fused.h"
@@ -69,6 +70,7 @@ struct Foot {
     float pw[4];       // weights (0 for out-of-range taps)
     uint32_t lidx[2];
     float lw[2];
+    int32_t pkey, lkey;  // identity of the plane cell (x0, y0) and of the line cell l0 the sample falls in
 };
 
 __device__ __forceinline__ void vm_normalise(const float* pos, const float* aabb, float (&xn)[3]) {
@@ -86,6 +88,7 @@ __device__ __forceinline__ void vm_foot(const float (&xn)[3], const uint32_t (&r
     const float fx = floorf(ix), fy = floorf(iy);
     const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
     const int x0 = (int)fx, y0 = (int)fy;
+    f.pkey = ((y0 + 2) << 16) | ((x0 + 2) & 0xffff);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
@@ -97,6 +100,7 @@ __device__ __forceinline__ void vm_foot(const float (&xn)[3], const uint32_t (&r
     const float fl = floorf(il);
     const float wl1 = il - fl;
     const int l0 = (int)fl;
+    f.lkey = l0 + 2;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         const int ll = l0 + t;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                                                       const float* __restrict__ dirs, const float* __restrict__ grad_sigmas,
                                                       const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
                                                       uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ gw,
-                                                      int32_t* status) {
+                                                      int32_t* status, uint32_t diag_skip) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -501,31 +505,74 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
             }
         }
         __syncthreads();  // d(APP) and dsf complete in shared memory
-        // ---- scatter: half a warp per sample, four components per lane (LaneMap); the re-gather of the next pair of samples is
-        //      in flight under the reductions of this pair
+        // ---- scatter: half a warp per RUN of 16 consecutive samples, four components per lane (LaneMap).  Consecutive samples of a
+        //      ray are dt = 2 sqrt(3) / 1024 apart, half a texel of a 300^2 plane: they fall into the same plane cell / line cell about
+        //      every other step, so their contributions are summed in registers while the cell does not change and leave the SM as
+        //      ONE red.global.add.v4.f32 per tap and run -- the backward is bound by reduction lane-operations (~1.3 cycles each per SM).
         {
             const LaneMap m;
-            const uint32_t row0 = tile * kTile + warp * 32;
-            const uint32_t n_s = (row0 < n_valid) ? min(32u, n_valid - row0) : 0u;
+            const uint32_t base = tile * kTile + warp * 32 + 16u * m.half;   // first sample of this half-warp's run
+            const uint32_t n_s = ((diag_skip & 1u) == 0u && base < n_valid) ? min(16u, n_valid - base) : 0u;
+            const uint32_t n_it = __reduce_max_sync(0xffffffffu, n_s);       // warp-uniform trip count (loads use shuffles)
+            const uint32_t l16 = lane & 15u;
             float mine[3] = {0.f, 0.f, 0.f};
-            if (lane < n_s) {
+            if (l16 < n_s) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) mine[d] = __ldg(xyzs + 3 * (size_t)(row0 + lane) + d);
+                for (int d = 0; d < 3; ++d) mine[d] = __ldg(xyzs + 3 * (size_t)(base + l16) + d);
             }
-            auto pos_of = [&](uint32_t s2, float (&pos)[3]) {
+            float4 accp[3][4], accl[3][2];
+            int32_t keyp[3] = {-1, -1, -1}, keyl[3] = {-1, -1, -1};
 #pragma unroll
-                for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)((s2 + m.half) & 31u));
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accp[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) accl[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            auto red4 = [](float* dst, const float4& v) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             };
-            auto reduce = [&](const SampleTaps& T, const float (&pos)[3], uint32_t s2) {
-                if (s2 + m.half >= n_s) return;   // the odd sample of the last pair
-                const uint32_t rr = warp * 32 + s2 + m.half;
+            auto flush_plane = [&](int i) {
+                if (keyp[i] < 0) return;
+                const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2;
+                const int W = (int)a.res[a0], Hh = (int)a.res[a1];
+                const int x0 = (keyp[i] & 0xffff) - 2, y0 = (keyp[i] >> 16) - 2;
+                float* gm = m.sig ? g.smat[i] : g.cmat[i];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+                    if (xx >= 0 && xx < W && yy >= 0 && yy < Hh) red4(gm + (size_t)(yy * W + xx) * m.R + m.ch, accp[i][k]);
+                    accp[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            auto flush_line = [&](int i) {
+                if (keyl[i] < 0) return;
+                const int D = (int)a.res[2 - i];
+                const int l0 = keyl[i] - 2;
+                float* gv = m.sig ? g.svec[i] : g.cvec[i];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int ll = l0 + k;
+                    if (ll >= 0 && ll < D) red4(gv + (size_t)ll * m.R + m.ch, accl[i][k]);
+                    accl[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+#pragma unroll 1
+            for (uint32_t s = 0; s < n_it; ++s) {
+                float pos[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)(16u * m.half + (s & 15u)));
+                SampleTaps T;
+                vm_issue(a, pos, m, T);
+                if (s >= n_s) continue;   // this half-warp's run is shorter (tail of the valid rows)
+                const uint32_t rr = warp * 32 + 16u * m.half + s;
                 float xn[3];
                 vm_normalise(pos, a.aabb, xn);
                 const float ds = dsf[rr];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     Foot f;
-                    vm_foot(xn, a.res, i, f);   // indices again (cheap ALU; keeps 18 registers out of the in-flight state)
+                    vm_foot(xn, a.res, i, f);   // weights and cell identity again (cheap ALU; T carries only the tap values)
                     float4 pv, lv;
                     vm_interp(T, i, pv, lv);
                     float4 dp;
@@ -540,46 +587,34 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                     }
                     const float4 dpv = make_float4(dp.x * lv.x, dp.y * lv.y, dp.z * lv.z, dp.w * lv.w);
                     const float4 dlv = make_float4(dp.x * pv.x, dp.y * pv.y, dp.z * pv.z, dp.w * pv.w);
-                    float* gm = m.sig ? g.smat[i] : g.cmat[i];
-                    float* gv = m.sig ? g.svec[i] : g.cvec[i];
+                    if (f.pkey != keyp[i]) {
+                        flush_plane(i);
+                        keyp[i] = f.pkey;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (f.pw[k] != 0.0f) {
-                            float* dst = gm + (size_t)f.pidx[k] * m.R + m.ch;
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.pw[k] * dpv.x), "f"(f.pw[k] * dpv.y),
-                                         "f"(f.pw[k] * dpv.z), "f"(f.pw[k] * dpv.w)
-                                         : "memory");
-                        }
+                        accp[i][k].x = __fmaf_rn(f.pw[k], dpv.x, accp[i][k].x);
+                        accp[i][k].y = __fmaf_rn(f.pw[k], dpv.y, accp[i][k].y);
+                        accp[i][k].z = __fmaf_rn(f.pw[k], dpv.z, accp[i][k].z);
+                        accp[i][k].w = __fmaf_rn(f.pw[k], dpv.w, accp[i][k].w);
+                    }
+                    if (f.lkey != keyl[i]) {
+                        flush_line(i);
+                        keyl[i] = f.lkey;
                     }
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (f.lw[k] != 0.0f) {
-                            float* dst = gv + (size_t)f.lidx[k] * m.R + m.ch;
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.lw[k] * dlv.x), "f"(f.lw[k] * dlv.y),
-                                         "f"(f.lw[k] * dlv.z), "f"(f.lw[k] * dlv.w)
-                                         : "memory");
-                        }
+                        accl[i][k].x = __fmaf_rn(f.lw[k], dlv.x, accl[i][k].x);
+                        accl[i][k].y = __fmaf_rn(f.lw[k], dlv.y, accl[i][k].y);
+                        accl[i][k].z = __fmaf_rn(f.lw[k], dlv.z, accl[i][k].z);
+                        accl[i][k].w = __fmaf_rn(f.lw[k], dlv.w, accl[i][k].w);
                     }
                 }
-            };
-            SampleTaps T0, T1;
-            float p0[3], p1[3];
-            if (n_s > 0) {
-                pos_of(0, p0);
-                vm_issue(a, p0, m, T0);
             }
-#pragma unroll 1
-            for (uint32_t s = 0; s < n_s; s += 4) {
-                if (s + 2 < n_s) {
-                    pos_of(s + 2, p1);
-                    vm_issue(a, p1, m, T1);
-                }
-                reduce(T0, p0, s);
-                if (s + 4 < n_s) {
-                    pos_of(s + 4, p0);
-                    vm_issue(a, p0, m, T0);
-                }
-                if (s + 2 < n_s) reduce(T1, p1, s + 2);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                flush_plane(i);
+                flush_line(i);
             }
         }
     }
@@ -683,8 +718,10 @@ int pvd_vm_field_backward(const PvdVmField* f, const PvdVmGrads* grads, const fl
     const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
     cudaError_t e = cudaFuncSetAttribute(k_vm_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmBwdSmem);
     if (e != cudaSuccess) return (int)e;
+    // PVD_VM_DIAG_SKIP=1 (timing diagnostics only, wrong gradients): leave out the plane / line gradient scatter
+    static const uint32_t diag_skip = []() { const char* v = getenv("PVD_VM_DIAG_SKIP"); return v ? (uint32_t)atoi(v) : 0u; }();
     k_vm_field_bwd<<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                                   gw_ws, status);
+                                                                   gw_ws, status, diag_skip);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }
