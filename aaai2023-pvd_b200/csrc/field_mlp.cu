@@ -36,6 +36,7 @@ struct MlpArgs {
     const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
     const uint8_t* tail_blob;  // PVD_FIELD_WBLOB_BYTES (sigma_net / color_net)
     float clip_min, clip_max, density_scale;
+    uint32_t diag;   // timing diagnostics only (PVD_MLP_DIAG): 1 no bias loads, 2 no operand stores, 4 no TMEM loads, 8 no PE
 };
 
 // layer schedule: for each of the 26 streamed chunks, which layer it belongs to and where its A operand comes from
@@ -255,7 +256,12 @@ constexpr uint32_t kPiece = 16384;                    // bytes per streamed piec
 constexpr uint32_t kPieces = 2 * kMlpChunks + 1;      // 52 half-chunks of layers 0-6 + layer 7
 constexpr uint32_t kStages = 4;
 constexpr uint32_t kV2Threads = 320;
-constexpr uint32_t kTailWOff = 32768;                 // tail weights inside a tile's operand buffer
+constexpr uint32_t kTailWOff = 32768;
+#ifndef PVD_MLP_STAGGER
+#define PVD_MLP_STAGGER 1
+#endif
+constexpr bool kStaggerDefault = PVD_MLP_STAGGER != 0;  // 1: per layer, tile 0's pass then tile 1's pass (weights streamed twice, MMA of one tile under
+                                                 // the epilogue of the other); 0: both tiles consume every piece (weights streamed once)                 // tail weights inside a tile's operand buffer
 
 struct V2Wait {  // bounded waits that stop costing time after the first failure (a wrong barrier must not hang the GPU)
     int32_t* status;
@@ -298,17 +304,30 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     const uint32_t n_pairs = (n_tiles + 1) / 2;
     V2Wait wait{status};
+    const bool kStagger = kStaggerDefault != ((a.diag & 16u) != 0u);   // diag bit 16 flips the schedule
 
     if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t pc = 0;  // pieces issued so far (ring position)
+            auto load = [&](uint32_t q) {
+                const uint32_t s = pc % kStages;
+                if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
+                tc5::mbar_expect_tx(&ring_full[s], kPiece);
+                tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), a.wblob + (size_t)q * kPiece, kPiece, &ring_full[s]);
+                ++pc;
+            };
             for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                for (uint32_t q = 0; q < kPieces; ++q, ++pc) {
-                    const uint32_t s = pc % kStages;
-                    if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
-                    tc5::mbar_expect_tx(&ring_full[s], kPiece);
-                    tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), a.wblob + (size_t)q * kPiece, kPiece, &ring_full[s]);
+                if (kStagger) {   // per layer: the pieces for tile 0's pass, then the same pieces again for tile 1's pass
+                    uint32_t q0 = 0;
+                    for (uint32_t layer = 0; layer < 8; ++layer) {
+                        const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : (layer == 7 ? 1u : 8u));
+                        for (uint32_t t = 0; t < 2; ++t)
+                            for (uint32_t j = 0; j < n_pieces; ++j) load(q0 + j);
+                        q0 += n_pieces;
+                    }
+                } else {
+                    for (uint32_t q = 0; q < kPieces; ++q) load(q);
                 }
             }
         }
@@ -319,48 +338,75 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
             const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
             const uint32_t idesc7 = tc5::instr_desc_f16(128, 32, 0, 0);
             for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                uint32_t q = 0;
+                uint32_t q0 = 0;
                 for (uint32_t layer = 0; layer < 7; ++layer) {
                     const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : 8u);
-                    for (uint32_t j = 0; j < n_pieces; ++j, ++q, ++pc) {
-                        const ChunkDesc cd = kSchedule[q >> 1];
-                        const uint32_t s = pc % kStages;
-                        wait(&ring_full[s], (pc / kStages) & 1u);
-                        const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                    if (kStagger) {
+                        // tile 0's whole layer, then tile 1's: while the tensor core runs tile 1, warpgroup 0 is already in its epilogue
                         for (uint32_t t = 0; t < 2; ++t) {
-                            if (j == 0) wait(&act_ready[t], acts & 1u);  // operand tile of this layer written, accumulator drained
-                            tc5::fence_after_sync();
-                            const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
-                                                               : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
-                            const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);   // which 32-column half of the 64-column slice
+                            wait(&act_ready[t], acts & 1u);  // operand tile of this layer written, accumulator drained
+                            for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
+                                const uint32_t q = q0 + j;
+                                const ChunkDesc cd = kSchedule[q >> 1];
+                                const uint32_t s = pc % kStages;
+                                wait(&ring_full[s], (pc / kStages) & 1u);
+                                tc5::fence_after_sync();
+                                const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                                const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
+                                                                   : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
+                                const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);
 #pragma unroll
-                            for (uint32_t k0 = 0; k0 < 32; k0 += 16)
-                                tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                                !(j == 0 && k0 == 0));
-                            if (j + 1 == n_pieces) tc5::mma_commit(&acc_full[t]);
+                                for (uint32_t k0 = 0; k0 < 32; k0 += 16)
+                                    tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
+                                                    !(j == 0 && k0 == 0));
+                                tc5::mma_commit(&ring_empty[s]);
+                            }
+                            tc5::mma_commit(&acc_full[t]);
                         }
-                        tc5::mma_commit(&ring_empty[s]);
-                    }
-                    ++acts;
-                }
-                {   // layer 7: 256 -> 28 (N = 32); the piece holds four [32 x 64] operand tiles
-                    const uint32_t s = pc % kStages;
-                    wait(&ring_full[s], (pc / kStages) & 1u);
-                    const uint32_t b_base = tc5::smem_u32(ring + s * kPiece);
-                    for (uint32_t t = 0; t < 2; ++t) {
-                        wait(&act_ready[t], acts & 1u);
-                        tc5::fence_after_sync();
-                        for (uint32_t c = 0; c < 4; ++c)
+                    } else {
+                        for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
+                            const uint32_t q = q0 + j;
+                            const ChunkDesc cd = kSchedule[q >> 1];
+                            const uint32_t s = pc % kStages;
+                            wait(&ring_full[s], (pc / kStages) & 1u);
+                            const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                            for (uint32_t t = 0; t < 2; ++t) {
+                                if (j == 0) wait(&act_ready[t], acts & 1u);
+                                tc5::fence_after_sync();
+                                const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
+                                                                   : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
+                                const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);   // which 32-column half of the 64-column slice
 #pragma unroll
-                            for (uint32_t k0 = 0; k0 < 64; k0 += 16)
-                                tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(tc5::smem_u32(smem + t * 65536) + c * 8u * (kTile * 16u), kTile, k0),
-                                                tc5::desc_kmajor(b_base + c * (32u * 64u * 2u), 32, k0), idesc7, !(c == 0 && k0 == 0));
-                        tc5::mma_commit(&acc_full[t]);
+                                for (uint32_t k0 = 0; k0 < 32; k0 += 16)
+                                    tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
+                                                    !(j == 0 && k0 == 0));
+                                if (j + 1 == n_pieces) tc5::mma_commit(&acc_full[t]);
+                            }
+                            tc5::mma_commit(&ring_empty[s]);
+                        }
                     }
-                    tc5::mma_commit(&ring_empty[s]);
-                    ++pc;
+                    q0 += n_pieces;
                     ++acts;
                 }
+                // layer 7: 256 -> 28 (N = 32); the piece holds four [32 x 64] operand tiles
+                for (uint32_t t = 0; t < 2; ++t) {
+                    const uint32_t s = pc % kStages;
+                    if (kStagger || t == 0) wait(&ring_full[s], (pc / kStages) & 1u);
+                    const uint32_t b_base = tc5::smem_u32(ring + s * kPiece);
+                    wait(&act_ready[t], acts & 1u);
+                    tc5::fence_after_sync();
+                    for (uint32_t c = 0; c < 4; ++c)
+#pragma unroll
+                        for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                            tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(tc5::smem_u32(smem + t * 65536) + c * 8u * (kTile * 16u), kTile, k0),
+                                            tc5::desc_kmajor(b_base + c * (32u * 64u * 2u), 32, k0), idesc7, !(c == 0 && k0 == 0));
+                    tc5::mma_commit(&acc_full[t]);
+                    if (kStagger || t == 1) {
+                        tc5::mma_commit(&ring_empty[s]);
+                        ++pc;
+                    }
+                }
+                ++acts;
             }
         }
     } else {
@@ -393,8 +439,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                 for (int k = 0; k < 10; ++k) {
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        float sn, cs;
-                        sincosf(pos[d] * freq, &sn, &cs);
+                        float sn = 0.f, cs = 0.f;
+                        if (!(a.diag & 8u)) sincosf(pos[d] * freq, &sn, &cs);
                         f[3 + 6 * k + d] = sn;
                         f[3 + 6 * k + 3 + d] = cs;
                     }
@@ -413,22 +459,27 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                 tc5::fence_after_sync();
                 const float4* __restrict__ bl = reinterpret_cast<const float4*>(bias + 256 * layer);
                 uint32_t buf[2][32];
-                tc5::tmem_ld32_issue(trow, buf[0]);
+                const bool no_bias = a.diag & 1u, no_store = a.diag & 2u, no_ld = a.diag & 4u;
+                if (!no_ld) tc5::tmem_ld32_issue(trow, buf[0]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    tc5::tmem_ld_wait();
-                    if (c + 1 < 8) tc5::tmem_ld32_issue(trow + 32 * (c + 1), buf[(c + 1) & 1]);
+                    if (!no_ld) {
+                        tc5::tmem_ld_wait();
+                        if (c + 1 < 8) tc5::tmem_ld32_issue(trow + 32 * (c + 1), buf[(c + 1) & 1]);
+                    }
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 b4 = __ldg(bl + 8 * c + i);
+                        const float4 b4 = no_bias ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bl + 8 * c + i);
                         v[4 * i + 0] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 0]) + b4.x, 0.0f);
                         v[4 * i + 1] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 1]) + b4.y, 0.0f);
                         v[4 * i + 2] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 2]) + b4.z, 0.0f);
                         v[4 * i + 3] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 3]) + b4.w, 0.0f);
                     }
+                    if (!no_store) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, r, 4 * c + i)) = tc5::pack8(v + 8 * i);
+                        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, r, 4 * c + i)) = tc5::pack8(v + 8 * i);
+                    }
                 }
                 tc5::fence_async_smem();
                 tc5::fence_before_sync();
@@ -548,6 +599,8 @@ int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* 
     a.wblob = reinterpret_cast<const uint8_t*>(f->wblob);
     a.tail_blob = reinterpret_cast<const uint8_t*>(f->tail_wblob);
     a.clip_min = f->sigma_clip_min; a.clip_max = f->sigma_clip_max; a.density_scale = f->density_scale;
+    static const uint32_t diag = []() { const char* v = getenv("PVD_MLP_DIAG"); return v ? (uint32_t)atoi(v) : 0u; }();
+    a.diag = diag;
     const uint32_t tiles = (M + kTile - 1) / kTile;
     static const bool use_v1 = []() { const char* v = getenv("PVD_MLP_V1"); return v != nullptr && v[0] == '1'; }();
     if (!use_v1) {

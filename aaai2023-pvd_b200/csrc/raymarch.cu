@@ -373,7 +373,11 @@ __global__ void __launch_bounds__(32) k_march_count(const float* __restrict__ ra
 #ifdef PVD_TRACE
     tr_c0 = clock64();
 #endif
-    while (!done) {
+    // A valid ray evaluates at most (far - near) / dt_min <= max_steps * bound lattice points, 32 per window: the cap is twice that.
+    // It only ever triggers on garbage input (non-finite rays, a zero direction), where the reference's loop would not terminate.
+    const uint32_t max_windows = max_steps * (uint32_t)ceilf(fmaxf(bound, 1.0f)) / 16u + 64u;
+    uint32_t windows = 0;
+    while (!done && windows++ < max_windows) {
         // ---- fast path: constant dt and a group of four windows (128 lattice points) inside one binade.  All four occupancy
         // probes of a lane are issued before any is consumed, which hides the L2 latency of the bitfield loads, and the four
         // chain preparations interleave.

@@ -40,14 +40,19 @@ class _RaySet:
     """What belongs to one batch of rays: the inputs and everything the march produces from them."""
 
     def __init__(self, N, dev):
-        self.rays_o = torch.empty(N, 3, device=dev)
-        self.rays_d = torch.empty(N, 3, device=dev)
-        self.gt = torch.empty(N, 3, device=dev)
+        # rays_o | rays_d | gt live in ONE buffer: a batch arriving from the host is a single H2D copy (147 KB at 4096 rays)
+        self.inputs = torch.empty(3, N, 3, device=dev)
+        self.host = None   # pinned staging twin of `inputs` (FieldTrainEngine.enable_host_io)
+        self.reset_views()
         self.nears = torch.empty(N, device=dev)
         self.fars = torch.empty(N, device=dev)
         self.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
         self.xyzs = self.dirs = self.deltas = None
+
+    def reset_views(self):
+        """rays_o / rays_d / gt are views of `inputs` (they may have been re-bound to caller tensors in eager use)."""
+        self.rays_o, self.rays_d, self.gt = self.inputs[0], self.inputs[1], self.inputs[2]
 
     def alloc_samples(self, M, dev):
         self.xyzs = torch.zeros(M, 3, device=dev)
@@ -277,53 +282,79 @@ class FieldTrainEngine:
         self._march_count(st, self.sets[k])
         self._march_write(st, self.sets[k], self.M)
 
-    def _pipelined_step(self, k: int):
-        """Field forward/backward of set k (already marched) with the march of set 1-k on a parallel branch.  The branch forks
-        after the composite backward: from there on the main branch runs k_hash_field_bwd (2 CTAs of 128 threads per SM) and the
-        scatter, which leave the thread slots the one-warp march CTAs need."""
+    # ------------------------------------------------------------------ host-resident batches (the end-to-end path)
+    n_host_inputs = 3   # rays_o, rays_d, gt  (a distillation step has no gt: PairDistillEngine copies two)
+
+    def _loss_dev(self):
+        return self.loss_slots
+
+    def enable_host_io(self):
+        """Pinned staging buffers so that a step fed from the HOST costs no extra launches: `capture_pipelined(host_io=True)` puts
+        the H2D copy of batch i+1 (sets[k].host -> sets[k].inputs, one copy) at the head of the march branch of step i's graph -- off
+        the critical path -- and the D2H copy of the loss words (-> self.host_loss) at its end."""
+        for rs in self.sets:
+            if rs.host is None:
+                rs.host = torch.empty(3, self.N, 3, dtype=torch.float32).pin_memory()
+                rs.host.copy_(rs.inputs)   # never feed uninitialised rays to the marcher (the capture pass runs the step once)
+        self.host_loss = torch.empty(self._loss_dev().numel(), dtype=torch.float32).pin_memory()
+
+    def _pipelined_step(self, k: int, host_io: bool = False):
+        """Field forward/backward of set k (already marched) with the march of set 1-k on a parallel branch, forked at the top of
+        the step (the march is a latency-bound chain of one-warp CTAs that fits beside the field kernels)."""
         rs, nxt = self.sets[k], self.sets[1 - k]
         cur = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(cur.cuda_stream)
         M = self.M
         self._zeros.zero_()
         self._clear_big(cur)
-        fork_early = os.environ.get("PVD_PIPE_FORK", "early") == "early"
-        if fork_early:
+
+        def march_branch():
             self._side2.wait_stream(cur)
             with torch.cuda.stream(self._side2):
                 st2 = C.c_void_p(self._side2.cuda_stream)
+                if host_io:
+                    n = self.n_host_inputs
+                    nxt.inputs[:n].copy_(nxt.host[:n], non_blocking=True)
                 self._march_count(st2, nxt)
                 self._march_write(st2, nxt, M)
+
+        fork_early = os.environ.get("PVD_PIPE_FORK", "early") == "early"
+        if fork_early:
+            march_branch()
         self._forward(st, rs, M, M)
         self._loss_backward(st, rs, M, M)
         if not fork_early:
-            self._side2.wait_stream(cur)
-            with torch.cuda.stream(self._side2):
-                st2 = C.c_void_p(self._side2.cuda_stream)
-                self._march_count(st2, nxt)
-                self._march_write(st2, nxt, M)
+            march_branch()
         cur.wait_stream(self._side)
         self._field_backward(st, rs, M, cur)
+        if host_io:
+            self.host_loss.copy_(self._loss_dev(), non_blocking=True)
         cur.wait_stream(self._side2)
 
-    def capture_pipelined(self):
+    def capture_pipelined(self, host_io: bool = False):
         """Two graphs (even / odd steps).  Protocol: write batch 0 into sets[0], call march(0); then for step i write batch i+1
-        into sets[(i+1) % 2] (rays_o, rays_d, gt) and replay_pipelined(i)."""
-        self.graphs = []
+        into sets[(i+1) % 2] (rays_o, rays_d, gt -- or, with host_io, into its pinned `host` twin) and replay_pipelined(i)."""
+        if host_io:
+            self.enable_host_io()
+        graphs = []
         for k in (0, 1):
             self.march(k)
-            self._pipelined_step(k)
+            self._pipelined_step(k, host_io)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._pipelined_step(k)
-            self.graphs.append(g)
+                self._pipelined_step(k, host_io)
+            graphs.append(g)
         torch.cuda.synchronize()
-        return self.graphs
+        if host_io:
+            self.graphs_host = graphs
+        else:
+            self.graphs = graphs
+        return graphs
 
-    def replay_pipelined(self, i: int):
+    def replay_pipelined(self, i: int, host_io: bool = False):
         self.cur = i & 1
-        self.graphs[i & 1].replay()
+        (self.graphs_host if host_io else self.graphs)[i & 1].replay()
 
     @property
     def loss(self):
@@ -403,6 +434,11 @@ class PairDistillEngine(FieldTrainEngine):
         if getattr(student, "model_type", None) != "vm" or self.distill_stage != 3:
             l1_reg_weight = 0.0
         super().__init__(student, bitfield, n_rays, l1_reg_weight=l1_reg_weight, **kw)
+
+    n_host_inputs = 2   # rays_o, rays_d: the teacher's rendering is the target
+
+    def _loss_dev(self):
+        return self.loss_out
 
     def _init_small_buffers(self):
         n_sum = PAIR_SUM_STRIDE * fused.LOSS_SLOTS

@@ -112,7 +112,8 @@ def make_workload(n_rays, n_batches, seed, rank):
     out = []
     for ro, rd in batches:
         gt = torch.rand(n_rays, 3, generator=g)
-        out.append((ro.pin_memory(), rd.pin_memory(), gt.pin_memory()))
+        packed = torch.stack([ro, rd, gt]).pin_memory()   # [3, N, 3]: what a loader hands over, one H2D copy per batch
+        out.append((packed[0], packed[1], packed[2], packed))
     return out
 
 
@@ -311,7 +312,7 @@ def run_ours(args, rank, world, local):
     eng.stage()
     n_b = 16 + args.warmup + args.steps
     host = make_workload(args.rays, min(n_b, 64), seed=0, rank=rank)
-    devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
+    devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c, _ in host]
 
     use_graph = False
     pipelined = False
@@ -321,7 +322,7 @@ def run_ours(args, rank, world, local):
         """Make batch i the input of the next step.  Pipelined: batch i goes into the set the NEXT replay marches (it is computed
         on one replay later), which is exactly one batch of look-ahead; the caller passes consecutive i.  A distillation step has
         no ground-truth colours (the teacher's rendering is the target): only the rays are copied."""
-        ro, rd, gt = (host if from_host else devb)[i % len(devb)]
+        ro, rd, gt = (host if from_host else devb)[i % len(devb)][:3]
         if pipelined:
             rs = eng.sets[(pipe["i"] + 1) & 1]
         elif use_graph or from_host:  # the captured graph reads the engine's static input buffers
@@ -385,7 +386,7 @@ def run_ours(args, rank, world, local):
     if not args.no_graph:
         try:  # CUDA graphs for the whole step: removes launch gaps and host work from the loop
             for rs in eng.sets:
-                rs.rays_o, rs.rays_d, rs.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
+                rs.reset_views()   # the graphs read the sets' own input buffers
             use_graph = True
             load(16)
             eng.capture()
@@ -458,18 +459,25 @@ def run_ours(args, rank, world, local):
         kt[k] /= reps
     S_mean = S_total / reps
     pipelined = was_pipelined
-    if pipelined:  # re-prime the pipeline for the end-to-end pass
+
+    # ---- end-to-end through the public API with HOST buffers: H2D of rays (+ gt), step, D2H of the loss.
+    # Pipelined engine: both copies are NODES of the step's graphs (engine.capture_pipelined(host_io=True)): the H2D of batch i+1 heads
+    # the march branch of step i, the D2H of the loss words ends it; the caller only writes the next batch into the pinned staging
+    # buffer.  The CPU may run at most two replays ahead of the GPU (a staging buffer is re-used every second step).
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    loss_dev = eng._loss_dev()   # pair: [total, 4 norms]; single model: 64 (loss, rays) slots, summed on the host
+    host_io = pipelined
+    if host_io:
+        eng.capture_pipelined(host_io=True)
         pipe["i"] = 0
         rs = eng.sets[0]
         ro, rd, gt = devb[nb % len(devb)]
         rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
         eng.march(0)
         nb += 1
-
-    # ---- end-to-end through the public API with HOST buffers: H2D of rays (+ gt), step, D2H of the loss
-    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    loss_dev = eng.loss_out if pair else eng.loss_slots   # pair: [total, 4 norms]; single model: 64 (loss, rays) slots, summed on the host
-    loss_host = torch.empty(loss_dev.numel(), dtype=torch.float32).pin_memory()
+        loss_host = eng.host_loss
+    else:
+        loss_host = torch.empty(loss_dev.numel(), dtype=torch.float32).pin_memory()
     if not use_graph:
         eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
     if world > 1:
@@ -478,10 +486,18 @@ def run_ours(args, rank, world, local):
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
         e2e_ev[i][0].record()
-        load(nb, from_host=True); nb += 1   # pinned host rays (+ gt) -> device (pipelined: the batch that is marched in this step)
-        run_step()
+        if host_io:
+            if i >= 2:
+                e2e_ev[i - 2][1].synchronize()          # the staging buffer's previous batch has been consumed
+            eng.sets[(pipe["i"] + 1) & 1].host.copy_(host[nb % len(host)][3]); nb += 1
+            eng.replay_pipelined(pipe["i"], host_io=True)
+            pipe["i"] += 1
+        else:
+            load(nb, from_host=True); nb += 1   # pinned host rays (+ gt) -> device
+            run_step()
         allreduce()
-        loss_host.copy_(loss_dev, non_blocking=True)
+        if not host_io:
+            loss_host.copy_(loss_dev, non_blocking=True)
         e2e_ev[i][1].record()
     torch.cuda.synchronize()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
@@ -532,7 +548,9 @@ def run_ours(args, rank, world, local):
         "roofline": dom,
         "roofline_all": roofs,
         "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * (6 if pair else 9) * 4,
-                "d2h_bytes_per_step": 4 * loss_dev.numel()},
+                "d2h_bytes_per_step": 4 * loss_dev.numel(),
+                "how": ("H2D of the next batch and D2H of the loss words are nodes of the step's CUDA graphs (pinned staging buffers)"
+                        if host_io else "copies issued on the step's stream around the step")},
         "gpu_launches": eng.launches_per_step * args.steps,
         "clocks": clocks,
     }
@@ -594,7 +612,7 @@ def run_reference(args, rank, world, local):
     tr = build_reference(args, dev, ext, bitfield)
     pair = args.workload in ("hash-vm", "mlp-hash")
     host = make_workload(args.rays, min(16 + args.warmup + args.steps, 64), seed=0, rank=0)
-    devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c in host]
+    devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c, _ in host]
     for i in range(16):  # the reference's 16 warm-up iterations with a D2H sync each, then mean_count
         tr.step(*devb[i % len(devb)])
     tr.update_mean_count()
@@ -616,7 +634,7 @@ def run_reference(args, rank, world, local):
     # e2e: host buffers in, loss out
     e2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
-        ro, rd, gt = host[(16 + args.warmup + i) % len(host)]
+        ro, rd, gt = host[(16 + args.warmup + i) % len(host)][:3]
         flush.fill_(i & 0xFF)
         e2[i][0].record()
         loss = tr.step(ro.to(dev, non_blocking=True), rd.to(dev, non_blocking=True), None if pair else gt.to(dev, non_blocking=True))

@@ -324,3 +324,26 @@ def test_inference_march_composite_compact(scene):
     oa, ot, oc = cpu.compact_rays(N, rays_alive.cpu().numpy(), rays_t.cpu().numpy())
     assert int(cnt.item()) == oc
     assert np.array_equal(new_alive[:oc].cpu().numpy(), oa[:oc]) and np.array_equal(new_t[:oc].cpu().numpy(), ot[:oc])
+
+
+def test_march_terminates_on_garbage_rays(scene):
+    """Non-finite or degenerate rays must not hang the marcher (the reference's loop would spin on them): a window cap bounds it."""
+    import raymarching
+    N = 256
+    g = torch.Generator().manual_seed(0)
+    ro = torch.randn(N, 3, generator=g)
+    rd = torch.randn(N, 3, generator=g)
+    rd[0] = 0.0
+    rd[1] = float("nan")
+    ro[2] = float("inf")
+    rd[3] = torch.tensor([1e-30, 0.0, 0.0])
+    rd[4] = float("inf")
+    ro[5] = float("nan")
+    ro, rd = ro.cuda(), rd.cuda()
+    bf = torch.from_numpy(scene["bitfield"]).cuda()
+    nears = torch.full((N,), 0.2, device="cuda")
+    fars = torch.full((N,), float("inf"), device="cuda")   # worst case: no far bound at all
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    out = raymarching.march_rays_train(ro, rd, 1.0, bf, 1, 128, nears, fars, counter, -1, True, 128, False, 0.0, 1024)
+    torch.cuda.synchronize()
+    assert out[3].shape == (N, 3) and int(counter[1]) == N
