@@ -129,3 +129,37 @@ def test_pipelined_graphs_match_the_serial_step(scene):
         assert _rel_l2(eng.grad_table, gt_r) < 1e-4
         assert _rel_l2(eng.gw_ws.view(16, -1).sum(0), gw_r) < 1e-4
     assert int(eng.status.item()) == 0
+
+
+def test_host_fed_pipelined_graphs(scene):
+    """capture_pipelined(host_io=True): batches written into the pinned staging twins reach the device through the H2D node of
+    the step's graph, the loss words come back through its D2H node; results equal the device-fed serial step."""
+    net, eng, ro0, rd0, gt0 = _setup(scene, n_rays=1024)
+    eng.step(warmup=True)
+    eng.finish_warmup()
+    batches = []
+    for b in range(4):
+        ro, rd = scene["batches"][b % 3]
+        sl = slice(1024 * (b // 3), 1024 * (b // 3) + 1024)
+        gt = torch.rand(1024, 3, generator=torch.Generator().manual_seed(20 + b))
+        batches.append(torch.stack([ro[sl], rd[sl], gt]).contiguous())   # [3, N, 3] on the host
+    ref = []
+    eng.cur = 0
+    for pk in batches:
+        eng.sets[0].inputs.copy_(pk)
+        eng.step()
+        torch.cuda.synchronize()
+        ref.append((eng.loss.clone(), eng.grad_table.clone(), eng.rays.clone()))
+    eng.capture_pipelined(host_io=True)
+    eng.sets[0].inputs.copy_(batches[0])
+    eng.march(0)
+    for i in range(4):
+        eng.sets[(i + 1) & 1].host.copy_(batches[(i + 1) % 4])
+        eng.replay_pipelined(i, host_io=True)
+        torch.cuda.synchronize()
+        loss_r, gt_r, rays_r = ref[i]
+        assert torch.equal(eng.rays, rays_r), f"step {i}: ray offsets"
+        host_loss = eng.host_loss.view(-1, 2).sum(0)
+        torch.testing.assert_close(host_loss, loss_r.cpu(), rtol=1e-5, atol=1e-7)
+        assert _rel_l2(eng.grad_table, gt_r) < 1e-4
+    assert int(eng.status.item()) == 0
