@@ -259,247 +259,15 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
 #endif
 }
 
-// =============================================================================================== backward kernel
-
-template <typename T>
-__global__ void __launch_bounds__(128) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
-                                                        const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
-                                                        const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
-                                                        uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
-                                                        __half* __restrict__ dx_out, float* __restrict__ grad_table,
-                                                        float* __restrict__ gw, int32_t* status) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar, wbar;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ LevelInfo lv[16];
-    uint8_t* smw = smem;                        // 20480
-    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;  // 8192
-    uint8_t* CIN = X + 8192;                    // 8192
-    uint8_t* H1 = CIN + 8192;                   // 16384
-    uint8_t* H3 = H1 + 16384;                   // 16384
-    uint8_t* H4 = H3 + 16384;                   // 16384
-    uint8_t* G16 = H4 + 16384;                  // 4096
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane_base = (tid >> 5) * 32;
-
-    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
-    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
-    if (tid == 0) PVD_T(2048u + blockIdx.x, 0);
-    if (tid == 0) {
-        tc5::mbar_init(&bar, 1);
-        tc5::mbar_init(&wbar, 1);
-        tc5::mbar_fence_init();
-        stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile's rows are loaded
-    }
-    level_info_init(lv, a.offsets, a.L, a.S, a.H);
-    tc5::fence_before_sync();
-    __syncthreads();
-    tc5::fence_after_sync();
-    Pipe p{&bar, 0u, tmem_base_s, status};
-    p.wbar = &wbar;
-    p.trec = 2048u + blockIdx.x;  // PVD_TRACE timeline record of this CTA (the last tile it processes wins)
-    if (tid == 0) PVD_T(p.trec, 1);
-    const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
-    const uint32_t sw = tc5::smem_u32(smw);
-    // this launch covers rows [row0, row0 + M) of the sample buffers, cut at n_valid (rows of padding contribute nothing)
-    const uint32_t row_end = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
-    const uint32_t n_valid = row_end;
-    const uint32_t lv_saddr = tc5::smem_u32(lv);
-
-    const uint32_t n_tiles = (row_end > row0) ? (row_end - row0 + kTile - 1) / kTile : 0u;
-    bool first = true;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t row = row0 + tile * kTile + tid;
-        const bool live = row < n_valid;
-        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-        float gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
-        if (live) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
-                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
-                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
-            }
-            gsig = __ldg(grad_sigmas + row);
-        }
-        // saved encoding -> X tile
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (live) u = __ldg(reinterpret_cast<const uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j));
-            *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
-        }
-        if (tid == 0) PVD_T(p.trec, 2);
-        float sigma, o16[16];
-        FwdRegs r;
-        mlp_forward(p, a, smw, X, H1, CIN, H3, H4, dir, tid, sigma, o16, r);
-
-        // ---- d(color_net.2 pre-activation) = grad_rgb * rgb * (1 - rgb)
-        {
-            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 3; ++i) g[i] = grgb[i] * r.rgb[i] * (1.0f - r.rgb[i]);
-            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
-            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = make_uint4(0, 0, 0, 0);
-        }
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            issue_wgrad(p.tmem + kAW5, tc5::smem_u32(H4), tc5::smem_u32(G16), 16, first);   // dW5^T += H4^T G5
-            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB5, 16, 64);             // dH4 = G5 W5
-            tc5::mma_commit(p.bar);
-        }
-        mma_wait(p);
-        if (tid == 0) PVD_T(p.trec, 3);
-        mask_grad_in_place(trow + kD, H4, tid);                                              // G4 (over H4)
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            issue_wgrad(p.tmem + kAW4, tc5::smem_u32(H4), tc5::smem_u32(H3), 64, first);    // dW4 += G4^T H3
-            issue_dgrad(p.tmem + kD, tc5::smem_u32(H4), 64, sw + kWB4, 64, 64);              // dH3 = G4 W4
-            tc5::mma_commit(p.bar);
-        }
-        mma_wait(p);
-        if (tid == 0) PVD_T(p.trec, 4);
-        mask_grad_in_place(trow + kD, H3, tid);                                              // G3 (over H3)
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            issue_wgrad(p.tmem + kAW3, tc5::smem_u32(H3), tc5::smem_u32(CIN), 32, first);   // dW3 += G3^T CIN
-            issue_dgrad(p.tmem + kD, tc5::smem_u32(H3), 64, sw + kWB3, 64, 32);              // dCIN = G3 W3
-            tc5::mma_commit(p.bar);
-        }
-        mma_wait(p);
-        if (tid == 0) PVD_T(p.trec, 5);
-        // ---- d(sigma_net.1 output): channel 0 through trunc_exp + clamp, channels 1..15 = geo part of dCIN
-        {
-            float dc[16];
-            tc5::tmem_ld16(trow + kD + 16, dc);  // columns 16..31 = d(geo 0..14), pad
-            float g[16];
-            const bool inside = (r.o0_raw >= a.clip_min) && (r.o0_raw <= a.clip_max);  // clamp backward
-            // trunc_exp backward: g * exp(clamp(x, -12, 12)) (tools/activation.py:15-21)
-            g[0] = gsig * a.density_scale * __expf(clampf(r.o0c, -12.0f, 12.0f));
-#pragma unroll
-            for (int i = 0; i < 15; ++i) g[i + 1] = dc[i];
-            if (grad_feat && live) {  // d(loss)/d(feature_sigma_color): the distillation feature / sigma_l losses
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 gf = __ldg(reinterpret_cast<const float4*>(grad_feat + 16 * (size_t)row) + q);
-                    g[4 * q] += gf.x; g[4 * q + 1] += gf.y; g[4 * q + 2] += gf.z; g[4 * q + 3] += gf.w;
-                }
-            }
-            if (!inside) g[0] = 0.0f;  // clamp backward (network.py:418-420)
-            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
-            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = tc5::pack8(g + 8);
-        }
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            issue_wgrad(p.tmem + kAW2, tc5::smem_u32(H1), tc5::smem_u32(G16), 16, first);   // dW2^T += H1^T G2
-            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB2, 16, 64);             // dH1 = G2 W2
-            tc5::mma_commit(p.bar);
-        }
-        mma_wait(p);
-        if (tid == 0) PVD_T(p.trec, 11);
-        mask_grad_in_place(trow + kD, H1, tid);                                              // G1 (over H1)
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            issue_wgrad(p.tmem + kAW1, tc5::smem_u32(H1), tc5::smem_u32(X), 32, first);     // dW1 += G1^T X
-            issue_dgrad(p.tmem + kD, tc5::smem_u32(H1), 64, sw + kWB1, 64, 32);              // dX = G1 W1
-            tc5::mma_commit(p.bar);
-        }
-        mma_wait(p);
-        if (tid == 0) PVD_T(p.trec, 12);
-        first = false;
-        // ---- scatter d(encoding) into the table gradient (gridencoder.cu:227-314 semantics, fp32 accumulation)
-        float dx[32];
-        tc5::tmem_ld16(trow + kD, *reinterpret_cast<float(*)[16]>(&dx[0]));
-        tc5::tmem_ld16(trow + kD + 16, *reinterpret_cast<float(*)[16]>(&dx[16]));
-        if (dx_out != nullptr) {  // split mode: hand d(encoding) to the stand-alone, high-occupancy scatter kernel
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(dx_out + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = tc5::pack8(dx + 8 * j);
-            }
-        } else if (live) {
-            float x01[3];
-            bool oob;
-            to_unit(pos, a.bound, x01, oob);
-            if (!oob) {
-#pragma unroll
-                for (uint32_t l = 0; l < 16; ++l) {
-                    if (l < a.L) {
-                        const LevelInfo v = ld_level(lv_saddr, l);
-                        Corners c;
-                        level_corners(v, x01, c);
-                        float* gt = grad_table + (size_t)v.offset * 2;
-                        const float g0 = dx[2 * l], g1 = dx[2 * l + 1];
-#pragma unroll
-                        for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g0, c.w[i] * g1);
-                    }
-                }
-            }
-        }
-    }
-    if (tid == 0) PVD_T(p.trec, 13);
-    if (tid == 0) weights_ready(p);  // a CTA without tiles must not exit under its own in-flight bulk copy
-    // ---- weight gradients leave the SM once per CTA
-    tc5::fence_before_sync();
-    __syncthreads();
-    tc5::fence_after_sync();
-    gw += (size_t)(blockIdx.x % PVD_FIELD_GW_COPIES) * PVD_FIELD_GW_FLOATS;
-    if (!first) {
-        flush_acc(p.tmem, kAW1, 32, gw + kGW1);
-        flush_acc(p.tmem, kAW2, 16, gw + kGW2);
-        flush_acc(p.tmem, kAW3, 32, gw + kGW3);
-        flush_acc(p.tmem, kAW4, 64, gw + kGW4);
-        flush_acc(p.tmem, kAW5, 16, gw + kGW5);
-    }
-    if (tid == 0) PVD_T(p.trec, 14);
-    tc5::fence_before_sync();
-    __syncthreads();
-    if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
-}
-
 // Stand-alone scatter of d(encoding) [M,32] fp16 into the fp32 table gradient: one thread per (sample, level), 256-thread CTAs,
 // ~40 registers -> full occupancy, so the reductions' issue latency is hidden by other warps instead of stalling a 128-thread
 // MLP CTA that also holds 88 KB of shared memory and 256 TMEM columns (gridencoder.cu:227-314 semantics, fp32 accumulation).
 constexpr uint32_t kAggMaxRes1 = 700;  // aggregate runs on levels whose resolution is below this (cell edge > ~0.85 dt at 1024 steps)
 
-__global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* __restrict__ xyzs, const __half* __restrict__ dx,
-                                                      uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
-                                                      float* __restrict__ grad_table) {
-    __shared__ LevelInfo lvs;
-    const uint32_t level = blockIdx.y;
-    if (threadIdx.x == 0) {
-        const GridLevel g = grid_level(a.offsets, level, a.S, a.H);
-        LevelInfo v;
-        v.scale = g.scale; v.res1 = g.resolution + 1; v.offset = g.offset; v.size = g.size; v.mask = g.size - 1;
-        const uint64_t dense = (uint64_t)v.res1 * v.res1 * v.res1;
-        const bool fits = ((uint64_t)v.res1 <= g.size) && ((uint64_t)v.res1 * v.res1 <= g.size) && (dense <= g.size);
-        v.mode = fits ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
-        v.pad0 = v.pad1 = 0;
-        lvs = v;
-    }
-    __syncthreads();
-    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
-    const uint32_t b = row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    const LevelInfo v = lvs;
-    bool active = b < n_valid;
-    float2 g = make_float2(0.f, 0.f);
-    float x01[3] = {0.5f, 0.5f, 0.5f};
-    if (active) {
-        g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dx + (size_t)b * PVD_FIELD_ENC_STRIDE + 2 * level)));
-        float pos[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)b + d);
-        bool oob;
-        to_unit(pos, a.bound, x01, oob);
-        active = !oob && !(g.x == 0.0f && g.y == 0.0f);
-    }
+// One warp = 32 consecutive samples at ONE level: reductions of w * g into the level's gradient slice (gridencoder.cu:227-314
+// semantics, fp32 accumulation).  `active` lanes carry a sample with a non-zero gradient `g` inside the unit cube.
+__device__ __forceinline__ void scatter_level(const LevelInfo& v, const float (&x01)[3], bool active, float2 g, uint32_t lane,
+                                              float* __restrict__ grad_table) {
     Corners c;
     level_corners(v, x01, c);
     float* gt = grad_table + (size_t)v.offset * 2;
@@ -541,6 +309,310 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
         for (uint32_t i = 0; i < 8; i += 2)
             tab_red_pair(gt, c.idx[i], c.idx[i + 1], val[2 * i], val[2 * i + 1], val[2 * i + 2], val[2 * i + 3]);
     }
+}
+
+
+// =============================================================================================== backward kernel
+
+// FUSE = true: 128 + 32 * kScatterWarps threads.  Threads 0-127 are the MLP group (everything below, on named barrier 1); the rest
+// are SCATTER warps: warp w takes the 32 samples [32 (w % 4), +32) of every tile through the levels l = w / 4 (mod kScatterWarps/4)
+// (scatter_level) while the MLP group is already in the tensor-core chain of the CTA's next tile.
+// Measured on B200 (hash workload, 73 k samples): two launches 31 + 31 us; fused with 4 scatter warps 54.9 us; with 12 scatter
+// warps and the register file re-partitioned by setmaxnreg (launch: 64 registers per thread; scatter warpgroups 40, MLP warpgroup
+// 128 -- ptxas honours it, USETMAXREG in the SASS) 54.2 us.  The reductions are bound by a chip-level resource (the L2 atomic
+// units: 8.2 M sector reductions per step), not by the number of warps issuing them, so the simple variant is the default; the
+// gain over two launches is the MLP chain of tile i+1 running under the reductions of tile i.  d(encoding) changes hands in shared memory (two 8 KB buffers,
+// dx_full / dx_empty mbarriers): the scatter is bound by the SM's reduction throughput, the MLP chain by tcgen05 latency, so the
+// two overlap almost perfectly and neither d(encoding) nor a second launch touches memory.
+constexpr uint32_t kScatterWarps = 4;    // FUSE: scatter warps beside the MLP warpgroup (4, 8 or 12; see the comment below)
+template <typename T, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? 128 + 32 * kScatterWarps : 128, 2) k_hash_field_bwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+                                                        const __half* __restrict__ enc, const float* __restrict__ grad_sigmas,
+                                                        const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
+                                                        uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                        __half* __restrict__ dx_out, float* __restrict__ grad_table,
+                                                        float* __restrict__ gw, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, wbar, dx_full[2], dx_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ LevelInfo lv[16];
+    uint8_t* smw = smem;                        // 20480
+    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;  // 8192
+    uint8_t* CIN = X + 8192;                    // 8192
+    uint8_t* H1 = CIN + 8192;                   // 16384
+    uint8_t* H3 = H1 + 16384;                   // 16384
+    uint8_t* H4 = H3 + 16384;                   // 16384
+    uint8_t* G16 = H4 + 16384;                  // 4096
+    uint8_t* DXB = G16 + 4096;                  // FUSE: 2 x 8192, d(encoding) tiles handed to the scatter warps
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane_base = ((tid >> 5) & 3u) * 32;
+
+    // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
+    // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) PVD_T(2048u + blockIdx.x, 0);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_init(&wbar, 1);
+        if (FUSE) {
+            for (int q = 0; q < 2; ++q) {
+                tc5::mbar_init(&dx_full[q], 128);
+                tc5::mbar_init(&dx_empty[q], 32 * kScatterWarps);
+            }
+        }
+        tc5::mbar_fence_init();
+        stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile's rows are loaded
+    }
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    p.wbar = &wbar;
+    p.trec = 2048u + blockIdx.x;  // PVD_TRACE timeline record of this CTA (the last tile it processes wins)
+    if (FUSE) p.team = 1u;
+    const bool leader = tid == 0;
+    if (tid == 0) PVD_T(p.trec, 1);
+    const uint32_t trow = tc5::tmem_addr(p.tmem, lane_base, 0);
+    const uint32_t sw = tc5::smem_u32(smw);
+    // this launch covers rows [row0, row0 + M) of the sample buffers, cut at n_valid (rows of padding contribute nothing)
+    const uint32_t row_end = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
+    const uint32_t n_valid = row_end;
+    const uint32_t lv_saddr = tc5::smem_u32(lv);
+
+    const uint32_t n_tiles = (row_end > row0) ? (row_end - row0 + kTile - 1) / kTile : 0u;
+    bool first = true;
+    if (FUSE && tid >= 128) {
+        // ------------------------------------------------------------------ scatter warps
+        if (kScatterWarps > 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const uint32_t sw = (tid - 128u) >> 5, lane = tid & 31u;
+        const uint32_t sgroup = sw & 3u, lsel = sw >> 2;      // sample group of the tile, level residue class
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t r = sgroup * 32u + lane;           // row inside the tile
+            const uint32_t srow = row0 + tile * kTile + r;
+            bool in = srow < n_valid;
+            float x01[3] = {0.5f, 0.5f, 0.5f};
+            if (in) {
+                float pos[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)srow + d);
+                bool oob;
+                to_unit(pos, a.bound, x01, oob);
+                in = !oob;
+                if (oob) x01[0] = x01[1] = x01[2] = 0.5f;
+            }
+            const uint32_t bsel = it & 1u;
+            if (!tc5::mbar_wait(&dx_full[bsel], (it >> 1) & 1u)) atomicExch(status, 3);
+            const uint8_t* dxt = DXB + bsel * 8192u;
+#pragma unroll 1
+            for (uint32_t level = lsel; level < a.L; level += kScatterWarps / 4u) {
+                const __half2 gh = *reinterpret_cast<const __half2*>(dxt + tc5::chunk_off(kTile, r, level >> 2) + (level & 3u) * 4u);
+                const float2 g = __half22float2(gh);
+                const bool active = in && !(g.x == 0.0f && g.y == 0.0f);
+                scatter_level(ld_level(lv_saddr, level), x01, active, g, lane, grad_table);
+            }
+            tc5::mbar_arrive(&dx_empty[bsel]);
+        }
+    } else {
+    if (FUSE && kScatterWarps > 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t row = row0 + tile * kTile + tid;
+        const bool live = row < n_valid;
+        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+        float gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
+                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
+            }
+            gsig = __ldg(grad_sigmas + row);
+        }
+        // saved encoding -> X tile
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (live) u = __ldg(reinterpret_cast<const uint4*>(enc + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j));
+            *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = u;
+        }
+        if (tid == 0) PVD_T(p.trec, 2);
+        float sigma, o16[16];
+        FwdRegs r;
+        mlp_forward(p, a, smw, X, H1, CIN, H3, H4, dir, tid, sigma, o16, r);
+
+        // ---- d(color_net.2 pre-activation) = grad_rgb * rgb * (1 - rgb)
+        {
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) g[i] = grgb[i] * r.rgb[i] * (1.0f - r.rgb[i]);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = make_uint4(0, 0, 0, 0);
+        }
+        operands_ready(p);
+        if (leader) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW5, tc5::smem_u32(H4), tc5::smem_u32(G16), 16, first);   // dW5^T += H4^T G5
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB5, 16, 64);             // dH4 = G5 W5
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 3);
+        mask_grad_in_place(trow + kD, H4, tid);                                              // G4 (over H4)
+        operands_ready(p);
+        if (leader) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW4, tc5::smem_u32(H4), tc5::smem_u32(H3), 64, first);    // dW4 += G4^T H3
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H4), 64, sw + kWB4, 64, 64);              // dH3 = G4 W4
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 4);
+        mask_grad_in_place(trow + kD, H3, tid);                                              // G3 (over H3)
+        operands_ready(p);
+        if (leader) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW3, tc5::smem_u32(H3), tc5::smem_u32(CIN), 32, first);   // dW3 += G3^T CIN
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H3), 64, sw + kWB3, 64, 32);              // dCIN = G3 W3
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 5);
+        // ---- d(sigma_net.1 output): channel 0 through trunc_exp + clamp, channels 1..15 = geo part of dCIN
+        {
+            float dc[16];
+            tc5::tmem_ld16(trow + kD + 16, dc);  // columns 16..31 = d(geo 0..14), pad
+            float g[16];
+            const bool inside = (r.o0_raw >= a.clip_min) && (r.o0_raw <= a.clip_max);  // clamp backward
+            // trunc_exp backward: g * exp(clamp(x, -12, 12)) (tools/activation.py:15-21)
+            g[0] = gsig * a.density_scale * __expf(clampf(r.o0c, -12.0f, 12.0f));
+#pragma unroll
+            for (int i = 0; i < 15; ++i) g[i + 1] = dc[i];
+            if (grad_feat && live) {  // d(loss)/d(feature_sigma_color): the distillation feature / sigma_l losses
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 gf = __ldg(reinterpret_cast<const float4*>(grad_feat + 16 * (size_t)row) + q);
+                    g[4 * q] += gf.x; g[4 * q + 1] += gf.y; g[4 * q + 2] += gf.z; g[4 * q + 3] += gf.w;
+                }
+            }
+            if (!inside) g[0] = 0.0f;  // clamp backward (network.py:418-420)
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 0)) = tc5::pack8(g);
+            *reinterpret_cast<uint4*>(G16 + tc5::chunk_off(kTile, tid, 1)) = tc5::pack8(g + 8);
+        }
+        operands_ready(p);
+        if (leader) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW2, tc5::smem_u32(H1), tc5::smem_u32(G16), 16, first);   // dW2^T += H1^T G2
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(G16), 16, sw + kWB2, 16, 64);             // dH1 = G2 W2
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 11);
+        mask_grad_in_place(trow + kD, H1, tid);                                              // G1 (over H1)
+        operands_ready(p);
+        if (leader) {
+            tc5::fence_after_sync();
+            issue_wgrad(p.tmem + kAW1, tc5::smem_u32(H1), tc5::smem_u32(X), 32, first);     // dW1 += G1^T X
+            issue_dgrad(p.tmem + kD, tc5::smem_u32(H1), 64, sw + kWB1, 64, 32);              // dX = G1 W1
+            tc5::mma_commit(p.bar);
+        }
+        mma_wait(p);
+        if (tid == 0) PVD_T(p.trec, 12);
+        first = false;
+        // ---- scatter d(encoding) into the table gradient (gridencoder.cu:227-314 semantics, fp32 accumulation)
+        float dx[32];
+        tc5::tmem_ld16(trow + kD, *reinterpret_cast<float(*)[16]>(&dx[0]));
+        tc5::tmem_ld16(trow + kD + 16, *reinterpret_cast<float(*)[16]>(&dx[16]));
+        if (FUSE) {  // hand d(encoding) to this CTA's scatter warps through shared memory
+            const uint32_t bsel = it & 1u;
+            if (it >= 2u && !tc5::mbar_wait(&dx_empty[bsel], ((it >> 1) - 1u) & 1u)) atomicExch(status, 3);
+            uint8_t* dxt = DXB + bsel * 8192u;
+            float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(dxt + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(live ? dx + 8 * j : z);
+            tc5::mbar_arrive(&dx_full[bsel]);
+        } else if (dx_out != nullptr) {  // split mode: hand d(encoding) to the stand-alone, high-occupancy scatter kernel
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(dx_out + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = tc5::pack8(dx + 8 * j);
+            }
+        } else if (live) {
+            float x01[3];
+            bool oob;
+            to_unit(pos, a.bound, x01, oob);
+            if (!oob) {
+#pragma unroll
+                for (uint32_t l = 0; l < 16; ++l) {
+                    if (l < a.L) {
+                        const LevelInfo v = ld_level(lv_saddr, l);
+                        Corners c;
+                        level_corners(v, x01, c);
+                        float* gt = grad_table + (size_t)v.offset * 2;
+                        const float g0 = dx[2 * l], g1 = dx[2 * l + 1];
+#pragma unroll
+                        for (uint32_t i = 0; i < 8; ++i) tab_red2(gt, (size_t)c.idx[i] * 2, c.w[i] * g0, c.w[i] * g1);
+                    }
+                }
+            }
+        }
+    }
+    if (tid == 0) PVD_T(p.trec, 13);
+    if (tid == 0) weights_ready(p);  // a CTA without tiles must not exit under its own in-flight bulk copy
+    // ---- weight gradients leave the SM once per CTA
+    operands_ready(p);
+    tc5::fence_after_sync();
+    gw += (size_t)(blockIdx.x % PVD_FIELD_GW_COPIES) * PVD_FIELD_GW_FLOATS;
+    if (!first) {
+        flush_acc(p.tmem, kAW1, 32, gw + kGW1);
+        flush_acc(p.tmem, kAW2, 16, gw + kGW2);
+        flush_acc(p.tmem, kAW3, 32, gw + kGW3);
+        flush_acc(p.tmem, kAW4, 64, gw + kGW4);
+        flush_acc(p.tmem, kAW5, 16, gw + kGW5);
+    }
+    if (tid == 0) PVD_T(p.trec, 14);
+    }  // MLP group
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
+}
+
+__global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* __restrict__ xyzs, const __half* __restrict__ dx,
+                                                      uint32_t row0, uint32_t M, const int32_t* __restrict__ n_valid_p,
+                                                      float* __restrict__ grad_table) {
+    __shared__ LevelInfo lvs;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const GridLevel g = grid_level(a.offsets, level, a.S, a.H);
+        LevelInfo v;
+        v.scale = g.scale; v.res1 = g.resolution + 1; v.offset = g.offset; v.size = g.size; v.mask = g.size - 1;
+        const uint64_t dense = (uint64_t)v.res1 * v.res1 * v.res1;
+        const bool fits = ((uint64_t)v.res1 <= g.size) && ((uint64_t)v.res1 * v.res1 <= g.size) && (dense <= g.size);
+        v.mode = fits ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
+        v.pad0 = v.pad1 = 0;
+        lvs = v;
+    }
+    __syncthreads();
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), row0 + M) : row0 + M;
+    const uint32_t b = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const LevelInfo v = lvs;
+    bool active = b < n_valid;
+    float2 g = make_float2(0.f, 0.f);
+    float x01[3] = {0.5f, 0.5f, 0.5f};
+    if (active) {
+        g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dx + (size_t)b * PVD_FIELD_ENC_STRIDE + 2 * level)));
+        float pos[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)b + d);
+        bool oob;
+        to_unit(pos, a.bound, x01, oob);
+        active = !oob && !(g.x == 0.0f && g.y == 0.0f);
+    }
+    scatter_level(v, x01, active, g, lane, grad_table);
 }
 
 __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
@@ -642,10 +714,20 @@ static int hash_backward_rows(const PvdHashField* f, const float* xyzs, const fl
         const uint32_t tiles = (rows + kTile - 1) / kTile;
         const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
         // the table is not read in the backward (the encoding was saved); one instantiation serves both table dtypes
-        cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-        if (e != cudaSuccess) return (int)e;
-        k_hash_field_bwd<float><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, row0,
-                                                             rows, n_valid, (__half*)dx_ws, grad_table, gw_ws, status);
+        if (dx_ws == nullptr) {  // one launch: the CTA's scatter warps reduce tile i while its MLP warps are in tile i+1
+            cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(kBwdSmem + 16384));
+            if (e != cudaSuccess) return (int)e;
+            k_hash_field_bwd<float, true><<<grid, 128 + 32 * kScatterWarps, kBwdSmem + 16384, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs,
+                                                                             grad_feat16, row0, rows, n_valid, nullptr, grad_table,
+                                                                             gw_ws, status);
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+            if (e != cudaSuccess) return (int)e;
+            k_hash_field_bwd<float, false><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs,
+                                                                      grad_feat16, row0, rows, n_valid, (__half*)dx_ws, grad_table,
+                                                                      gw_ws, status);
+        }
         PVD_LAUNCH_CHECK();
     }
     if ((phases & PVD_BWD_SCATTER) && dx_ws != nullptr) {

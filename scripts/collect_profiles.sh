@@ -25,9 +25,12 @@ done
 [ "$2" = "quick" ] && exit 0
 # launch list of the bench command itself (graph nodes are profiled one by one: cold-cache, serialised -> compare SHARES)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file $O/${T}_ncu_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_l.log 2>&1
-# one full capture of each kernel of the step (eager launches of the same step; 19 sizing/warm-up steps skipped)
-timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_hash_field_bwd|k_hash_scatter|k_hash_field_fwd|k_composite_train_mse|k_march_count' -s 100 -c 5 -o $O/${T}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_f.log 2>&1
+# one full capture of each kernel of the step (eager launches of the same step; 19 sizing/warm-up steps x 4 kernels skipped)
+timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_hash_field_bwd|k_hash_field_fwd|k_composite_train_mse|k_march_count' -s 76 -c 4 -o $O/${T}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_f.log 2>&1
 ncu -i $O/${T}_full.ncu-rep --page raw --csv > $O/${T}_ncu_full_raw.csv 2>/dev/null
+# the two-launch variant of the backward (PVD_SPLIT_SCATTER=1): the MLP backward and the stand-alone scatter kernel
+PVD_SPLIT_SCATTER=1 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_hash_field_bwd|k_hash_scatter' -s 38 -c 2 -o $O/${T}_split_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_fs.log 2>&1
+ncu -i $O/${T}_split_full.ncu-rep --page raw --csv > $O/${T}_split_ncu_full_raw.csv 2>/dev/null
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_vm_field_fwd|k_vm_field_bwd|k_pair_sample_sq|k_pair_composite|k_pair_combine' -s 100 -c 5 -o $O/${T}_pair_full python bench.py --workload hash-vm --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_fp.log 2>&1
 ncu -i $O/${T}_pair_full.ncu-rep --page raw --csv > $O/${T}_pair_ncu_full_raw.csv 2>/dev/null
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_mlp_field_fwd' -s 20 -c 1 -o $O/${T}_mlp_full python bench.py --workload mlp-hash --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_fm.log 2>&1
