@@ -11,7 +11,9 @@ The dead pure-PyTorch `run` path of the reference (it calls `self.color`, which 
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -140,6 +142,72 @@ class NeRFRenderer(nn.Module):
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "inherited_params": inherited_params}
 
+    def _update_extra_state_fused(self, decay):
+        """update_extra_state through pvd_density_grid_points / _update / pvd_packbits_mean (include/pvd_b200.h): per cascade one
+        kernel builds the jittered query points of all cells, the field's density kernel evaluates them, one kernel applies the EMA
+        rule and accumulates the mean, one packs the bitfield with the threshold formed on the device.  The random numbers are the
+        reference's (torch.rand_like / torch.randint, same shapes, same order), so a run with the same seed visits the same points."""
+        from . import _native as nv
+        l = nv.lib()
+        dev = self.density_grid.device
+        H = self.grid_size
+        n_cells = H ** 3
+        grid = self.density_grid
+        if not hasattr(self, "_upkeep_sum") or self._upkeep_sum.device != dev:
+            self._upkeep_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._upkeep_tmp = torch.empty(n_cells, dtype=torch.float32, device=dev)
+            self._mean_density_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._upkeep_sum.zero_()
+        full = self.iter_density < 16
+        with nv.on_device(grid):
+            st = nv.stream_of(grid)
+            for cas in range(self.cascade):
+                bound = float(min(2 ** cas, self.bound))
+                if full:
+                    n, indices = n_cells, None
+                    # the reference draws rand_like over the meshgrid-ordered points; here element j belongs to Morton cell j --
+                    # the same distribution, one draw per cell
+                    noise = torch.rand(n, 3, device=dev)
+                else:
+                    n = n_cells // 4
+                    coords = torch.randint(0, H, (n, 3), device=dev)
+                    indices = raymarching.morton3D(coords)
+                    occ = torch.nonzero(grid[cas] > 0).squeeze(-1)
+                    if occ.numel() > 0:   # the one size the host must know (the reference reads it the same way, renderer.py:716-727)
+                        occ = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=dev)]
+                        indices = torch.cat([indices, occ.to(indices.dtype)], dim=0)
+                    indices = indices.to(torch.int32).contiguous()
+                    n = indices.shape[0]
+                    noise = torch.rand(n, 3, device=dev)
+                xyzs = torch.empty(n, 3, device=dev)
+                nv.check(l.pvd_density_grid_points(nv.ptr(indices), nv.ptr(noise), C.c_uint32(n), C.c_uint32(H), C.c_float(bound),
+                                                   nv.ptr(xyzs), st))
+                sig = self.density(xyzs)["sigma"].reshape(-1).detach().float().contiguous()
+                g = grid[cas]
+                nv.check(l.pvd_density_grid_update(nv.ptr(g), nv.ptr(self._upkeep_tmp), nv.ptr(indices), nv.ptr(sig), C.c_uint32(n),
+                                                   C.c_uint32(n_cells), C.c_float(self.density_scale), C.c_float(decay),
+                                                   nv.ptr(self._upkeep_sum), st))
+            nv.check(l.pvd_packbits_mean(nv.ptr(grid), C.c_uint32(self.cascade * n_cells // 8), nv.ptr(self._upkeep_sum),
+                                         C.c_uint32(self.cascade * n_cells), C.c_float(self.density_thresh),
+                                         nv.ptr(self.density_bitfield), nv.ptr(self._mean_density_dev), st))
+        self._mean_density = None      # read lazily from the device (see the property)
+        self.iter_density += 1
+        total = min(16, self.local_step)
+        if total > 0:
+            self.mean_count = int(self.step_counter[:total, 0].sum().item() / total)
+        self.local_step = 0
+
+    @property
+    def mean_density(self):
+        """renderer.py:750-752.  After a fused update the value lives on the device and is fetched only when somebody asks."""
+        if getattr(self, "_mean_density", 0) is None:
+            self._mean_density = float(self._mean_density_dev.item())
+        return getattr(self, "_mean_density", 0)
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = v
+
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, **kwargs):
         if not self.cuda_ray:
             raise RuntimeError("only the cuda_ray path exists (the reference's pure-PyTorch `run` is dead code: network.py:516)")
@@ -182,10 +250,16 @@ class NeRFRenderer(nn.Module):
         self.density_grid[count == 0] = -1
 
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128):
-        """EMA update of the density grid from the field, repack the bitfield, refresh mean_count (renderer.py:647-773)."""
+    def update_extra_state(self, decay=0.95, S=128, fused=None):
+        """EMA update of the density grid from the field, repack the bitfield, refresh mean_count (renderer.py:647-773).
+        `fused` (default: PVD_FUSED_UPKEEP != 0) takes the three-kernel path of csrc/density_grid.cu, which draws the same torch
+        random numbers in the same order and gives the same grid (bit for bit in the full sweep) without reading anything back."""
         if not self.cuda_ray:
             return
+        if fused is None:
+            fused = os.environ.get("PVD_FUSED_UPKEEP", "1") != "0"
+        if fused and self.density_grid.is_cuda:
+            return self._update_extra_state_fused(decay)
         dev = self.density_grid.device
         tmp = -torch.ones_like(self.density_grid)
         H = self.grid_size

@@ -195,6 +195,26 @@ int pvd_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, u
 int pvd_tc_probe(int mode, const void* A, uint32_t RA, uint32_t CA, const void* B, uint32_t RB, uint32_t CB,
                  float* out, uint32_t N, int* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Density-grid upkeep: NeRFRenderer.update_extra_state (distill_mutual/renderer.py:647-773) without host round trips.
+ *   pvd_density_grid_points   one jittered query point per cell: cell index indices[j] (Morton code; NULL = cell j, the full sweep
+ *                             of renderer.py:657-699), noise [n,3] uniform in [0,1) (what torch.rand_like supplies, :690-693),
+ *                             bound_cas = min(2^cas, bound); xyzs [n,3], bit-identical to the reference's torch arithmetic.
+ *   pvd_density_grid_update   tmp[indices] = sigmas * density_scale (NULL indices: cell i <- sigmas[i]); valid = grid >= 0 & tmp >= 0;
+ *                             grid[valid] = max(grid[valid] * decay, tmp[valid]) (:746-749); *sum += sum(clamp(grid, 0)) over the
+ *                             n_cells cells of this cascade (double, caller zeroes it before the first cascade).  Duplicate
+ *                             indices keep the LARGEST candidate (the reference's index_put_ keeps an arbitrary one).
+ *                             tmp: [n_cells] scratch, only read/written when indices != NULL.
+ *   pvd_packbits_mean         mean = *sum / count (:750-752), thresh = min(mean, density_thresh), packbits (raymarching.cu:270-291);
+ *                             mean_out (device float, optional) receives the mean -- nothing is read back to the host.
+ * ---------------------------------------------------------------------------------------- */
+int pvd_density_grid_points(const int32_t* indices, const float* noise, uint32_t n, uint32_t H, float bound_cas, float* xyzs,
+                            void* stream);
+int pvd_density_grid_update(float* grid, float* tmp, const int32_t* indices, const float* sigmas, uint32_t n, uint32_t n_cells,
+                            float density_scale, float decay, double* sum, void* stream);
+int pvd_packbits_mean(const float* grid, uint32_t N, const double* sum, uint32_t count, float density_thresh, uint8_t* bitfield,
+                      float* mean_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,3 +244,55 @@ def sh_encode_forward(inputs, degree):
     if rc != 0:
         raise ValueError("C oracle covers SH degree 1..4; use oracle.sh_reference for higher degrees")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ density-grid upkeep
+def _morton_invert_np(ind):
+    def compact(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xC30C30C3
+        x = (x | (x >> 4)) & 0x0F00F00F
+        x = (x | (x >> 8)) & 0xFF0000FF
+        x = (x | (x >> 16)) & 0x0000FFFF
+        return x
+    ind = ind.astype(np.uint32)
+    return np.stack([compact(ind), compact(ind >> 1), compact(ind >> 2)], axis=-1)
+
+
+def density_grid_points(indices, noise, H, bound_cas):
+    """Query points of NeRFRenderer.update_extra_state (distill_mutual/renderer.py:679-694) for the cells `indices` (Morton codes;
+    None = all H^3 cells in Morton order) with the uniform noise `noise` [n,3]: fp32, operation by operation as torch evaluates
+        xyzs = 2 * coords.float() / (H - 1) - 1 ; cas = xyzs * (bound - half) ; cas += (rand * 2 - 1) * half
+    on the GPU (ATen's CUDA division by a host scalar multiplies by the fp32 reciprocal; Python scalars are cast to fp32)."""
+    f = np.float32
+    n = noise.shape[0]
+    ind = np.arange(n, dtype=np.uint32) if indices is None else np.asarray(indices)
+    c = _morton_invert_np(ind).astype(f)
+    rcp = f(1.0) / f(H - 1)
+    base = (f(2.0) * c) * rcp - f(1.0)
+    scale = f(float(bound_cas) - float(bound_cas) / H)
+    half = f(float(bound_cas) / H)
+    return (base * scale + (noise.astype(f) * f(2.0) - f(1.0)) * half).astype(f)
+
+
+def density_grid_update(grid, sigmas, indices, density_scale, decay):
+    """tmp[indices] = sigmas * density_scale; valid = (grid >= 0) & (tmp >= 0); grid[valid] = max(grid[valid] * decay, tmp[valid])
+    (renderer.py:737,746-749).  Duplicate indices keep the largest candidate (the reference keeps an arbitrary one).  Returns the new
+    grid (fp32) and sum(clamp(grid, 0)) in double."""
+    f = np.float32
+    g = grid.astype(f).copy()
+    tmp = np.full(g.shape, -1.0, f)
+    s = (sigmas.astype(f) * f(density_scale)).astype(f)
+    if indices is None:
+        tmp[:] = s
+    else:
+        np.maximum.at(tmp, np.asarray(indices, dtype=np.int64), s)
+    valid = (g >= 0) & (tmp >= 0)
+    g[valid] = np.maximum(g[valid] * f(decay), tmp[valid])
+    return g, float(np.clip(g, 0, None).astype(np.float64).sum())
+
+
+def packbits_mean(grid, total_sum, density_thresh):
+    """mean = sum / count; thresh = min(mean, density_thresh); packbits (renderer.py:750-759)."""
+    mean = np.float32(total_sum / grid.size)
+    return packbits(grid.reshape(-1), float(min(mean, np.float32(density_thresh)))), float(mean)

@@ -2,7 +2,8 @@
 """Turns `ncu -i <rep> --page raw --csv` of the step's kernels into (1) profiles/ncu_traffic.json, the per-launch DRAM traffic
 bench.py reports as roofline.traffic, and (2) a short text table.   usage: python scripts/ncu_summary.py RAW.csv [TAG] [--merge]
 
---merge keeps kernels already present in ncu_traffic.json that this capture does not contain (captures of different workloads)."""
+--merge keeps kernels already present in ncu_traffic.json that this capture does not contain (captures of different workloads);
+--suffix=S appends S to every kernel name of this capture (a variant of a kernel that is already in the table)."""
 import csv
 import json
 import os
@@ -31,6 +32,7 @@ def main():
     raw = sys.argv[1]
     tag = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else os.path.basename(raw).split("_ncu")[0]
     merge = "--merge" in sys.argv
+    suffix = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--suffix=")), "")
     rows = list(csv.reader(l for l in open(raw) if not l.startswith("==")))
     hdr, units, body = rows[0], rows[1], rows[2:]
     ix = {k: hdr.index(v) for k, v in COLS.items() if v in hdr}
@@ -43,7 +45,7 @@ def main():
 
     kernels, lines = {}, []
     for r in body:
-        name = re.sub(r"^(void\s+)?(pvd::)?", "", r[kn]).split("(")[0].split("<")[0]
+        name = re.sub(r"^(void\s+)?(pvd::)?", "", r[kn]).split("(")[0].split("<")[0] + suffix
         d = {k: val(r, k) for k in COLS}
         d["dram_bytes"] = (d["dram_read"] or 0.0) + (d["dram_write"] or 0.0)
         kernels.setdefault(name, d)   # first launch of each kernel
