@@ -402,6 +402,7 @@ class VMTrainEngine(FieldTrainEngine):
 
 
 PAIR_SUM_STRIDE = 4   # PVD_PAIR_SUM_STRIDE
+PAIR_PARALLEL_FWD = os.environ.get("PVD_PAIR_PARALLEL_FWD", "1") != "0"
 
 
 class PvdPairRates(C.Structure):
@@ -479,8 +480,21 @@ class PairDistillEngine(FieldTrainEngine):
                                                nv.ptr(rs.dirs), nv.ptr(rs.deltas), st))
 
     def _forward(self, st, rs, M, M_drop):
-        self.tea.forward(st, rs.xyzs, rs.dirs, M, self.sigmas_tea, self.rgbs_tea, self.feat_tea, self.status)
+        """Teacher and student are independent given the samples: the teacher's query runs on a parallel branch (its gathers /
+        GEMMs and the student's are bound by different units).  PVD_PAIR_PARALLEL_FWD=0 issues them back to back."""
+        if not PAIR_PARALLEL_FWD:
+            self.tea.forward(st, rs.xyzs, rs.dirs, M, self.sigmas_tea, self.rgbs_tea, self.feat_tea, self.status)
+            self.ops.forward(st, rs.xyzs, rs.dirs, M, self.sigmas, self.rgbs, self.feat, self.status)
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "_side4"):
+            self._side4 = torch.cuda.Stream(device=self.dev)
+        self._side4.wait_stream(cur)
+        with torch.cuda.stream(self._side4):
+            self.tea.forward(C.c_void_p(self._side4.cuda_stream), rs.xyzs, rs.dirs, M, self.sigmas_tea, self.rgbs_tea, self.feat_tea,
+                             self.status)
         self.ops.forward(st, rs.xyzs, rs.dirs, M, self.sigmas, self.rgbs, self.feat, self.status)
+        cur.wait_stream(self._side4)
 
     def _loss_backward(self, st, rs, M, M_drop):
         l = nv.lib()
