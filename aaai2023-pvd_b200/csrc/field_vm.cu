@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                                                       const float* __restrict__ dirs, const float* __restrict__ grad_sigmas,
                                                       const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
                                                       uint32_t M, const int32_t* __restrict__ n_valid_p, float* __restrict__ gw,
-                                                      int32_t* status, uint32_t diag_skip) {
+                                                      int32_t* status, uint32_t diag_skip, uint8_t* __restrict__ dapp_ws,
+                                                      float* __restrict__ dsf_ws) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -504,6 +505,16 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                 *reinterpret_cast<uint4*>(APP + tc5::chunk_off(kTile, tid, 6 * piece + 2 * c + 1)) = tc5::pack8(v + 8);
             }
         }
+        if (dapp_ws != nullptr) {
+            // two-kernel backward: d(APP) (fp16, the tile's chunk layout, 36 KB per tile) and d(sigma feature) go to a workspace;
+            // k_vm_scatter reduces them into the plane / line gradients at four times this kernel's occupancy
+            uint8_t* dst = dapp_ws + (size_t)tile * 36864u;
+#pragma unroll
+            for (uint32_t j = 0; j < 18; ++j)
+                *reinterpret_cast<uint4*>(dst + tc5::chunk_off(kTile, tid, j)) = *reinterpret_cast<const uint4*>(APP + tc5::chunk_off(kTile, tid, j));
+            dsf_ws[(size_t)tile * kTile + tid] = dsf[tid];
+            continue;   // the loop head's __syncthreads() orders the next gather after these reads
+        }
         __syncthreads();  // d(APP) and dsf complete in shared memory
         // ---- scatter: half a warp per RUN of 16 consecutive samples, four components per lane (LaneMap).  Consecutive samples of a
         //      ray are dt = 2 sqrt(3) / 1024 apart, half a texel of a 300^2 plane: they fall into the same plane cell / line cell about
@@ -635,6 +646,143 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
     if (tid < 32) tc5::tmem_dealloc(p.tmem, 256);
 }
 
+// =============================================================================================== stand-alone gradient scatter
+// Second kernel of the two-kernel backward: reads d(APP) / d(sigma feature) from the workspace, re-gathers the plane / line values
+// and reduces into the channels-last gradients.  Half a warp walks a run of 16 consecutive samples (LaneMap), the (plane, line)
+// pair is the OUTER loop, so only 6 taps and 6 accumulators are live at a time: ~90 registers, 256-thread CTAs, 16-24 warps per
+// SM instead of the 8 the MLP kernel can hold (212 registers, 100 KB of shared memory) -- this phase is bound by the latency of
+// its own loads and reductions, not by a chip-level unit (its 6 M sector reductions are fewer than k_hash_scatter's 8 M).
+__global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
+                                                       const uint8_t* __restrict__ dapp_ws, const float* __restrict__ dsf_ws, uint32_t M,
+                                                       const int32_t* __restrict__ n_valid_p) {
+    const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, l16 = lane & 15u;
+    const LaneMap m;
+    const uint32_t base = (blockIdx.x * 8u + warp) * 32u + 16u * m.half;   // first sample of this half-warp's run
+    const uint32_t n_s = (base < n_valid) ? min(16u, n_valid - base) : 0u;
+    const uint32_t n_it = __reduce_max_sync(0xffffffffu, n_s);
+    if (n_it == 0) return;
+    float mine[3] = {0.f, 0.f, 0.f};
+    float ds_mine = 0.0f;
+    if (l16 < n_s) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) mine[d] = __ldg(xyzs + 3 * (size_t)(base + l16) + d);
+        ds_mine = __ldg(dsf_ws + base + l16);
+    }
+    auto red4 = [](float* dst, const float4& v) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {   // unrolled: a runtime index into the kernel-parameter arrays would move them to local memory
+        const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2;
+        const int W = (int)a.res[a0], Hh = (int)a.res[a1], D = (int)a.res[2 - i];
+        const float* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
+        const float* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
+        float* gm = m.sig ? g.smat[i] : g.cmat[i];
+        float* gv = m.sig ? g.svec[i] : g.cvec[i];
+        float4 accp[4], accl[2];
+        int32_t keyp = -1, keyl = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) accl[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto flush_plane = [&]() {
+            if (keyp < 0) return;
+            const int x0 = (keyp & 0xffff) - 2, y0 = (keyp >> 16) - 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+                if (xx >= 0 && xx < W && yy >= 0 && yy < Hh) red4(gm + (size_t)(yy * W + xx) * m.R + m.ch, accp[k]);
+                accp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto flush_line = [&]() {
+            if (keyl < 0) return;
+            const int l0 = keyl - 2;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int ll = l0 + k;
+                if (ll >= 0 && ll < D) red4(gv + (size_t)ll * m.R + m.ch, accl[k]);
+                accl[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // software pipeline over the run: the taps and the d(APP) slice of sample s+1 are in flight under the arithmetic of sample s
+        float4 t[2][4], u[2][2];
+        Foot f[2];
+        uint2 draw[2];
+        auto issue = [&](uint32_t s2, int b) {
+            float pos[3], xn[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)(16u * m.half + (s2 & 15u)));
+            vm_normalise(pos, a.aabb, xn);
+            vm_foot(xn, a.res, i, f[b]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[b][k] = ldg_v4_issue(mat + (size_t)f[b].pidx[k] * m.R + m.ch);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) u[b][k] = ldg_v4_issue(vec + (size_t)f[b].lidx[k] * m.R + m.ch);
+            draw[b] = make_uint2(0u, 0u);
+            if (!m.sig && s2 < n_s) {
+                const uint32_t row = base + s2, col = (uint32_t)i * 48u + m.ch;
+                draw[b] = __ldg(reinterpret_cast<const uint2*>(dapp_ws + (size_t)(row / kTile) * 36864u +
+                                                               tc5::chunk_off(kTile, row % kTile, col >> 3) + (col & 7u) * 2u));
+            }
+        };
+        issue(0, 0);
+#pragma unroll 1
+        for (uint32_t s = 0; s < n_it; s += 2) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t sc = s + (uint32_t)b;
+                if (sc >= n_it) break;                       // warp-uniform
+                if (sc + 1 < n_it) issue(sc + 1, b ^ 1);
+                const float ds = __shfl_sync(0xffffffffu, ds_mine, (int)(16u * m.half + (sc & 15u)));
+                if (sc >= n_s) continue;                     // this half-warp's run is shorter
+                float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), lv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pv.x = __fmaf_rn(f[b].pw[k], t[b][k].x, pv.x); pv.y = __fmaf_rn(f[b].pw[k], t[b][k].y, pv.y);
+                    pv.z = __fmaf_rn(f[b].pw[k], t[b][k].z, pv.z); pv.w = __fmaf_rn(f[b].pw[k], t[b][k].w, pv.w);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    lv.x = __fmaf_rn(f[b].lw[k], u[b][k].x, lv.x); lv.y = __fmaf_rn(f[b].lw[k], u[b][k].y, lv.y);
+                    lv.z = __fmaf_rn(f[b].lw[k], u[b][k].z, lv.z); lv.w = __fmaf_rn(f[b].lw[k], u[b][k].w, lv.w);
+                }
+                float4 dp;
+                if (m.sig) {
+                    dp = make_float4(ds, ds, ds, ds);
+                } else {
+                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&draw[b].x));
+                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&draw[b].y));
+                    dp = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+                const float4 dpv = make_float4(dp.x * lv.x, dp.y * lv.y, dp.z * lv.z, dp.w * lv.w);
+                const float4 dlv = make_float4(dp.x * pv.x, dp.y * pv.y, dp.z * pv.z, dp.w * pv.w);
+                if (f[b].pkey != keyp) {
+                    flush_plane();
+                    keyp = f[b].pkey;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    accp[k].x = __fmaf_rn(f[b].pw[k], dpv.x, accp[k].x); accp[k].y = __fmaf_rn(f[b].pw[k], dpv.y, accp[k].y);
+                    accp[k].z = __fmaf_rn(f[b].pw[k], dpv.z, accp[k].z); accp[k].w = __fmaf_rn(f[b].pw[k], dpv.w, accp[k].w);
+                }
+                if (f[b].lkey != keyl) {
+                    flush_line();
+                    keyl = f[b].lkey;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    accl[k].x = __fmaf_rn(f[b].lw[k], dlv.x, accl[k].x); accl[k].y = __fmaf_rn(f[b].lw[k], dlv.y, accl[k].y);
+                    accl[k].z = __fmaf_rn(f[b].lw[k], dlv.z, accl[k].z); accl[k].w = __fmaf_rn(f[b].lw[k], dlv.w, accl[k].w);
+                }
+            }
+        }
+        flush_plane();
+        flush_line();
+    }
+}
+
 __global__ void k_vm_pack_weights(const float* __restrict__ basis, const float* __restrict__ wc0, const float* __restrict__ wc1,
                                   const float* __restrict__ wc2, uint8_t* __restrict__ blob) {
     pack_matrix(basis, 15, 144, blob + kVB, 16, 144);
@@ -702,9 +850,31 @@ int pvd_vm_field_forward(const PvdVmField* f, const float* xyzs, const float* di
     return PVD_OK;
 }
 
+static int vm_backward(const PvdVmField* f, const PvdVmGrads* grads, const float* xyzs, const float* dirs, const float* grad_sigmas,
+                       const float* grad_rgbs, const float* grad_feat16, uint32_t M, const int32_t* n_valid, float* gw_ws,
+                       void* scatter_ws, int32_t* status, void* stream);
+
 int pvd_vm_field_backward(const PvdVmField* f, const PvdVmGrads* grads, const float* xyzs, const float* dirs,
                           const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
                           const int32_t* n_valid, float* gw_ws, int32_t* status, void* stream) {
+    return vm_backward(f, grads, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid, gw_ws, nullptr, status, stream);
+}
+
+uint64_t pvd_vm_backward_workspace_bytes(uint32_t M) {
+    const uint64_t tiles = ((uint64_t)M + kTile - 1) / kTile;
+    return tiles * 36864u + tiles * kTile * sizeof(float);
+}
+
+int pvd_vm_field_backward_ws(const PvdVmField* f, const PvdVmGrads* grads, const float* xyzs, const float* dirs,
+                             const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                             const int32_t* n_valid, float* gw_ws, void* scatter_ws, int32_t* status, void* stream) {
+    PVD_REQUIRE(scatter_ws != nullptr && (reinterpret_cast<uintptr_t>(scatter_ws) & 15u) == 0);
+    return vm_backward(f, grads, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid, gw_ws, scatter_ws, status, stream);
+}
+
+static int vm_backward(const PvdVmField* f, const PvdVmGrads* grads, const float* xyzs, const float* dirs, const float* grad_sigmas,
+                       const float* grad_rgbs, const float* grad_feat16, uint32_t M, const int32_t* n_valid, float* gw_ws,
+                       void* scatter_ws, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
     PVD_REQUIRE(f && grads && xyzs && dirs && grad_sigmas && grad_rgbs && gw_ws && status);
     VmArgs a;
@@ -720,9 +890,15 @@ int pvd_vm_field_backward(const PvdVmField* f, const PvdVmGrads* grads, const fl
     if (e != cudaSuccess) return (int)e;
     // PVD_VM_DIAG_SKIP=1 (timing diagnostics only, wrong gradients): leave out the plane / line gradient scatter
     static const uint32_t diag_skip = []() { const char* v = getenv("PVD_VM_DIAG_SKIP"); return v ? (uint32_t)atoi(v) : 0u; }();
+    uint8_t* dapp_ws = reinterpret_cast<uint8_t*>(scatter_ws);
+    float* dsf_ws = scatter_ws ? reinterpret_cast<float*>(dapp_ws + (size_t)tiles * 36864u) : nullptr;
     k_vm_field_bwd<<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                                   gw_ws, status, diag_skip);
+                                                                   gw_ws, status, diag_skip, dapp_ws, dsf_ws);
     PVD_LAUNCH_CHECK();
+    if (scatter_ws != nullptr && !(diag_skip & 1u)) {
+        k_vm_scatter<<<ceil_div(M, 256u), 256, 0, (cudaStream_t)stream>>>(a, g, xyzs, dapp_ws, dsf_ws, M, n_valid);
+        PVD_LAUNCH_CHECK();
+    }
     return PVD_OK;
 }
 

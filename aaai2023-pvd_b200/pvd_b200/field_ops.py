@@ -13,6 +13,7 @@ parameter-gradient buffers (the engines run it on a side stream); `grads()` retu
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -90,10 +91,13 @@ class HashOps:
         return L * 8 * 2 * 2, (L * 8 * 2 * 4 + 64) if self.trainable else 0
 
 
+# vm backward as two kernels (MLP kernel -> workspace -> high-occupancy scatter kernel; default) or as one (0)
+VM_SPLIT_SCATTER = os.environ.get("PVD_VM_SPLIT_SCATTER", "1") != "0"
+
+
 class VmOps:
     kind = "vm"
     kernels_fwd = 1
-    kernels_bwd = 1
 
     def __init__(self, field, dev, trainable: bool = True):
         from . import fused_vm
@@ -104,6 +108,8 @@ class VmOps:
             for p in grp:
                 assert p.is_contiguous(memory_format=torch.channels_last), "vm planes/lines must be torch.channels_last"
         self._flat = None
+        self.scatter_ws = None
+        self.kernels_bwd = 2 if VM_SPLIT_SCATTER else 1
         if trainable:
             # every plane/line gradient lives in ONE flat buffer (one memset per step); each view has its parameter's shape and
             # channels-last strides ([H][W][R] in memory), sigma planes and lines first (the L1 penalty covers exactly that prefix)
@@ -129,13 +135,21 @@ class VmOps:
                                           float(density_scale))
 
     def alloc(self, M):
-        pass
+        if self.trainable and VM_SPLIT_SCATTER:
+            l = nv.lib()
+            l.pvd_vm_backward_workspace_bytes.restype = C.c_uint64
+            self.scatter_ws = torch.empty(int(l.pvd_vm_backward_workspace_bytes(_u32(M))), dtype=torch.uint8, device=self.dev)
 
     def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
         nv.check(nv.lib().pvd_vm_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
                                                nv.ptr(feat), nv.ptr(status), st))
 
     def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status):
+        if self.scatter_ws is not None:
+            nv.check(nv.lib().pvd_vm_field_backward_ws(C.byref(self.cfield), C.byref(self._cgrads), nv.ptr(xyzs), nv.ptr(dirs),
+                                                       nv.ptr(grad_sigmas), nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid),
+                                                       nv.ptr(gw_ws), nv.ptr(self.scatter_ws), nv.ptr(status), st))
+            return
         nv.check(nv.lib().pvd_vm_field_backward(C.byref(self.cfield), C.byref(self._cgrads), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(grad_sigmas),
                                                 nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid), nv.ptr(gw_ws),
                                                 nv.ptr(status), st))

@@ -151,6 +151,14 @@ int pvd_vm_field_backward(const PvdVmField* field, const PvdVmGrads* grads, cons
                           const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
                           const int32_t* n_valid, float* gw_ws, int32_t* status, void* stream);
 
+/* The same backward as TWO kernels: the MLP kernel leaves d(appearance) (fp16) and d(sigma feature) in `scatter_ws`
+ * (pvd_vm_backward_workspace_bytes(M) bytes, 16-byte aligned) and a second, high-occupancy kernel re-gathers the taps and reduces
+ * into the plane / line gradients.  Same results up to the order of the fp32 reductions; 141 -> ~100 us at 73 k samples. */
+uint64_t pvd_vm_backward_workspace_bytes(uint32_t M);
+int pvd_vm_field_backward_ws(const PvdVmField* field, const PvdVmGrads* grads, const float* xyzs, const float* dirs,
+                             const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                             const int32_t* n_valid, float* gw_ws, void* scatter_ws, int32_t* status, void* stream);
+
 int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, float* gw_color1, float* gw_color2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
