@@ -423,7 +423,13 @@ class PairDistillEngine(FieldTrainEngine):
     """
 
     def __init__(self, teacher, student, bitfield: torch.Tensor, n_rays: int, rates=(1.0, 0.002, 0.002, 0.002), stage: int = 3,
-                 l1_reg_weight: float = 1e-4, **kw):
+                 l1_reg_weight: float = 1e-4, group=None, dist_sync: bool = True, **kw):
+        # Ray-sharded data parallelism: the normL2 losses are norms over the GLOBAL batch, so the four sums of squares
+        # are all-reduced (1 KB, between k_pair_composite and k_pair_combine) before the coefficients rate / ||.|| are formed; summing
+        # the ranks' parameter gradients afterwards reproduces the single-process gradient (pvd_b200/dist.py::ShardedNormL2).
+        import torch.distributed as dist
+        self._dist = dist if (dist_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
+        self._group = group
         self.teacher_field = teacher
         self.distill_stage = int(stage)
         r = [float(v) for v in rates]
@@ -449,6 +455,9 @@ class PairDistillEngine(FieldTrainEngine):
         self.gw_ws = self._zeros[n_sum + 2 * fused.LOSS_SLOTS:]
         self.loss_out = torch.zeros(5, dtype=torch.float32, device=self.dev)   # total, ||rgb||, ||fea||, ||color||, ||sigma||
         self.pred_tea = torch.empty(self.N, 3, device=self.dev)
+        if self._dist is not None:   # create the communicator now: it cannot be created inside a CUDA-graph capture
+            self._dist.all_reduce(self.pair_sums, group=self._group)
+            self.pair_sums.zero_()
 
     def _init_fields(self):
         self.ops = field_ops.make_ops(self.field, self.dev, trainable=True)
@@ -505,6 +514,8 @@ class PairDistillEngine(FieldTrainEngine):
                                           nv.ptr(self.rgbs), nv.ptr(rs.deltas), nv.ptr(rs.rays), _u32(M_drop), _u32(self.N),
                                           nv.ptr(self.pred_tea), nv.ptr(self.weights_sum), nv.ptr(self.depth), nv.ptr(self.image),
                                           nv.ptr(self.grad_sigmas), nv.ptr(self.grad_rgbs), nv.ptr(self.pair_sums), st))
+        if self._dist is not None:
+            self._dist.all_reduce(self.pair_sums, group=self._group)   # global sums of squares (the slots add up the same way)
         nv.check(l.pvd_pair_combine(nv.ptr(self.feat_tea), nv.ptr(self.feat), nv.ptr(self.rgbs_tea), nv.ptr(self.rgbs),
                                     nv.ptr(self.pair_sums), C.byref(self.rates), _f32(self.loss_scale), _u32(M),
                                     nv.ptr(rs.counter) if self.distill_stage == 3 else None, nv.ptr(self.grad_sigmas),

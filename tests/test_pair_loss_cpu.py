@@ -24,7 +24,7 @@ def _fake_pair(seed, n_rays=37, max_cnt=70, pad=19):
     return rays, deltas, stu, tea, total, M
 
 
-def decomposed_pair_grads(rays, deltas, stu, tea, rates, total, bg=1.0, loss_scale=1.0, stage=3):
+def decomposed_pair_grads(rays, deltas, stu, tea, rates, total, bg=1.0, loss_scale=1.0, stage=3, reduce_sums=None):
     """What k_pair_sample_sq -> k_pair_composite -> k_pair_combine compute, restated with numpy + the C composite oracle."""
     r_rgb, r_fea, r_col, r_sig = rates
     if stage == 1:
@@ -47,6 +47,8 @@ def decomposed_pair_grads(rays, deltas, stu, tea, rates, total, bg=1.0, loss_sca
         gs_u, gc_u = cpu.composite_rays_train_backward(gws, diff.astype(np.float32), ss, cs, d, r, ws, img)
         gs_u[total:] = 0
         gc_u[total:] = 0
+    if reduce_sums is not None:   # ray-sharded run: the sums of squares are all-reduced before the coefficients are formed
+        sums = reduce_sums(sums)
     coef = {k: (loss_scale * rate / np.sqrt(sums[k]) if sums[k] > 0 and rate else 0.0)
             for k, rate in (("rgb", r_rgb), ("fea", r_fea), ("color", r_col), ("sigma", r_sig))}
     g_sigma = coef["rgb"] * gs_u
@@ -117,3 +119,36 @@ def test_pair_step_oracle_terms_and_stages():
     # a student equal to its teacher: every term vanishes
     same = field.pair_distill_step(ro, rd, bitfield, f_t, f_t, rates, stage=3)
     assert float(same["loss"]) == 0.0
+
+
+def test_sharded_pair_gradients_with_global_sums():
+    """Two shards of the rays (PairDistillEngine under ray sharding): each shard runs the decomposition on its own rays
+    and samples, the four sums of squares are added across the shards before the coefficients are formed (the engine's 1 KB
+    all-reduce); the concatenated per-sample gradients then equal those of the single-process step on the whole batch."""
+    rates = (1.0, 0.5, 0.25, 0.125)
+    rays, deltas, stu, tea, total, M = _fake_pair(7, n_rays=40, pad=1)
+    for k in stu:   # the one padding row carries no difference (both networks agree there), so it can be replicated per shard
+        stu[k].data[-1] = tea[k][-1]
+    want = _autograd(rays, deltas, stu, tea, rates, 3)
+    cut_ray = 17
+    cut = int(rays[cut_ray, 1])
+    shards = []
+    for lo_r, hi_r, lo_s, hi_s in ((0, cut_ray, 0, cut), (cut_ray, rays.shape[0], cut, total)):
+        r = rays[lo_r:hi_r].clone()
+        r[:, 0] -= lo_r   # a shard numbers its own rays and samples from zero
+        r[:, 1] -= lo_s
+        # the shard's samples + one padding row (a ray whose samples end exactly at M is dropped, raymarching.cu:419)
+        rows = torch.cat([torch.arange(lo_s, hi_s), torch.tensor([M - 1])])
+        sl = lambda d: {k: (v[rows].detach().clone().requires_grad_(v.requires_grad)) for k, v in d.items()}
+        shards.append((r, deltas[rows], sl(stu), sl(tea), hi_s - lo_s))
+    local = []
+    for r, d, s_, t_, tot in shards:   # first pass: every shard's own sums
+        box = {}
+        decomposed_pair_grads(r, d, s_, t_, rates, tot, reduce_sums=lambda sm: box.update(sm) or sm)
+        local.append(dict(box))
+    glob = {k: sum(l[k] for l in local) for k in local[0]}
+    parts = [decomposed_pair_grads(r, d, s_, t_, rates, tot, reduce_sums=lambda sm: glob) for r, d, s_, t_, tot in shards]
+    assert abs(parts[0][0] - want[0]) < 1e-5 * want[0] and abs(parts[1][0] - want[0]) < 1e-5 * want[0]
+    for i, name in ((1, "sigma"), (2, "rgb"), (3, "feat")):
+        got = np.concatenate([p_[i][:-1] for p_ in parts], axis=0)   # without the shards' padding rows
+        np.testing.assert_allclose(got, want[i][:-1], rtol=2e-4, atol=1e-7, err_msg=name)
