@@ -285,7 +285,8 @@ def roofline_kernels(eng):
             out.append(("k_hash_field_bwd", "field_bwd", "hbm", bb))
     else:
         out.append(("k_vm_field_fwd", "field_fwd", "hbm", fb))
-        out.append(("k_vm_field_bwd", "field_bwd", "hbm", fb + bb))             # the backward re-gathers the taps, then reduces into them
+        two = getattr(o, "scatter_ws", None) is not None                           # MLP kernel + stand-alone scatter kernel
+        out.append(("k_vm_field_bwd+k_vm_scatter" if two else "k_vm_field_bwd", "field_bwd", "hbm", fb + bb))   # re-gather + reductions
     return out
 
 
@@ -293,8 +294,10 @@ def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        k = t["kernels"].get(kernel.split("(")[0])
-        return (k["dram_bytes"], t.get("source")) if k else (None, None)
+        parts = [t["kernels"].get(k.split("(")[0]) for k in kernel.split("+")]   # "a+b": a phase made of two launches
+        if any(p is None for p in parts):
+            return None, None
+        return sum(p["dram_bytes"] for p in parts), " + ".join(sorted({p.get("source", "profiles/") for p in parts}))
     except Exception:
         return None, None
 

@@ -48,9 +48,11 @@ def main():
         name = re.sub(r"^(void\s+)?(pvd::)?", "", r[kn]).split("(")[0].split("<")[0] + suffix
         d = {k: val(r, k) for k in COLS}
         d["dram_bytes"] = (d["dram_read"] or 0.0) + (d["dram_write"] or 0.0)
+        d["source"] = f"profiles/{os.path.basename(raw)}"
         kernels.setdefault(name, d)   # first launch of each kernel
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    out = {"source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, one launch per kernel, cold caches)", "kernels": {}}
+    out = {"how": "ncu --set full --clock-control none --import-source on, one launch per kernel, cold caches; per-kernel `source` names the raw "
+                  "metric table under profiles/", "kernels": {}}
     if merge and os.path.exists(path):
         out["kernels"] = json.load(open(path))["kernels"]
     out["kernels"].update(kernels)
@@ -58,6 +60,7 @@ def main():
     f = lambda v, p=1: "-" if v is None else f"{v:.{p}f}"
     lines.append(f"{'kernel':28s} {'us':>7s} {'DRAM rd MB':>10s} {'wr MB':>7s} {'DRAM%':>6s} {'L2hit%':>6s} {'L1hit%':>6s} {'SM%':>5s} {'tensor%':>7s} {'warps%':>6s} {'regs':>4s} {'grid':>6s}")
     for n, d in kernels.items():
+        d = {k: v for k, v in d.items() if k != "source"}
         lines.append(f"{n:28s} {f(d['duration_us'], 2):>7s} {f((d['dram_read'] or 0) / 1e6, 2):>10s} {f((d['dram_write'] or 0) / 1e6, 2):>7s} {f(d['dram_pct']):>6s} "
                      f"{f(d['l2_hit_pct']):>6s} {f(d['l1_hit_pct']):>6s} {f(d['sm_pct']):>5s} {f(d['tensor_pct'], 2):>7s} {f(d['warps_active_pct']):>6s} "
                      f"{f(d['regs'], 0):>4s} {f(d['grid'], 0):>6s}")
