@@ -79,8 +79,10 @@ class FieldTrainEngine:
 
     def __init__(self, field, bitfield: torch.Tensor, n_rays: int, bound: float = 1.0, cascade: int = 1,
                  grid_size: int = 128, min_near: float = 0.2, max_steps: int = 1024, dt_gamma: float = 0.0, bg_color=(1.0, 1.0, 1.0),
-                 loss_scale: float = 1.0, density_scale: float = 1.0, l1_reg_weight: float = 0.0, device="cuda"):
+                 loss_scale: float = 1.0, density_scale: float = 1.0, l1_reg_weight: float = 0.0, perturb: bool = True,
+                 device="cuda"):
         self.field = field
+        self.perturb = bool(perturb)   # per-ray jitter of the first sample (renderer.py:387: perturb=True in training)
         self.dev = torch.device(device)
         self.N = int(n_rays)
         self.bound, self.cascade, self.grid_size = float(bound), int(cascade), int(grid_size)
@@ -183,7 +185,7 @@ class FieldTrainEngine:
         nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(rs.rays_o), nv.ptr(rs.rays_d), nv.ptr(self.bitfield), nv.ptr(self.aabb),
                                                    _f32(self.min_near), _f32(self.bound), _f32(self.dt_gamma), _u32(self.max_steps),
                                                    _u32(self.N), _u32(self.cascade), _u32(self.grid_size), nv.ptr(rs.nears),
-                                                   nv.ptr(rs.fars), nv.ptr(rs.rays), nv.ptr(rs.counter), _u32(1),
+                                                   nv.ptr(rs.fars), nv.ptr(rs.rays), nv.ptr(rs.counter), _u32(1 if self.perturb else 0),
                                                    _u32(1 if self._coarse_valid else 0), nv.ptr(self.ws_march), st))
         self._coarse_valid = True
 
