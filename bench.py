@@ -604,7 +604,7 @@ def run_reference(args, rank, world, local):
     cfg = {"workload": WORKLOADS[args.workload].format(L=args.levels, R=args.rays), "workload_key": args.workload,
            "rays_per_gpu": args.rays, "levels": args.levels}
     if not have_ref:
-        cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=max(20.0, args.cpu_budget))
+        cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget if args.cpu_budget != 15.0 else 20.0)
         out = {"metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * args.rays / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": cb,
