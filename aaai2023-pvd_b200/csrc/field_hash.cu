@@ -15,7 +15,8 @@
 //   * backward: forward recomputed from the saved fp16 encoding, then per layer one weight-gradient GEMM
 //     (reduction over the 128 samples, both operands MN-major views of the SAME tiles, fp32 accumulators persistent
 //     in TMEM across all tiles a CTA processes) and one data-gradient GEMM (weights as MN-major operand, so no
-//     transposed weight copy exists); the encoding gradient is scattered with red.global.add.v2.f32.
+//     transposed weight copy exists); the encoding gradient is scattered with red.global.add.v2/v4.f32 by four extra
+//     scatter warps of the same CTA (default) or by a second kernel (k_hash_scatter).
 // CTAs are persistent (grid = min(#tiles, 2 x #SMs)) so weights are staged and TMEM is allocated once per CTA and
 // weight gradients leave the SM once.
 #include "common.cuh"

@@ -58,8 +58,10 @@ int pvd_hash_field_forward(const PvdHashField* field, const float* xyzs, const f
  *   (zero padded; pvd_field_unpack_wgrads adds them onto parameter-shaped [out, in] buffers).
  * grad_feat16 [M,16] (or NULL) is d(loss)/d(feat16): the gradient of the distillation losses that read
  * `feature_sigma_color` / `sigma_l` directly (distill_mutual/utils.py:1046-1108); channel 0 passes the clamp mask.
- * dx_ws: optional [M, 32] fp16 scratch.  When given, the MLP kernel writes d(encoding) there and a second, full-occupancy
- * kernel (one thread per sample x level) scatters it into grad_table; when NULL the scatter runs inside the MLP kernel.
+ * dx_ws: optional [M, 32] fp16 scratch.  NULL (the engines' default): ONE launch -- four scatter warps inside every MLP CTA reduce
+ * tile i's d(encoding), handed over in shared memory, into grad_table while the MLP warps run the tensor-core chain of tile i+1.
+ * When given: TWO launches -- the MLP kernel writes d(encoding) there and a second, full-occupancy kernel (one thread per
+ * sample x level) scatters it into grad_table.
  * `enc` is the tensor the forward saved.  Rows >= *n_valid (device pointer, e.g. the march counter; NULL = all M)
  * are padding and contribute nothing. */
 #define PVD_FIELD_GW_FLOATS 10240u

@@ -1,6 +1,6 @@
-"""Diagnostic: VMTrainEngine gradients vs (a) the autograd module path on the GPU, (b) the CPU oracle.  Prints rel-L2 per parameter."""
+"""Diagnostic (test infrastructure; run by hand on a GPU box: `python tests/diag_vm_engine.py`): VMTrainEngine gradients vs (a) the autograd module path on the GPU, (b) the CPU oracle.  Prints rel-L2 per parameter."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "aaai2023-pvd_b200"), os.path.join(ROOT, "tests")]
 import torch
 from oracle import field
