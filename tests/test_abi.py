@@ -82,3 +82,33 @@ def test_no_cpu_fallback():
     ours = src[src.index("def build_engine("):src.index("# ------------------------------------------------------------------------------------------------ reference arm")]
     ours = ours.replace('cpu_baseline(args.workload', "")   # the one call of the baseline leg at the end of run_ours
     assert "oracle" not in ours
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Empty work is a no-op, NULL pointers are rejected before any launch (pair-loss, upkeep and vm two-kernel entry points)."""
+    from pvd_b200 import _native
+    l = _native.lib()
+    u32, f32, u64 = ctypes.c_uint32, ctypes.c_float, ctypes.c_uint64
+    assert l.pvd_pair_sample_sq(None, None, None, None, u32(0), None, None) == 0
+    assert l.pvd_pair_sample_sq(None, None, None, None, u32(128), None, None) == -1
+    assert l.pvd_pair_composite(None, None, None, None, None, None, None, u32(128), u32(0), None, None, None, None, None, None, None, None) == 0
+    assert l.pvd_pair_composite(None, None, None, None, None, None, None, u32(128), u32(4), None, None, None, None, None, None, None, None) == -1
+    assert l.pvd_pair_combine(None, None, None, None, None, None, f32(1.0), u32(0), None, None, None, None, None, None) == 0
+    assert l.pvd_pair_combine(None, None, None, None, None, None, f32(1.0), u32(8), None, None, None, None, None, None) == -1
+    assert l.pvd_zero_sample_tail(None, None, u32(4), u32(0), None, None, None, None) == 0
+    assert l.pvd_zero_sample_tail(None, None, u32(4), u32(128), None, None, None, None) == -1
+    assert l.pvd_l1_mean_reg(None, u64(0), f32(1e-4), f32(1.0), None, None, None) == 0
+    assert l.pvd_l1_mean_reg(None, u64(16), f32(0.0), f32(1.0), None, None, None) == 0      # zero weight: nothing to do
+    assert l.pvd_l1_mean_reg(None, u64(16), f32(1e-4), f32(1.0), None, None, None) == -1
+    assert l.pvd_density_grid_points(None, None, u32(0), u32(128), f32(1.0), None, None) == 0
+    assert l.pvd_density_grid_points(None, None, u32(8), u32(128), f32(1.0), None, None) == -1
+    assert l.pvd_density_grid_update(None, None, None, None, u32(0), u32(0), f32(1.0), f32(0.95), None, None) == 0
+    assert l.pvd_density_grid_update(None, None, None, None, u32(8), u32(8), f32(1.0), f32(0.95), None, None) == -1
+    assert l.pvd_packbits_mean(None, u32(0), None, u32(8), f32(0.01), None, None, None) == 0
+    assert l.pvd_packbits_mean(None, u32(1), None, u32(8), f32(0.01), None, None, None) == -1
+    l.pvd_vm_backward_workspace_bytes.restype = ctypes.c_uint64
+    assert l.pvd_vm_backward_workspace_bytes(u32(129)) == 2 * 36864 + 2 * 128 * 4
+    assert l.pvd_vm_field_backward_ws(None, None, None, None, None, None, None, u32(128), None, None, None, None, None) == -1
+    assert l.pvd_vm_field_backward(None, None, None, None, None, None, None, u32(0), None, None, None, None) == 0
+    assert l.pvd_mlp_field_forward(None, None, None, u32(0), None, None, None, None, None) == 0
+    assert l.pvd_hash_field_backward(None, None, None, None, None, None, None, u32(0), None, None, None, None, None, None) == 0
