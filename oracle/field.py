@@ -124,6 +124,41 @@ def render_train_step(rays_o, rays_d, bitfield, gt_rgb, field_fn, bound=1.0, cas
                 counter=counter, sigma=sigma, rgb=rgb)
 
 
+def render_uniform(rays_o, rays_d, field_fn, aabb, num_steps=64, min_near=0.2, bg_color=1.0, density_scale=1.0, noise=None):
+    """`NeRFRenderer.run` without upsampling (distill_mutual/renderer.py:139-317, upsample_steps=0) -- the pure-PyTorch renderer of
+    BASELINE configs[0] (mlp model, 256 rays x 64 uniform samples, CPU).  The reference's own `run` ends in `self.color(...)`, which
+    asserts False (network.py:516); as SURVEY.md 8c prescribes, `field_fn(xyzs, dirs) -> (sigma, rgb)` (= `forward`) stands in for
+    the dead density / color split, everything else is restated line by line:
+        z = near + (far - near) * linspace(0, 1, T)  [+ (noise - 0.5) * sample_dist]          :168-182
+        xyz = clip(o + d z, aabb)                                                               :185-188
+        delta_i = z_{i+1} - z_i, last = sample_dist ; alpha = 1 - exp(-delta * density_scale * sigma)   :262-268
+        w = alpha * cumprod([1, 1 - alpha + 1e-15])[:-1] ; image = sum w rgb + (1 - sum w) * bg ; depth = sum w * clamp((z - near) / (far - near))  :269-311
+    Returns dict(image [N,3], depth [N], weights_sum [N], weights [N,T], z_vals, xyzs [N*T,3], dirs, sigma, rgb)."""
+    N = rays_o.shape[0]
+    nears, fars = cpu.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), np.asarray(aabb, np.float32), min_near)
+    nears, fars = torch.from_numpy(nears).unsqueeze(-1), torch.from_numpy(fars).unsqueeze(-1)
+    z = torch.linspace(0.0, 1.0, num_steps).unsqueeze(0).expand(N, num_steps)
+    z = nears + (fars - nears) * z
+    sample_dist = (fars - nears) / num_steps
+    if noise is not None:
+        z = z + (noise - 0.5) * sample_dist
+    aabb_t = torch.as_tensor(aabb, dtype=torch.float32)
+    xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)
+    xyzs = torch.min(torch.max(xyzs, aabb_t[:3]), aabb_t[3:])
+    dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+    sigma, rgb = field_fn(xyzs.reshape(-1, 3), dirs.reshape(-1, 3))
+    sigma, rgb = sigma.view(N, num_steps), rgb.view(N, num_steps, 3)
+    deltas = torch.cat([z[..., 1:] - z[..., :-1], sample_dist * torch.ones_like(z[..., :1])], dim=-1)
+    alphas = 1 - torch.exp(-deltas * density_scale * sigma)
+    shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+    weights = alphas * torch.cumprod(shifted, dim=-1)[..., :-1]
+    ws = weights.sum(dim=-1)
+    depth = torch.sum(weights * ((z - nears) / (fars - nears)).clamp(0, 1), dim=-1)
+    image = torch.sum(weights.unsqueeze(-1) * rgb, dim=-2) + (1 - ws).unsqueeze(-1) * bg_color
+    return dict(image=image, depth=depth, weights_sum=ws, weights=weights, z_vals=z, deltas=deltas, xyzs=xyzs.reshape(-1, 3),
+                dirs=dirs.reshape(-1, 3), sigma=sigma, rgb=rgb)
+
+
 def pair_distill_step(rays_o, rays_d, bitfield, student_fn, teacher_fn, rates=(1.0, 0.002, 0.002, 0.002), stage=3, l1_reg=None,
                       bg_color=1.0, density_scale=1.0, M=None, **march_kw):
     """One distillation step of `Trainer.train_step` (distill_mutual/utils.py:954-1189, loss_type normL2) on the CPU.
