@@ -279,8 +279,10 @@ class RefTrainer:
     """run_cuda (training branch) + MSE + scaled backward, as the reference's train_one_epoch does per iteration."""
 
     def __init__(self, ext, net, bitfield, bound=1.0, cascade=1, grid_size=128, min_near=0.2, max_steps=1024,
-                 loss_scale=65536.0, l1_reg_weight=0.0):
+                 loss_scale=65536.0, l1_reg_weight=0.0, autocast=True):
         self.ext, self.net = ext, net
+        self.autocast = autocast   # False = the same flow in fp32 (parity tests: the noise floor of the reference's own fp16 path)
+        self.last = {}             # per-ray outputs / samples of the last step (parity tests)
         self.bitfield = bitfield
         self.bound, self.cascade, self.grid_size, self.min_near, self.max_steps = bound, cascade, grid_size, min_near, max_steps
         dev = bitfield.device
@@ -315,7 +317,7 @@ class RefTrainer:
         Composite = self.net.ops[3]
         for p in self.net.parameters():
             p.grad = None
-        with torch.autocast("cuda", dtype=torch.float16):  # fp16=True is forced by both CLIs (main_distill_mutual.py:251-254)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=self.autocast):  # fp16=True is forced by both CLIs (main_distill_mutual.py:251-254)
             N = rays_o.shape[0]
             nears = torch.empty(N, device=rays_o.device)
             fars = torch.empty(N, device=rays_o.device)
@@ -331,6 +333,8 @@ class RefTrainer:
             loss = torch.mean((image - gt) ** 2)
             if self.l1_reg_weight and hasattr(self.net, "density_loss"):      # just_train_tea/utils.py:843-844
                 loss = loss + self.net.density_loss() * self.l1_reg_weight
+            self.last = {"image": image.detach(), "depth": depth.detach(), "weights_sum": ws.detach(), "rays": rays, "xyzs": xyzs,
+                         "dirs": dirs, "deltas": deltas, "nears": nears, "fars": fars, "total": counter.clone()}
         (loss * self.loss_scale).backward()
         return loss
 
@@ -367,7 +371,7 @@ class RefPairTrainer(RefTrainer):
         for p in stu.parameters():
             p.grad = None
         r_rgb, r_fea, r_col, r_sig = self.rates
-        with torch.autocast("cuda", dtype=torch.float16):
+        with torch.autocast("cuda", dtype=torch.float16, enabled=self.autocast):
             N = rays_o.shape[0]
             nears = torch.empty(N, device=rays_o.device)
             fars = torch.empty(N, device=rays_o.device)
@@ -381,12 +385,19 @@ class RefPairTrainer(RefTrainer):
                 # the teacher's run_cuda recomputes near/far and then re-uses the samples (renderer.py:342,393-394)
                 rm.near_far_from_aabb(rays_o, rays_d, self.aabb, N, self.min_near, nears, fars)
                 pred_tea = self._render(tea, xyzs, dirs, deltas, rays, nears, fars, bg_color)
-            loss = r_rgb * torch.norm(pred_tea - pred_stu)                                            # :1110-1111
+            t_rgb = torch.norm(pred_tea - pred_stu)
+            t_fea = torch.norm(stu.feature_sigma_color - tea.feature_sigma_color)
+            t_col = torch.norm(stu.color_l - tea.color_l)
+            t_sig = torch.norm(stu.sigma_l - tea.sigma_l)
+            loss = r_rgb * t_rgb                                                                      # :1110-1111
             if self.l1_reg_weight and hasattr(stu, "density_loss"):
                 loss = loss + stu.density_loss() * self.l1_reg_weight                                 # :1135-1136
-            loss = loss + r_fea * torch.norm(stu.feature_sigma_color - tea.feature_sigma_color)       # :1137-1149
-            loss = loss + r_col * torch.norm(stu.color_l - tea.color_l)                               # :1158-1165
-            loss = loss + r_sig * torch.norm(stu.sigma_l - tea.sigma_l)                               # :1166-1173
+            loss = loss + r_fea * t_fea                                                               # :1137-1149
+            loss = loss + r_col * t_col                                                               # :1158-1165
+            loss = loss + r_sig * t_sig                                                               # :1166-1173
+            self.last = {"image": pred_stu.detach(), "image_tea": pred_tea.detach(), "rays": rays, "xyzs": xyzs, "dirs": dirs,
+                         "deltas": deltas, "total": counter.clone(),
+                         "terms": {"rgb": t_rgb.detach(), "fea": t_fea.detach(), "color": t_col.detach(), "sigma": t_sig.detach()}}
         (loss * self.loss_scale).backward()
         return loss
 

@@ -41,15 +41,19 @@ def scene():
 
 @pytest.fixture(scope="session")
 def ref_ext():
-    """The reference's own CUDA extensions (oracle/_ref), or None when they were not built."""
+    """The reference's own CUDA extensions (oracle/_ref = /root/reference compiled unmodified by oracle/build_ref.py).
+
+    None ONLY when oracle/_ref was never built (a checkout without the reference).  When the directory holds the built modules
+    and they do not import, that is a hard failure: the comparisons with the reference must not be skipped silently."""
     d = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.isdir(d):
+    built = os.path.isdir(d) and any(f.endswith(".so") for f in os.listdir(d))
+    if not built:
         return None
     if d not in sys.path:
         sys.path.insert(0, d)
     try:
         import torch  # noqa: F401  (libtorch must be loaded first)
         import _raymarching, _gridencoder, _shencoder
-    except Exception:
-        return None
+    except Exception as ex:  # noqa: BLE001
+        pytest.fail(f"oracle/_ref exists but the reference extensions do not import ({ex!r}): the reference comparisons would be skipped")
     return {"raymarching": _raymarching, "gridencoder": _gridencoder, "shencoder": _shencoder}
