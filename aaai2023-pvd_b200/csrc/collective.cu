@@ -45,6 +45,108 @@ __global__ void __launch_bounds__(256) k_multimem_allreduce_f16(__half* __restri
     }
 }
 
+// ---- the same reduction as ONE launch: device-side barriers instead of two signal-pad barrier launches around the kernel ----------
+// (each of those costs ~13 us on the stream; scripts/micro/exchange_probe.py).  Protocol per launch, all ranks run the same grid:
+//   1. block 0, threads < W: cross-rank barrier over the symmetric-memory signal pads (CAS 0->1 on the peer's slot, CAS 1->0 on
+//      mine: torch's own sync_remote_blocks protocol, other channel slots) -- every rank's payload is complete once its kernel
+//      runs (stream order behind the cast); then `flag` releases this GPU's other blocks;
+//   2. every block: multimem.ld_reduce of its part of this rank's shard, multimem.st of the sums to all ranks;
+//   3. every block counts itself done; block 0 waits for all of them, fences at system scope, runs the cross-rank barrier again
+//      (all ranks' stores into my copy are issued and fenced) and resets flag / counter for the next launch.
+// Blocks only ever wait for block 0 (step 1) and block 0 only for blocks that wait for nothing else (step 3): no co-residency
+// requirement beyond block 0 being scheduled, which a grid of at most 148 x 8 blocks of 256 threads guarantees.
+// Every spin is bounded (~2 s of SM clocks): a peer that never arrives must not wedge the GPU; local[2] reports it.
+constexpr long long kSpinLimit = 4000000000ll;
+__device__ __forceinline__ bool sig_put(uint32_t* addr) {
+    const long long t0 = clock64();
+    while (atomicCAS_system(addr, 0u, 1u) != 0u)
+        if (clock64() - t0 > kSpinLimit) return false;
+    return true;
+}
+__device__ __forceinline__ bool sig_wait(uint32_t* addr) {
+    const long long t0 = clock64();
+    while (atomicCAS_system(addr, 1u, 0u) != 1u)
+        if (clock64() - t0 > kSpinLimit) return false;
+    return true;
+}
+__device__ __forceinline__ void cross_rank_barrier(uint32_t* const* pads, uint32_t rank, uint32_t world, uint32_t channel, uint32_t* err) {
+    if (threadIdx.x < world) {
+        const uint32_t peer = threadIdx.x;
+        __threadfence_system();
+        if (!sig_put(pads[peer] + channel * world + rank)) atomicExch(err, 1u);
+        if (!sig_wait(pads[rank] + channel * world + peer)) atomicExch(err, 2u);
+        __threadfence_system();
+    }
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_multimem_allreduce_f16_fused(__half* __restrict__ mc, uint64_t first_vec, uint64_t n_vec,
+                                                                      uint32_t* const* __restrict__ pads, uint32_t rank, uint32_t world,
+                                                                      uint32_t* __restrict__ local /* [0] flag, [1] done, [2] error */) {
+    if (blockIdx.x == 0) {
+        cross_rank_barrier(pads, rank, world, 8u, local + 2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicExch(local, 1u);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (atomicAdd(local, 0u) == 0u)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(local + 2, 3u); break; }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += UNROLL * stride) {
+        uint32_t v[UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < n_vec) {
+                __half* p = mc + (first_vec + i) * 8;
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                             : "l"(p)
+                             : "memory");
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i < n_vec) {
+                __half* p = mc + (first_vec + i) * 8;
+                asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v[u][0]), "r"(v[u][1]),
+                             "r"(v[u][2]), "r"(v[u][3])
+                             : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd(local + 1, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (atomicAdd(local + 1, 0u) < gridDim.x)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(local + 2, 4u); break; }
+            __threadfence_system();
+        }
+        __syncthreads();
+        cross_rank_barrier(pads, rank, world, 9u, local + 2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            local[1] = 0u;
+            __threadfence();
+            local[0] = 0u;
+        }
+    }
+}
+
 // fp32 gradient -> fp16 payload, and the inverse
 __global__ void __launch_bounds__(256) k_f32_to_f16(const float4* __restrict__ src, uint2* __restrict__ dst, uint64_t n_vec4) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -67,6 +169,27 @@ int pvd_multimem_allreduce_f16(void* multicast_ptr, uint64_t elem_offset, uint64
     const uint64_t n_vec = elem_count / 8u;
     const uint32_t grid = (uint32_t)min((unsigned long long)((n_vec + 1023u) / 1024u), 148ull * 8ull);
     k_multimem_allreduce_f16<<<grid, 256, 0, (cudaStream_t)stream>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
+                                     uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream) {
+    PVD_REQUIRE(multicast_ptr != nullptr && signal_pad_ptrs_dev != nullptr && local_state != nullptr);
+    PVD_REQUIRE((elem_offset % 8u) == 0 && (elem_count % 8u) == 0 && world >= 1 && world <= 32 && rank < world);
+    PVD_REQUIRE((reinterpret_cast<uintptr_t>(multicast_ptr) & 15u) == 0);
+    const uint64_t n_vec = elem_count / 8u;
+    uint32_t grid = blocks ? blocks : 148u * 4u;
+    grid = max(1u, min(grid, 148u * 8u));
+    uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pad_ptrs_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (unroll >= 8) {
+        k_multimem_allreduce_f16_fused<8><<<grid, 256, 0, st>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec, pads, rank, world, local_state);
+    } else if (unroll >= 4) {
+        k_multimem_allreduce_f16_fused<4><<<grid, 256, 0, st>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec, pads, rank, world, local_state);
+    } else {
+        k_multimem_allreduce_f16_fused<2><<<grid, 256, 0, st>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec, pads, rank, world, local_state);
+    }
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

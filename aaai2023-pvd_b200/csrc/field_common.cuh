@@ -138,10 +138,11 @@ __device__ __forceinline__ void stage_blob(uint8_t* smw, const uint8_t* __restri
         reinterpret_cast<uint4*>(smw)[i] = __ldg(reinterpret_cast<const uint4*>(blob) + i);
 }
 
-// pack one fp32 [out, in] matrix into an fp16 chunk tile of R rows x K cols (zero padded)
+// pack one fp32 [out, in] matrix into an fp16 chunk tile of R rows x K cols (zero padded); the whole GRID strides over the tile
+// (the pack sits on the critical path of a step whose parameters an optimizer has just changed: one CTA took 12 us)
 __device__ __forceinline__ void pack_matrix(const float* __restrict__ w, uint32_t out, uint32_t in, uint8_t* tile, uint32_t R,
                                             uint32_t K) {
-    for (uint32_t e = threadIdx.x; e < R * K; e += blockDim.x) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < R * K; e += gridDim.x * blockDim.x) {
         const uint32_t r = e / K, k = e - r * K;
         const float v = (r < out && k < in) ? w[(size_t)r * in + k] : 0.0f;
         *reinterpret_cast<__half*>(tile + tc5::chunk_off(R, r, k >> 3) + (k & 7u) * 2) = __float2half_rn(v);

@@ -673,7 +673,7 @@ int pvd_field_pack_weights(const float* w_sigma0, const float* w_sigma1, const f
                            const float* w_color2, uint32_t in_dim, void* wblob, void* stream) {
     PVD_REQUIRE(w_sigma0 && w_sigma1 && w_color0 && w_color1 && w_color2 && wblob);
     if (in_dim == 0 || in_dim > 32 || (in_dim & 1u)) return PVD_EUNSUPPORTED;
-    k_pack_weights<<<1, 256, 0, (cudaStream_t)stream>>>(w_sigma0, w_sigma1, w_color0, w_color1, w_color2, in_dim, (uint8_t*)wblob);
+    k_pack_weights<<<16, 256, 0, (cudaStream_t)stream>>>(w_sigma0, w_sigma1, w_color0, w_color1, w_color2, in_dim, (uint8_t*)wblob);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

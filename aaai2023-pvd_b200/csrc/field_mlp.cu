@@ -56,186 +56,6 @@ __constant__ ChunkDesc kSchedule[kMlpChunks] = {
     {6, 0, 0, 0}, {6, 0, 1, 0}, {6, 0, 2, 0}, {6, 0, 3, 1},
 };
 
-__global__ void __launch_bounds__(128, 1) k_mlp_field_fwd_v1(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
-                                                          uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
-                                                          float* __restrict__ feat16, int32_t* status) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_layer, bar_full[2], bar_empty[2];
-    __shared__ uint32_t tmem_base_s;
-    uint8_t* X0 = smem;                              // 16384 : PE features [128 x 64]
-    uint8_t* A = X0 + 16384;                         // 65536 : activations [128 x 256]; later the tail's tiles
-    uint8_t* WB = A + 65536;                         // 2 x 32768 : streamed weight chunks
-    uint8_t* smw = WB + 2 * kMlpChunkBytes;          // 20480 : tail weights
-    float* bias = reinterpret_cast<float*>(smw + PVD_FIELD_WBLOB_BYTES);  // 8 x 256 floats
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane_base = (tid >> 5) * 32;
-
-    stage_blob(smw, a.tail_blob, PVD_FIELD_WBLOB_BYTES);
-    stage_blob(reinterpret_cast<uint8_t*>(bias), a.wblob + kMlpBiasOff, kMlpBiasBytes);
-    if (tid == 0) {
-        tc5::mbar_init(&bar_layer, 1);
-        tc5::mbar_init(&bar_full[0], 1);
-        tc5::mbar_init(&bar_full[1], 1);
-        tc5::mbar_init(&bar_empty[0], 1);
-        tc5::mbar_init(&bar_empty[1], 1);
-        tc5::mbar_fence_init();
-    }
-    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 256);
-    tc5::fence_before_sync();
-    __syncthreads();
-    tc5::fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
-    const uint32_t trow = tc5::tmem_addr(tmem, lane_base, 0);
-    Pipe p{&bar_layer, 0u, tmem, status};
-    // weight pipeline state, meaningful in thread 0 only: running counts of chunk loads issued / chunks consumed
-    uint32_t issued = 0, consumed = 0;
-
-    // chunk `c` of a tile: 0..25 = the 32 KB slices of layers 0..6, 26 = the four [32 x 64] slices of layer 7
-    auto issue_load = [&](uint32_t c) {
-        const uint32_t buf = issued & 1u;
-        if (issued >= 2u) {  // the buffer's previous user must have been read by the tensor core
-            if (!tc5::mbar_wait(&bar_empty[buf], ((issued >> 1) - 1u) & 1u)) atomicExch(status, 1);
-        }
-        const uint32_t bytes = (c < kMlpChunks) ? kMlpChunkBytes : kMlpL7Bytes;
-        tc5::mbar_expect_tx(&bar_full[buf], bytes);
-        tc5::bulk_g2s(tc5::smem_u32(WB + buf * kMlpChunkBytes), a.wblob + (size_t)c * kMlpChunkBytes, bytes, &bar_full[buf]);
-        ++issued;
-    };
-    auto wait_full = [&]() -> uint32_t {
-        const uint32_t buf = consumed & 1u;
-        if (!tc5::mbar_wait(&bar_full[buf], (consumed >> 1) & 1u)) atomicExch(status, 1);
-        return buf;
-    };
-
-    const uint32_t n_tiles = (M + kTile - 1) / kTile;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kTile + tid;
-        const bool live = row < M;
-        const bool more_tiles = tile + gridDim.x < n_tiles;
-        float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-        if (live) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
-                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
-            }
-        }
-        if (tid == 0 && issued == consumed) issue_load(0);  // first tile of this CTA (later tiles were prefetched)
-        {   // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9
-            float f[64];
-            f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2];
-            float freq = 1.0f;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    float sn, cs;
-                    sincosf(pos[d] * freq, &sn, &cs);
-                    f[3 + 6 * k + d] = sn;
-                    f[3 + 6 * k + 3 + d] = cs;
-                }
-                freq *= 2.0f;
-            }
-            f[63] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(X0 + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(f + 8 * j);
-        }
-        // ---- layers 0..6: thread 0 streams the layer's chunks and issues its MMAs; everybody meets at the layer barrier
-        uint32_t ci = 0;
-        for (uint32_t layer = 0; layer < 7; ++layer) {
-            operands_ready();  // publishes X0 / the activation tile written by the previous epilogue, orders the TMEM reads
-            const uint32_t n_chunks = (layer == 0) ? 1u : (layer == 4 ? 5u : 4u);
-            if (tid == 0) {
-                tc5::fence_after_sync();
-                const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
-                for (uint32_t j = 0; j < n_chunks; ++j) {
-                    const ChunkDesc cd = kSchedule[ci + j];
-                    issue_load(ci + j + 1);  // next chunk of the tile (26 = layer 7) into the other buffer
-                    const uint32_t buf = wait_full();
-                    tc5::fence_after_sync();
-                    const uint32_t a_tile = cd.from_x0 ? tc5::smem_u32(X0) : tc5::smem_u32(A) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
-                    const uint32_t b_tile = tc5::smem_u32(WB + buf * kMlpChunkBytes);
-#pragma unroll
-                    for (uint32_t k0 = 0; k0 < 64; k0 += 16)
-                        tc5::mma_f16_ss(tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                        !(j == 0 && k0 == 0));
-                    tc5::mma_commit(&bar_empty[buf]);  // buffer reusable once these MMAs have read it
-                    ++consumed;
-                }
-                tc5::mma_commit(&bar_layer);
-            }
-            ci += n_chunks;
-            mma_wait(p);
-            // epilogue: bias + ReLU -> next layer's A operand (the MMAs that read the old A have all completed)
-            const float* bl = bias + 256 * layer;
-#pragma unroll 1
-            for (int c = 0; c < 16; ++c) {
-                float v[16];
-                tc5::tmem_ld16(trow + 16 * c, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[16 * c + i], 0.0f);
-                *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c)) = tc5::pack8(v);
-                *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, tid, 2 * c + 1)) = tc5::pack8(v + 8);
-            }
-        }
-        // ---- layer 7: 256 -> 28 (N = 32), its four [32 x 64] slices arrived as "chunk 26"
-        operands_ready();
-        if (tid == 0) {
-            tc5::fence_after_sync();
-            if (more_tiles) issue_load(0);  // next tile's first chunk streams in under the tail
-            const uint32_t buf = wait_full();
-            tc5::fence_after_sync();
-            const uint32_t idesc = tc5::instr_desc_f16(128, 32, 0, 0);
-            for (uint32_t c = 0; c < 4; ++c)
-                for (uint32_t k0 = 0; k0 < 64; k0 += 16)
-                    tc5::mma_f16_ss(tmem, tc5::desc_kmajor(tc5::smem_u32(A) + c * 8u * (kTile * 16u), kTile, k0),
-                                    tc5::desc_kmajor(tc5::smem_u32(WB + buf * kMlpChunkBytes) + c * (32u * 64u * 2u), 32, k0), idesc,
-                                    !(c == 0 && k0 == 0));
-            tc5::mma_commit(&bar_empty[buf]);
-            ++consumed;
-            tc5::mma_commit(&bar_layer);
-        }
-        mma_wait(p);
-        // x28 = D[0..27] + bias7 -> the tail's encoding tile (reuses the activation region; its MMAs have completed)
-        uint8_t* X = A;                 // 8192
-        uint8_t* CIN = A;               // aliases X (dead after the first tail layer)
-        uint8_t* H = A + 8192;          // 16384 : H1, H3, H4
-        {
-            float v[32];
-            tc5::tmem_ld16(trow, *reinterpret_cast<float(*)[16]>(&v[0]));
-            tc5::tmem_ld16(trow + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-            const float* b7 = bias + 256 * 7;
-#pragma unroll
-            for (int i = 0; i < 28; ++i) v[i] += b7[i];
-#pragma unroll
-            for (int i = 28; i < 32; ++i) v[i] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(v + 8 * j);
-        }
-        FieldArgs fa;
-        fa.clip_min = a.clip_min; fa.clip_max = a.clip_max; fa.density_scale = a.density_scale;
-        float sigma, o16[16];
-        FwdRegs r;
-        mlp_forward(p, fa, smw, X, H, CIN, H, H, dir, tid, sigma, o16, r);
-        if (live) {
-            sigmas[row] = sigma;
-            rgbs[3 * (size_t)row] = r.rgb[0];
-            rgbs[3 * (size_t)row + 1] = r.rgb[1];
-            rgbs[3 * (size_t)row + 2] = r.rgb[2];
-            if (feat16) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(feat16 + 16 * (size_t)row + 4 * q) =
-                        make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
-            }
-        }
-    }
-    tc5::fence_before_sync();
-    __syncthreads();
-    if (tid < 32) tc5::tmem_dealloc(tmem, 256);
-}
-
-
 // =============================================================================================== v2: warp-specialised, two tiles per CTA
 // One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream:
 //   warps 0-3 (warpgroup 0) own the rows of tile 0, warps 4-7 (warpgroup 1) the rows of tile 1: PE, layer epilogues (TMEM -> bias ->
@@ -602,20 +422,11 @@ int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* 
     static const uint32_t diag = []() { const char* v = getenv("PVD_MLP_DIAG"); return v ? (uint32_t)atoi(v) : 0u; }();
     a.diag = diag;
     const uint32_t tiles = (M + kTile - 1) / kTile;
-    static const bool use_v1 = []() { const char* v = getenv("PVD_MLP_V1"); return v != nullptr && v[0] == '1'; }();
-    if (!use_v1) {
-        const uint32_t pairs = (tiles + 1) / 2;
-        const uint32_t grid2 = min(pairs, (uint32_t)sm_count());
-        cudaError_t e2 = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
-        if (e2 != cudaSuccess) return (int)e2;
-        k_mlp_field_fwd<<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
-        PVD_LAUNCH_CHECK();
-        return PVD_OK;
-    }
-    const uint32_t grid = min(tiles, (uint32_t)sm_count());
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_field_fwd_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem);
-    if (e != cudaSuccess) return (int)e;
-    k_mlp_field_fwd_v1<<<grid, 128, kMlpSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    const uint32_t pairs = (tiles + 1) / 2;
+    const uint32_t grid2 = min(pairs, (uint32_t)sm_count());
+    cudaError_t e2 = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
+    if (e2 != cudaSuccess) return (int)e2;
+    k_mlp_field_fwd<<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

@@ -830,7 +830,7 @@ extern "C" {
 int pvd_vm_pack_weights(const float* basis_mat, const float* w_color0, const float* w_color1, const float* w_color2, void* wblob,
                         void* stream) {
     PVD_REQUIRE(basis_mat && w_color0 && w_color1 && w_color2 && wblob);
-    k_vm_pack_weights<<<1, 256, 0, (cudaStream_t)stream>>>(basis_mat, w_color0, w_color1, w_color2, (uint8_t*)wblob);
+    k_vm_pack_weights<<<16, 256, 0, (cudaStream_t)stream>>>(basis_mat, w_color0, w_color1, w_color2, (uint8_t*)wblob);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

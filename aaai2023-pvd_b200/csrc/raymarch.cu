@@ -1088,6 +1088,23 @@ int pvd_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
 
 constexpr uint64_t kCoarseWords = 2ull * kCoarseMaskWords;  // dilated 64^3 block mask, then the undilated one
 
+// The block mask is built from cascade 0 of a 128^3 grid and probed with cells mapped by 1 / bound; cascade 0 spans
+// [-min(1, bound), min(1, bound)] (march_locate), so the two agree only for bound <= 1 (then C == 1 anyway, renderer.py:81).
+static inline bool coarse_mask_applies(uint32_t C, uint32_t H, float bound) { return (C == 1) && (H == 2 * kCoarseB) && (bound <= 1.0f); }
+
+int pvd_march_coarse_mask(const uint8_t* grid, uint32_t C, uint32_t H, float bound, int32_t* ws_i32, void* stream) {
+    PVD_REQUIRE(grid && ws_i32);
+    if (!coarse_mask_applies(C, H, bound)) return PVD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* coarse = reinterpret_cast<uint32_t*>(ws_i32);
+    uint32_t* any = coarse + kCoarseMaskWords;
+    k_coarse_any<<<kCoarseMaskWords / 256, 256, 0, st>>>(grid, any);
+    PVD_LAUNCH_CHECK();
+    k_coarse_dilate<<<kCoarseMaskWords / 256, 256, 0, st>>>(any, coarse);
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
 uint64_t pvd_march_rays_train_workspace_words(uint32_t N, uint32_t max_steps) {
     // coarse mask[8192] + any[8192] | num_steps[N] | t0[N] | stash[N*max_steps] float2   (stash kept 8-byte aligned)
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
@@ -1109,7 +1126,7 @@ int pvd_march_rays_train_count(const float* rays_o, const float* rays_d, const u
     float2* stash = reinterpret_cast<float2*>(ws_i32 + kCoarseWords + head);
     const Pcg32 rng = pcg32_seeded(42u);  // hard-coded seed, raymarching.cu:488
     // coarse pruning: one cascade, the reference's 128^3 grid (a 2x2x2 block of cells = one byte of the Morton bitfield)
-    const bool use_coarse = (C == 1) && (H == 2 * kCoarseB);
+    const bool use_coarse = coarse_mask_applies(C, H, bound);
     if (use_coarse) {
         uint32_t* any = reinterpret_cast<uint32_t*>(ws_i32) + kCoarseMaskWords;
         k_coarse_any<<<kCoarseMaskWords / 256, 256, 0, st>>>(grid, any);
@@ -1141,7 +1158,7 @@ int pvd_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, co
     const uint64_t head = ((2ull * N + 1ull) / 2ull) * 2ull;
     float2* stash = reinterpret_cast<float2*>(ws_i32 + kCoarseWords + head);
     const Pcg32 rng = pcg32_seeded(42u);
-    const bool use_coarse = (C == 1) && (H == 2 * kCoarseB);
+    const bool use_coarse = coarse_mask_applies(C, H, bound);
     if (use_coarse && !reuse_coarse) {
         uint32_t* any = reinterpret_cast<uint32_t*>(ws_i32) + kCoarseMaskWords;
         k_coarse_any<<<kCoarseMaskWords / 256, 256, 0, st>>>(grid, any);

@@ -6,8 +6,9 @@ base_resolution, calc_grad_inputs=False, gridtype=0, align_corners=False)` (:20-
 checkpoints load unchanged.
 
 B200-side differences: the kernels write / read activations sample-major ([B, L*C]) so the reference's two permute
-copies (grid.py:84,104) disappear; under autocast the fp16 copy of the table is cached per parameter version instead
-of re-cast on every forward (grid.py:52 converts all 10.6 M entries each call).
+copies (grid.py:84,104) disappear.  Under autocast the fp16 copy of the table is re-cast on every forward like the reference
+(grid.py:52); the dense cast is taken out of the hot path by the training engines (explicit stage() / fused optimizer), not by a
+cache here.
 """
 from __future__ import annotations
 
@@ -24,18 +25,13 @@ from pvd_b200 import _native as nv
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 _u32, _f32, _int = C.c_uint32, C.c_float, C.c_int
 
-# fp16 shadow copies of embedding tables, keyed by the parameter's storage; refreshed when _version changes
-_half_shadow: dict = {}
-
-
 def _half_table(emb: torch.Tensor) -> torch.Tensor:
-    key = (emb.data_ptr(), emb.device, tuple(emb.shape))
-    hit = _half_shadow.get(key)
-    if hit is not None and hit[0] == emb._version:
-        return hit[1]
-    sh = emb.detach().to(torch.half)
-    _half_shadow[key] = (emb._version, sh)
-    return sh
+    """fp16 copy of the table for an autocast forward -- cast on EVERY call, exactly as the reference does (grid.py:51-52).
+    A copy cached per parameter version is not safe here: in-place writes through `.data` (torch_ema's copy_to() / restore(),
+    distill_mutual/utils.py:1210-1212, and reset_parameters) leave `_version` untouched, so evaluation after an EMA swap would
+    silently gather stale weights.  The training engines do not come through here: they own an explicit `stage()` (or let the fused
+    optimizer write the fp16 shadow), pvd_b200/engine.py."""
+    return emb.detach().to(torch.half)
 
 
 class _grid_encode(Function):

@@ -82,17 +82,24 @@ def sharded_norm_l2(x, group=None):
 
 
 class TableGradExchange:
-    """The per-step gradient exchange of the ray-sharded training path: sum over ranks of the hash table's gradient (fp16
-    payload) and of the small MLP-gradient workspace (fp32).
+    """The per-step gradient exchange of the ray-sharded training path: the big parameter gradient (hash table / vm planes) as an
+    fp16 payload, the small MLP-gradient workspace in fp32.
 
-    Fast path (NVSwitch, CUDA ranks): the payload lives in a torch symmetric-memory buffer that is also mapped through a
-    multicast address; after the cast each rank reduces ITS 1/W of the buffer in the switch with `pvd_multimem_allreduce_f16`
-    (multimem.ld_reduce / multimem.st, csrc/collective.cu) between two signal-pad barriers.  The small fp32 workspace goes
-    through NCCL on a side stream at the same time.  Anything that does not set up (no NVLS, an older torch, one GPU) falls back
-    to NCCL for both, with the same result layout: `self.payload` holds the reduced fp16 table gradient.
+    Payload convention: every rank casts `grad * (1 / W)` (saturating at +-65504: a finite gradient never becomes inf on the way) and
+    the payloads are SUMMED, so `self.payload` ends up holding the MEAN over ranks of the (loss-scaled) rank gradients -- for per-ray
+    mean losses (every rank normalises by its own ray count) that IS the global-batch gradient; for losses whose coefficients are
+    already global (PairDistillEngine: rank gradients add up) the consumer multiplies by W.  `small` is summed as it is.
+    Consumers: `write_back(reduction)` puts the reduced gradient back into the fp32 buffers (`engine.grads()` does it), and
+    `optim.for_engine(..., exchange=...)` reads the payload directly with the right factors.
+
+    Kinds: "nccl" (cast kernel + ncclAllReduce of the payload), "multimem" (NVSwitch: the payload lives in a symmetric buffer that is
+    also mapped through a multicast address; each rank reduces ITS 1/W of it in the switch with multimem.ld_reduce / multimem.st,
+    csrc/collective.cu) either with the barriers inside the kernel (`fused_barrier`, one launch) or between two signal-pad barrier
+    launches.  Anything that does not set up falls back to NCCL with the same result layout.
     """
 
-    def __init__(self, grad_table: torch.Tensor, small: torch.Tensor, mode: str = "auto", group=None):
+    def __init__(self, grad_table: torch.Tensor, small: torch.Tensor, mode: str = "auto", group=None, fused_barrier: bool = True,
+                 blocks: int = 0, unroll: int = 4):
         import ctypes as C
         self._C = C
         self.group = group if group is not None else dist.group.WORLD
@@ -102,9 +109,11 @@ class TableGradExchange:
         self.grad_table = grad_table
         self.kind = "nccl"
         self.why = ""
-        self._side = torch.cuda.Stream(device=grad_table.device)
+        self.pre_scale = 1.0 / self.world
+        self.fused_barrier, self.blocks, self.unroll = bool(fused_barrier), int(blocks), int(unroll)
+        self._side = torch.cuda.Stream(device=grad_table.device) if grad_table.is_cuda else None
         self.payload = None
-        if mode in ("auto", "multimem") and self.world > 1 and self.n % 8 == 0:
+        if mode in ("auto", "multimem") and self.world > 1 and self.n % 8 == 0 and grad_table.is_cuda:
             try:
                 import torch.distributed._symmetric_memory as symm
                 buf = symm.empty(self.n, dtype=torch.float16, device=grad_table.device)
@@ -117,6 +126,10 @@ class TableGradExchange:
                 lo = (vecs * self.rank) // self.world
                 hi = (vecs * (self.rank + 1)) // self.world
                 self._off, self._cnt = 8 * lo, 8 * (hi - lo)
+                self._pads = int(getattr(hdl, "signal_pad_ptrs_dev", 0) or 0)
+                self._local = torch.zeros(4, dtype=torch.int32, device=grad_table.device)
+                if self._pads == 0:
+                    self.fused_barrier = False
                 self.kind = "multimem"
             except Exception as ex:  # noqa: BLE001  (any failure: NCCL carries the exchange)
                 self.why = repr(ex)[:160]
@@ -124,6 +137,10 @@ class TableGradExchange:
                     raise
         if self.payload is None:
             self.payload = torch.empty(self.n, dtype=torch.float16, device=grad_table.device)
+
+    # the factor that turns the payload (mean over ranks) into what the optimizer needs
+    def result_scale(self, reduction: str) -> float:
+        return 1.0 if reduction == "mean" else float(self.world)
 
     def __call__(self):
         from . import _native as nv
@@ -134,11 +151,37 @@ class TableGradExchange:
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             dist.all_reduce(self.small, group=self.group)
-        nv.check(nv.lib().pvd_cast_f32_to_f16(nv.ptr(self.grad_table), nv.ptr(self.payload), C.c_uint64(self.n), st))
-        if self.kind == "multimem":
+        nv.check(nv.lib().pvd_cast_f32_to_f16_scaled(nv.ptr(self.grad_table), nv.ptr(self.payload), C.c_uint64(self.n),
+                                                     C.c_float(self.pre_scale), st))
+        if self.kind == "multimem" and self.fused_barrier:
+            nv.check(nv.lib().pvd_multimem_allreduce_f16_fused(C.c_void_p(self._mc), C.c_uint64(self._off), C.c_uint64(self._cnt),
+                                                               C.c_void_p(self._pads), C.c_uint32(self.rank), C.c_uint32(self.world),
+                                                               nv.ptr(self._local), C.c_uint32(self.blocks), C.c_uint32(self.unroll), st))
+        elif self.kind == "multimem":
             self._hdl.barrier(channel=0)     # every rank's payload is written
             nv.check(nv.lib().pvd_multimem_allreduce_f16(C.c_void_p(self._mc), C.c_uint64(self._off), C.c_uint64(self._cnt), st))
             self._hdl.barrier(channel=1)     # every rank's shard of sums is visible everywhere
         else:
             dist.all_reduce(self.payload, group=self.group)
         cur.wait_stream(self._side)
+
+    def barrier_error(self) -> int:
+        """Non-zero if a device-side barrier of the fused kernel timed out (host sync)."""
+        return int(self._local[2].item()) if self.kind == "multimem" else 0
+
+    def write_back(self, reduction: str = "mean"):
+        """Reduced gradient -> the fp32 buffers a caller's optimizer reads: grad_table = payload * result_scale; the small workspace
+        (already summed in fp32) is divided by W for mean-type losses.  Call once per exchange."""
+        from . import _native as nv
+        C = self._C
+        st = C.c_void_p(torch.cuda.current_stream(self.grad_table.device).cuda_stream)
+        nv.check(nv.lib().pvd_cast_f16_to_f32(nv.ptr(self.payload), nv.ptr(self.grad_table), C.c_uint64(self.n),
+                                              C.c_float(self.result_scale(reduction)), st))
+        if reduction == "mean":
+            self.small.mul_(1.0 / self.world)
+
+
+def reduce_gradients_reference(rank_grads, reduction: str):
+    """What the exchange + write_back compute, in plain fp32 torch, for tests: list of per-rank tensors -> global-batch gradient."""
+    total = torch.stack([g.float() for g in rank_grads]).sum(0)
+    return total / len(rank_grads) if reduction == "mean" else total

@@ -72,6 +72,8 @@ def _set_attr(name):
 class FieldTrainEngine:
     """Training from images of ONE model of type hash or vm (`main_just_train_tea.py`; BASELINE configs 2 and 3): MSE against
     gt_rgb (just_train_tea/utils.py:841-846), plus l1_reg_weight * density_loss() for vm models (:843-844)."""
+    # how rank gradients combine into the global-batch gradient under ray sharding: every rank's MSE is a mean over ITS rays
+    grad_reduction = "mean"
     # the "current" ray set is what step() and every single-set accessor works on
     rays_o, rays_d, gt = _set_attr("rays_o"), _set_attr("rays_d"), _set_attr("gt")
     nears, fars, rays, counter = _set_attr("nears"), _set_attr("fars"), _set_attr("rays"), _set_attr("counter")
@@ -90,7 +92,7 @@ class FieldTrainEngine:
         self.loss_scale = float(loss_scale)
         self.density_scale = float(density_scale)
         self.l1_reg_weight = float(l1_reg_weight)
-        self.bitfield = bitfield.to(self.dev).contiguous()
+        self.bitfield = bitfield.to(self.dev).contiguous().clone()   # persistent: set_bitfield() copies into it
         d = self.dev
         N = self.N
         self.aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=d)
@@ -112,6 +114,11 @@ class FieldTrainEngine:
         self._counts = []
         self._alloc_samples(N * 32)
         self._coarse_valid = False
+        # what surrounds forward + backward in a training iteration (all of it CUDA-graph capturable, see `_prologue` / `_epilogue`)
+        self.restage_each_step = False   # parameters are changed by an EXTERNAL optimizer between steps: re-cast / re-pack at the top
+        self.unpack_each_step = False    # leave the small weight gradients in parameter shapes (ops.wgrads) at the end of the step
+        self.exchange = None             # dist.TableGradExchange: the one all-reduce of the multi-GPU path, after the backward
+        self.optimizer = None            # optim.FusedAdamW: updates parameters, fp16 shadow and weight tiles, zeroes the gradients
 
     def _init_small_buffers(self):
         # what must be zero before a backward lives in ONE buffer (one memset node): loss slots [64][2] f32 | gw_ws
@@ -162,9 +169,17 @@ class FieldTrainEngine:
         self.ops.alloc(M)
 
     def set_bitfield(self, bitfield: torch.Tensor):
-        """New occupancy bitfield (after a density-grid update): the cached coarse rejection mask is invalid."""
-        self.bitfield = bitfield.to(self.dev).contiguous()
-        self._coarse_valid = False
+        """New occupancy bitfield (after a density-grid update, renderer.py:647-773).  The bytes are copied INTO the engine's
+        persistent buffer -- captured graphs hold its address -- and the coarse rejection mask in the march workspace is rebuilt
+        right away on the current stream, so that a replay of an existing graph marches against the new grid."""
+        bitfield = bitfield.to(self.dev)
+        if bitfield.shape != self.bitfield.shape or bitfield.dtype != self.bitfield.dtype:
+            raise ValueError(f"bitfield must stay {tuple(self.bitfield.shape)} {self.bitfield.dtype} (captured graphs hold its address)")
+        self.bitfield.copy_(bitfield)
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        nv.check(nv.lib().pvd_march_coarse_mask(nv.ptr(self.bitfield), _u32(self.cascade), _u32(self.grid_size), _f32(self.bound),
+                                                nv.ptr(self.ws_march), st))
+        self._coarse_valid = True
 
     def set_mean_count(self, mean_count: int):
         """M = mean_count rounded up strictly to a multiple of 128 (raymarching.py:235-238)."""
@@ -234,7 +249,8 @@ class FieldTrainEngine:
         latency-bound); parameter-only loss terms (the vm L1 penalty) follow it on the same branch."""
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            self.ops.clear_grads()
+            if self.optimizer is None:   # a fused optimizer leaves the big gradient buffer zeroed (same pass as the update)
+                self.ops.clear_grads()
             if self.l1_reg_weight:
                 self.ops.regularise(C.c_void_p(self._side.cuda_stream), self.loss_scale, self.loss_slots, self.l1_reg_weight)
 
@@ -243,8 +259,7 @@ class FieldTrainEngine:
         rs = self.sets[self.cur]
         cur = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(cur.cuda_stream)
-        self._zeros.zero_()                    # loss, weight-gradient workspace
-        self._clear_big(cur)
+        self._prologue(cur)
         self._march_count(st, rs)
         if warmup:  # size the sample buffers from this step's count (one D2H read, raymarching.py:277)
             total = int(rs.counter[0].item())
@@ -261,6 +276,29 @@ class FieldTrainEngine:
         self._loss_backward(st, rs, M, M_drop)
         cur.wait_stream(self._side)            # join: the table gradient is clear before the first reduction into it
         self._field_backward(st, rs, M, cur)
+        self._epilogue(st)
+
+    def _prologue(self, cur):
+        if self.restage_each_step and self.optimizer is None:
+            self.ops.stage(self.density_scale)     # trainable parameters only: a frozen teacher stays staged
+        self._zeros.zero_()                    # loss, weight-gradient workspace
+        self._clear_big(cur)
+
+    def _epilogue(self, st):
+        """After the backward: gradient exchange (multi-GPU), then either the fused optimizer or -- for an external optimizer -- the
+        small weight gradients in parameter shapes."""
+        if self.exchange is not None:
+            self.exchange()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        elif self.unpack_each_step:
+            self.ops.unpack_weight_grads(self.gw_ws, st)
+
+    def attach_optimizer(self, optimizer):
+        """From here on every step ends with `optimizer.step()` (graphs must be captured afterwards)."""
+        self.optimizer = optimizer
+        self.ops.clear_grads()                 # once: the optimizer keeps them zero from now on
+        return optimizer
 
     # ------------------------------------------------------------------ CUDA graph of one steady-state step
     def capture(self):
@@ -307,8 +345,7 @@ class FieldTrainEngine:
         cur = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(cur.cuda_stream)
         M = self.M
-        self._zeros.zero_()
-        self._clear_big(cur)
+        self._prologue(cur)
 
         def march_branch():
             self._side2.wait_stream(cur)
@@ -320,17 +357,25 @@ class FieldTrainEngine:
                 self._march_count(st2, nxt)
                 self._march_write(st2, nxt, M)
 
-        fork_early = os.environ.get("PVD_PIPE_FORK", "early") == "early"
-        if fork_early:
+        # Where the next batch's march runs.  Single GPU: forked at the top, beside forward / backward (it fills the SMs' idle
+        # issue slots).  With a gradient exchange attached: forked AFTER the backward, beside the exchange -- the collective leaves
+        # the SMs almost idle, and forward / backward no longer share them with 4096 one-warp march CTAs.
+        where = os.environ.get("PVD_PIPE_FORK", "auto")
+        if where == "auto":
+            where = "exchange" if self.exchange is not None else "early"
+        if where == "early":
             march_branch()
         self._forward(st, rs, M, M)
         self._loss_backward(st, rs, M, M)
-        if not fork_early:
+        if where == "late":
             march_branch()
         cur.wait_stream(self._side)
         self._field_backward(st, rs, M, cur)
         if host_io:
             self.host_loss.copy_(self._loss_dev(), non_blocking=True)
+        if where == "exchange":
+            march_branch()
+        self._epilogue(st)
         cur.wait_stream(self._side2)
 
     def capture_pipelined(self, host_io: bool = False):
@@ -375,7 +420,10 @@ class FieldTrainEngine:
         return list(self.ops.weight_grads(self.gw_ws).values())
 
     def grads(self):
-        """{reference parameter name: gradient} for every trainable parameter of the model."""
+        """{reference parameter name: gradient} for every trainable parameter of the model (loss-scaled).  With a gradient exchange
+        attached these are the REDUCED gradients: the fp16 payload is written back over the rank-local fp32 buffer first."""
+        if self.exchange is not None:
+            self.exchange.write_back(self.grad_reduction)
         return self.ops.grads(self.gw_ws)
 
     def final_image(self):
@@ -433,6 +481,8 @@ class PairDistillEngine(FieldTrainEngine):
         self._dist = dist if (dist_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else None
         self._group = group
         self.teacher_field = teacher
+        for p_ in teacher.parameters():
+            p_.requires_grad_(False)               # main_distill_mutual.py:320-321 (and it lets the teacher's staged copies be cached)
         self.distill_stage = int(stage)
         r = [float(v) for v in rates]
         if self.distill_stage == 1:
@@ -443,8 +493,12 @@ class PairDistillEngine(FieldTrainEngine):
         if getattr(student, "model_type", None) != "vm" or self.distill_stage != 3:
             l1_reg_weight = 0.0
         super().__init__(student, bitfield, n_rays, l1_reg_weight=l1_reg_weight, **kw)
+        if self._dist is not None and self.l1_reg_weight:
+            # a parameter-only term must enter the SUM over ranks once: every rank contributes 1/W of it
+            self.l1_reg_weight /= self._dist.get_world_size(self._group)
 
     n_host_inputs = 2   # rays_o, rays_d: the teacher's rendering is the target
+    grad_reduction = "sum"   # the normL2 coefficients rate / ||.|| are formed from GLOBAL sums: rank gradients simply add up
 
     def _loss_dev(self):
         return self.loss_out

@@ -32,6 +32,23 @@ class HashOps:
         self.grad_table = torch.zeros(field.encoder.embeddings.shape, dtype=torch.float32, device=self.dev) if trainable else None
         self.enc = self.dx_ws = None
         self.kernels_bwd = 2 if fused.SPLIT_SCATTER else 1
+        self.table = self.wblob = self.cfield = None
+        ws = self._weights()
+        # the small weight gradients in parameter shapes, ONE flat buffer (one memset), for callers with an external optimizer
+        self._wflat = torch.zeros(sum(w.numel() for w in ws), dtype=torch.float32, device=self.dev) if trainable else None
+        self.wgrads, off = [], 0
+        for w in ws if trainable else []:
+            self.wgrads.append(self._wflat[off:off + w.numel()].view_as(w))
+            off += w.numel()
+
+    def _weights(self):
+        f = self.field
+        return (f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
+
+    def unpack_weight_grads(self, gw_ws, st):
+        """gw_ws (kernel-native, 16 replicas) -> self.wgrads (parameter shapes); two nodes: memset + k_unpack_wgrads."""
+        self._wflat.zero_()
+        nv.check(nv.lib().pvd_field_unpack_wgrads(nv.ptr(gw_ws), _u32(2 * self.cfg.num_levels), *[nv.ptr(g) for g in self.wgrads], st))
 
     def stage(self, density_scale=1.0):
         f = self.field
@@ -39,8 +56,7 @@ class HashOps:
         cfg.density_scale = density_scale
         self.cfg = cfg
         self.table = f._staged.table_for(f.encoder.embeddings, cfg.table_fp16)
-        self.wblob = f._staged.wblob_for((f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight,
-                                          f.color_net[1].weight, f.color_net[2].weight), 2 * cfg.num_levels)
+        self.wblob = f._staged.wblob_for(self._weights(), 2 * cfg.num_levels)
         self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
 
     def alloc(self, M):
@@ -110,6 +126,14 @@ class VmOps:
         self._flat = None
         self.scatter_ws = None
         self.kernels_bwd = 2 if VM_SPLIT_SCATTER else 1
+        self.wblob = self.cfield = None
+        self._aabb = [float(v) for v in field.aabb_train.tolist()]   # read once: stage() must stay free of host syncs (graph capture)
+        ws = self._weights()
+        self._wflat = torch.zeros(sum(w.numel() for w in ws), dtype=torch.float32, device=self.dev) if trainable else None
+        self.wgrads, off = [], 0
+        for w in ws if trainable else []:
+            self.wgrads.append(self._wflat[off:off + w.numel()].view_as(w))
+            off += w.numel()
         if trainable:
             # every plane/line gradient lives in ONE flat buffer (one memset per step); each view has its parameter's shape and
             # channels-last strides ([H][W][R] in memory), sigma planes and lines first (the L1 penalty covers exactly that prefix)
@@ -126,10 +150,18 @@ class VmOps:
             self._cgrads = fused_vm.PvdVmGrads(sigma_mat=fused_vm._ptrs3(self.grad_groups[0]), sigma_vec=fused_vm._ptrs3(self.grad_groups[1]),
                                                color_mat=fused_vm._ptrs3(self.grad_groups[2]), color_vec=fused_vm._ptrs3(self.grad_groups[3]))
 
+    def _weights(self):
+        f = self.field
+        return (f.basis_mat.weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
+
+    def unpack_weight_grads(self, gw_ws, st):
+        self._wflat.zero_()
+        nv.check(nv.lib().pvd_vm_unpack_wgrads(nv.ptr(gw_ws), *[nv.ptr(g) for g in self.wgrads], st))
+
     def stage(self, density_scale=1.0):
         f = self.field
-        self.wblob = f._staged.get((f.basis_mat.weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight))
-        aabb = [float(v) for v in f.aabb_train.tolist()]
+        self.wblob = f._staged.get(self._weights())
+        aabb = self._aabb
         planes = [[p.detach() for p in grp] for grp in self.groups]
         self.cfield = self._vm._vm_struct(planes, self.wblob, f.resolution, aabb, float(f.args.sigma_clip_min), float(f.args.sigma_clip_max),
                                           float(density_scale))

@@ -58,37 +58,65 @@ def _cstruct(cfg: HashFieldConfig, table, offsets, wblob):
                         density_scale=cfg.density_scale)
 
 
+def frozen_key(params):
+    """Cache key for staged copies of FROZEN parameters (a distillation teacher: requires_grad False on every tensor,
+    main_distill_mutual.py:320-321), None for anything trainable.
+
+    Staged copies of trainable parameters are never cached: a key built from `param._version` is not safe for them -- in-place
+    writes through `.data` (torch_ema copy_to() / restore(), distill_mutual/utils.py:1210-1212, reset_parameters) do not bump it,
+    so an evaluation after an EMA swap would run on stale weights.  Nobody optimises or EMA-swaps a frozen teacher; loading a
+    checkpoint into it goes through `param.copy_`, which does bump the version (`invalidate()` exists for anything more exotic)."""
+    params = list(params)
+    if any(p.requires_grad for p in params):
+        return None
+    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+
+
 class StagedParams:
-    """fp16 table shadow + packed tensor-core weight tiles, refreshed only when a parameter's version changes."""
+    """fp16 table shadow + packed tensor-core weight tiles of one model, in persistent buffers.
+
+    Trainable parameters are re-staged on every call (one cast kernel / one pack kernel), see `frozen_key`.  The training engines
+    call `stage()` once per optimizer step, or not at all when the fused optimizer (pvd_b200/optim.py) writes the shadow and the
+    packed tiles itself."""
 
     def __init__(self):
-        self._table_key = None
         self.table = None
-        self._w_key = None
         self.wblob = None
+        self._table_key = None
+        self._w_key = None
+
+    def invalidate(self):
+        self._table_key = self._w_key = None
 
     def table_for(self, emb: torch.Tensor, fp16: bool):
         if not fp16:
             return emb.detach()
-        key = (emb.data_ptr(), emb._version)
-        if key != self._table_key:
-            if self.table is None or self.table.shape != emb.shape:
-                self.table = torch.empty_like(emb, dtype=torch.float16)
-            self.table.copy_(emb.detach())
-            self._table_key = key
+        key = frozen_key([emb])
+        if key is not None and key == self._table_key and self.table is not None:
+            return self.table
+        if self.table is None or self.table.shape != emb.shape or self.table.device != emb.device:
+            self.table = torch.empty_like(emb, dtype=torch.float16)
+        src = emb.detach()
+        if src.dtype == torch.float32 and src.is_contiguous() and src.numel() % 4 == 0:
+            with nv.on_device(src):
+                nv.check(nv.lib().pvd_cast_f32_to_f16(nv.ptr(src), nv.ptr(self.table), C.c_uint64(src.numel()), nv.stream_of(src)))
+        else:
+            self.table.copy_(src)
+        self._table_key = key
         return self.table
 
     def wblob_for(self, ws, in_dim: int):
-        key = tuple((w.data_ptr(), w._version) for w in ws)
-        if key != self._w_key:
-            if self.wblob is None:
-                self.wblob = torch.empty(WBLOB_BYTES, dtype=torch.uint8, device=ws[0].device)
-            w32 = [w.detach().float().contiguous() for w in ws]
-            with nv.on_device(self.wblob):
-                nv.check(nv.lib().pvd_field_pack_weights(nv.ptr(w32[0]), nv.ptr(w32[1]), nv.ptr(w32[2]), nv.ptr(w32[3]),
-                                                         nv.ptr(w32[4]), C.c_uint32(in_dim), nv.ptr(self.wblob),
-                                                         nv.stream_of(self.wblob)))
-            self._w_key = key
+        key = frozen_key(ws)
+        if key is not None and key == self._w_key and self.wblob is not None:
+            return self.wblob
+        if self.wblob is None or self.wblob.device != ws[0].device:
+            self.wblob = torch.empty(WBLOB_BYTES, dtype=torch.uint8, device=ws[0].device)
+        w32 = [w.detach().float().contiguous() for w in ws]
+        with nv.on_device(self.wblob):
+            nv.check(nv.lib().pvd_field_pack_weights(nv.ptr(w32[0]), nv.ptr(w32[1]), nv.ptr(w32[2]), nv.ptr(w32[3]),
+                                                     nv.ptr(w32[4]), C.c_uint32(in_dim), nv.ptr(self.wblob),
+                                                     nv.stream_of(self.wblob)))
+        self._w_key = key
         return self.wblob
 
 
@@ -141,7 +169,11 @@ class _FusedHashField(Function):
         sigmas, rgbs, enc, feat, status = hash_field_forward_raw(cfg, table, offsets, wblob, xyzs, dirs, need_bwd, want_feat)
         if enc is None:
             enc = torch.empty(0, dtype=torch.float16, device=xyzs.device)
-        ctx.save_for_backward(xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4)
+        # the staged table / weight tiles are shared buffers that the next forward re-writes: not autograd-saved tensors.  The
+        # backward reads the tiles only (the encoding was saved), so it re-packs them from the saved parameters.
+        ctx.save_for_backward(xyzs, dirs, enc, offsets, embeddings, w0, w1, w2, w3, w4)
+        ctx.table = table
+        ctx.staged = staged
         ctx.cfg = cfg
         ctx.status = status
         if want_feat:
@@ -150,9 +182,11 @@ class _FusedHashField(Function):
 
     @staticmethod
     def backward(ctx, grad_sigmas, grad_rgbs, grad_feat=None):
-        xyzs, dirs, enc, table, offsets, wblob, embeddings, w0, w1, w2, w3, w4 = ctx.saved_tensors
+        xyzs, dirs, enc, offsets, embeddings, w0, w1, w2, w3, w4 = ctx.saved_tensors
         cfg = ctx.cfg
         dev = xyzs.device
+        table = ctx.table   # pointer only: the backward kernel does not read table entries
+        wblob = ctx.staged.wblob_for((w0, w1, w2, w3, w4), 2 * cfg.num_levels)
         gs = (grad_sigmas if grad_sigmas is not None else torch.zeros(xyzs.shape[0], device=dev)).float().contiguous()
         gc = (grad_rgbs if grad_rgbs is not None else torch.zeros(xyzs.shape[0], 3, device=dev)).float().contiguous()
         grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)

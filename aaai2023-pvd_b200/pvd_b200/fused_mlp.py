@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _native as nv
-from .fused import StagedParams, _Args
+from .fused import StagedParams, _Args, frozen_key
 from .renderer import NeRFRenderer
 
 MLP_WBLOB_BYTES = 876544
@@ -57,8 +57,8 @@ class MLPNeRFField(NeRFRenderer):
     # ---------------------------------------------------------------- fused (no-grad) forward
     def _blob(self):
         ps = [p for l in self.nerf_mlp for p in (l.weight, l.bias)]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
-        if key != self._mlp_key:
+        key = frozen_key(ps)   # None for a trainable model: re-packed on every call (fused.frozen_key)
+        if key is None or key != self._mlp_key or self._mlp_blob is None:
             dev = ps[0].device
             if self._mlp_blob is None:
                 self._mlp_blob = torch.empty(MLP_WBLOB_BYTES, dtype=torch.uint8, device=dev)

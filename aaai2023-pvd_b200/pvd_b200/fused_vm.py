@@ -15,7 +15,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from . import _native as nv
-from .fused import GW_WS_FLOATS, _Args
+from .fused import GW_WS_FLOATS, _Args, frozen_key
 from .renderer import NeRFRenderer
 
 VM_WBLOB_BYTES = 18944
@@ -53,9 +53,12 @@ class StagedVmWeights:
         self._key = None
         self.wblob = None
 
+    def invalidate(self):
+        self._key = None
+
     def get(self, ws):
-        key = tuple((w.data_ptr(), w._version) for w in ws)
-        if key != self._key:
+        key = frozen_key(ws)   # None for trainable weights: re-packed on every call (fused.frozen_key)
+        if key is None or key != self._key or self.wblob is None:
             if self.wblob is None:
                 self.wblob = torch.empty(VM_WBLOB_BYTES, dtype=torch.uint8, device=ws[0].device)
             w32 = [w.detach().float().contiguous() for w in ws]

@@ -35,6 +35,10 @@ class NeRFRenderer(nn.Module):
         self.density_scale = density_scale
         self.min_near = min_near
         self.density_thresh = density_thresh
+        if bg_radius > 0:
+            # distill_mutual/renderer.py:350-355 (polar_from_ray + self.background) is not built: the reference's own background
+            # model asserts (`assert 1 == 2`), both CLIs keep bg_radius = -1.  Refuse rather than silently render on white.
+            raise NotImplementedError("bg_radius > 0 (spherical background model) is not supported by the B200 renderer")
         self.bg_radius = bg_radius
         aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
         self.register_buffer("aabb_train", aabb)
@@ -252,8 +256,11 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128, fused=None):
         """EMA update of the density grid from the field, repack the bitfield, refresh mean_count (renderer.py:647-773).
-        `fused` (default: PVD_FUSED_UPKEEP != 0) takes the three-kernel path of csrc/density_grid.cu, which draws the same torch
-        random numbers in the same order and gives the same grid (bit for bit in the full sweep) without reading anything back."""
+        `fused` (default: PVD_FUSED_UPKEEP != 0) takes the three-kernel path of csrc/density_grid.cu without reading anything
+        back.  It consumes the same torch random numbers in the same order as the torch flow below (`fused=False`), and
+        tests/test_density_grid.py checks that 19 updates leave the same grid / bitfield / mean as that flow.  Against the
+        REFERENCE the full sweep is statistically, not bitwise, equivalent: the reference draws its noise per 128^3-cell chunk of
+        the meshgrid sweep (renderer.py:690-693), here one triple is drawn per Morton cell."""
         if not self.cuda_ray:
             return
         if fused is None:

@@ -302,25 +302,55 @@ def ncu_traffic(kernel):
         return None, None
 
 
-def run_ours(args, rank, world, local):
+def _timed(fn_load, fn_step, flush, steps, world, dev):
+    """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps outside the brackets; returns the
+    summed milliseconds, MAX over ranks."""
     import torch.distributed as dist
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        fn_load()
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        fn_step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+def measure_ours(args, workload, n_rays, rank, world, local, headline):
+    """Everything bench.py reports for ONE workload on this rank's GPU; a dict on every rank (times are max over ranks)."""
+    import torch.distributed as dist
+    from pvd_b200 import optim as pvd_optim
     from pvd_b200 import synthetic as syn
 
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     _, bitfield, sha = syn.lego_bitfield()
-    eng = build_engine(args, dev, bitfield)
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload, wargs.rays = workload, n_rays
+    eng = build_engine(wargs, dev, bitfield)
     pair = hasattr(eng, "tea")
+    steps = args.steps if headline else min(args.steps, args.secondary_steps)
     eng.stage()
-    n_b = 16 + args.warmup + args.steps
-    host = make_workload(args.rays, min(n_b, 64), seed=0, rank=rank)
+    # the timed step is a whole fwd+bwd as a trainer with an EXTERNAL optimizer must run it: the parameters changed since the last
+    # step, so the fp16 table shadow is re-cast and the weight tiles re-packed at the top of every step (the reference pays its
+    # equivalent inside its forward, gridencoder/grid.py:52), and the small weight gradients leave the step in parameter shapes
+    eng.restage_each_step = True
+    eng.unpack_each_step = True
+    n_b = 16 + args.warmup + steps
+    host = make_workload(n_rays, min(n_b, 64), seed=0, rank=rank)
     devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c, _ in host]
 
     use_graph = False
     pipelined = False
-    pipe = {"i": 0}   # pipelined mode: index of the next replay (its parity selects the ray set that is computed on)
+    pipe = {"i": 0, "nb": 17}   # pipelined mode: index of the next replay (its parity selects the ray set that is computed on)
 
     def load(i, from_host=False):
         """Make batch i the input of the next step.  Pipelined: batch i goes into the set the NEXT replay marches (it is computed
@@ -338,6 +368,9 @@ def run_ours(args, rank, world, local):
         if not pair:
             rs.gt.copy_(gt, non_blocking=True)
 
+    def load_next():
+        load(pipe["nb"]); pipe["nb"] += 1
+
     def run_step():
         if pipelined:
             eng.replay_pipelined(pipe["i"])
@@ -349,22 +382,23 @@ def run_ours(args, rank, world, local):
 
     exchange = None
     big = eng.ops.big_grad()
-    if world > 1 and args.grad_comm != "fp32":
+    if world > 1:
+        # one gradient exchange per step, INSIDE the step (engine._epilogue; in the pipelined graphs the next batch's march runs beside
+        # it).  fp16 payload (default): the big parameter gradient is cast once (x 1/W, saturating) and summed in half precision -- the
+        # precision the reference ACCUMULATES table gradients in (gridencoder.cu:299-305); on NVSwitch the sum is done by the switch
+        # (multimem, csrc/collective.cu), else by NCCL.  The small MLP gradients stay fp32.  --grad-comm fp32: plain NCCL on fp32.
         from pvd_b200.dist import TableGradExchange
-        exchange = TableGradExchange(big, eng.gw_ws, mode={"fp16": "nccl", "multimem": "auto"}[args.grad_comm])
+        if args.grad_comm == "fp32":
+            class _Fp32Exchange:
+                kind, why, world = "nccl-fp32", "", dist.get_world_size()
+                def __call__(self):
+                    dist.all_reduce(big); dist.all_reduce(eng.gw_ws)
+            exchange = _Fp32Exchange()
+        else:
+            exchange = TableGradExchange(big, eng.gw_ws, mode={"fp16": "nccl", "multimem": "multimem", "auto": "auto"}[args.grad_comm],
+                                         blocks=args.mm_blocks, unroll=args.mm_unroll)
         if rank == 0:
-            print(f"[bench] gradient exchange: {exchange.kind} {exchange.why}", file=sys.stderr)
-
-    def allreduce():
-        # one gradient exchange per step.  fp16 payload (default for N > 1): the big parameter gradient (hash table / vm planes) is cast
-        # once and summed in half precision -- the precision the reference ACCUMULATES table gradients in (gridencoder.cu:299-305); on
-        # NVSwitch the sum can be done by the switch (multimem, csrc/collective.cu), else by NCCL.  The small MLP gradients stay fp32.
-        if world > 1:
-            if exchange is not None:
-                exchange()
-            else:
-                dist.all_reduce(big)
-                dist.all_reduce(eng.gw_ws)
+            print(f"[bench] {workload}: gradient exchange = {exchange.kind} {exchange.why}", file=sys.stderr)
 
     # ---- 16 sizing steps (the reference's mean_count warm-up), then W untimed steps at the steady-state M
     for i in range(16):
@@ -373,20 +407,30 @@ def run_ours(args, rank, world, local):
     eng.finish_warmup()
     if exchange is not None and exchange.kind == "multimem":
         # self-check of the in-switch reduction against NCCL on this step's real gradients; any rank's mismatch -> all fall back
-        ref = big.to(torch.float16)
+        ref = (big * exchange.pre_scale).clamp(-65504, 65504).to(torch.float16)
         dist.all_reduce(ref)
         exchange()
         torch.cuda.synchronize()
         err = (exchange.payload.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-20)
-        bad = torch.tensor([0.0 if float(err) < 2e-2 else 1.0], device=dev)
+        bad = torch.tensor([0.0 if (float(err) < 2e-2 and exchange.barrier_error() == 0) else 1.0], device=dev)
         dist.all_reduce(bad)
         if float(bad.item()) > 0:
             exchange.kind, exchange.why = "nccl", f"multimem self-check failed (rel err {float(err):.3g})"
         if rank == 0:
             print(f"[bench] multimem exchange self-check: max rel err {float(err):.3g} -> using {exchange.kind}", file=sys.stderr)
         del ref
+    eng.exchange = exchange
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     serial_ms = None
+
+    def prime_pipeline():
+        pipe["i"] = 0
+        rs = eng.sets[0]   # prime: the next batch is marched eagerly, its compute is replay 0
+        ro, rd, gt = devb[pipe["nb"] % len(devb)]
+        pipe["nb"] += 1
+        rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
+        eng.march(0)
+
     if not args.no_graph:
         try:  # CUDA graphs for the whole step: removes launch gaps and host work from the loop
             for rs in eng.sets:
@@ -397,60 +441,34 @@ def run_ours(args, rank, world, local):
             if not args.no_pipeline:
                 # reference point: the serial single-graph step, timed the same way (reported as serial_ms_per_step)
                 for i in range(args.warmup):
-                    load(16 + i); run_step()
-                sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
-                for i, (a, b) in enumerate(sev):
-                    load(16 + i); flush.fill_(i & 0xFF); a.record(); run_step(); b.record()
-                torch.cuda.synchronize()
-                serial_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
-                # steady state: the march of batch i+1 runs beside the field backward of batch i (two graphs, two ray sets)
+                    load_next(); run_step()
+                n_ser = min(steps, 50)
+                serial_ms = _timed(load_next, run_step, flush, n_ser, world, dev) / n_ser
+                # steady state: the march of batch i+1 runs beside the field kernels / the exchange of batch i (two graphs, two ray sets)
                 eng.capture_pipelined()
                 pipelined = True
-                pipe["i"] = 0
-                rs = eng.sets[0]   # prime: batch 16 is marched eagerly, its compute is replay 0
-                ro, rd, gt = devb[16 % len(devb)]
-                rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
-                eng.march(0)
+                prime_pipeline()
         except Exception as ex:  # noqa: BLE001
             print(f"[bench] CUDA graph capture failed ({ex!r}); running eagerly", file=sys.stderr)
             use_graph = pipelined = False
-    nb = 17   # next batch to feed (pipelined: one ahead of the batch being computed)
     for i in range(args.warmup):
-        load(nb); nb += 1
+        load_next()
         run_step()
-        allreduce()
     torch.cuda.synchronize()
     assert int(eng.status.item()) == 0, "tensor-core pipeline reported a timeout"
 
     sampler = ClockSampler(local)
     sampler.start()
     # ---- timed region: K steps, each bracketed by events, L2 flushed between steps (outside the brackets)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        load(nb); nb += 1
-        flush.fill_(i & 0xFF)
-        ev[i][0].record()
-        run_step()
-        allreduce()
-        ev[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = float(tt.item())
+    t_ms = _timed(load_next, run_step, flush, steps, world, dev)
 
     # ---- per-kernel pass (same steps again, events around the field kernels; used for the roofline only)
     plan = phase_plan(eng)
     kt = {name: 0.0 for name, _ in plan}
     S_total = 0
-    reps = min(args.steps, 50)
+    reps = min(steps, 50)
     was_pipelined, pipelined = pipelined, False
+    saved_exchange, eng.exchange = eng.exchange, None
     eng.cur = 0
     for i in range(reps):
         load(16 + args.warmup + i)
@@ -463,31 +481,29 @@ def run_ours(args, rank, world, local):
         kt[k] /= reps
     S_mean = S_total / reps
     pipelined = was_pipelined
+    eng.exchange = saved_exchange
 
     # ---- end-to-end through the public API with HOST buffers: H2D of rays (+ gt), step, D2H of the loss.
     # Pipelined engine: both copies are NODES of the step's graphs (engine.capture_pipelined(host_io=True)): the H2D of batch i+1 heads
     # the march branch of step i, the D2H of the loss words ends it; the caller only writes the next batch into the pinned staging
     # buffer.  The CPU may run at most two replays ahead of the GPU (a staging buffer is re-used every second step).
-    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     loss_dev = eng._loss_dev()   # pair: [total, 4 norms]; single model: 64 (loss, rays) slots, summed on the host
     host_io = pipelined
+    nb = pipe["nb"]
     if host_io:
         eng.capture_pipelined(host_io=True)
-        pipe["i"] = 0
-        rs = eng.sets[0]
-        ro, rd, gt = devb[nb % len(devb)]
-        rs.rays_o.copy_(ro); rs.rays_d.copy_(rd); rs.gt.copy_(gt)
-        eng.march(0)
-        nb += 1
+        prime_pipeline()
+        nb = pipe["nb"]
         loss_host = eng.host_loss
     else:
         loss_host = torch.empty(loss_dev.numel(), dtype=torch.float32).pin_memory()
     if not use_graph:
-        eng.rays_o, eng.rays_d, eng.gt = (torch.empty(args.rays, 3, device=dev) for _ in range(3))
+        eng.rays_o, eng.rays_d, eng.gt = (torch.empty(n_rays, 3, device=dev) for _ in range(3))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(i & 0xFF)
         e2e_ev[i][0].record()
         if host_io:
@@ -499,8 +515,6 @@ def run_ours(args, rank, world, local):
         else:
             load(nb, from_host=True); nb += 1   # pinned host rays (+ gt) -> device
             run_step()
-        allreduce()
-        if not host_io:
             loss_host.copy_(loss_dev, non_blocking=True)
         e2e_ev[i][1].record()
     torch.cuda.synchronize()
@@ -511,13 +525,41 @@ def run_ours(args, rank, world, local):
     e2e_ms = float(tt.item())
     clocks = sampler.stop()
     assert int(eng.status.item()) == 0
+    pipe["nb"] = nb
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    # ---- the same step WITHOUT the per-step re-stage / unpack (round 1's definition of a step), for continuity
+    extra = {}
+    n_x = min(steps, 50)
+    if use_graph and pipelined:
+        try:
+            if exchange is not None and not hasattr(exchange, "payload"):
+                raise RuntimeError("iteration timing needs the fp16-payload exchange")
+            eng.restage_each_step = eng.unpack_each_step = False
+            eng.capture_pipelined()
+            prime_pipeline()
+            for i in range(3):
+                load_next(); run_step()
+            extra["ms_per_step_no_restage"] = _timed(load_next, run_step, flush, n_x, world, dev) / n_x
+            # ---- the whole training ITERATION: step + exchange + fused AdamW (GradScaler check, fp32 masters, fp16 shadow, weight
+            # tiles, gradient zeroing) in the same graphs; no re-stage, no gradient memset (csrc/optim.cu)
+            opt = pvd_optim.for_engine(eng, lr=1e-3, lr2=1e-4, exchange=exchange if hasattr(exchange, "payload") else None)
+            eng.attach_optimizer(opt)
+            eng.capture_pipelined()
+            prime_pipeline()
+            for i in range(3):
+                load_next(); run_step()
+            it_ms = _timed(load_next, run_step, flush, n_x, world, dev) / n_x
+            stt = opt.read_state()
+            extra["iteration"] = {"ms": it_ms, "rays_per_s": n_rays * world / (it_ms * 1e-3), "optimizer_steps": int(stt.step), "skipped": int(stt.skipped),
+                                  "what": "step + gradient exchange + fused AdamW (found_inf check, fp32 master update, fp16 table shadow, weight "
+                                          "tiles re-packed, gradients zeroed): a complete training iteration per graph replay",
+                                  "launches_per_iteration": eng.launches_per_step + opt.kernels_per_step}
+            assert int(eng.status.item()) == 0
+        except Exception as ex:  # noqa: BLE001
+            extra["iteration_error"] = repr(ex)[:200]
+
     peaks, peak_kind = measured_peaks()
-    rays_total = args.rays * world * args.steps
+    rays_total = n_rays * world * steps
     value = rays_total / (t_ms * 1e-3)
     L = args.levels
     # roofline of every field kernel; the headline object is the dominant one (longest average launch)
@@ -533,19 +575,23 @@ def run_ours(args, rank, world, local):
                       "traffic": traffic, "traffic_source": src, "peak_kind": peak_kind,
                       ("algorithmic_bytes_per_sample" if bound == "hbm" else "algorithmic_flops_per_sample"): per_sample})
     # the workload's bound: the table / plane traffic (HBM roofline) -- except mlp -> hash, where the teacher's GEMMs dominate
-    want = "tensor" if args.workload == "mlp-hash" else "hbm"
+    want = "tensor" if workload == "mlp-hash" else "hbm"
     dom = max((r for r in roofs if r["bound"] == want), key=lambda r: r["ms"])
+    n_extra = 2 + (1 if eng.ops.kind == "hash" else 0)   # per step: weight pack, weight-gradient unpack (+ the table cast for hash)
     out = {
-        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": WORKLOADS[args.workload].format(L=L, R=args.rays), "workload_key": args.workload,
-                   "rays_per_gpu": args.rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
+        "config": {"workload": WORKLOADS[workload].format(L=L, R=n_rays), "workload_key": workload,
+                   "rays_per_gpu": n_rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
                    "precision": "fp16 table + fp16 tcgen05 MLP, fp32 planes / accumulate / composite / gradients", "loss_scale": 65536,
-                   "parallelism": (f"rays sharded over {world} GPU(s), one NCCL all-reduce of the gradients per step "
-                                   f"({'fp32 NCCL' if exchange is None else 'fp16 payload, ' + ('in-switch multimem reduction' if exchange.kind == 'multimem' else 'NCCL')})") if world > 1 else "single GPU",
-                   "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch beside the field "
-                              "backward of batch i (one batch of look-ahead, double-buffered ray sets)") if pipelined else
+                   "step": "fwd+bwd of a trainer with an external optimizer: fp16 table shadow re-cast + weight tiles re-packed at the top of "
+                           "EVERY timed step, small weight gradients unpacked to parameter shapes at its end" + ("; gradient exchange inside" if world > 1 else ""),
+                   "parallelism": (f"rays sharded over {world} GPU(s), one all-reduce of the gradients per step inside the step graph ({exchange.kind}: "
+                                   f"{'fp32 NCCL' if exchange.kind == 'nccl-fp32' else 'fp16 payload, ' + ('in-switch multimem reduction, barriers inside the kernel' if exchange.kind == 'multimem' else 'NCCL')}); "
+                                   "the next batch's march runs beside the exchange") if world > 1 else "single GPU",
+                   "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch of step i's graph "
+                              "(one batch of look-ahead, double-buffered ray sets)") if pipelined else
                              ("one CUDA graph per step" if use_graph else "eager (one launch per kernel)"),
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write, outside the timed brackets)",
                    "scene_bitfield_sha256": sha[:16]},
@@ -553,16 +599,49 @@ def run_ours(args, rank, world, local):
         "kernel_ms": kt,
         "roofline": dom,
         "roofline_all": roofs,
-        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * (6 if pair else 9) * 4,
+        "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * (6 if pair else 9) * 4,
                 "d2h_bytes_per_step": 4 * loss_dev.numel(),
                 "how": ("H2D of the next batch and D2H of the loss words are nodes of the step's CUDA graphs (pinned staging buffers)"
                         if host_io else "copies issued on the step's stream around the step")},
-        "gpu_launches": eng.launches_per_step * args.steps,
+        "gpu_launches": (eng.launches_per_step + n_extra) * steps,
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget)
-    print(json.dumps(out), flush=True)
+    out.update(extra)
+    del eng, flush, devb
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, rank, world, local):
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    head = measure_ours(args, args.workload, args.rays, rank, world, local, headline=True)
+    # the other BASELINE configurations in the same line (shorter runs): configs[1]-[4] all measured by one invocation
+    others = {}
+    if args.all_workloads:
+        for w in ("hash", "vm", "hash-vm", "mlp-hash"):
+            if w == args.workload:
+                continue
+            try:
+                r = measure_ours(args, w, DEFAULT_RAYS[w], rank, world, local, headline=False)
+                others[w] = {k: r[k] for k in ("value", "unit", "ms_per_step", "serial_ms_per_step", "steps", "e2e", "roofline", "kernel_ms", "gpu_launches",
+                                               "ms_per_step_no_restage", "iteration", "iteration_error") if k in r}
+                others[w]["config"] = {k: r["config"][k] for k in ("workload", "rays_per_gpu", "samples_per_step", "M_rows")}
+            except Exception as ex:  # noqa: BLE001  (a secondary workload must not take the headline line down)
+                others[w] = {"error": repr(ex)[:300]}
+                torch.cuda.empty_cache()
+    if rank == 0:
+        head["workloads"] = {args.workload: {k: head[k] for k in ("value", "unit", "ms_per_step", "serial_ms_per_step", "steps", "e2e", "roofline", "kernel_ms",
+                                                                   "gpu_launches", "ms_per_step_no_restage", "iteration") if k in head}}
+        head["workloads"][args.workload]["config"] = {k: head["config"][k] for k in ("workload", "rays_per_gpu", "samples_per_step", "M_rows")}
+        head["workloads"].update(others)
+        if world == 1 and not args.no_cpu_baseline:
+            head["cpu_baseline"] = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget)
+        print(json.dumps(head), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -587,37 +666,16 @@ def build_reference(args, dev, ext, bitfield):
     return rp.RefPairTrainer(ext, hash_net(), rp.RefMlpNetwork(ext).to(dev), bf, rates=PAIR_RATES, l1_reg_weight=0.0)
 
 
-def run_reference(args, rank, world, local):
-    """The reference's own CUDA extensions + its Python flow (oracle/ref_pipeline.py) on ONE GPU; if oracle/_ref cannot be
-    loaded, the CPU oracle port on the host cores instead."""
-    if rank != 0:
-        return
+def measure_reference(args, workload, n_rays, local, ext, steps):
+    """The reference's own CUDA extensions + its Python flow (oracle/ref_pipeline.py) on ONE GPU for one workload."""
     from pvd_b200 import synthetic as syn
-    why = "no CUDA device"
-    try:
-        from oracle import ref_pipeline
-        ext = ref_pipeline.load_ext()
-        have_ref = torch.cuda.is_available()
-    except Exception as ex:  # noqa: BLE001
-        ext, have_ref = None, False
-        why = repr(ex)
-    cfg = {"workload": WORKLOADS[args.workload].format(L=args.levels, R=args.rays), "workload_key": args.workload,
-           "rays_per_gpu": args.rays, "levels": args.levels}
-    if not have_ref:
-        cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget if args.cpu_budget != 15.0 else 20.0)
-        out = {"metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * args.rays / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": cb,
-               "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-               "note": "oracle/_ref not loadable (" + why[:80] + "); CPU oracle port timed instead"}
-        print(json.dumps(out), flush=True)
-        return
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _, bitfield, sha = syn.lego_bitfield()
-    tr = build_reference(args, dev, ext, bitfield)
-    pair = args.workload in ("hash-vm", "mlp-hash")
-    host = make_workload(args.rays, min(16 + args.warmup + args.steps, 64), seed=0, rank=0)
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload, wargs.rays = workload, n_rays
+    tr = build_reference(wargs, dev, ext, bitfield)
+    pair = workload in ("hash-vm", "mlp-hash")
+    host = make_workload(n_rays, min(16 + args.warmup + steps, 64), seed=0, rank=0)
     devb = [(a.to(dev), b.to(dev), c.to(dev)) for a, b, c, _ in host]
     for i in range(16):  # the reference's 16 warm-up iterations with a D2H sync each, then mean_count
         tr.step(*devb[i % len(devb)])
@@ -628,8 +686,8 @@ def run_reference(args, rank, world, local):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
         b = devb[(16 + args.warmup + i) % len(devb)]
         flush.fill_(i & 0xFF)
         ev[i][0].record()
@@ -638,8 +696,8 @@ def run_reference(args, rank, world, local):
     torch.cuda.synchronize()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     # e2e: host buffers in, loss out
-    e2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
+    e2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
         ro, rd, gt = host[(16 + args.warmup + i) % len(host)][:3]
         flush.fill_(i & 0xFF)
         e2[i][0].record()
@@ -648,18 +706,90 @@ def run_reference(args, rank, world, local):
         e2[i][1].record()
     torch.cuda.synchronize()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2)
+    # the whole iteration as the reference runs it (distill_mutual/utils.py:802-819): + GradScaler.unscale_/step with torch.optim.AdamW
+    it_ms = None
+    try:
+        params = [p for p in tr.net.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.99), eps=1e-15)
+        n_it = min(steps, 20)
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_it)]
+        inv = 1.0 / tr.loss_scale
+        for i in range(n_it + 2):
+            b = devb[(16 + i) % len(devb)]
+            flush.fill_(i & 0xFF)
+            if i >= 2:
+                ev3[i - 2][0].record()
+            tr.step(*b)
+            grads = [p.grad for p in params if p.grad is not None]
+            found = torch.zeros(1, device=dev)
+            torch._amp_foreach_non_finite_check_and_unscale_(grads, found, torch.full((1,), inv, device=dev))   # GradScaler.unscale_
+            opt.step()
+            if i >= 2:
+                ev3[i - 2][1].record()
+        torch.cuda.synchronize()
+        it_ms = sum(a.elapsed_time(b) for a, b in ev3) / n_it
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] reference iteration timing failed: {ex!r}", file=sys.stderr)
     clocks = sampler.stop()
-    rays_total = args.rays * args.steps
-    cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
-    cfg.update({"M_rows": tr.mean_count + (128 - tr.mean_count % 128), "precision": "torch autocast fp16 (the reference's -O default), GradScaler-style loss scale 65536",
-                "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)", "scene_bitfield_sha256": sha[:16],
-                "what": "unmodified reference CUDA extensions (oracle/_ref, sm_100a rebuild) + cuBLAS GEMMs via F.linear + F.grid_sample + torch "
-                        "autograd, Python flow restated in oracle/ref_pipeline.py"})
-    out = {"metric": METRIC, "value": rays_total / (t_ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+    rays_total = n_rays * steps
+    cfg = {"workload": WORKLOADS[workload].format(L=args.levels, R=n_rays), "workload_key": workload, "rays_per_gpu": n_rays, "levels": args.levels,
+           "M_rows": tr.mean_count + (128 - tr.mean_count % 128), "precision": "torch autocast fp16 (the reference's -O default), GradScaler-style loss scale 65536",
+           "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)", "scene_bitfield_sha256": sha[:16],
+           "what": "unmodified reference CUDA extensions (oracle/_ref, sm_100a rebuild) + cuBLAS GEMMs via F.linear + F.grid_sample + torch "
+                   "autograd, Python flow restated in oracle/ref_pipeline.py"}
+    out = {"metric": METRIC, "value": rays_total / (t_ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+           "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
            "data": "synthetic", "impl": "reference", "config": cfg,
-           "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": args.rays * (6 if pair else 9) * 4, "d2h_bytes_per_step": 4},
+           "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * (6 if pair else 9) * 4, "d2h_bytes_per_step": 4},
            "clocks": clocks}
+    if it_ms:
+        out["iteration"] = {"ms": it_ms, "rays_per_s": n_rays / (it_ms * 1e-3), "what": "step + GradScaler.unscale_ + torch.optim.AdamW.step (foreach)"}
+    del tr, devb, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_reference(args, rank, world, local):
+    """The reference's own CUDA extensions + its Python flow (oracle/ref_pipeline.py) on ONE GPU; if oracle/_ref cannot be
+    loaded, the CPU oracle port on the host cores instead.  Under torchrun rank 0 alone runs: the reference has no multi-GPU path
+    (tools/details.md:25), so at N > 1 this line is a ONE-GPU reference (`n_gpus` 1)."""
+    if rank != 0:
+        return
+    why = "no CUDA device"
+    try:
+        from oracle import ref_pipeline
+        ext = ref_pipeline.load_ext()
+        have_ref = torch.cuda.is_available()
+    except Exception as ex:  # noqa: BLE001
+        ext, have_ref = None, False
+        why = repr(ex)
+    if not have_ref:
+        cfg = {"workload": WORKLOADS[args.workload].format(L=args.levels, R=args.rays), "workload_key": args.workload,
+               "rays_per_gpu": args.rays, "levels": args.levels}
+        cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget if args.cpu_budget != 15.0 else 20.0)
+        out = {"metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * args.rays / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "impl": "reference", "config": cfg, "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "note": "oracle/_ref not loadable (" + why[:80] + "); CPU oracle port timed instead"}
+        print(json.dumps(out), flush=True)
+        return
+    torch.cuda.set_device(local)
+    out = measure_reference(args, args.workload, args.rays, local, ext, args.steps)
+    if world > 1:
+        out["note"] = f"launched under torchrun with {world} ranks: ONE-GPU reference (the reference has no multi-GPU path), rank 0 only"
+    out["workloads"] = {args.workload: {k: out[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "iteration") if k in out}}
+    if args.all_workloads:
+        for w in ("hash", "vm", "hash-vm", "mlp-hash"):
+            if w == args.workload:
+                continue
+            try:
+                r = measure_reference(args, w, DEFAULT_RAYS[w], local, ext, min(args.steps, args.secondary_steps))
+                out["workloads"][w] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "iteration") if k in r}
+            except Exception as ex:  # noqa: BLE001
+                out["workloads"][w] = {"error": repr(ex)[:300]}
+                torch.cuda.empty_cache()
+    cb = cpu_baseline(args.workload, args.levels, args.rays, budget_s=args.cpu_budget) if not args.no_cpu_baseline else None
     if cb:
         out["cpu_baseline"] = cb
     print(json.dumps(out), flush=True)
@@ -677,7 +807,12 @@ def main():
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (default 4096; 8192 for mlp-hash)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-comm", default="fp16", choices=["multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (default), fp16 payload reduced in the NVSwitch (multimem; measured slower on 2 GPUs: 106 vs 89 us), or fp32 over NCCL")
+    ap.add_argument("--grad-comm", default="fp16", choices=["auto", "multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (fp16), fp16 payload reduced in the NVSwitch by one kernel with device-side barriers (multimem; auto = multimem if it sets up and passes its self-check, else NCCL), or fp32 over NCCL")
+    ap.add_argument("--mm-blocks", type=int, default=0, help="multimem exchange kernel: CTAs (0 = default)")
+    ap.add_argument("--mm-unroll", type=int, default=4, help="multimem exchange kernel: 16-byte switch reductions in flight per thread (2 | 4 | 8)")
+    ap.add_argument("--only", dest="all_workloads", action="store_false", help="measure only --workload (default: the other BASELINE configurations "
+                    "are measured too, with --secondary-steps steps each, and reported under \"workloads\")")
+    ap.add_argument("--secondary-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="serial step graph: do not overlap the next batch's march with the backward")
     args = ap.parse_args()

@@ -102,6 +102,10 @@ int pvd_march_rays_train_count_aabb(const float* rays_o, const float* rays_d, co
                                     float min_near, float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
                                     uint32_t H, float* nears, float* fars, int32_t* rays, int32_t* counter, uint32_t perturb,
                                     uint32_t reuse_coarse, int32_t* ws_i32, void* stream);
+/* (Re)build the coarse rejection mask in ws_i32 from `grid` alone -- what a caller that replays a captured step with
+ * reuse_coarse != 0 runs after every density-grid update (renderer.py:647-773 rewrites density_bitfield every 16 steps).
+ * No-op when the mask does not apply (C != 1, H != 128 or bound > 1). */
+int pvd_march_coarse_mask(const uint8_t* grid, uint32_t C, uint32_t H, float bound, int32_t* ws_i32, void* stream);
 int pvd_march_rays_train_write(const float* rays_o, const float* rays_d, float bound, uint32_t max_steps,
                                uint32_t N, uint32_t M, const int32_t* rays, const int32_t* ws_i32, float* xyzs,
                                float* dirs, float* deltas, void* stream);
@@ -188,12 +192,6 @@ int pvd_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint3
  * grad_inputs [B,3] is accumulated into (+=), as in the reference. */
 int pvd_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C,
                            const float* dy_dx, float* grad_inputs, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * tcgen05 building-block self-test (csrc/tc_probe.cu): one CTA, one accumulator tile; see that file for modes.
- * ---------------------------------------------------------------------------------------- */
-int pvd_tc_probe(int mode, const void* A, uint32_t RA, uint32_t CA, const void* B, uint32_t RB, uint32_t CB,
-                 float* out, uint32_t N, int* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Density-grid upkeep: NeRFRenderer.update_extra_state (distill_mutual/renderer.py:647-773) without host round trips.

@@ -233,6 +233,12 @@ int pvd_l1_mean_reg(const float* param, uint64_t n, float weight, float loss_sca
  * buffer, between two all-rank barriers supplied by the caller.  Offsets and counts in elements, multiples of 8. */
 int pvd_multimem_allreduce_f16(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, void* stream);
 /* fp32 gradient -> fp16 exchange payload (elem_count multiple of 4, 16-byte aligned source) */
+/* The same reduction with the two cross-rank barriers INSIDE the kernel (one launch instead of barrier + kernel + barrier):
+ * `signal_pad_ptrs_dev` = device array of the ranks' symmetric-memory signal pads (uint32 slots, all zero between calls; slots
+ * [8W, 10W) are used), `local_state` = 4 zero-initialised uint32 of this rank ([2] != 0 afterwards: a barrier timed out).
+ * blocks (0 = default) and unroll (2 | 4 | 8) are tuning knobs; every rank must pass the same values. */
+int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
+                                     uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream);
 int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
 
 #ifdef __cplusplus

@@ -5,7 +5,7 @@
 //   mode 1: D[128,N]  = A[128,K] * W[K,N]               (A K-major, B MN-major)      -- data gradient
 //   mode 2: D[64,N]   = sum_s T1[s,0:64]^T T2[s,0:N]    (both MN-major, M = 64)      -- weight gradient
 //   mode 3: as mode 2 with M = 128 (T1 has 128 columns)
-// Exposed through the C ABI as pvd_tc_probe (tests/test_gpu_tcgen05.py checks it against torch.matmul).
+// A stand-alone diagnostic (scripts/micro/tc_probe.py builds and runs it); not part of libpvd_b200.so or its ABI.
 #include "common.cuh"
 #include "tc5.cuh"
 

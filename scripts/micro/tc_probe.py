@@ -1,20 +1,31 @@
-"""Diagnostic (not a pytest file): run the tcgen05 probe kernel in all modes and report errors / TMEM lane mapping.
-Usage on the GPU box: python tests/diag_tc_probe.py"""
+"""Diagnostic: run the tcgen05 probe kernel (scripts/micro/tc_probe.cu -- NOT part of libpvd_b200.so) in all modes and report
+errors / the TMEM lane mapping.  Builds its own small shared object next to this file.
+Usage on the GPU box: python scripts/micro/tc_probe.py"""
 import ctypes as C
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "aaai2023-pvd_b200"))
 from pvd_b200 import _native as nv  # noqa: E402
+
+_SO = os.path.join(HERE, "libtc_probe.so")
+if not os.path.exists(_SO):
+    subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                           f"-I{os.path.join(ROOT, 'aaai2023-pvd_b200', 'csrc')}", f"-I{os.path.join(ROOT, 'include')}", "-DPVD_BUILDING",
+                           os.path.join(HERE, "tc_probe.cu"), "-o", _SO])
+_probe = C.CDLL(_SO)
 
 
 def probe(mode, A, B, N):
     out = torch.full((128, N), float("nan"), device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    rc = nv.lib().pvd_tc_probe(C.c_int(mode), nv.ptr(A), C.c_uint32(A.shape[0]), C.c_uint32(A.shape[1]), nv.ptr(B),
+    rc = _probe.pvd_tc_probe(C.c_int(mode), nv.ptr(A), C.c_uint32(A.shape[0]), C.c_uint32(A.shape[1]), nv.ptr(B),
                                C.c_uint32(B.shape[0]), C.c_uint32(B.shape[1]), nv.ptr(out), C.c_uint32(N), nv.ptr(status),
                                nv.stream_of(A))
     nv.check(rc)

@@ -163,3 +163,79 @@ def test_host_fed_pipelined_graphs(scene):
         torch.testing.assert_close(host_loss, loss_r.cpu(), rtol=1e-5, atol=1e-7)
         assert _rel_l2(eng.grad_table, gt_r) < 1e-4
     assert int(eng.status.item()) == 0
+
+
+def test_set_bitfield_reaches_a_captured_graph(scene):
+    """A density-grid update between replays (renderer.py:647-773 rewrites density_bitfield every 16 steps): set_bitfield() copies
+    into the buffer the captured graph marches against and rebuilds the coarse rejection mask, so the next REPLAY of the existing
+    graph gives what a fresh eager step on the new grid gives."""
+    import numpy as np
+    from pvd_b200 import synthetic as syn
+    net, eng, ro, rd, gt = _setup(scene, n_rays=1024, seed=2)
+    eng.step(warmup=True)
+    eng.finish_warmup()
+    eng.capture()
+    eng.replay()
+    torch.cuda.synchronize()
+    rays_old = eng.rays.clone()
+    # a different scene: the same boxes shifted / one removed -> other cells occupied, other rays hit
+    boxes = syn.LEGO_BOXES.copy()
+    boxes[:, [0, 3]] += 0.12
+    boxes = boxes[:-1]
+    grid2 = syn.lego_density_grid(boxes=boxes)
+    bf2 = syn.pack_bitfield(grid2)
+    assert bf2.shape == scene["bitfield"].shape and not np.array_equal(bf2, scene["bitfield"])
+    eng.set_bitfield(torch.from_numpy(bf2))
+    eng.replay()
+    torch.cuda.synchronize()
+    rays_graph, img_graph, loss_graph = eng.rays.clone(), eng.image.clone(), float(eng.loss[0])
+    assert not torch.equal(rays_graph, rays_old), "the replay still marched against the old grid"
+    # the same step on a FRESH engine built on the new grid (same M so the same rays are dropped, if any)
+    from pvd_b200.engine import HashTrainEngine
+    eng2 = HashTrainEngine(net, torch.from_numpy(bf2), 1024, loss_scale=512.0)
+    eng2.stage()
+    eng2.rays_o.copy_(ro); eng2.rays_d.copy_(rd); eng2.gt.copy_(gt)
+    eng2.set_mean_count(eng.mean_count)
+    eng2.step()
+    torch.cuda.synchronize()
+    assert torch.equal(eng2.rays, rays_graph), "sample counts / offsets after set_bitfield differ from a fresh engine's"
+    torch.testing.assert_close(img_graph, eng2.image, rtol=0, atol=0)
+    assert abs(loss_graph - float(eng2.loss[0])) < 1e-6 * max(1.0, loss_graph)
+    # and the oracle's march on the new grid agrees on the counts
+    from oracle import cpu
+    on, of = cpu.near_far_from_aabb(ro.numpy(), rd.numpy(), np.array([-1, -1, -1, 1, 1, 1], np.float32), 0.2)
+    o = cpu.march_rays_train(ro.numpy(), rd.numpy(), 1.0, bf2, 1, 128, on, of, M=eng.M, perturb=True)
+    assert np.array_equal(rays_graph.cpu().numpy(), o[3])
+
+
+def test_coarse_mask_is_not_used_beyond_bound_one(scene):
+    """A direct caller with C == 1 and bound > 1 (the mask maps cells with 1/bound, the marcher with min(1, bound)): the fused count
+    entry must give the plain two-phase march's counts (samples were pruned)."""
+    import ctypes as C
+    from pvd_b200 import _native as nv
+    ro, rd = scene["batches"][0]
+    ro, rd = ro[:512].contiguous().cuda(), rd[:512].contiguous().cuda()
+    bf = torch.from_numpy(scene["bitfield"]).cuda()
+    bound = 2.0
+    aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device="cuda")
+    N = 512
+    l = nv.lib()
+    ws = torch.empty(int(l.pvd_march_rays_train_workspace_words(N, 1024)), dtype=torch.int32, device="cuda")
+    nears, fars = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    rays = torch.empty(N, 3, dtype=torch.int32, device="cuda")
+    counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    st = nv.stream_of(ro)
+    nv.check(l.pvd_march_rays_train_count_aabb(nv.ptr(ro), nv.ptr(rd), nv.ptr(bf), nv.ptr(aabb), C.c_float(0.2), C.c_float(bound), C.c_float(0.0),
+                                               C.c_uint32(1024), C.c_uint32(N), C.c_uint32(1), C.c_uint32(128), nv.ptr(nears), nv.ptr(fars),
+                                               nv.ptr(rays), nv.ptr(counter), C.c_uint32(1), C.c_uint32(0), nv.ptr(ws), st))
+    import raymarching
+    n2, f2 = raymarching.near_far_from_aabb(ro, rd, aabb, 0.2)
+    rays2 = torch.empty(N, 3, dtype=torch.int32, device="cuda")
+    counter2 = torch.zeros(2, dtype=torch.int32, device="cuda")
+    # the reference semantics from the CPU oracle (no mask anywhere)
+    from oracle import cpu
+    import numpy as np
+    o = cpu.march_rays_train(ro.cpu().numpy(), rd.cpu().numpy(), bound, scene["bitfield"], 1, 128, n2.cpu().numpy(), f2.cpu().numpy(),
+                             M=N * 1024, perturb=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(rays.cpu().numpy(), o[3]), "C == 1 with bound > 1: counts differ from the oracle (coarse mask misapplied)"
