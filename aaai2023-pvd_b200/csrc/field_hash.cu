@@ -19,6 +19,7 @@
 //     scatter warps of the same CTA (default) or by a second kernel (k_hash_scatter).
 // CTAs are persistent (grid = min(#tiles, 2 x #SMs)) so weights are staged and TMEM is allocated once per CTA and
 // weight gradients leave the SM once.
+#include <stdlib.h>
 #include "common.cuh"
 PVD_TRACE_TU(pvd_debug_trace_field_hash)
 #include "gridenc.cuh"
@@ -157,14 +158,20 @@ __device__ __forceinline__ void encode4(const T* __restrict__ table, uint32_t lv
 __device__ __forceinline__ void stage_weights(uint8_t* smw, const uint8_t* __restrict__ blob) { stage_blob(smw, blob, PVD_FIELD_WBLOB_BYTES); }
 
 // =============================================================================================== forward kernel
-template <typename T>
+// TMA_IN: the tile's sample block -- 128 consecutive rows of xyzs and of dirs, 1536 contiguous bytes each -- is staged into shared
+// memory by two TMA bulk copies (cp.async.bulk, mbarrier complete_tx) issued by one thread: the first tile's while the CTA is still in
+// its prologue (TMEM allocation, level table, barrier), every further tile's one iteration ahead (double buffered), so no thread
+// ever waits on a global load for its position / direction.  A tile whose byte count is not a multiple of 16 (only the last, when
+// M % 4 != 0) is loaded per thread.
+template <typename T, bool TMA_IN>
 __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                         uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                         __half* __restrict__ enc, float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar, wbar;
+    __shared__ uint64_t bar, wbar, sbar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelInfo lv[16];
+    __shared__ __align__(16) float sxyz[TMA_IN ? 2 : 1][TMA_IN ? kTile * 3 : 1], sdir[TMA_IN ? 2 : 1][TMA_IN ? kTile * 3 : 1];
     // Forward-only tiles alias: the encoding X is dead once layer 1's MMAs completed, so the colour-net input CIN reuses its
     // buffer; H1, H3, H4 are each dead when the next one is written (its consumer MMA has been waited for).  44 KB per CTA
     // instead of 68 KB -> 4 resident CTAs per SM (the TMEM limit) instead of 3, i.e. one tile per CTA at 4096 rays.
@@ -187,11 +194,25 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     }
     // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
     // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+    auto tile_rows = [&](uint32_t tile) { return min(kTile, M - tile * kTile); };
+    auto tma_tile = [&](uint32_t tile) { return TMA_IN && (tile_rows(tile) & 3u) == 0u; };   // 12 B rows: a multiple of 16 bytes
+    auto stage_samples = [&](uint32_t tile, uint32_t buf) {   // thread 0
+        const uint32_t bytes = tile_rows(tile) * 12u;
+        tc5::mbar_expect_tx(&sbar[buf], 2u * bytes);
+        tc5::bulk_g2s(tc5::smem_u32(sxyz[buf]), xyzs + 3 * (size_t)tile * kTile, bytes, &sbar[buf]);
+        tc5::bulk_g2s(tc5::smem_u32(sdir[buf]), dirs + 3 * (size_t)tile * kTile, bytes, &sbar[buf]);
+    };
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_init(&wbar, 1);
+        if (TMA_IN) {
+            tc5::mbar_init(&sbar[0], 1);
+            tc5::mbar_init(&sbar[1], 1);
+        }
         tc5::mbar_fence_init();
+        if (TMA_IN && blockIdx.x < n_tiles && tma_tile(blockIdx.x)) stage_samples(blockIdx.x, 0u);  // first: the gather waits on it
         stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile is gathered
     }
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
@@ -205,12 +226,25 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     const T* table = reinterpret_cast<const T*>(a.table);
     const uint32_t lv_saddr = tc5::smem_u32(lv);
 
-    const uint32_t n_tiles = (M + kTile - 1) / kTile;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t row = tile * kTile + tid;
         const bool live = row < M;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-        if (live) {
+        if (tma_tile(tile)) {
+            const uint32_t buf = it & 1u;
+            if (!tc5::mbar_wait(&sbar[buf], (it >> 1) & 1u)) atomicExch(status, 4);
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    pos[d] = sxyz[buf][3 * tid + d];
+                    dir[d] = sdir[buf][3 * tid + d];
+                }
+            }
+            // the other buffer was last read one iteration ago, before that iteration's barriers: free to be overwritten
+            const uint32_t next = tile + gridDim.x;
+            if (tid == 0 && next < n_tiles && tma_tile(next)) stage_samples(next, buf ^ 1u);
+        } else if (live) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
@@ -688,17 +722,25 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
     const uint32_t grid = min(tiles, (uint32_t)(4 * sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    // sample blocks through TMA bulk copies (default) or per-thread loads (PVD_FWD_TMA=0, and whenever the buffers are not
+    // 16-byte aligned)
+    static const bool want_tma = []() { const char* v = getenv("PVD_FWD_TMA"); return !(v != nullptr && v[0] == '0'); }();
+    const bool tma = want_tma && ((reinterpret_cast<uintptr_t>(xyzs) | reinterpret_cast<uintptr_t>(dirs)) & 15u) == 0;
+    auto launch = [&](auto kern) -> int {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+        return PVD_OK;
+    };
+    int rc;
     if (f->table_dtype == PVD_DTYPE_F16) {
-        e = cudaFuncSetAttribute(k_hash_field_fwd<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
-        if (e != cudaSuccess) return (int)e;
-        k_hash_field_fwd<__half><<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+        rc = tma ? launch(k_hash_field_fwd<__half, true>) : launch(k_hash_field_fwd<__half, false>);
     } else if (f->table_dtype == PVD_DTYPE_F32) {
-        e = cudaFuncSetAttribute(k_hash_field_fwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
-        if (e != cudaSuccess) return (int)e;
-        k_hash_field_fwd<float><<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+        rc = tma ? launch(k_hash_field_fwd<float, true>) : launch(k_hash_field_fwd<float, false>);
     } else {
         return PVD_EUNSUPPORTED;
     }
+    if (rc != PVD_OK) return rc;
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

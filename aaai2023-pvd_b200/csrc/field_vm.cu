@@ -48,10 +48,10 @@ constexpr uint32_t kVG5 = 9216;    // [64][16]
 static_assert(kVG5 + 1024 == PVD_FIELD_GW_FLOATS, "vm workspace size");
 
 struct VmArgs {
-    const float* smat[3];
-    const float* svec[3];
-    const float* cmat[3];
-    const float* cvec[3];
+    const void* smat[3];   // planes / lines, channels-last: fp32 (the parameters themselves) or fp16 (a shadow copy: half the
+    const void* svec[3];   // gather bytes; the kernels are instantiated for either, template parameter PF16)
+    const void* cmat[3];
+    const void* cvec[3];
     const uint8_t* wblob;
     uint32_t res[3];
     float aabb[6];
@@ -139,56 +139,81 @@ __device__ __forceinline__ float4 ldg_v4_issue(const float* p) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// A tap of four consecutive components starting at element `e` of a plane / line: 16 bytes of fp32, or 8 bytes of the fp16 shadow
+// (kept packed in two registers until it is consumed: `Tap` is what stays in flight).
+template <bool PF16> struct TapT { using type = float4; };
+template <> struct TapT<true> { using type = uint2; };
+template <bool PF16>
+__device__ __forceinline__ typename TapT<PF16>::type tap_issue(const void* base, size_t e) {
+    if constexpr (PF16) {
+        uint2 v;
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(reinterpret_cast<const __half*>(base) + e));
+        return v;
+    } else {
+        return ldg_v4_issue(reinterpret_cast<const float*>(base) + e);
+    }
+}
+__device__ __forceinline__ float4 tap_value(const float4& v) { return v; }
+__device__ __forceinline__ float4 tap_value(const uint2& v) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 
+template <bool PF16>
 struct SampleTaps {
-    float4 t[3][4], u[3][2];
+    typename TapT<PF16>::type t[3][4], u[3][2];
     float pw[3][4], lw[3][2];
 };
 
-__device__ __forceinline__ void vm_issue(const VmArgs& a, const float (&pos)[3], const LaneMap& m, SampleTaps& T) {
+template <bool PF16>
+__device__ __forceinline__ void vm_issue(const VmArgs& a, const float (&pos)[3], const LaneMap& m, SampleTaps<PF16>& T) {
     float xn[3];
     vm_normalise(pos, a.aabb, xn);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         Foot f;
         vm_foot(xn, a.res, i, f);
-        const float* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
-        const float* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
+        const void* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
+        const void* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            T.t[i][k] = ldg_v4_issue(mat + (size_t)f.pidx[k] * m.R + m.ch);
+            T.t[i][k] = tap_issue<PF16>(mat, (size_t)f.pidx[k] * m.R + m.ch);
             T.pw[i][k] = f.pw[k];
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            T.u[i][k] = ldg_v4_issue(vec + (size_t)f.lidx[k] * m.R + m.ch);
+            T.u[i][k] = tap_issue<PF16>(vec, (size_t)f.lidx[k] * m.R + m.ch);
             T.lw[i][k] = f.lw[k];
         }
     }
 }
 
 // interpolated plane and line value of pair i (grid_sample's bilinear sum, tap order 00, 01, 10, 11)
-__device__ __forceinline__ void vm_interp(const SampleTaps& T, int i, float4& pv, float4& lv) {
+template <bool PF16>
+__device__ __forceinline__ void vm_interp(const SampleTaps<PF16>& T, int i, float4& pv, float4& lv) {
     pv = make_float4(0.f, 0.f, 0.f, 0.f);
     lv = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        pv.x = __fmaf_rn(T.pw[i][k], T.t[i][k].x, pv.x);
-        pv.y = __fmaf_rn(T.pw[i][k], T.t[i][k].y, pv.y);
-        pv.z = __fmaf_rn(T.pw[i][k], T.t[i][k].z, pv.z);
-        pv.w = __fmaf_rn(T.pw[i][k], T.t[i][k].w, pv.w);
+        const float4 t = tap_value(T.t[i][k]);
+        pv.x = __fmaf_rn(T.pw[i][k], t.x, pv.x);
+        pv.y = __fmaf_rn(T.pw[i][k], t.y, pv.y);
+        pv.z = __fmaf_rn(T.pw[i][k], t.z, pv.z);
+        pv.w = __fmaf_rn(T.pw[i][k], t.w, pv.w);
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        lv.x = __fmaf_rn(T.lw[i][k], T.u[i][k].x, lv.x);
-        lv.y = __fmaf_rn(T.lw[i][k], T.u[i][k].y, lv.y);
-        lv.z = __fmaf_rn(T.lw[i][k], T.u[i][k].z, lv.z);
-        lv.w = __fmaf_rn(T.lw[i][k], T.u[i][k].w, lv.w);
+        const float4 u = tap_value(T.u[i][k]);
+        lv.x = __fmaf_rn(T.lw[i][k], u.x, lv.x);
+        lv.y = __fmaf_rn(T.lw[i][k], u.y, lv.y);
+        lv.z = __fmaf_rn(T.lw[i][k], u.z, lv.z);
+        lv.w = __fmaf_rn(T.lw[i][k], u.w, lv.w);
     }
 }
 
 // products -> APP tile row r (colour, fp16) and sfeat[r] (sigma, summed over the four sigma lanes of the half-warp)
-__device__ __forceinline__ void vm_finish(const SampleTaps& T, const LaneMap& m, uint32_t r, uint8_t* APP, float* sfeat) {
+template <bool PF16>
+__device__ __forceinline__ void vm_finish(const SampleTaps<PF16>& T, const LaneMap& m, uint32_t r, uint8_t* APP, float* sfeat) {
     float sacc = 0.0f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -212,6 +237,7 @@ __device__ __forceinline__ void vm_finish(const SampleTaps& T, const LaneMap& m,
 
 // Gather phase for the 32 samples of this warp, two at a time: APP tile (colour products, fp16) and sfeat[row] (sigma feature,
 // fp32).  Lane l first fetches the position of the warp's sample l; a sample's position is then a shuffle away.
+template <bool PF16>
 __device__ __forceinline__ void vm_gather(const VmArgs& a, const float* __restrict__ xyzs, uint32_t tile_row0, uint32_t M,
                                           uint8_t* APP, float* sfeat) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -229,9 +255,9 @@ __device__ __forceinline__ void vm_gather(const VmArgs& a, const float* __restri
         float pos[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)(s + m.half));
-        SampleTaps T;
-        vm_issue(a, pos, m, T);
-        vm_finish(T, m, warp * 32 + s + m.half, APP, sfeat);
+        SampleTaps<PF16> T;
+        vm_issue<PF16>(a, pos, m, T);
+        vm_finish<PF16>(T, m, warp * 32 + s + m.half, APP, sfeat);
     }
 }
 
@@ -307,6 +333,7 @@ __device__ __forceinline__ void vm_mlp_forward(Pipe& p, const VmArgs& a, uint8_t
 }
 
 // =============================================================================================== forward
+template <bool PF16>
 __global__ void __launch_bounds__(128, 3) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                       uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                       float* __restrict__ feat16, int32_t* status) {
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(128, 3) k_vm_field_fwd(VmArgs a, const float* 
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();  // previous tile's sfeat / APP consumers are done
-        vm_gather(a, xyzs, tile * kTile, M, APP, sfeat);
+        vm_gather<PF16>(a, xyzs, tile * kTile, M, APP, sfeat);
         const uint32_t row = tile * kTile + tid;
         const bool live = row < M;
         float dir[3] = {0.f, 0.f, 0.f};
@@ -363,6 +390,7 @@ __global__ void __launch_bounds__(128, 3) k_vm_field_fwd(VmArgs a, const float* 
 }
 
 // =============================================================================================== backward
+template <bool PF16>
 __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
                                                       const float* __restrict__ dirs, const float* __restrict__ grad_sigmas,
                                                       const float* __restrict__ grad_rgbs, const float* __restrict__ grad_feat,
@@ -400,7 +428,7 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
     bool first = true;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
-        vm_gather(a, xyzs, tile * kTile, M, APP, sfeat);
+        vm_gather<PF16>(a, xyzs, tile * kTile, M, APP, sfeat);
         const uint32_t row = tile * kTile + tid;
         const bool live = row < n_valid;
         float dir[3] = {0.f, 0.f, 0.f}, gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
@@ -573,8 +601,8 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                 float pos[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) pos[d] = __shfl_sync(0xffffffffu, mine[d], (int)(16u * m.half + (s & 15u)));
-                SampleTaps T;
-                vm_issue(a, pos, m, T);
+                SampleTaps<PF16> T;
+                vm_issue<PF16>(a, pos, m, T);
                 if (s >= n_s) continue;   // this half-warp's run is shorter (tail of the valid rows)
                 const uint32_t rr = warp * 32 + 16u * m.half + s;
                 float xn[3];
@@ -585,7 +613,7 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
                     Foot f;
                     vm_foot(xn, a.res, i, f);   // weights and cell identity again (cheap ALU; T carries only the tap values)
                     float4 pv, lv;
-                    vm_interp(T, i, pv, lv);
+                    vm_interp<PF16>(T, i, pv, lv);
                     float4 dp;
                     if (m.sig) {
                         dp = make_float4(ds, ds, ds, ds);
@@ -652,6 +680,7 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
 // pair is the OUTER loop, so only 6 taps and 6 accumulators are live at a time: ~90 registers, 256-thread CTAs, 16-24 warps per
 // SM instead of the 8 the MLP kernel can hold (212 registers, 100 KB of shared memory) -- this phase is bound by the latency of
 // its own loads and reductions, not by a chip-level unit (its 6 M sector reductions are fewer than k_hash_scatter's 8 M).
+template <bool PF16>
 __global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, const float* __restrict__ xyzs,
                                                        const uint8_t* __restrict__ dapp_ws, const float* __restrict__ dsf_ws, uint32_t M,
                                                        const int32_t* __restrict__ n_valid_p) {
@@ -676,8 +705,8 @@ __global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, c
     for (int i = 0; i < 3; ++i) {   // unrolled: a runtime index into the kernel-parameter arrays would move them to local memory
         const int a0 = (i == 2) ? 1 : 0, a1 = (i == 0) ? 1 : 2;
         const int W = (int)a.res[a0], Hh = (int)a.res[a1], D = (int)a.res[2 - i];
-        const float* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
-        const float* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
+        const void* __restrict__ mat = m.sig ? a.smat[i] : a.cmat[i];
+        const void* __restrict__ vec = m.sig ? a.svec[i] : a.cvec[i];
         float* gm = m.sig ? g.smat[i] : g.cmat[i];
         float* gv = m.sig ? g.svec[i] : g.cvec[i];
         float4 accp[4], accl[2];
@@ -707,7 +736,7 @@ __global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, c
             }
         };
         // software pipeline over the run: the taps and the d(APP) slice of sample s+1 are in flight under the arithmetic of sample s
-        float4 t[2][4], u[2][2];
+        typename TapT<PF16>::type t[2][4], u[2][2];
         Foot f[2];
         uint2 draw[2];
         auto issue = [&](uint32_t s2, int b) {
@@ -717,9 +746,9 @@ __global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, c
             vm_normalise(pos, a.aabb, xn);
             vm_foot(xn, a.res, i, f[b]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) t[b][k] = ldg_v4_issue(mat + (size_t)f[b].pidx[k] * m.R + m.ch);
+            for (int k = 0; k < 4; ++k) t[b][k] = tap_issue<PF16>(mat, (size_t)f[b].pidx[k] * m.R + m.ch);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) u[b][k] = ldg_v4_issue(vec + (size_t)f[b].lidx[k] * m.R + m.ch);
+            for (int k = 0; k < 2; ++k) u[b][k] = tap_issue<PF16>(vec, (size_t)f[b].lidx[k] * m.R + m.ch);
             draw[b] = make_uint2(0u, 0u);
             if (!m.sig && s2 < n_s) {
                 const uint32_t row = base + s2, col = (uint32_t)i * 48u + m.ch;
@@ -740,13 +769,15 @@ __global__ void __launch_bounds__(256, 2) k_vm_scatter(VmArgs a, VmGradPtrs g, c
                 float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), lv = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    pv.x = __fmaf_rn(f[b].pw[k], t[b][k].x, pv.x); pv.y = __fmaf_rn(f[b].pw[k], t[b][k].y, pv.y);
-                    pv.z = __fmaf_rn(f[b].pw[k], t[b][k].z, pv.z); pv.w = __fmaf_rn(f[b].pw[k], t[b][k].w, pv.w);
+                    const float4 tv = tap_value(t[b][k]);
+                    pv.x = __fmaf_rn(f[b].pw[k], tv.x, pv.x); pv.y = __fmaf_rn(f[b].pw[k], tv.y, pv.y);
+                    pv.z = __fmaf_rn(f[b].pw[k], tv.z, pv.z); pv.w = __fmaf_rn(f[b].pw[k], tv.w, pv.w);
                 }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    lv.x = __fmaf_rn(f[b].lw[k], u[b][k].x, lv.x); lv.y = __fmaf_rn(f[b].lw[k], u[b][k].y, lv.y);
-                    lv.z = __fmaf_rn(f[b].lw[k], u[b][k].z, lv.z); lv.w = __fmaf_rn(f[b].lw[k], u[b][k].w, lv.w);
+                    const float4 uv = tap_value(u[b][k]);
+                    lv.x = __fmaf_rn(f[b].lw[k], uv.x, lv.x); lv.y = __fmaf_rn(f[b].lw[k], uv.y, lv.y);
+                    lv.z = __fmaf_rn(f[b].lw[k], uv.z, lv.z); lv.w = __fmaf_rn(f[b].lw[k], uv.w, lv.w);
                 }
                 float4 dp;
                 if (m.sig) {
@@ -806,7 +837,10 @@ __global__ void k_vm_unpack_wgrads(const float* __restrict__ gw, float* __restri
     if (t < 3 * 64) { const uint32_t o = t / 64, i = t - o * 64; g2[t] += sum(kVG5 + i * 16 + o); }
 }
 
+static bool vm_planes_f16(const PvdVmField* f) { return f->plane_dtype == PVD_DTYPE_F16; }
+
 static bool to_vm_args(const PvdVmField* f, VmArgs& a) {
+    if (f->plane_dtype != PVD_DTYPE_F16 && f->plane_dtype != PVD_DTYPE_F32) return false;
     for (int i = 0; i < 3; ++i) {
         a.smat[i] = f->sigma_mat[i]; a.svec[i] = f->sigma_vec[i]; a.cmat[i] = f->color_mat[i]; a.cvec[i] = f->color_vec[i];
         a.res[i] = f->res[i];
@@ -843,9 +877,15 @@ int pvd_vm_field_forward(const PvdVmField* f, const float* xyzs, const float* di
     if (!to_vm_args(f, a)) return PVD_EINVAL;
     const uint32_t tiles = (M + kTile - 1) / kTile;
     const uint32_t grid = min(tiles, (uint32_t)(3 * sm_count()));
-    cudaError_t e = cudaFuncSetAttribute(k_vm_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmFwdSmem);
-    if (e != cudaSuccess) return (int)e;
-    k_vm_field_fwd<<<grid, 128, kVmFwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    if (vm_planes_f16(f)) {
+        cudaError_t e = cudaFuncSetAttribute(k_vm_field_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_vm_field_fwd<true><<<grid, 128, kVmFwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(k_vm_field_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_vm_field_fwd<false><<<grid, 128, kVmFwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    }
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }
@@ -886,17 +926,26 @@ static int vm_backward(const PvdVmField* f, const PvdVmGrads* grads, const float
     }
     const uint32_t tiles = (M + kTile - 1) / kTile;
     const uint32_t grid = min(tiles, (uint32_t)(2 * sm_count()));
-    cudaError_t e = cudaFuncSetAttribute(k_vm_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmBwdSmem);
+    const bool pf16 = vm_planes_f16(f);
+    cudaError_t e = pf16 ? cudaFuncSetAttribute(k_vm_field_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmBwdSmem)
+                         : cudaFuncSetAttribute(k_vm_field_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmBwdSmem);
     if (e != cudaSuccess) return (int)e;
     // PVD_VM_DIAG_SKIP=1 (timing diagnostics only, wrong gradients): leave out the plane / line gradient scatter
     static const uint32_t diag_skip = []() { const char* v = getenv("PVD_VM_DIAG_SKIP"); return v ? (uint32_t)atoi(v) : 0u; }();
     uint8_t* dapp_ws = reinterpret_cast<uint8_t*>(scatter_ws);
     float* dsf_ws = scatter_ws ? reinterpret_cast<float*>(dapp_ws + (size_t)tiles * 36864u) : nullptr;
-    k_vm_field_bwd<<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                                   gw_ws, status, diag_skip, dapp_ws, dsf_ws);
+    if (pf16)
+        k_vm_field_bwd<true><<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
+                                                                             gw_ws, status, diag_skip, dapp_ws, dsf_ws);
+    else
+        k_vm_field_bwd<false><<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
+                                                                              gw_ws, status, diag_skip, dapp_ws, dsf_ws);
     PVD_LAUNCH_CHECK();
     if (scatter_ws != nullptr && !(diag_skip & 1u)) {
-        k_vm_scatter<<<ceil_div(M, 256u), 256, 0, (cudaStream_t)stream>>>(a, g, xyzs, dapp_ws, dsf_ws, M, n_valid);
+        if (pf16)
+            k_vm_scatter<true><<<ceil_div(M, 256u), 256, 0, (cudaStream_t)stream>>>(a, g, xyzs, dapp_ws, dsf_ws, M, n_valid);
+        else
+            k_vm_scatter<false><<<ceil_div(M, 256u), 256, 0, (cudaStream_t)stream>>>(a, g, xyzs, dapp_ws, dsf_ws, M, n_valid);
         PVD_LAUNCH_CHECK();
     }
     return PVD_OK;

@@ -108,9 +108,9 @@ __global__ void k_adamw_advance(PvdAdamState* state, PvdAdamSlot* slots, uint32_
     st.beta2_f = (float)st.beta2;
     *state = st;
     for (uint32_t i = 0; i < n_slots; ++i) {
-        const double lr = (double)slots[i].lr;
+        const double lr = slots[i].lr;
         slots[i].neg_step_size = (float)(-(lr / bc1));
-        slots[i].decay = (float)(1.0 - lr * (double)slots[i].weight_decay);
+        slots[i].decay = (float)(1.0 - lr * slots[i].weight_decay);
     }
 }
 
@@ -185,6 +185,20 @@ __global__ void __launch_bounds__(256) k_f32_to_f16_scaled(const float4* __restr
     }
 }
 
+// several fp32 -> fp16 casts in one launch (blockIdx.y = tensor): the vm model's 12 plane / line tensors -> their fp16 shadows
+__global__ void __launch_bounds__(256) k_f32_to_f16_multi(const PvdCastDesc* __restrict__ descs) {
+    const PvdCastDesc d = descs[blockIdx.y];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(d.src) & 15u) | (reinterpret_cast<uintptr_t>(d.dst) & 7u)) == 0;
+    const uint64_t n4 = vec ? d.n / 4u : 0u;
+    for (uint64_t i = t0; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(d.src) + i);
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(d.dst)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    for (uint64_t i = 4u * n4 + t0; i < d.n; i += stride) reinterpret_cast<__half*>(d.dst)[i] = __float2half_rn(d.src[i]);
+}
+
 static inline uint32_t stream_grid(uint64_t n_vec, uint32_t per_sm) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -237,6 +251,16 @@ int pvd_adamw_step(const PvdAdamState* state, const PvdAdamSlot* slots, uint32_t
     k_adamw_multi<<<grid, 256, 0, (cudaStream_t)stream>>>(state, slots);
     PVD_LAUNCH_CHECK();
     k_adamw_finish<<<1, 32, 0, (cudaStream_t)stream>>>(const_cast<PvdAdamState*>(state));
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_cast_f32_to_f16_multi(const PvdCastDesc* descs_dev, uint32_t n_descs, uint64_t max_n, void* stream) {
+    PVD_REQUIRE(descs_dev != nullptr || n_descs == 0);
+    if (n_descs == 0) return PVD_OK;
+    PVD_REQUIRE(n_descs <= 65535u);
+    const dim3 grid(stream_grid((max_n + 3u) / 4u, 8), n_descs, 1);
+    k_f32_to_f16_multi<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

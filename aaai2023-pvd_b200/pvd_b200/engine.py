@@ -345,7 +345,6 @@ class FieldTrainEngine:
         cur = torch.cuda.current_stream(self.dev)
         st = C.c_void_p(cur.cuda_stream)
         M = self.M
-        self._prologue(cur)
 
         def march_branch():
             self._side2.wait_stream(cur)
@@ -364,7 +363,8 @@ class FieldTrainEngine:
         if where == "auto":
             where = "exchange" if self.exchange is not None else "early"
         if where == "early":
-            march_branch()
+            march_branch()             # forked BEFORE the prologue: the march must not wait for the re-stage / memsets
+        self._prologue(cur)
         self._forward(st, rs, M, M)
         self._loss_backward(st, rs, M, M)
         if where == "late":

@@ -104,11 +104,20 @@ class HashOps:
     def algorithmic_bytes(self):
         """(forward, backward) bytes per sample: L x 8 corners x 2 features x 2 B gathered; fp32 reductions + the saved encoding."""
         L = self.cfg.num_levels
-        return L * 8 * 2 * 2, (L * 8 * 2 * 4 + 64) if self.trainable else 0
+        entry = 2 if self.cfg.table_fp16 else 4   # bytes per feature gathered: fp16 shadow or the fp32 master
+        return L * 8 * 2 * entry, (L * 8 * 2 * 4 + 64) if self.trainable else 0
 
 
 # vm backward as two kernels (MLP kernel -> workspace -> high-occupancy scatter kernel; default) or as one (0)
 VM_SPLIT_SCATTER = os.environ.get("PVD_VM_SPLIT_SCATTER", "1") != "0"
+# The engines gather the vm planes / lines from an fp16 channels-last SHADOW (2304 B/sample instead of 4608; the kernels are
+# byte-bound on these taps), refreshed by stage() or written by the fused optimizer; masters and gradients stay fp32.  0 = gather
+# the fp32 parameters in place (what the autograd module path does).
+VM_PLANE_F16 = os.environ.get("PVD_VM_PLANE_F16", "1") != "0"
+
+
+class PvdCastDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_uint64)]
 
 
 class VmOps:
@@ -127,6 +136,10 @@ class VmOps:
         self.scatter_ws = None
         self.kernels_bwd = 2 if VM_SPLIT_SCATTER else 1
         self.wblob = self.cfield = None
+        self.plane_f16 = VM_PLANE_F16
+        self._shadow = self._cast_descs = None
+        self.shadow_groups = None
+        self._shadow_key = None
         self._aabb = [float(v) for v in field.aabb_train.tolist()]   # read once: stage() must stay free of host syncs (graph capture)
         ws = self._weights()
         self._wflat = torch.zeros(sum(w.numel() for w in ws), dtype=torch.float32, device=self.dev) if trainable else None
@@ -162,9 +175,41 @@ class VmOps:
         f = self.field
         self.wblob = f._staged.get(self._weights())
         aabb = self._aabb
-        planes = [[p.detach() for p in grp] for grp in self.groups]
+        if self.plane_f16:
+            planes = self._stage_shadow()
+        else:
+            planes = [[p.detach() for p in grp] for grp in self.groups]
         self.cfield = self._vm._vm_struct(planes, self.wblob, f.resolution, aabb, float(f.args.sigma_clip_min), float(f.args.sigma_clip_max),
                                           float(density_scale))
+
+    def _stage_shadow(self):
+        """fp16 channels-last shadows of the 12 plane / line tensors in ONE flat buffer (same order as the gradient buffer), cast by
+        one multi-tensor launch.  Frozen parameters (a teacher) are cast once (fused.frozen_key)."""
+        params = [p for grp in self.groups for p in grp]
+        if self._shadow is None:
+            total = sum(p.numel() for p in params)
+            self._shadow = torch.empty(total, dtype=torch.float16, device=self.dev)
+            descs = (PvdCastDesc * len(params))()
+            off, self.shadow_groups, flat = 0, [], []
+            for grp in self.groups:
+                views = []
+                for p in grp:
+                    assert p.dtype == torch.float32
+                    v = self._shadow[off:off + p.numel()]
+                    descs[len(flat)] = PvdCastDesc(src=p.data_ptr(), dst=v.data_ptr(), n=p.numel())
+                    views.append(v); flat.append(v)
+                    off += p.numel()
+                self.shadow_groups.append(views)
+            self.shadow_flat = flat
+            raw = bytes(memoryview(descs).cast("B"))
+            self._cast_descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
+            self._cast_n = (len(params), max(p.numel() for p in params))
+        key = fused.frozen_key(params)
+        if key is None or key != self._shadow_key:
+            st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            nv.check(nv.lib().pvd_cast_f32_to_f16_multi(nv.ptr(self._cast_descs), _u32(self._cast_n[0]), C.c_uint64(self._cast_n[1]), st))
+            self._shadow_key = key
+        return self.shadow_groups
 
     def alloc(self, M):
         if self.trainable and VM_SPLIT_SCATTER:
@@ -217,9 +262,10 @@ class VmOps:
         return out
 
     def algorithmic_bytes(self):
-        """3 (plane, line) pairs x (4 + 2) taps x (16 + 48) components x 4 B, forward; the same again as reductions backward."""
-        b = 3 * (4 + 2) * (16 + 48) * 4
-        return b, (b if self.trainable else 0)
+        """(forward gather, backward reductions) per sample: 3 (plane, line) pairs x (4 + 2) taps x (16 + 48) components x 2 B (fp16
+        shadow) or 4 B gathered; always 4 B per component reduced (fp32 gradients)."""
+        taps = 3 * (4 + 2) * (16 + 48)
+        return taps * (2 if self.plane_f16 else 4), (taps * 4 if self.trainable else 0)
 
 
 class MlpOps:

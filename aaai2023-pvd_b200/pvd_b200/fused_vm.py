@@ -24,7 +24,7 @@ VM_WBLOB_BYTES = 18944
 class PvdVmField(C.Structure):
     _fields_ = [("sigma_mat", C.c_void_p * 3), ("sigma_vec", C.c_void_p * 3), ("color_mat", C.c_void_p * 3),
                 ("color_vec", C.c_void_p * 3), ("wblob", C.c_void_p), ("res", C.c_uint32 * 3), ("aabb", C.c_float * 6),
-                ("sigma_clip_min", C.c_float), ("sigma_clip_max", C.c_float), ("density_scale", C.c_float)]
+                ("sigma_clip_min", C.c_float), ("sigma_clip_max", C.c_float), ("density_scale", C.c_float), ("plane_dtype", C.c_int32)]
 
 
 class PvdVmGrads(C.Structure):
@@ -43,7 +43,9 @@ def _ptrs3(ts):
 
 def _vm_struct(planes, wblob, res, aabb, clip_min, clip_max, density_scale):
     smat, svec, cmat, cvec = planes
-    return PvdVmField(sigma_mat=_ptrs3(smat), sigma_vec=_ptrs3(svec), color_mat=_ptrs3(cmat), color_vec=_ptrs3(cvec),
+    dts = {t.dtype for grp in planes for t in grp}
+    assert len(dts) == 1 and dts <= {torch.float32, torch.float16}, "planes / lines must all be fp32 or all be fp16 shadows"
+    return PvdVmField(plane_dtype=nv.F16 if torch.float16 in dts else nv.F32, sigma_mat=_ptrs3(smat), sigma_vec=_ptrs3(svec), color_mat=_ptrs3(cmat), color_vec=_ptrs3(cvec),
                       wblob=wblob.data_ptr(), res=(C.c_uint32 * 3)(*res), aabb=(C.c_float * 6)(*aabb),
                       sigma_clip_min=clip_min, sigma_clip_max=clip_max, density_scale=density_scale)
 

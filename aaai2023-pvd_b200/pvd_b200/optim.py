@@ -24,8 +24,8 @@ from . import _native as nv
 
 class PvdAdamSlot(C.Structure):
     _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("grad", C.c_void_p),
-                ("grad_f16", C.c_void_p), ("shadow_f16", C.c_void_p), ("n", C.c_uint64), ("lr", C.c_float),
-                ("weight_decay", C.c_float), ("neg_step_size", C.c_float), ("decay", C.c_float), ("zero_grad", C.c_uint32),
+                ("grad_f16", C.c_void_p), ("shadow_f16", C.c_void_p), ("n", C.c_uint64), ("lr", C.c_double),
+                ("weight_decay", C.c_double), ("neg_step_size", C.c_float), ("decay", C.c_float), ("zero_grad", C.c_uint32),
                 ("grad_mul", C.c_float)]
 
 
@@ -165,14 +165,16 @@ def for_engine(engine, lr=1e-2, lr2=1e-3, betas=(0.9, 0.99), eps=1e-15, weight_d
         def post(st):
             nv.check(l.pvd_field_pack_weights(*[nv.ptr(w.data) for w in ws], C.c_uint32(in_dim), nv.ptr(ops.wblob), st))
     elif ops.kind == "vm":
-        off = 0
+        off, k = 0, 0
         for grp, views in zip(ops.groups, ops.grad_groups):
             for p, gv in zip(grp, views):
                 n = p.numel()
                 gh = gh_all[off:off + n] if gh_all is not None else None
                 assert gv.data_ptr() == ops._flat[off:off + n].data_ptr()
-                entries.append(dict(param=p.data, grad=ops._flat[off:off + n], lr=lrs[id(p)], grad_f16=gh, zero_grad=True, grad_mul=big_mul))
+                sh = ops.shadow_flat[k] if ops.plane_f16 else None   # the fp16 shadow the field kernels gather from
+                entries.append(dict(param=p.data, grad=ops._flat[off:off + n], lr=lrs[id(p)], grad_f16=gh, shadow=sh, zero_grad=True, grad_mul=big_mul))
                 off += n
+                k += 1
         ws = [field.basis_mat.weight, field.color_net[0].weight, field.color_net[1].weight, field.color_net[2].weight]
         wg = [torch.zeros_like(w, dtype=torch.float32) for w in ws]
 

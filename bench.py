@@ -208,8 +208,12 @@ def build_engine(args, dev, bitfield):
     bf = torch.from_numpy(bitfield)
     kw = dict(loss_scale=65536.0, device=dev)
     w = args.workload
+    # A TRAINED hash model gathers its fp32 master table in place (table_fp16=False): random 8-byte gathers run at the same sector rate
+    # as 4-byte ones (scripts/micro/red_peak.cu: 231 vs 244 G loads/s), so the per-step fp32 -> fp16 re-cast of the whole table that an
+    # fp16 shadow needs after every optimizer step (63 MB of traffic, the reference's grid.py:52) buys nothing.  The frozen teacher of a
+    # distillation pair keeps its fp16 shadow (cast once, half the L2 footprint).
     if w == "hash":
-        return HashTrainEngine(HashNeRFField(num_levels=args.levels, desired_resolution=2048).to(dev), bf, args.rays, **kw)
+        return HashTrainEngine(HashNeRFField(num_levels=args.levels, desired_resolution=2048, table_fp16=False).to(dev), bf, args.rays, **kw)
     if w == "vm":
         from pvd_b200.fused_vm import VMNeRFField
         return VMTrainEngine(VMNeRFField(resolution0=300).to(dev), bf, args.rays, l1_reg_weight=L1_REG, **kw)
@@ -219,8 +223,8 @@ def build_engine(args, dev, bitfield):
         return PairDistillEngine(tea, VMNeRFField(resolution0=300).to(dev), bf, args.rays, rates=PAIR_RATES, stage=3, l1_reg_weight=L1_REG, **kw)
     from pvd_b200.fused_mlp import MLPNeRFField
     tea = MLPNeRFField().to(dev)
-    return PairDistillEngine(tea, HashNeRFField(num_levels=args.levels, desired_resolution=2048).to(dev), bf, args.rays, rates=PAIR_RATES,
-                             stage=3, **kw)
+    return PairDistillEngine(tea, HashNeRFField(num_levels=args.levels, desired_resolution=2048, table_fp16=False).to(dev), bf, args.rays,
+                             rates=PAIR_RATES, stage=3, **kw)
 
 
 def phase_plan(eng):
@@ -584,7 +588,7 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOADS[workload].format(L=L, R=n_rays), "workload_key": workload,
                    "rays_per_gpu": n_rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
-                   "precision": "fp16 table + fp16 tcgen05 MLP, fp32 planes / accumulate / composite / gradients", "loss_scale": 65536,
+                   "precision": "fp16 tcgen05 MLP (fp32 accumulate); trained hash table gathered as fp32 master, frozen teacher table / vm planes as fp16 shadows; fp32 composite / gradients", "loss_scale": 65536,
                    "step": "fwd+bwd of a trainer with an external optimizer: fp16 table shadow re-cast + weight tiles re-packed at the top of "
                            "EVERY timed step, small weight gradients unpacked to parameter shapes at its end" + ("; gradient exchange inside" if world > 1 else ""),
                    "parallelism": (f"rays sharded over {world} GPU(s), one all-reduce of the gradients per step inside the step graph ({exchange.kind}: "

@@ -119,16 +119,17 @@ int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma
 #define PVD_VM_WBLOB_BYTES 18944u
 
 typedef struct PvdVmField {
-    const float* sigma_mat[3];
-    const float* sigma_vec[3];
-    const float* color_mat[3];
-    const float* color_vec[3];
+    const void* sigma_mat[3]; /* planes [1,16,H,W] / lines [1,16,D,1] / [1,48,..] in channels-last memory ([H][W][R]): the fp32 */
+    const void* sigma_vec[3]; /* parameters themselves (plane_dtype PVD_DTYPE_F32) or an fp16 shadow copy of them (PVD_DTYPE_F16: */
+    const void* color_mat[3]; /* half the gather bytes; gradients are fp32 either way)                                          */
+    const void* color_vec[3];
     const void* wblob;      /* PVD_VM_WBLOB_BYTES from pvd_vm_pack_weights */
     uint32_t res[3];
     float aabb[6];          /* aabb_train: positions are mapped to [-1,1] (network.py:345-350) */
     float sigma_clip_min;   /* clamp of both sigma_feat and color_feat (network.py:353-361) */
     float sigma_clip_max;
     float density_scale;
+    int32_t plane_dtype;    /* PVD_DTYPE_F32 (0) | PVD_DTYPE_F16 (1) */
 } PvdVmField;
 
 typedef struct PvdVmGrads { /* channels-last fp32 gradient buffers, same shapes as the parameters; accumulated into */

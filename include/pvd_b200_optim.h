@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-/* One parameter tensor (dense in memory, any shape: the step is elementwise). 80 bytes. */
+/* One parameter tensor (dense in memory, any shape: the step is elementwise). 88 bytes. */
 typedef struct PvdAdamSlot {
     float* param;          /* fp32 master, n elements */
     float* exp_avg;        /* fp32 first moment */
@@ -36,8 +36,8 @@ typedef struct PvdAdamSlot {
     const void* grad_f16;  /* optional fp16 gradient (the reduced payload of the multi-GPU exchange); read instead of `grad` */
     void* shadow_f16;      /* optional fp16 copy of the updated parameter (the hash table the field kernels gather from) */
     uint64_t n;
-    float lr;              /* per group (network.py:646-683 builds groups with lr / lr2) */
-    float weight_decay;    /* decoupled (AdamW); torch's default 0.01 */
+    double lr;             /* per group (network.py:646-683 builds groups with lr / lr2); double: torch forms lr / bias_correction1 and */
+    double weight_decay;   /* 1 - lr * weight_decay in Python doubles before rounding to fp32.  Decoupled decay (AdamW), torch default 0.01 */
     float neg_step_size;   /* derived by pvd_adamw_advance: -(lr / (1 - beta1^step)) */
     float decay;           /* derived: 1 - lr * weight_decay */
     uint32_t zero_grad;
@@ -72,6 +72,14 @@ int pvd_adamw_advance(PvdAdamState* state, PvdAdamSlot* slots, uint32_t n_slots,
 /* The multi-tensor step over `n_slots` slots (device array). Skipped entirely (gradients still zeroed) when found_inf != 0.
  * found_inf is consumed (cleared) afterwards. */
 int pvd_adamw_step(const PvdAdamState* state, const PvdAdamSlot* slots, uint32_t n_slots, uint64_t max_n, void* stream);
+
+/* Several fp32 -> fp16 casts in one launch (device array of descriptors): the fp16 shadows of the vm planes / lines. */
+typedef struct PvdCastDesc {
+    const float* src;
+    void* dst;
+    uint64_t n;
+} PvdCastDesc;
+int pvd_cast_f32_to_f16_multi(const PvdCastDesc* descs_dev, uint32_t n_descs, uint64_t max_n, void* stream);
 
 /* fp16 -> fp32 (the write-back of an exchanged gradient payload), scaled. */
 int pvd_cast_f16_to_f32(const void* src, float* dst, uint64_t elem_count, float scale, void* stream);

@@ -2,8 +2,10 @@
 (tests/golden/ref_network_golden.npz, generated in the build container by tests/golden/make_network_golden.py: fp32, CPU).
 
 The fused fields compute in the reference's autocast precision (fp16 table / fp16 tensor-core MLP, fp32 accumulation), the golden
-is the fp32 result, so the bound is north_star's fp16 one: relative L2 <= 1e-2 per tensor (recorded in
-gpurun_out/network_golden.json).
+is the fp32 result, so the bound is north_star's fp16 one: relative L2 <= 1e-2 per tensor -- or, where the REFERENCE's own
+autocast path (the same network through oracle/ref_pipeline.py's modules = the reference's kernels + cuBLAS under autocast, run here
+on the same seeded parameters and points) is further than that from the fp32 golden, no further than 1.25 x its distance.  All three
+distances are recorded in gpurun_out/network_golden.json.
 """
 import json
 import os
@@ -48,6 +50,37 @@ def _net(mt):
     return net
 
 
+def _reference_autocast(mt, ref_ext):
+    """{record: value} of the reference's OWN autocast path on the golden's parameters / points (None without oracle/_ref)."""
+    if ref_ext is None or mt == "mlp":
+        return None
+    from oracle import ref_pipeline as rp
+    P = netgold.seeded_params(mt)
+    if mt == "hash":
+        from oracle import cpu
+        offsets, pls = cpu.grid_offsets(3, 14, 16, 19, desired_resolution=2048)
+        net = rp.RefHashNetwork(ref_ext, offsets, pls).cuda()
+        P = {("embeddings" if k == "encoder.embeddings" else k): v for k, v in P.items()}
+    else:
+        net = rp.RefVmNetwork(ref_ext, resolution=netgold.VM_RES).cuda()
+        offsets = None
+    netgold.load_into(net, P)
+    x, d, cs, cc, cf = (t.cuda() for t in netgold.query_points(mt))
+    with torch.autocast("cuda", dtype=torch.float16):
+        sigma, color = net(x, d)
+        feat = net.feature_sigma_color
+        loss = netgold.scalar(sigma.float(), color.float(), feat.float(), cs, cc, cf)
+    scale = 128.0                       # GradScaler-style: keeps the fp16 gradients of the autocast backward out of the subnormals
+    (loss * scale).backward()
+    out = {"sigma": sigma.detach().float().cpu().numpy(), "color": color.detach().float().cpu().numpy(), "feat": feat.detach().float().cpu().numpy()}
+    for name, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        name = "encoder.embeddings" if name == "embeddings" else name
+        out.update(netgold.summarise_grad(name, p.grad.float() / scale, offsets))
+    return out
+
+
 def _dump():
     try:
         os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
@@ -58,7 +91,8 @@ def _dump():
 
 
 @pytest.mark.parametrize("mt", ["hash", "vm", "mlp"])
-def test_fused_field_matches_reference_network_golden(gold, mt):
+def test_fused_field_matches_reference_network_golden(gold, ref_ext, mt):
+    amp = _reference_autocast(mt, ref_ext)
     net = _net(mt)
     net.train()
     x, d, cs, cc, cf = (t.cuda() for t in netgold.query_points(mt))
@@ -66,26 +100,33 @@ def test_fused_field_matches_reference_network_golden(gold, mt):
     feat = net.feature_sigma_color
     netgold.scalar(sigma, color, feat, cs, cc, cf).backward()
     torch.cuda.synchronize()
-    rec = {"sigma": _rel(sigma.detach().cpu().numpy(), gold[f"{mt}/sigma"]), "color": _rel(color.detach().cpu().numpy(), gold[f"{mt}/color"]),
-           "feat": _rel(feat.detach().cpu().numpy(), gold[f"{mt}/feat"])}
+    rec, noise = {}, {}
+
+    def judge(key, ours, golden, ref_amp):
+        if key.startswith("gradsum/"):    # per level (sum f0, sum f1, norm): the sums are signed and cancel; measure them against the norms
+            dist = lambda a: max(_rel(a[:, 2], golden[:, 2]), float(np.abs(a[:, :2] - golden[:, :2]).max() / (np.abs(golden[:, 2]).max() + 1e-30)))
+        else:
+            dist = lambda a: _rel(a, golden)
+        rec[key] = dist(ours)
+        if ref_amp is not None:
+            noise[key] = dist(ref_amp)
+
+    judge("sigma", sigma.detach().cpu().numpy(), gold[f"{mt}/sigma"], amp and amp["sigma"])
+    judge("color", color.detach().cpu().numpy(), gold[f"{mt}/color"], amp and amp["color"])
+    judge("feat", feat.detach().cpu().numpy(), gold[f"{mt}/feat"], amp and amp["feat"])
     offsets = net.encoder.offsets.cpu().numpy() if mt == "hash" else None
     seen = 0
     for name, p in net.named_parameters():
         if p.grad is None:
             continue
         for k, v in netgold.summarise_grad(name, p.grad, offsets).items():
-            g = gold[f"{mt}/{k}"]
-            if k.startswith("gradsum/"):    # per level: the two feature sums are signed and cancel; the norm column is the robust one
-                rec[k + ":norm"] = _rel(v[:, 2], g[:, 2])
-                rec[k + ":sums"] = float(np.abs(v[:, :2] - g[:, :2]).max() / (np.abs(g[:, 2]).max() + 1e-30))
-            else:
-                rec[k] = _rel(v, g)
+            judge(k, v, gold[f"{mt}/{k}"], amp and amp.get(k))
             seen += 1
     assert seen == sum(1 for k in gold if k.startswith(mt + "/grad")), "a parameter received no gradient"
-    _report[mt] = rec
+    _report[mt] = {"ours_vs_golden_fp32": rec, "reference_autocast_vs_golden_fp32": noise}
     _dump()
-    bad = {k: v for k, v in rec.items() if not v <= TOL}
-    assert not bad, f"{mt}: rel-L2 vs the reference network's golden above {TOL}: {bad}"
+    bad = {k: (v, noise.get(k)) for k, v in rec.items() if not (v <= TOL or v <= 1.25 * noise.get(k, 0.0))}
+    assert not bad, f"{mt}: (ours, reference-autocast) rel-L2 vs the reference network's fp32 golden: {bad}"
 
 
 def test_fused_mlp_teacher_forward_matches_golden(gold):
