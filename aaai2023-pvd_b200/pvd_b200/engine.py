@@ -22,6 +22,8 @@ their mean becomes `mean_count`; afterwards M = mean_count rounded up strictly t
 from __future__ import annotations
 
 import ctypes as C
+import contextlib
+import gc
 import os
 
 import numpy as np
@@ -34,6 +36,20 @@ _u32, _f32 = C.c_uint32, C.c_float
 # opt-in experiment (measured SLOWER on B200, 0.129 vs 0.120 ms/step: the full-occupancy scatter CTAs crowd out the MLP CTAs of the
 # other half instead of overlapping with them); the default issues MLP backward and scatter back to back on one stream
 SPLIT_HALVES = os.environ.get("PVD_SPLIT_HALVES", "0") == "1"
+
+
+@contextlib.contextmanager
+def _no_gc():
+    """No cyclic garbage collection while a stream is capturing: collecting some unrelated object that owns pinned host memory (or
+    anything else whose release records a CUDA event) in the middle of a capture invalidates it."""
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class _RaySet:
@@ -307,7 +323,7 @@ class FieldTrainEngine:
         self.step()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with _no_gc(), torch.cuda.graph(g):
             self.step()
         self.graph = g
         return g
@@ -389,7 +405,7 @@ class FieldTrainEngine:
             self._pipelined_step(k, host_io)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with _no_gc(), torch.cuda.graph(g):
                 self._pipelined_step(k, host_io)
             graphs.append(g)
         torch.cuda.synchronize()
@@ -449,6 +465,14 @@ class VMTrainEngine(FieldTrainEngine):
         assert getattr(field, "model_type", None) == "vm"
         super().__init__(field, *a, l1_reg_weight=l1_reg_weight, **k)
 
+
+
+class TensorsTrainEngine(FieldTrainEngine):
+    """tensors (Plenoxels-style dense volume) teacher training (`main_just_train_tea.py --model_type tensors`)."""
+
+    def __init__(self, field, *a, **k):
+        assert getattr(field, "model_type", None) == "tensors"
+        super().__init__(field, *a, **k)
 
 
 PAIR_SUM_STRIDE = 4   # PVD_PAIR_SUM_STRIDE

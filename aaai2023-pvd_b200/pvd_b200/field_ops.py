@@ -298,6 +298,69 @@ class MlpOps:
         return 0, 0   # FLOP-bound: 865 280 FLOP/sample forward
 
 
+class TensorsOps:
+    """model_type "tensors" (fused_tensors.TensorsNeRFField): one trilinear gather of the channels-last-3d volume, no MLP.
+    csrc/field_tensors.cu.  Trains from images (FieldTrainEngine); the reference leaves feature_sigma_color = None for this type
+    (network.py:407), so it takes no part in the feature losses of a distillation pair."""
+    kind = "tensors"
+    kernels_fwd = 1
+    kernels_bwd = 1
+
+    def __init__(self, field, dev, trainable: bool = True):
+        from . import fused_tensors
+        self._ft = fused_tensors
+        self.field, self.dev, self.trainable = field, torch.device(dev), trainable
+        vol = field.tensor_volume[0]
+        assert vol.is_contiguous(memory_format=torch.channels_last_3d), "the plenoxel volume must be torch.channels_last_3d"
+        self._flat = torch.zeros(vol.numel(), dtype=torch.float32, device=self.dev) if trainable else None
+        self.grad_volume = None
+        if trainable:
+            _, Cc, D, H, W = vol.shape
+            self.grad_volume = self._flat.view(1, D, H, W, Cc).permute(0, 4, 1, 2, 3)   # the parameter's shape, channels-last-3d memory
+        self._aabb = [float(v) for v in field.aabb_train.tolist()]
+        self.cfield = None
+        self.wgrads = []
+
+    def stage(self, density_scale=1.0):
+        f = self.field
+        self.cfield = self._ft.tensors_struct(f.tensor_volume[0].detach(), f.plenoxel_degree, self._aabb, float(f.args.sigma_clip_min),
+                                              float(f.args.sigma_clip_max), float(density_scale))
+
+    def alloc(self, M):
+        pass
+
+    def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
+        assert feat is None, "the tensors field has no feature_sigma_color (network.py:407)"
+        nv.check(nv.lib().pvd_tensors_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs), st))
+
+    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status):
+        nv.check(nv.lib().pvd_tensors_field_backward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(grad_sigmas), nv.ptr(grad_rgbs),
+                                                     _u32(M), nv.ptr(n_valid), nv.ptr(self._flat), st))
+
+    def clear_grads(self):
+        self._flat.zero_()
+
+    def big_grad(self):
+        return self._flat
+
+    def regularise(self, st, loss_scale, loss_slots, weight):
+        pass
+
+    def unpack_weight_grads(self, gw_ws, st):
+        pass
+
+    def weight_grads(self, gw_ws):
+        return {}
+
+    def grads(self, gw_ws):
+        return {"tensor_volume.0": self.grad_volume}
+
+    def algorithmic_bytes(self):
+        """8 corners x C channels x 4 B gathered forward; the same again re-gathered + reduced backward."""
+        b = 8 * (3 * self.field.plenoxel_degree ** 2 + 1) * 4
+        return b, (2 * b if self.trainable else 0)
+
+
 def make_ops(field, dev, trainable):
     mt = getattr(field, "model_type", None)
     if mt == "hash":
@@ -306,4 +369,6 @@ def make_ops(field, dev, trainable):
         return VmOps(field, dev, trainable)
     if mt == "mlp":
         return MlpOps(field, dev, trainable)
-    raise ValueError(f"no fused field for model_type {mt!r} (hash | vm | mlp)")
+    if mt == "tensors":
+        return TensorsOps(field, dev, trainable)
+    raise ValueError(f"no fused field for model_type {mt!r} (hash | vm | mlp | tensors)")

@@ -39,8 +39,15 @@ ADDCMUL_LEFT = 1
 
 
 def _dense(p: torch.Tensor) -> bool:
-    """True when the tensor's elements occupy one gap-free block of memory (any permutation of a contiguous layout)."""
-    return p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last) or p.numel() == p.untyped_storage().nbytes() // p.element_size()
+    """True when the tensor's elements occupy one gap-free block of memory (any permutation of a contiguous layout: row-major,
+    channels_last, channels_last_3d, ...)."""
+    dims = sorted(((st, sz) for st, sz in zip(p.stride(), p.shape) if sz > 1), key=lambda t: t[0])
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
 
 
 class FusedAdamW:
@@ -183,6 +190,11 @@ def for_engine(engine, lr=1e-2, lr2=1e-3, betas=(0.9, 0.99), eps=1e-15, weight_d
 
         def post(st):
             nv.check(l.pvd_vm_pack_weights(*[nv.ptr(w.data) for w in ws], nv.ptr(ops.wblob), st))
+    elif ops.kind == "tensors":
+        vol = field.tensor_volume[0]
+        entries.append(dict(param=vol.data, grad=ops._flat, lr=lrs[id(vol)], grad_f16=gh_all, zero_grad=True, grad_mul=big_mul))
+        ws, wg = [], []
+        pre = post = lambda st: None
     else:
         raise ValueError(f"no fused optimizer wiring for model_type {ops.kind!r}")
     for w, g in zip(ws, wg):

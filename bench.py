@@ -18,6 +18,7 @@ One JSON line on rank 0 (keys: see the repo's DESIGN.md "measurement").
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -623,7 +624,12 @@ def run_ours(args, rank, world, local):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # The cyclic garbage collector must not run while a stream is capturing: a collected engine of an EARLIER workload owns pinned host
+    # buffers whose release records CUDA events, which invalidates the capture in progress.  Collect explicitly between workloads.
+    gc.disable()
     head = measure_ours(args, args.workload, args.rays, rank, world, local, headline=True)
+    gc.collect()
+    torch.cuda.synchronize()
     # the other BASELINE configurations in the same line (shorter runs): configs[1]-[4] all measured by one invocation
     others = {}
     if args.all_workloads:
@@ -637,8 +643,24 @@ def run_ours(args, rank, world, local):
                 others[w]["config"] = {k: r["config"][k] for k in ("workload", "rays_per_gpu", "samples_per_step", "M_rows")}
             except Exception as ex:  # noqa: BLE001  (a secondary workload must not take the headline line down)
                 others[w] = {"error": repr(ex)[:300]}
-                torch.cuda.empty_cache()
+            gc.collect()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+    strong = None
+    if world > 1 and args.strong:
+        # strong scaling beside the weak headline: the SAME total batch (args.rays) split over the ranks
+        try:
+            per = max(128, args.rays // world)
+            r = measure_ours(args, args.workload, per, rank, world, local, headline=False)
+            strong = {"rays_total": per * world, "rays_per_gpu": per, "value": r["value"], "unit": "rays/s", "ms_per_step": r["ms_per_step"],
+                      "steps": r["steps"], "e2e": r["e2e"], "note": "same step, total batch fixed: per-GPU work shrinks with N, the gradient exchange does not"}
+        except Exception as ex:  # noqa: BLE001
+            strong = {"error": repr(ex)[:300]}
+        gc.collect()
+        torch.cuda.synchronize()
     if rank == 0:
+        if strong is not None:
+            head["strong_scaling"] = strong
         head["workloads"] = {args.workload: {k: head[k] for k in ("value", "unit", "ms_per_step", "serial_ms_per_step", "steps", "e2e", "roofline", "kernel_ms",
                                                                    "gpu_launches", "ms_per_step_no_restage", "iteration") if k in head}}
         head["workloads"][args.workload]["config"] = {k: head["config"][k] for k in ("workload", "rays_per_gpu", "samples_per_step", "M_rows")}
@@ -780,6 +802,7 @@ def run_reference(args, rank, world, local):
         return
     torch.cuda.set_device(local)
     out = measure_reference(args, args.workload, args.rays, local, ext, args.steps)
+    gc.collect()
     if world > 1:
         out["note"] = f"launched under torchrun with {world} ranks: ONE-GPU reference (the reference has no multi-GPU path), rank 0 only"
     out["workloads"] = {args.workload: {k: out[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "iteration") if k in out}}
@@ -817,6 +840,7 @@ def main():
     ap.add_argument("--only", dest="all_workloads", action="store_false", help="measure only --workload (default: the other BASELINE configurations "
                     "are measured too, with --secondary-steps steps each, and reported under \"workloads\")")
     ap.add_argument("--secondary-steps", type=int, default=50)
+    ap.add_argument("--no-strong", dest="strong", action="store_false", help="N > 1: skip the strong-scaling measurement (same total batch split over the ranks)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-pipeline", action="store_true", help="serial step graph: do not overlap the next batch's march with the backward")
     args = ap.parse_args()

@@ -242,6 +242,34 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
                                      uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream);
 int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * "tensors" (Plenoxels-style) field: NeRFNetwork.forward for model_type "tensors" (distill_mutual/network.py:184-191,311-322,383-409):
+ * one trilinear grid_sample (align_corners=True, zero padding) of the [1, C, D, H, W] volume, C = 3 * degree^2 + 1, then
+ * sigma = trunc_exp(clamp(h[0])), rgb_k = sigmoid(sum_j h[1 + k * degree^2 + j] * SH_j(dir)).  `volume` is the parameter in
+ * torch.channels_last_3d memory ([D][H][W][C]).  Supported: degree 1 and 3 (C = 4, 28: the kernels move four channels per lane;
+ * the reference's default is 3, main_distill_mutual.py:218).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct PvdTensorsField {
+    const float* volume;
+    uint32_t res[3];        /* D, H, W */
+    uint32_t degree;        /* plenoxel_degree */
+    float aabb[6];          /* aabb_train */
+    float sigma_clip_min;
+    float sigma_clip_max;
+    float density_scale;
+} PvdTensorsField;
+int pvd_tensors_field_forward(const PvdTensorsField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                              void* stream);
+/* accumulates into grad_volume (same layout as volume, fp32); rows at or above *n_valid (if given) contribute nothing */
+int pvd_tensors_field_backward(const PvdTensorsField* field, const float* xyzs, const float* dirs, const float* grad_sigmas,
+                               const float* grad_rgbs, uint32_t M, const int32_t* n_valid, float* grad_volume, void* stream);
+
+/* get_rays (distill_mutual/utils.py:324-404) on the device: poses [B, 4, 4] row-major cam2world, intrinsics (fx, fy, cx, cy), pixel
+ * indices inds [B, N] int64 (element (b, n) at inds[b * inds_batch_stride + n]; stride 0 = one index row shared by all poses, as the
+ * reference's `inds.expand([B, N])`; NULL = all H*W pixels in order) -> rays_o, rays_d [B, N, 3]. */
+int pvd_get_rays(const float* poses, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, const int64_t* inds,
+                 uint32_t inds_batch_stride, uint32_t B, uint32_t N, float* rays_o, float* rays_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

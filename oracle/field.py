@@ -280,3 +280,34 @@ def mlp_field_forward(x, d, nerf_w, nerf_b, tail_ws, PE=10, skips=3, clip_min=-2
     c = q(F.relu(F.linear(q(c), q(wc0))))
     c = q(F.relu(F.linear(c, q(wc1))))
     return sigma, torch.sigmoid(F.linear(c, q(wc2))), feat
+
+
+# ------------------------------------------------------------------------------------------------ tensors (Plenoxels-style) field
+def tensors_field_forward(x, d, volume, degree, aabb, clip_min=-2.0, clip_max=7.0):
+    """`NeRFNetwork.forward` for model_type "tensors" (network.py:311-322 compute_plenoxel_fea, :383-409): trilinear
+    F.grid_sample (align_corners=True) of volume [1, C, D, H, W], C = 3 degree^2 + 1; sigma = trunc_exp(clamp(h0));
+    rgb_k = sigmoid(sum_j h[1 + k degree^2 + j] SH_j(d)).  Returns sigma [N], color [N, 3]."""
+    xn = 2 * (x - aabb[:3]) / (aabb[3:] - aabb[:3]) - 1
+    h = F.grid_sample(volume, xn.view(1, 1, -1, 1, 3), align_corners=True).view(-1, x.shape[0]).permute(1, 0)   # [N, C]
+    h0 = torch.clamp(h[..., 0], clip_min, clip_max)
+    sigma = _TruncExp.apply(h0)
+    sh = h[..., 1:].view(-1, 3, degree ** 2)
+    enc = torch.from_numpy(cpu.sh_encode_forward(d.detach().numpy(), degree)).unsqueeze(1)
+    color = torch.sigmoid((sh * enc).sum(-1))
+    return sigma, color
+
+
+def get_rays(poses, intrinsics, H, W, inds=None):
+    """get_rays (distill_mutual/utils.py:324-404) for given pixel indices inds [B, N] (None: all pixels): rays_o, rays_d [B, N, 3]."""
+    fx, fy, cx, cy = intrinsics
+    B = poses.shape[0]
+    if inds is None:
+        inds = torch.arange(H * W).expand([B, H * W])
+    i = (inds % W).float() + 0.5
+    j = torch.div(inds, W, rounding_mode="floor").float() + 0.5
+    zs = torch.ones_like(i)
+    directions = torch.stack(((i - cx) / fx * zs, (j - cy) / fy * zs, zs), dim=-1)
+    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
+    rays_d = directions @ poses[:, :3, :3].transpose(-1, -2)
+    rays_o = poses[..., :3, 3][..., None, :].expand_as(rays_d)
+    return rays_o, rays_d

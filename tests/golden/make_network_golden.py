@@ -24,8 +24,8 @@ import refnet  # noqa: E402
 
 
 def build(net_mod, model_type):
-    args = refnet.make_args(resolution0=netgold.VM_RES)
-    net = net_mod.NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10, bg_radius=-1,
+    args = refnet.make_args(resolution0=netgold.VM_RES, plenoxel_degree=3, plenoxel_res=str(list(netgold.TENSORS_RES)))
+    net = refnet.construct(net_mod.NeRFNetwork, encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10, bg_radius=-1,
                               model_type=model_type, args=args, is_teacher=False)
     netgold.load_into(net, netgold.seeded_params(model_type))
     return refnet.cpu_standins(net)
@@ -35,17 +35,18 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     net_mod, _ = refnet.load()
     out = {}
-    for mt in ("hash", "vm", "mlp"):
+    for mt in ("hash", "vm", "mlp", "tensors"):
         net = build(net_mod, mt)
         net.train()
         x, d, cs, cc, cf = netgold.query_points(mt)
         sigma, color = net(x, d)
         feat = net.feature_sigma_color
-        assert torch.equal(net.sigma_l, feat[..., 0]) and net.color_l is color
+        assert net.color_l is color and (feat is None if mt == "tensors" else torch.equal(net.sigma_l, feat[..., 0]))
         netgold.scalar(sigma, color, feat, cs, cc, cf).backward()
         out[f"{mt}/sigma"] = sigma.detach().numpy()
         out[f"{mt}/color"] = color.detach().numpy()
-        out[f"{mt}/feat"] = feat.detach().numpy()
+        if feat is not None:
+            out[f"{mt}/feat"] = feat.detach().numpy()
         offsets = net.encoder.enc.offsets.numpy() if mt == "hash" else None
         for name, p in net.named_parameters():
             name = name.replace("encoder.enc.", "encoder.")

@@ -22,7 +22,9 @@ SHAPES = {
            + [("sigma_net.0.weight", (64, 28)), ("sigma_net.1.weight", (16, 64)), ("color_net.0.weight", (64, 31)),
               ("color_net.1.weight", (64, 64)), ("color_net.2.weight", (3, 64))],
 }
-SEEDS = {"hash": 101, "vm": 202, "mlp": 303}
+TENSORS_RES = (12, 10, 14)   # D, H, W of the golden's plenoxel volume (degree 3 -> 28 channels)
+SHAPES["tensors"] = [("tensor_volume.0", (1, 28) + TENSORS_RES)]
+SEEDS = {"hash": 101, "vm": 202, "mlp": 303, "tensors": 404}
 
 
 def seeded_params(model_type: str) -> dict:
@@ -34,6 +36,8 @@ def seeded_params(model_type: str) -> dict:
             a = rs.uniform(-0.5, 0.5, shape)
         elif name.startswith(("sigma_mat", "sigma_vec", "color_mat", "color_vec")):
             a = 0.4 * rs.standard_normal(shape)
+        elif name.startswith("tensor_volume"):
+            a = 0.8 * rs.standard_normal(shape)
         elif name.endswith("bias"):
             a = rs.uniform(-0.1, 0.1, shape)
         else:  # Linear weight [out, in]: keeps activations of order one through the ReLU stacks
@@ -63,8 +67,9 @@ def load_into(module: torch.nn.Module, params: dict):
 
 
 def scalar(sigma, color, feat, cs, cc, cf):
-    """The fixed scalar whose gradients are committed: <sigma, cs> + <color, cc> + <feat, cf>."""
-    return (sigma * cs).sum() + (color * cc).sum() + (feat * cf).sum()
+    """The fixed scalar whose gradients are committed: <sigma, cs> + <color, cc> + <feat, cf> (feat None for the tensors model)."""
+    out = (sigma * cs).sum() + (color * cc).sum()
+    return out if feat is None else out + (feat * cf).sum()
 
 
 SMALL = 8192   # gradients of tensors up to this many elements are stored whole; larger ones as summaries

@@ -90,6 +90,17 @@ def make_args(**over):
     return a
 
 
+def construct(cls, *a, **k):
+    """Construct a reference module on a box without a GPU: `init_plenoxel_volume` calls `.cuda()` on its ParameterList
+    (network.py:191); that one call is made a no-op for the duration of the constructor."""
+    orig = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, device=None: self
+    try:
+        return cls(*a, **k)
+    finally:
+        torch.nn.Module.cuda = orig
+
+
 class _CpuGrid(torch.nn.Module):
     """GridEncoder.forward(x, bound) on the CPU through the C oracle (differentiable w.r.t. the table)."""
 

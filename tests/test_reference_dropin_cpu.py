@@ -43,6 +43,10 @@ def _oracle_forward(mt, P, x, d):
         aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
         return field.vm_field_forward(x, d, g("sigma_mat"), g("sigma_vec"), g("color_mat"), g("color_vec"), P["basis_mat.weight"],
                                       [P[f"color_net.{i}.weight"] for i in range(3)], aabb), None
+    if mt == "tensors":
+        aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+        sigma, color = field.tensors_field_forward(x, d, P["tensor_volume.0"], 3, aabb)
+        return (sigma, color, None), None
     nw = [P[f"nerf_mlp.{i}.weight"] for i in range(8)]
     nb = [P[f"nerf_mlp.{i}.bias"] for i in range(8)]
     tw = [P[k] for k in ("sigma_net.0.weight", "sigma_net.1.weight", "color_net.0.weight", "color_net.1.weight", "color_net.2.weight")]
@@ -56,7 +60,10 @@ def check_against_gold(gold, mt, sigma, color, feat, grads, offsets, rtol, atol_
         np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_scale * max(float(np.abs(b).max()), 1e-30), err_msg=f"{mt}: {what}")
     close(sigma.detach().cpu().numpy(), gold[f"{mt}/sigma"], "sigma")
     close(color.detach().cpu().numpy(), gold[f"{mt}/color"], "color")
-    close(feat.detach().cpu().numpy(), gold[f"{mt}/feat"], "feature_sigma_color")
+    if feat is not None:
+        close(feat.detach().cpu().numpy(), gold[f"{mt}/feat"], "feature_sigma_color")
+    else:
+        assert f"{mt}/feat" not in gold
     seen = 0
     for name, g in grads.items():
         for k, v in netgold.summarise_grad(name, g, offsets).items():
@@ -67,7 +74,7 @@ def check_against_gold(gold, mt, sigma, color, feat, grads, offsets, rtol, atol_
     assert seen == want, f"{mt}: compared {seen} gradient records, golden holds {want}"
 
 
-@pytest.mark.parametrize("mt", ["hash", "vm", "mlp"])
+@pytest.mark.parametrize("mt", ["hash", "vm", "mlp", "tensors"])
 def test_oracle_networks_match_reference_golden(gold, mt):
     """oracle/field.py::{hash,vm,mlp}_field_forward (fp32) == the reference's NeRFNetwork.forward, values and all gradients."""
     P = {k: v.clone().requires_grad_(True) for k, v in netgold.seeded_params(mt).items()}
@@ -84,15 +91,19 @@ def ref_modules():
 
 
 def _ref_net(net_mod, mt, res=netgold.VM_RES):
-    return net_mod.NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10, bg_radius=-1,
-                               model_type=mt, args=refnet.make_args(resolution0=res), is_teacher=False)
+    args = refnet.make_args(resolution0=res, plenoxel_degree=3, plenoxel_res=str(list(netgold.TENSORS_RES)))
+    return refnet.construct(net_mod.NeRFNetwork, encoding="hashgrid", bound=1, cuda_ray=True, density_scale=1, min_near=0.2, density_thresh=10,
+                            bg_radius=-1, model_type=mt, args=args, is_teacher=False)
 
 
 def _our_net(mt, res=netgold.VM_RES):
     from pvd_b200.fused import HashNeRFField
     from pvd_b200.fused_mlp import MLPNeRFField
+    from pvd_b200.fused_tensors import TensorsNeRFField
     from pvd_b200.fused_vm import VMNeRFField
     kw = dict(cuda_ray=True, density_thresh=10)
+    if mt == "tensors":
+        return TensorsNeRFField(plenoxel_degree=3, plenoxel_res=netgold.TENSORS_RES, **kw)
     if mt == "hash":
         return HashNeRFField(num_levels=14, desired_resolution=2048, **kw)
     if mt == "vm":
@@ -101,7 +112,7 @@ def _our_net(mt, res=netgold.VM_RES):
 
 
 @needs_ref
-@pytest.mark.parametrize("mt", ["hash", "vm", "mlp"])
+@pytest.mark.parametrize("mt", ["hash", "vm", "mlp", "tensors"])
 def test_reference_network_constructs_over_dropin_packages(ref_modules, mt):
     net_mod, ren_mod = ref_modules
     ref = _ref_net(net_mod, mt)
@@ -126,7 +137,7 @@ def test_reference_network_constructs_over_dropin_packages(ref_modules, mt):
 
 
 @needs_ref
-@pytest.mark.parametrize("mt", ["hash", "vm", "mlp"])
+@pytest.mark.parametrize("mt", ["hash", "vm", "mlp", "tensors"])
 def test_golden_vectors_are_current(ref_modules, gold, mt):
     """Re-run the reference's forward/backward here: the committed golden must be exactly what it produces."""
     net_mod, _ = ref_modules
@@ -155,3 +166,24 @@ def test_reference_trunc_exp_and_freq_encoder_are_the_dropins(ref_modules):
     y.sum().backward()
     torch.testing.assert_close(y, torch.exp(x.detach()))
     torch.testing.assert_close(x.grad, torch.exp(x.detach().clamp(-12, 12)))       # tools/activation.py:15-21
+
+
+def test_oracle_get_rays_is_the_reference_formula():
+    """oracle/field.py::get_rays against a direct evaluation of utils.py:391-399 in float64, full frame and chosen pixels."""
+    from oracle import field
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 9, 7
+    poses = torch.eye(4).repeat(B, 1, 1)
+    poses[:, :3, :3] = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    poses[:, :3, 3] = torch.randn(B, 3, generator=g)
+    intr = (11.0, 12.5, 3.4, 4.6)
+    inds = torch.randint(0, H * W, (B, 5), generator=g)
+    for sel in (None, inds):
+        ro, rd = field.get_rays(poses, intr, H, W, sel)
+        idx = torch.arange(H * W).expand(B, H * W) if sel is None else sel
+        i, j = (idx % W).double() + 0.5, (idx // W).double() + 0.5
+        dirs = torch.stack(((i - intr[2]) / intr[0], (j - intr[3]) / intr[1], torch.ones_like(i)), -1)
+        dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+        want = dirs @ poses[:, :3, :3].double().transpose(-1, -2)
+        torch.testing.assert_close(rd.double(), want, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(ro, poses[:, :3, 3][:, None, :].expand_as(rd))
