@@ -160,18 +160,19 @@ __device__ __forceinline__ void stage_weights(uint8_t* smw, const uint8_t* __res
 // =============================================================================================== forward kernel
 // TMA_IN: the tile's sample block -- 128 consecutive rows of xyzs and of dirs, 1536 contiguous bytes each -- is staged into shared
 // memory by two TMA bulk copies (cp.async.bulk, mbarrier complete_tx) issued by one thread: the first tile's while the CTA is still in
-// its prologue (TMEM allocation, level table, barrier), every further tile's one iteration ahead (double buffered), so no thread
-// ever waits on a global load for its position / direction.  A tile whose byte count is not a multiple of 16 (only the last, when
-// M % 4 != 0) is loaded per thread.
+// its prologue (TMEM allocation, level table, barrier), a further tile's as soon as the previous tile's last layer has completed.
+// The staging area is the first 3 KB of the H1/H3/H4 activation tile, which is dead between a tile's last MMA and the next tile's
+// first epilogue -- no shared memory is added (a first version with its own double buffer cost 8 KB per CTA, the fourth resident
+// CTA per SM with it, and ran 48.8 us instead of 32.0: profiles/README.md).  A tile whose byte count is not a multiple of 16 (only
+// the last, when M % 4 != 0) is loaded per thread.
 template <typename T, bool TMA_IN>
 __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                         uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                         __half* __restrict__ enc, float* __restrict__ feat16, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar, wbar, sbar[2];
+    __shared__ uint64_t bar, wbar, sbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelInfo lv[16];
-    __shared__ __align__(16) float sxyz[TMA_IN ? 2 : 1][TMA_IN ? kTile * 3 : 1], sdir[TMA_IN ? 2 : 1][TMA_IN ? kTile * 3 : 1];
     // Forward-only tiles alias: the encoding X is dead once layer 1's MMAs completed, so the colour-net input CIN reuses its
     // buffer; H1, H3, H4 are each dead when the next one is written (its consumer MMA has been waited for).  44 KB per CTA
     // instead of 68 KB -> 4 resident CTAs per SM (the TMEM limit) instead of 3, i.e. one tile per CTA at 4096 rays.
@@ -180,6 +181,8 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     uint8_t* CIN = X;
     uint8_t* HA = X + 8192;                            // 16384 (H1, then H3, then H4)
     uint8_t* HB = HA;
+    float* const sxyz = reinterpret_cast<float*>(HA);            // TMA_IN staging: 2 x 1536 B at the head of the activation tile
+    float* const sdir = sxyz + kTile * 3;
     const uint32_t tid = threadIdx.x;
 
     if (tid == 0) {
@@ -197,22 +200,19 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     auto tile_rows = [&](uint32_t tile) { return min(kTile, M - tile * kTile); };
     auto tma_tile = [&](uint32_t tile) { return TMA_IN && (tile_rows(tile) & 3u) == 0u; };   // 12 B rows: a multiple of 16 bytes
-    auto stage_samples = [&](uint32_t tile, uint32_t buf) {   // thread 0
+    auto stage_samples = [&](uint32_t tile) {   // thread 0
         const uint32_t bytes = tile_rows(tile) * 12u;
-        tc5::mbar_expect_tx(&sbar[buf], 2u * bytes);
-        tc5::bulk_g2s(tc5::smem_u32(sxyz[buf]), xyzs + 3 * (size_t)tile * kTile, bytes, &sbar[buf]);
-        tc5::bulk_g2s(tc5::smem_u32(sdir[buf]), dirs + 3 * (size_t)tile * kTile, bytes, &sbar[buf]);
+        tc5::mbar_expect_tx(&sbar, 2u * bytes);
+        tc5::bulk_g2s(tc5::smem_u32(sxyz), xyzs + 3 * (size_t)tile * kTile, bytes, &sbar);
+        tc5::bulk_g2s(tc5::smem_u32(sdir), dirs + 3 * (size_t)tile * kTile, bytes, &sbar);
     };
     if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
     if (tid == 0) {
         tc5::mbar_init(&bar, 1);
         tc5::mbar_init(&wbar, 1);
-        if (TMA_IN) {
-            tc5::mbar_init(&sbar[0], 1);
-            tc5::mbar_init(&sbar[1], 1);
-        }
+        if (TMA_IN) tc5::mbar_init(&sbar, 1);
         tc5::mbar_fence_init();
-        if (TMA_IN && blockIdx.x < n_tiles && tma_tile(blockIdx.x)) stage_samples(blockIdx.x, 0u);  // first: the gather waits on it
+        if (TMA_IN && blockIdx.x < n_tiles && tma_tile(blockIdx.x)) stage_samples(blockIdx.x);  // first: the gather waits on it
         stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile is gathered
     }
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
@@ -226,24 +226,24 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
     const T* table = reinterpret_cast<const T*>(a.table);
     const uint32_t lv_saddr = tc5::smem_u32(lv);
 
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    uint32_t n_staged = 0;   // TMA-staged tiles so far: the parity of `sbar` to wait for
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t row = tile * kTile + tid;
         const bool live = row < M;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         if (tma_tile(tile)) {
-            const uint32_t buf = it & 1u;
-            if (!tc5::mbar_wait(&sbar[buf], (it >> 1) & 1u)) atomicExch(status, 4);
+            // a tile after the first: the previous tile's last MMA (the only reader of the activation tile) has been waited for by
+            // every thread, so the staging area is free; the first tile's copy was issued in the prologue
+            if (tile != blockIdx.x && tid == 0) stage_samples(tile);
+            if (!tc5::mbar_wait(&sbar, n_staged & 1u)) atomicExch(status, 4);
+            ++n_staged;
             if (live) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    pos[d] = sxyz[buf][3 * tid + d];
-                    dir[d] = sdir[buf][3 * tid + d];
+                    pos[d] = sxyz[3 * tid + d];
+                    dir[d] = sdir[3 * tid + d];
                 }
             }
-            // the other buffer was last read one iteration ago, before that iteration's barriers: free to be overwritten
-            const uint32_t next = tile + gridDim.x;
-            if (tid == 0 && next < n_tiles && tma_tile(next)) stage_samples(next, buf ^ 1u);
         } else if (live) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {

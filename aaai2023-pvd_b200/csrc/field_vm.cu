@@ -334,16 +334,18 @@ __device__ __forceinline__ void vm_mlp_forward(Pipe& p, const VmArgs& a, uint8_t
 
 // =============================================================================================== forward
 template <bool PF16>
-__global__ void __launch_bounds__(128, 3) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
+__global__ void __launch_bounds__(128, 4) k_vm_field_fwd(VmArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                       uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
                                                       float* __restrict__ feat16, int32_t* status) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];   // no-swizzle operand tiles need 16 B; 1024 would pad the static part by 1.5 KB and cost the 4th CTA
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float sfeat[kTile];
     uint8_t* smw = smem;                          // 18944
+    // APP is dead once the basis GEMM has completed: CIN aliases its first 8 KB and the H3 / H4 activation tile the next 16 KB, so the
+    // CTA needs 54.5 KB and FOUR of them fit an SM (592 slots for the 576 tiles of a 4096-ray batch: one wave instead of 1.3)
     uint8_t* APP = smem + PVD_VM_WBLOB_BYTES;     // 36864 ; CIN aliases its first 8 KB
-    uint8_t* H = APP + 36864;                     // 16384 ; H3 then H4
+    uint8_t* H = APP + 8192;                      // 16384 ; H3 then H4, inside the dead APP tile
     const uint32_t tid = threadIdx.x;
     // TMEM first: the SM does not launch the next CTA of a tcgen05 kernel until the previous one has relinquished its allocation
     // permit (measured: scripts/micro/cta_launch.cu), so anything placed before the alloc delays every later CTA of the SM.
@@ -852,7 +854,7 @@ static bool to_vm_args(const PvdVmField* f, VmArgs& a) {
     return a.wblob != nullptr;
 }
 
-constexpr size_t kVmFwdSmem = PVD_VM_WBLOB_BYTES + 36864 + 16384;                       // 72192
+constexpr size_t kVmFwdSmem = PVD_VM_WBLOB_BYTES + 36864;                               // 55808
 constexpr size_t kVmBwdSmem = PVD_VM_WBLOB_BYTES + 36864 + 8192 + 16384 + 16384 + 4096; // 100864
 
 }  // namespace pvd
@@ -876,7 +878,7 @@ int pvd_vm_field_forward(const PvdVmField* f, const float* xyzs, const float* di
     VmArgs a;
     if (!to_vm_args(f, a)) return PVD_EINVAL;
     const uint32_t tiles = (M + kTile - 1) / kTile;
-    const uint32_t grid = min(tiles, (uint32_t)(3 * sm_count()));
+    const uint32_t grid = min(tiles, (uint32_t)(4 * sm_count()));
     if (vm_planes_f16(f)) {
         cudaError_t e = cudaFuncSetAttribute(k_vm_field_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVmFwdSmem);
         if (e != cudaSuccess) return (int)e;

@@ -794,92 +794,6 @@ __global__ void __launch_bounds__(32) k_composite_train_mse(const float* __restr
     const float gt0 = gt_rgb[3 * (size_t)index], gt1 = gt_rgb[3 * (size_t)index + 1], gt2 = gt_rgb[3 * (size_t)index + 2];
     const float bgr = bg[0], bgg = bg[1], bgb = bg[2];
     float r = 0, g = 0, b = 0, ws = 0, d = 0;
-    // ---- rays of at most 256 samples (nearly all: dt = 2 sqrt(3) / 1024 and the scene's occupied stretches are short): every load of the
-    // ray is issued up front (ONE memory latency), and everything the backward sweep needs -- the weights, the transmittance after
-    // each sample, the running colour / weight sums -- stays in registers from the forward sweep, so the second sweep neither
-    // re-loads nor re-scans.  Same operations in the same order as the general path below: identical results.
-    if (!skip && cnt <= 256u) {
-        constexpr int Q = 8;
-        float sg[Q], c0[Q], c1[Q], c2[Q], wq[Q], ta[Q], rr[Q], gg_[Q], bb[Q], ww[Q];
-        float2 dl[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t i = 32u * q + lane;
-            const bool ok = i < cnt;
-            const size_t row = (size_t)offset + (ok ? i : 0);
-            sg[q] = ok ? __ldg(sigmas + row) : 0.0f;
-            dl[q] = ok ? __ldg(reinterpret_cast<const float2*>(deltas + 2 * row)) : make_float2(0.f, 0.f);
-            c0[q] = ok ? __ldg(rgbs + 3 * row) : 0.f;
-            c1[q] = ok ? __ldg(rgbs + 3 * row + 1) : 0.f;
-            c2[q] = ok ? __ldg(rgbs + 3 * row + 2) : 0.f;
-        }
-        float T = 1.0f, tcarry = 0.0f, rc = 0, gc = 0, bc = 0, wc = 0;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t base = 32u * q;
-            if (base >= cnt) break;  // warp-uniform
-            const bool ok = base + lane < cnt;
-            const float alpha = ok ? 1.0f - __expf(-sg[q] * dl[q].x) : 0.0f;
-            const float om = 1.0f - alpha;
-            const float incl = warp_scan_mul(om, lane);
-            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = 1.0f;
-            const float w = alpha * (T * excl);
-            const float tin = tcarry + warp_scan_add(dl[q].y, lane);
-            if (ok) {
-                r += w * c0[q];
-                g += w * c1[q];
-                b += w * c2[q];
-                d += w * tin;
-                ws += w;
-            }
-            wq[q] = w;
-            ta[q] = T * incl;
-            rr[q] = rc + warp_scan_add(w * c0[q], lane);
-            gg_[q] = gc + warp_scan_add(w * c1[q], lane);
-            bb[q] = bc + warp_scan_add(w * c2[q], lane);
-            ww[q] = wc + warp_scan_add(w, lane);
-            T *= __shfl_sync(0xffffffffu, incl, 31);
-            tcarry = __shfl_sync(0xffffffffu, tin, 31);
-            rc = __shfl_sync(0xffffffffu, rr[q], 31);
-            gc = __shfl_sync(0xffffffffu, gg_[q], 31);
-            bc = __shfl_sync(0xffffffffu, bb[q], 31);
-            wc = __shfl_sync(0xffffffffu, ww[q], 31);
-        }
-        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
-        if (lane == 0) {
-            weights_sum[index] = ws;
-            depth[index] = d;
-            image[3 * (size_t)index] = r;
-            image[3 * (size_t)index + 1] = g;
-            image[3 * (size_t)index + 2] = b;
-        }
-        const float om_f = 1.0f - ws;
-        const float dr = r + om_f * bgr - gt0, dg = g + om_f * bgg - gt1, db = b + om_f * bgb - gt2;
-        const float k = 2.0f / (3.0f * (float)N);
-        if (lane == 0) {
-            float* slot = loss_out + 2u * (n % PVD_LOSS_SLOTS);
-            atomicAdd(slot, (dr * dr + dg * dg + db * db) / (3.0f * (float)N));
-            atomicAdd(slot + 1, 1.0f);
-        }
-        const float gr = k * dr * loss_scale, gg = k * dg * loss_scale, gb = k * db * loss_scale;
-        const float gws = -(gr * bgr + gg * bgg + gb * bgb);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t i = 32u * q + lane;
-            if (32u * q >= cnt) break;  // warp-uniform
-            if (i < cnt) {
-                const size_t row = (size_t)offset + i;
-                const float w = wq[q], T_after = ta[q], d0 = dl[q].x;
-                grad_rgbs[3 * row] = gr * w;
-                grad_rgbs[3 * row + 1] = gg * w;
-                grad_rgbs[3 * row + 2] = gb * w;
-                grad_sigmas[row] = d0 * (gr * (T_after * c0[q] - (r - rr[q])) + gg * (T_after * c1[q] - (g - gg_[q])) +
-                                         gb * (T_after * c2[q] - (b - bb[q])) + gws * (T_after - (ws - ww[q])));
-            }
-        }
-        return;
-    }
     if (!skip) {
         float T = 1.0f, tcarry = 0.0f;
         for (uint32_t base0 = 0; base0 < cnt; base0 += 128) {

@@ -24,6 +24,10 @@ COLS = {
     "regs": "launch__registers_per_thread",
     "grid": "launch__grid_size",
     "smem_dyn": "launch__shared_mem_per_block_dynamic",
+    # L2-side work of the scattered field kernels, quoted against the MEASURED random-access peaks of scripts/micro/red_peak.cu
+    "ld_sectors": "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "red_sectors": "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts_sectors": "lts__t_sectors.sum",
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ns": 1e-3, "ms": 1e3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}
 

@@ -17,7 +17,12 @@ pytestmark = pytest.mark.gpu
 BETAS, EPS, WD = (0.9, 0.99), 1e-15, 0.01
 
 
-def _run_pair(flags, steps=12, loss_scale=65536.0, inf_at=None, seed=0):
+def _mem(t):
+    """elements in MEMORY order (a channels-last 4-D tensor is [N][H][W][C] in memory)"""
+    return (t.permute(0, 2, 3, 1) if t.dim() == 4 else t).reshape(-1)
+
+
+def _run_pair(flags, steps=12, loss_scale=65536.0, inf_at=None, seed=0, trace=None):
     """(ours, torch) parameter / moment tensors after `steps` AdamW steps on identical gradient sequences."""
     from pvd_b200.optim import FusedAdamW
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -50,6 +55,13 @@ def _run_pair(flags, steps=12, loss_scale=65536.0, inf_at=None, seed=0):
             for r, rg in zip(ref, raw):
                 r.grad = rg.clone(memory_format=torch.preserve_format)
             topt.step()
+        if trace is not None:              # fraction of bit-identical elements after this step: (param, exp_avg, exp_avg_sq) per tensor
+            row = []
+            for i, (p, r) in enumerate(zip(ours, ref)):
+                stt = topt.state[r]
+                row.append((round(float((p == r.detach()).float().mean()), 6), round(float((opt.exp_avg[i] == _mem(stt["exp_avg"])).float().mean()), 6),
+                            round(float((opt.exp_avg_sq[i] == _mem(stt["exp_avg_sq"])).float().mean()), 6)))
+            trace.append(row)
     st = opt.read_state()
     return opt, ours, ref, topt, shadow, st
 
@@ -57,11 +69,13 @@ def _run_pair(flags, steps=12, loss_scale=65536.0, inf_at=None, seed=0):
 def test_fused_adamw_is_bitwise_torch_adamw():
     from pvd_b200.optim import ADDCMUL_LEFT
     verdict = {}
+    traces = {}
     for flags in (0, ADDCMUL_LEFT):
-        opt, ours, ref, topt, shadow, st = _run_pair(flags)
+        traces[flags] = []
+        opt, ours, ref, topt, shadow, st = _run_pair(flags, trace=traces[flags])
         assert st.step == 12 and st.skipped == 0 and st.found_inf == 0
         same = True
-        mem = lambda t: (t.permute(0, 2, 3, 1) if t.dim() == 4 else t).reshape(-1)   # memory order of a channels-last 4-D tensor
+        mem = _mem
         for i, (p, r) in enumerate(zip(ours, ref)):
             state = topt.state[r]
             same &= torch.equal(p, r.detach())
@@ -70,7 +84,8 @@ def test_fused_adamw_is_bitwise_torch_adamw():
         if flags == 0:
             assert torch.equal(shadow, ours[0].to(torch.float16)), "fp16 shadow != half(master)"
             worst = max(float((p - r.detach()).abs().max()) for p, r in zip(ours, ref))
-    assert verdict[0], f"default arithmetic is not bit-identical to torch.optim.AdamW (single-tensor): {verdict}, max |diff| {worst:.3g}"
+    assert verdict[0], (f"default arithmetic is not bit-identical to torch.optim.AdamW (single-tensor): {verdict}, max |diff| {worst:.3g}; "
+                        f"per step [(param, m, v) equal fractions per tensor], default flags: {traces[0][:4]} ... {traces[0][-1]}")
 
 
 def test_fused_adamw_skips_nonfinite_steps_like_gradscaler():
