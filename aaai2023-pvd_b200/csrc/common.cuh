@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <float.h>
 
 #include "../../include/pvd_b200.h"
@@ -49,6 +50,35 @@
 #endif
 
 namespace pvd {
+
+// ---- programmatic dependent launch (griddepcontrol): a kernel launched with launch_pdl() may start -- prologue, anything that does not
+// read its predecessor's output -- as soon as every CTA of the predecessor has called pdl_launch_dependents() (or exited); it must call
+// pdl_wait() before touching what the predecessor writes (that returns once the predecessor grid has completed and its memory is
+// visible).  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+// PVD_PDL=0 turns the attribute off (every launch a full dependency): the A/B switch of DESIGN.md's measurement
+inline bool pdl_enabled() {
+    static const bool on = []() { const char* v = getenv("PVD_PDL"); return !(v != nullptr && v[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 constexpr float kSqrt3 = 1.7320508075688772f;  // raymarching.cu:21
 constexpr float kRPi = 0.3183098861837907f;    // raymarching.cu:24

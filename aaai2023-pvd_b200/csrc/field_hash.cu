@@ -451,21 +451,31 @@ __global__ void __launch_bounds__(FUSE ? 128 + 32 * kScatterWarps : 128, 2) k_ha
         }
     } else {
     if (FUSE && kScatterWarps > 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    bool pdl_pending = true;
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t row = row0 + tile * kTile + tid;
         const bool live = row < n_valid;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         float gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
+        auto load_grads = [&]() {   // what the preceding loss kernel wrote
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
+                gsig = __ldg(grad_sigmas + row);
+            }
+        };
         if (live) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
                 dir[d] = __ldg(dirs + 3 * (size_t)row + d);
-                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
             }
-            gsig = __ldg(grad_sigmas + row);
         }
+        // Programmatic dependent launch: this kernel may have started while the loss kernel (composite / pair combine) was still
+        // running.  Its first tile's forward recomputation needs only the samples and the saved encoding (older kernels); the
+        // upstream gradients are read after pdl_wait().  Later tiles issue the loads early, under the recomputation.
+        if (!pdl_pending) load_grads();
         // saved encoding -> X tile
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
@@ -477,6 +487,11 @@ __global__ void __launch_bounds__(FUSE ? 128 + 32 * kScatterWarps : 128, 2) k_ha
         float sigma, o16[16];
         FwdRegs r;
         mlp_forward(p, a, smw, X, H1, CIN, H3, H4, dir, tid, sigma, o16, r);
+        if (pdl_pending) {
+            pdl_wait();
+            pdl_pending = false;
+            load_grads();
+        }
 
         // ---- d(color_net.2 pre-activation) = grad_rgb * rgb * (1 - rgb)
         {
@@ -761,15 +776,15 @@ static int hash_backward_rows(const PvdHashField* f, const float* xyzs, const fl
             cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(kBwdSmem + 16384));
             if (e != cudaSuccess) return (int)e;
-            k_hash_field_bwd<float, true><<<grid, 128 + 32 * kScatterWarps, kBwdSmem + 16384, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs,
-                                                                             grad_feat16, row0, rows, n_valid, nullptr, grad_table,
-                                                                             gw_ws, status);
+            e = launch_pdl(k_hash_field_bwd<float, true>, dim3(grid), dim3(128 + 32 * kScatterWarps), kBwdSmem + 16384, st, a, xyzs, dirs,
+                           (const __half*)enc, grad_sigmas, grad_rgbs, grad_feat16, row0, rows, n_valid, (__half*)nullptr, grad_table, gw_ws, status);
+            if (e != cudaSuccess) return (int)e;
         } else {
             cudaError_t e = cudaFuncSetAttribute(k_hash_field_bwd<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
             if (e != cudaSuccess) return (int)e;
-            k_hash_field_bwd<float, false><<<grid, 128, kBwdSmem, st>>>(a, xyzs, dirs, (const __half*)enc, grad_sigmas, grad_rgbs,
-                                                                      grad_feat16, row0, rows, n_valid, (__half*)dx_ws, grad_table,
-                                                                      gw_ws, status);
+            e = launch_pdl(k_hash_field_bwd<float, false>, dim3(grid), dim3(128), kBwdSmem, st, a, xyzs, dirs, (const __half*)enc, grad_sigmas,
+                           grad_rgbs, grad_feat16, row0, rows, n_valid, (__half*)dx_ws, grad_table, gw_ws, status);
+            if (e != cudaSuccess) return (int)e;
         }
         PVD_LAUNCH_CHECK();
     }

@@ -428,23 +428,35 @@ __global__ void __launch_bounds__(128, 2) k_vm_field_bwd(VmArgs a, VmGradPtrs g,
     const uint32_t n_valid = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
     const uint32_t n_tiles = (n_valid + kTile - 1) / kTile;
     bool first = true;
+    bool pdl_pending = true;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
         vm_gather<PF16>(a, xyzs, tile * kTile, M, APP, sfeat);
         const uint32_t row = tile * kTile + tid;
         const bool live = row < n_valid;
         float dir[3] = {0.f, 0.f, 0.f}, gsig = 0.0f, grgb[3] = {0.f, 0.f, 0.f};
+        auto load_grads = [&]() {   // what the preceding loss kernel wrote
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
+                gsig = __ldg(grad_sigmas + row);
+            }
+        };
         if (live) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                dir[d] = __ldg(dirs + 3 * (size_t)row + d);
-                grgb[d] = __ldg(grad_rgbs + 3 * (size_t)row + d);
-            }
-            gsig = __ldg(grad_sigmas + row);
+            for (int d = 0; d < 3; ++d) dir[d] = __ldg(dirs + 3 * (size_t)row + d);
         }
+        // programmatic dependent launch (see k_hash_field_bwd): the first tile's gather + forward recomputation run under the loss
+        // kernel; the upstream gradients are read after pdl_wait()
+        if (!pdl_pending) load_grads();
         float sigma, feat[16];
         VmRegs r;
         vm_mlp_forward(p, a, smw, APP, CIN, H3, H4, sfeat, dir, tid, sigma, feat, r);
+        if (pdl_pending) {
+            pdl_wait();
+            pdl_pending = false;
+            load_grads();
+        }
         // ---- colour net backward (same sequence as the hash field)
         {
             float gq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -936,12 +948,11 @@ static int vm_backward(const PvdVmField* f, const PvdVmGrads* grads, const float
     static const uint32_t diag_skip = []() { const char* v = getenv("PVD_VM_DIAG_SKIP"); return v ? (uint32_t)atoi(v) : 0u; }();
     uint8_t* dapp_ws = reinterpret_cast<uint8_t*>(scatter_ws);
     float* dsf_ws = scatter_ws ? reinterpret_cast<float*>(dapp_ws + (size_t)tiles * 36864u) : nullptr;
-    if (pf16)
-        k_vm_field_bwd<true><<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                                             gw_ws, status, diag_skip, dapp_ws, dsf_ws);
-    else
-        k_vm_field_bwd<false><<<grid, 128, kVmBwdSmem, (cudaStream_t)stream>>>(a, g, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat16, M, n_valid,
-                                                                              gw_ws, status, diag_skip, dapp_ws, dsf_ws);
+    e = pf16 ? launch_pdl(k_vm_field_bwd<true>, dim3(grid), dim3(128), kVmBwdSmem, (cudaStream_t)stream, a, g, xyzs, dirs, grad_sigmas, grad_rgbs,
+                          grad_feat16, M, n_valid, gw_ws, status, diag_skip, dapp_ws, dsf_ws)
+             : launch_pdl(k_vm_field_bwd<false>, dim3(grid), dim3(128), kVmBwdSmem, (cudaStream_t)stream, a, g, xyzs, dirs, grad_sigmas, grad_rgbs,
+                          grad_feat16, M, n_valid, gw_ws, status, diag_skip, dapp_ws, dsf_ws);
+    if (e != cudaSuccess) return (int)e;
     PVD_LAUNCH_CHECK();
     if (scatter_ws != nullptr && !(diag_skip & 1u)) {
         if (pf16)

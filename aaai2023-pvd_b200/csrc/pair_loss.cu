@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256) k_pair_combine(const float* __restrict__ 
                                                       uint32_t M, const int32_t* __restrict__ n_composite_p,
                                                       float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
                                                       float* __restrict__ grad_feat, float* __restrict__ loss_out) {
+    pdl_launch_dependents();   // the student field backward may start its prologue + forward recomputation now
     __shared__ float coef[4];
     if (threadIdx.x < 32) {  // warp 0: the four sums over the slots -> norms -> gradient coefficients rate / ||.||
         float s[4];

@@ -784,6 +784,7 @@ __global__ void __launch_bounds__(32) k_composite_train_mse(const float* __restr
                                                            float* __restrict__ weights_sum, float* __restrict__ depth,
                                                            float* __restrict__ image, float* __restrict__ grad_sigmas,
                                                            float* __restrict__ grad_rgbs, float* __restrict__ loss_out) {
+    pdl_launch_dependents();   // the field backward (launched with launch_pdl) may start its prologue + forward recomputation now
     const uint32_t n = blockIdx.x;
     const uint32_t lane = threadIdx.x;
     if (n >= N) return;

@@ -289,8 +289,10 @@ class FieldTrainEngine:
             M = M_drop = self.M
         self._march_write(st, rs, M_drop)
         self._forward(st, rs, M, M_drop)
+        # join BEFORE the loss kernel: the table gradient is clear before the first reduction into it, and the field backward's only
+        # predecessor is then the loss kernel -- which lets it start early as a programmatic dependent launch (csrc/common.cuh)
+        cur.wait_stream(self._side)
         self._loss_backward(st, rs, M, M_drop)
-        cur.wait_stream(self._side)            # join: the table gradient is clear before the first reduction into it
         self._field_backward(st, rs, M, cur)
         self._epilogue(st)
 
@@ -382,10 +384,10 @@ class FieldTrainEngine:
             march_branch()             # forked BEFORE the prologue: the march must not wait for the re-stage / memsets
         self._prologue(cur)
         self._forward(st, rs, M, M)
-        self._loss_backward(st, rs, M, M)
         if where == "late":
             march_branch()
-        cur.wait_stream(self._side)
+        cur.wait_stream(self._side)    # before the loss kernel (see step()): the backward follows it as a programmatic dependent launch
+        self._loss_backward(st, rs, M, M)
         self._field_backward(st, rs, M, cur)
         if host_io:
             self.host_loss.copy_(self._loss_dev(), non_blocking=True)

@@ -110,10 +110,12 @@ class HashOps:
 
 # vm backward as two kernels (MLP kernel -> workspace -> high-occupancy scatter kernel; default) or as one (0)
 VM_SPLIT_SCATTER = os.environ.get("PVD_VM_SPLIT_SCATTER", "1") != "0"
-# The engines gather the vm planes / lines from an fp16 channels-last SHADOW (2304 B/sample instead of 4608; the kernels are
-# byte-bound on these taps), refreshed by stage() or written by the fused optimizer; masters and gradients stay fp32.  0 = gather
-# the fp32 parameters in place (what the autograd module path does).
-VM_PLANE_F16 = os.environ.get("PVD_VM_PLANE_F16", "1") != "0"
+# PVD_VM_PLANE_F16=1: the engines gather the vm planes / lines from an fp16 channels-last SHADOW (2304 B/sample instead of 4608),
+# refreshed by stage() or written by the fused optimizer; masters and gradients stay fp32.  MEASURED on B200 (4096 rays, 300^3,
+# profiles/README.md): forward 45.6 -> 39.9 us, backward 123.7 -> 120.6 us -- the gather is bound by requests, not bytes -- while
+# re-casting 69 MB of planes per step costs 16 us when an external optimizer owns the parameters (step 209.9 -> 225.7 us) and the
+# fused optimizer only gains 1 % (324.0 -> 321.2 us).  So the default gathers the fp32 parameters in place, like the module path.
+VM_PLANE_F16 = os.environ.get("PVD_VM_PLANE_F16", "0") != "0"
 
 
 class PvdCastDesc(C.Structure):

@@ -94,3 +94,52 @@ p1 = fma(torch.tensor(-(lr / bc1), device=dev, dtype=torch.float32), m1 / d1, pm
 st = opt.state[P]
 out["first_step_vs_formula"] = {"param": frac_equal(P.detach(), p1), "exp_avg": frac_equal(st["exp_avg"], m1), "exp_avg_sq": frac_equal(st["exp_avg_sq"], v1)}
 print(json.dumps(out))
+
+# ---- three whole steps: torch.optim.AdamW vs (a) the formulas above with HOST-computed scalars, (b) the fused kernel; and the fused
+# kernel's DEVICE-computed scalars against the host's
+import ctypes as C
+import os
+import struct
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "aaai2023-pvd_b200"))
+from pvd_b200.optim import FusedAdamW, PvdAdamSlot  # noqa: E402
+
+hexf = lambda x: struct.pack(">f", float(x)).hex()
+n2 = 1 << 18
+p0 = torch.randn(n2, device=dev) * 0.3
+P = torch.nn.Parameter(p0.clone())
+topt = torch.optim.AdamW([P], lr=lr, betas=(beta1, beta2), eps=eps, weight_decay=wd, foreach=False, fused=False)
+pe, me, ve = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)          # (a) emulation
+pk, gk = p0.clone(), torch.zeros_like(p0)                                      # (b) kernel
+fopt = FusedAdamW([dict(param=pk, grad=gk, lr=lr, zero_grad=True)], betas=(beta1, beta2), eps=eps, weight_decay=wd, loss_scale=1.0, check_finite=False)
+T = lambda x: torch.tensor(x, device=dev, dtype=torch.float32)
+rows = []
+for step in range(1, 4):
+    gg = torch.randn(n2, device=dev)
+    P.grad = gg.clone()
+    topt.step()
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    step_size, bc2s = lr / bc1, bc2 ** 0.5
+    pe = pe * T(1 - lr * wd)
+    me = fma(T(w1), gg - me, me)
+    ve = fma(T(w2), gg * gg, ve * T(beta2))
+    inv = T(1.0) / T(bc2s)
+    de = ve.sqrt() * inv + T(eps)
+    pe = fma(T(-step_size), me / de, pe)
+    gk.copy_(gg)
+    fopt.step()
+    torch.cuda.synchronize()
+    st = fopt.read_state()
+    slot = PvdAdamSlot.from_buffer_copy(bytes(fopt.slots.cpu().numpy().tobytes())[:C.sizeof(PvdAdamSlot)])
+    tst = topt.state[P]
+    rows.append({"step": step,
+                 "emulation_vs_torch": {"param": frac_equal(pe, P.detach()), "m": frac_equal(me, tst["exp_avg"]), "v": frac_equal(ve, tst["exp_avg_sq"])},
+                 "kernel_vs_torch": {"param": frac_equal(pk, P.detach()), "m": frac_equal(fopt.exp_avg[0], tst["exp_avg"]), "v": frac_equal(fopt.exp_avg_sq[0], tst["exp_avg_sq"])},
+                 "kernel_vs_emulation_param": frac_equal(pk, pe),
+                 "scalars_device_vs_host(hex)": {"neg_step_size": (hexf(slot.neg_step_size), hexf(-step_size)), "decay": (hexf(slot.decay), hexf(1 - lr * wd)),
+                                                 "inv_bc2_sqrt": (hexf(st.inv_bc2_sqrt), hexf(float(inv))), "w1": (hexf(st.w1), hexf(w1)), "w2": (hexf(st.w2), hexf(w2)),
+                                                 "beta2": (hexf(st.beta2_f), hexf(beta2)), "eps": (hexf(st.eps), hexf(eps)), "grad_scale": st.grad_scale,
+                                                 "device_step": st.step}})
+print(json.dumps({"three_steps": rows}))
