@@ -147,6 +147,88 @@ __global__ void __launch_bounds__(256) k_multimem_allreduce_f16_fused(__half* __
     }
 }
 
+// ---- two-shot all-reduce over PEER pointers (no switch reduction): rank r owns 1/W of the payload, loads that shard from every
+// rank's symmetric buffer with plain 16-byte NVLink loads (W independent loads in flight per thread), sums in fp32, and stores the
+// fp16 result into every rank's buffer.  Per GPU: (W-1)/W of the payload in over NVLink and the same out -- both directions of the
+// links are busy at once -- against multimem's fixed cost per switch request (scripts/micro/exchange_probe.py: 78 us for a 10.6 MB
+// shard on two GPUs).  Barriers as above, inside the kernel.
+template <int W>
+__global__ void __launch_bounds__(512) k_p2p_allreduce_f16(__half* const* __restrict__ bufs, uint64_t first_vec, uint64_t n_vec,
+                                                           uint32_t* const* __restrict__ pads, uint32_t rank,
+                                                           uint32_t* __restrict__ local /* [0] flag, [1] done, [2] error */) {
+    if (blockIdx.x == 0) {
+        cross_rank_barrier(pads, rank, W, 10u, local + 2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicExch(local, 1u);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (atomicAdd(local, 0u) == 0u)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(local + 2, 3u); break; }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const uint4* src[W];
+    uint4* dst[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+        // start with my own copy, then the peers in ring order: the ranks do not all hit the same peer at the same time
+        const uint32_t q = (rank + (uint32_t)r) % (uint32_t)W;
+        src[r] = reinterpret_cast<const uint4*>(bufs[q]) + first_vec;
+        dst[r] = reinterpret_cast<uint4*>(bufs[q]) + first_vec;
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        uint4 v[W];
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "l"(src[r] + i) : "memory");
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < W; ++r) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[r]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                acc[2 * k] += f.x;
+                acc[2 * k + 1] += f.y;
+            }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst[r] + i), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd(local + 1, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (atomicAdd(local + 1, 0u) < gridDim.x)
+                if (clock64() - t0 > kSpinLimit) { atomicExch(local + 2, 4u); break; }
+            __threadfence_system();
+        }
+        __syncthreads();
+        cross_rank_barrier(pads, rank, W, 11u, local + 2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            local[1] = 0u;
+            __threadfence();
+            local[0] = 0u;
+        }
+    }
+}
+
 // fp32 gradient -> fp16 payload, and the inverse
 __global__ void __launch_bounds__(256) k_f32_to_f16(const float4* __restrict__ src, uint2* __restrict__ dst, uint64_t n_vec4) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -189,6 +271,26 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
         k_multimem_allreduce_f16_fused<4><<<grid, 256, 0, st>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec, pads, rank, world, local_state);
     } else {
         k_multimem_allreduce_f16_fused<2><<<grid, 256, 0, st>>>((__half*)multicast_ptr, elem_offset / 8u, n_vec, pads, rank, world, local_state);
+    }
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
+}
+
+int pvd_p2p_allreduce_f16(const void* buffer_ptrs_dev, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
+                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, void* stream) {
+    PVD_REQUIRE(buffer_ptrs_dev != nullptr && signal_pad_ptrs_dev != nullptr && local_state != nullptr);
+    PVD_REQUIRE((elem_offset % 8u) == 0 && (elem_count % 8u) == 0 && rank < world);
+    const uint64_t n_vec = elem_count / 8u;
+    uint32_t grid = blocks ? blocks : 148u * 2u;
+    grid = max(1u, min(grid, 148u * 4u));
+    __half* const* bufs = reinterpret_cast<__half* const*>(buffer_ptrs_dev);
+    uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pad_ptrs_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (world) {
+        case 2: k_p2p_allreduce_f16<2><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        case 4: k_p2p_allreduce_f16<4><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        case 8: k_p2p_allreduce_f16<8><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        default: return PVD_EUNSUPPORTED;
     }
     PVD_LAUNCH_CHECK();
     return PVD_OK;

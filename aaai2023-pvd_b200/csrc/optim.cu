@@ -11,8 +11,8 @@
 //     param.mul_(1 - lr * wd)                                   -> p = p * decay
 //     exp_avg.lerp_(grad, 1 - beta1)                            -> m = fma(w1, g - m, m)          (ATen lerp, |w| < 0.5 branch)
 //     exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-b2)   -> v = fma(w2, g*g, v*beta2)       (or fma(w2*g, g, .), see flags)
-//     denom = (exp_avg_sq.sqrt() / bc2_sqrt).add_(eps)          -> d = sqrt(v) * (1/bc2_sqrt) + eps (ATen divides a tensor by a CPU
-//                                                                  scalar by multiplying with its fp32 reciprocal)
+//     denom = (exp_avg_sq.sqrt() / bc2_sqrt).add_(eps)          -> d = sqrt(v) * fl32(1 / bc2_sqrt) + eps (ATen divides a tensor by a CPU
+//                                                                  scalar by multiplying with its reciprocal, formed in double)
 //     param.addcdiv_(exp_avg, denom, value=-step_size)          -> p = fma(-step_size, m / d, p)
 // with explicit round-to-nearest intrinsics so that nvcc's contraction choices cannot change the result.
 #include "common.cuh"
@@ -101,8 +101,9 @@ __global__ void k_adamw_advance(PvdAdamState* state, PvdAdamSlot* slots, uint32_
     const double step = (double)max(st.step, 1);
     const double bc1 = 1.0 - pow(st.beta1, step);
     const double bc2 = 1.0 - pow(st.beta2, step);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    st.inv_bc2_sqrt = __fdiv_rn(1.0f, bc2_sqrt);
+    // ATen divides a tensor by a CPU scalar by multiplying with the scalar's reciprocal, formed in DOUBLE and then rounded to fp32
+    // (scripts/micro/adam_probe.py: 1.0f / (float)b differs from it by an ulp at most steps, and with it 6 % of the updated parameters)
+    st.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     st.w1 = (float)(1.0 - st.beta1);
     st.w2 = (float)(1.0 - st.beta2);
     st.beta2_f = (float)st.beta2;

@@ -92,10 +92,11 @@ class TableGradExchange:
     Consumers: `write_back(reduction)` puts the reduced gradient back into the fp32 buffers (`engine.grads()` does it), and
     `optim.for_engine(..., exchange=...)` reads the payload directly with the right factors.
 
-    Kinds: "nccl" (cast kernel + ncclAllReduce of the payload), "multimem" (NVSwitch: the payload lives in a symmetric buffer that is
-    also mapped through a multicast address; each rank reduces ITS 1/W of it in the switch with multimem.ld_reduce / multimem.st,
-    csrc/collective.cu) either with the barriers inside the kernel (`fused_barrier`, one launch) or between two signal-pad barrier
-    launches.  Anything that does not set up falls back to NCCL with the same result layout.
+    Kinds: "nccl" (cast kernel + ncclAllReduce of the payload); "p2p" (the payload lives in a torch symmetric-memory buffer; each
+    rank loads ITS 1/W shard from every rank over NVLink, sums in fp32 and stores the result into every rank's buffer -- one kernel,
+    device-side barriers, csrc/collective.cu::k_p2p_allreduce_f16; what mode "auto" picks on 2 / 4 / 8 ranks); "multimem" (the same
+    shard reduced BY THE SWITCH through the buffer's multicast address, multimem.ld_reduce / multimem.st, barriers inside the kernel
+    (`fused_barrier`) or as two signal-pad launches).  Anything that does not set up falls back to NCCL with the same result layout.
     """
 
     def __init__(self, grad_table: torch.Tensor, small: torch.Tensor, mode: str = "auto", group=None, fused_barrier: bool = True,
@@ -113,27 +114,34 @@ class TableGradExchange:
         self.fused_barrier, self.blocks, self.unroll = bool(fused_barrier), int(blocks), int(unroll)
         self._side = torch.cuda.Stream(device=grad_table.device) if grad_table.is_cuda else None
         self.payload = None
-        if mode in ("auto", "multimem") and self.world > 1 and self.n % 8 == 0 and grad_table.is_cuda:
+        if mode in ("auto", "multimem", "p2p") and self.world > 1 and self.n % 8 == 0 and grad_table.is_cuda:
             try:
                 import torch.distributed._symmetric_memory as symm
                 buf = symm.empty(self.n, dtype=torch.float16, device=grad_table.device)
                 hdl = symm.rendezvous(buf, self.group.group_name)
-                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-                if mc == 0:
-                    raise RuntimeError("no multicast mapping (NVLS unavailable)")
-                self.payload, self._hdl, self._mc = buf, hdl, mc
                 vecs = self.n // 8
                 lo = (vecs * self.rank) // self.world
                 hi = (vecs * (self.rank + 1)) // self.world
                 self._off, self._cnt = 8 * lo, 8 * (hi - lo)
                 self._pads = int(getattr(hdl, "signal_pad_ptrs_dev", 0) or 0)
+                self._bufs = int(getattr(hdl, "buffer_ptrs_dev", 0) or 0)
                 self._local = torch.zeros(4, dtype=torch.int32, device=grad_table.device)
-                if self._pads == 0:
-                    self.fused_barrier = False
-                self.kind = "multimem"
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                want_p2p = mode == "p2p" or (mode == "auto" and self.world in (2, 4, 8))
+                if want_p2p:
+                    if not (self._pads and self._bufs and self.world in (2, 4, 8)):
+                        raise RuntimeError("peer pointers / signal pads not exposed by this torch, or world not in (2, 4, 8)")
+                    self.kind = "p2p"
+                else:
+                    if mc == 0:
+                        raise RuntimeError("no multicast mapping (NVLS unavailable)")
+                    if self._pads == 0:
+                        self.fused_barrier = False
+                    self.kind = "multimem"
+                self.payload, self._hdl, self._mc = buf, hdl, mc
             except Exception as ex:  # noqa: BLE001  (any failure: NCCL carries the exchange)
                 self.why = repr(ex)[:160]
-                if mode == "multimem":
+                if mode in ("multimem", "p2p"):
                     raise
         if self.payload is None:
             self.payload = torch.empty(self.n, dtype=torch.float16, device=grad_table.device)
@@ -153,7 +161,10 @@ class TableGradExchange:
             dist.all_reduce(self.small, group=self.group)
         nv.check(nv.lib().pvd_cast_f32_to_f16_scaled(nv.ptr(self.grad_table), nv.ptr(self.payload), C.c_uint64(self.n),
                                                      C.c_float(self.pre_scale), st))
-        if self.kind == "multimem" and self.fused_barrier:
+        if self.kind == "p2p":
+            nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(self._bufs), C.c_uint64(self._off), C.c_uint64(self._cnt), C.c_void_p(self._pads),
+                                                    C.c_uint32(self.rank), C.c_uint32(self.world), nv.ptr(self._local), C.c_uint32(self.blocks), st))
+        elif self.kind == "multimem" and self.fused_barrier:
             nv.check(nv.lib().pvd_multimem_allreduce_f16_fused(C.c_void_p(self._mc), C.c_uint64(self._off), C.c_uint64(self._cnt),
                                                                C.c_void_p(self._pads), C.c_uint32(self.rank), C.c_uint32(self.world),
                                                                nv.ptr(self._local), C.c_uint32(self.blocks), C.c_uint32(self.unroll), st))
@@ -167,7 +178,7 @@ class TableGradExchange:
 
     def barrier_error(self) -> int:
         """Non-zero if a device-side barrier of the fused kernel timed out (host sync)."""
-        return int(self._local[2].item()) if self.kind == "multimem" else 0
+        return int(self._local[2].item()) if self.kind in ("multimem", "p2p") else 0
 
     def write_back(self, reduction: str = "mean"):
         """Reduced gradient -> the fp32 buffers a caller's optimizer reads: grad_table = payload * result_scale; the small workspace

@@ -400,7 +400,7 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
                     dist.all_reduce(big); dist.all_reduce(eng.gw_ws)
             exchange = _Fp32Exchange()
         else:
-            exchange = TableGradExchange(big, eng.gw_ws, mode={"fp16": "nccl", "multimem": "multimem", "auto": "auto"}[args.grad_comm],
+            exchange = TableGradExchange(big, eng.gw_ws, mode={"fp16": "nccl", "multimem": "multimem", "p2p": "p2p", "auto": "auto"}[args.grad_comm],
                                          blocks=args.mm_blocks, unroll=args.mm_unroll)
         if rank == 0:
             print(f"[bench] {workload}: gradient exchange = {exchange.kind} {exchange.why}", file=sys.stderr)
@@ -410,7 +410,7 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
         load(i)
         eng.step(warmup=True)
     eng.finish_warmup()
-    if exchange is not None and exchange.kind == "multimem":
+    if exchange is not None and exchange.kind in ("multimem", "p2p"):
         # self-check of the in-switch reduction against NCCL on this step's real gradients; any rank's mismatch -> all fall back
         ref = (big * exchange.pre_scale).clamp(-65504, 65504).to(torch.float16)
         dist.all_reduce(ref)
@@ -420,9 +420,9 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
         bad = torch.tensor([0.0 if (float(err) < 2e-2 and exchange.barrier_error() == 0) else 1.0], device=dev)
         dist.all_reduce(bad)
         if float(bad.item()) > 0:
-            exchange.kind, exchange.why = "nccl", f"multimem self-check failed (rel err {float(err):.3g})"
+            exchange.kind, exchange.why = "nccl", f"{exchange.kind} self-check failed (rel err {float(err):.3g})"
         if rank == 0:
-            print(f"[bench] multimem exchange self-check: max rel err {float(err):.3g} -> using {exchange.kind}", file=sys.stderr)
+            print(f"[bench] custom exchange self-check: max rel err {float(err):.3g} -> using {exchange.kind}", file=sys.stderr)
         del ref
     eng.exchange = exchange
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -593,7 +593,7 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
                    "step": "fwd+bwd of a trainer with an external optimizer: fp16 table shadow re-cast + weight tiles re-packed at the top of "
                            "EVERY timed step, small weight gradients unpacked to parameter shapes at its end" + ("; gradient exchange inside" if world > 1 else ""),
                    "parallelism": (f"rays sharded over {world} GPU(s), one all-reduce of the gradients per step inside the step graph ({exchange.kind}: "
-                                   f"{'fp32 NCCL' if exchange.kind == 'nccl-fp32' else 'fp16 payload, ' + ('in-switch multimem reduction, barriers inside the kernel' if exchange.kind == 'multimem' else 'NCCL')}); "
+                                   f"{'fp32 NCCL' if exchange.kind == 'nccl-fp32' else 'fp16 payload, ' + ({'multimem': 'in-switch multimem reduction, barriers inside the kernel', 'p2p': 'two-shot reduction over NVLink peer pointers, one kernel with device-side barriers'}.get(exchange.kind, 'NCCL'))}); "
                                    "the next batch's march runs beside the exchange") if world > 1 else "single GPU",
                    "launch": ("two CUDA graphs (even/odd steps): the march of batch i+1 runs on a parallel branch of step i's graph "
                               "(one batch of look-ahead, double-buffered ray sets)") if pipelined else
@@ -834,7 +834,7 @@ def main():
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (default 4096; 8192 for mlp-hash)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-comm", default="fp16", choices=["auto", "multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (fp16), fp16 payload reduced in the NVSwitch by one kernel with device-side barriers (multimem; auto = multimem if it sets up and passes its self-check, else NCCL), or fp32 over NCCL")
+    ap.add_argument("--grad-comm", default="fp16", choices=["auto", "p2p", "multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (fp16), fp16 payload reduced in the NVSwitch by one kernel with device-side barriers (multimem; auto = multimem if it sets up and passes its self-check, else NCCL), or fp32 over NCCL")
     ap.add_argument("--mm-blocks", type=int, default=0, help="multimem exchange kernel: CTAs (0 = default)")
     ap.add_argument("--mm-unroll", type=int, default=4, help="multimem exchange kernel: 16-byte switch reductions in flight per thread (2 | 4 | 8)")
     ap.add_argument("--only", dest="all_workloads", action="store_false", help="measure only --workload (default: the other BASELINE configurations "

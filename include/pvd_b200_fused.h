@@ -240,6 +240,11 @@ int pvd_multimem_allreduce_f16(void* multicast_ptr, uint64_t elem_offset, uint64
  * blocks (0 = default) and unroll (2 | 4 | 8) are tuning knobs; every rank must pass the same values. */
 int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
                                      uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream);
+/* Two-shot all-reduce over peer pointers (plain NVLink loads / stores, fp32 accumulation, no switch reduction), barriers inside the
+ * kernel: `buffer_ptrs_dev` = device array of the ranks' symmetric payload buffers; world 2, 4 or 8; the other arguments as above
+ * (signal-pad slots [10W, 12W)). */
+int pvd_p2p_allreduce_f16(const void* buffer_ptrs_dev, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
+                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, void* stream);
 int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------

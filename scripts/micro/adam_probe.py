@@ -66,6 +66,11 @@ out["div_scalar"] = {"fl(s * fl32(1 / fl32(b)))": frac_equal(ref, s * inv), "tru
                      "fl32(f64(s) / b)": frac_equal(ref, f32(f64(s) / bc2s)), "fl(s * fl32(1 / b))": frac_equal(ref, s * torch.tensor(1.0 / bc2s, device=dev, dtype=torch.float32))}
 d = (s / bc2s).add_(eps)
 out["add_eps"] = {"fl(x + fl32(eps))": frac_equal(d, (s / bc2s) + torch.tensor(eps, device=dev, dtype=torch.float32))}
+for stp in (2, 3, 5, 11):                  # the two reciprocal candidates coincide at some steps and differ at others
+    b = (1 - beta2 ** stp) ** 0.5
+    ref = s / b
+    out[f"div_scalar_step{stp}"] = {"fl(s * fl32(1 / fl32(b)))": frac_equal(ref, s * (torch.tensor(1.0, device=dev) / torch.tensor(b, device=dev, dtype=torch.float32))),
+                                    "fl(s * fl32(1 / b))": frac_equal(ref, s * torch.tensor(1.0 / b, device=dev, dtype=torch.float32))}
 # ---- addcdiv_
 step_size = lr / bc1
 ref = p.clone().addcdiv_(m, d, value=-step_size)
@@ -125,7 +130,7 @@ for step in range(1, 4):
     pe = pe * T(1 - lr * wd)
     me = fma(T(w1), gg - me, me)
     ve = fma(T(w2), gg * gg, ve * T(beta2))
-    inv = T(1.0) / T(bc2s)
+    inv = T(1.0 / bc2s)                      # reciprocal in double, then fp32 (what ATen's div-by-scalar does)
     de = ve.sqrt() * inv + T(eps)
     pe = fma(T(-step_size), me / de, pe)
     gk.copy_(gg)

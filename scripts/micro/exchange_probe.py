@@ -59,7 +59,7 @@ try:
     if ex._pads:
         ex.fused_barrier = True
         best = None
-        for blocks in (148, 296, 592, 1184):
+        for blocks in (16, 32, 64, 148, 296):
             for unroll in (2, 4, 8):
                 ex.blocks, ex.unroll = blocks, unroll
                 k = lambda: nv.check(nv.lib().pvd_multimem_allreduce_f16_fused(C.c_void_p(ex._mc), C.c_uint64(ex._off), C.c_uint64(ex._cnt), C.c_void_p(ex._pads),
@@ -83,6 +83,29 @@ try:
         out["fused barrier"] = "signal_pad_ptrs_dev not exposed by this torch"
 except Exception as e:  # noqa: BLE001
     out["multimem"] = f"unavailable: {e!r}"[:200]
+try:
+    exp = TableGradExchange(g, small, mode="p2p")
+    bestp = None
+    for blocks in (37, 74, 148, 296, 592):
+        exp.blocks = blocks
+        k = lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(exp._bufs), C.c_uint64(exp._off), C.c_uint64(exp._cnt), C.c_void_p(exp._pads),
+                                                            C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local), C.c_uint32(blocks), st()))
+        t = timeit(k, n=20, warm=3)
+        out[f"  p2p kernel only (barriers inside), {blocks} CTAs x 512"] = t
+        if exp.barrier_error():
+            out[f"  !! p2p barrier error at {blocks}"] = exp.barrier_error()
+        if bestp is None or t < bestp[0]:
+            bestp = (t, blocks)
+    exp.blocks = bestp[1]
+    out[f"p2p two-shot ({bestp[1]} CTAs): cast + kernel + small, total"] = timeit(exp)
+    ref = (g * exp.pre_scale).clamp(-65504, 65504).to(torch.float16)
+    dist.all_reduce(ref)
+    exp()
+    torch.cuda.synchronize()
+    out["p2p result vs NCCL: max rel err"] = float((exp.payload.float() - ref.float()).abs().max() / ref.float().abs().max())
+    out["best_p2p"] = {"blocks": bestp[1], "kernel_us": bestp[0]}
+except Exception as e:  # noqa: BLE001
+    out["p2p"] = f"unavailable: {e!r}"[:200]
 if rank == 0:
     for k, v in out.items():
         print(f"{k:72s}: {v:8.1f} us" if isinstance(v, float) else f"{k:72s}: {v}")
