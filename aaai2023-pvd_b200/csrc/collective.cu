@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_multimem_allreduce_f16_fused(__half* __
 // fp16 result into every rank's buffer.  Per GPU: (W-1)/W of the payload in over NVLink and the same out -- both directions of the
 // links are busy at once -- against multimem's fixed cost per switch request (scripts/micro/exchange_probe.py: 78 us for a 10.6 MB
 // shard on two GPUs).  Barriers as above, inside the kernel.
-template <int W>
+template <int W, int UNROLL, bool WEAK>
 __global__ void __launch_bounds__(512) k_p2p_allreduce_f16(__half* const* __restrict__ bufs, uint64_t first_vec, uint64_t n_vec,
                                                            uint32_t* const* __restrict__ pads, uint32_t rank,
                                                            uint32_t* __restrict__ local /* [0] flag, [1] done, [2] error */) {
@@ -181,30 +181,49 @@ __global__ void __launch_bounds__(512) k_p2p_allreduce_f16(__half* const* __rest
         src[r] = reinterpret_cast<const uint4*>(bufs[q]) + first_vec;
         dst[r] = reinterpret_cast<uint4*>(bufs[q]) + first_vec;
     }
+    // every address is read once per launch and written once: WEAK uses plain (non-coherent-path-free) accesses, ordered against the
+    // other ranks by the system-scope fences of the two barriers; otherwise relaxed.sys accesses
+    auto ld16 = [](const uint4* p) {
+        uint4 v;
+        if (WEAK) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        else asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        return v;
+    };
+    auto st16 = [](uint4* p, const uint4& o) {
+        if (WEAK) asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        else asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    };
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        uint4 v[W];
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += UNROLL * stride) {
+        uint4 v[UNROLL][W];
 #pragma unroll
-        for (int r = 0; r < W; ++r)
-            asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "l"(src[r] + i) : "memory");
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * stride;
 #pragma unroll
-        for (int r = 0; r < W; ++r) {
-            const __half2* h = reinterpret_cast<const __half2*>(&v[r]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
-                acc[2 * k] += f.x;
-                acc[2 * k + 1] += f.y;
-            }
+            for (int r = 0; r < W; ++r) v[u][r] = (i < n_vec) ? ld16(src[r] + i) : make_uint4(0u, 0u, 0u, 0u);
         }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (i >= n_vec) break;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int r = 0; r < W; ++r)
-            asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst[r] + i), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            for (int r = 0; r < W; ++r) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u][r]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h[k]);
+                    acc[2 * k] += f.x;
+                    acc[2 * k + 1] += f.y;
+                }
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+#pragma unroll
+            for (int r = 0; r < W; ++r) st16(dst[r] + i, o);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -237,6 +256,23 @@ __global__ void __launch_bounds__(256) k_f32_to_f16(const float4* __restrict__ s
         dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     }
 }
+
+namespace {
+template <int W>
+void p2p_launch(uint32_t grid, cudaStream_t st, uint32_t unroll, bool weak, __half* const* bufs, uint64_t first_vec, uint64_t n_vec,
+                       uint32_t* const* pads, uint32_t rank, uint32_t* local) {
+    if (weak) {
+        if (unroll >= 4) k_p2p_allreduce_f16<W, 4, true><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+        else if (unroll >= 2) k_p2p_allreduce_f16<W, 2, true><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+        else k_p2p_allreduce_f16<W, 1, true><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+    } else {
+        if (unroll >= 4) k_p2p_allreduce_f16<W, 4, false><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+        else if (unroll >= 2) k_p2p_allreduce_f16<W, 2, false><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+        else k_p2p_allreduce_f16<W, 1, false><<<grid, 512, 0, st>>>(bufs, first_vec, n_vec, pads, rank, local);
+    }
+}
+
+}  // namespace
 
 }  // namespace pvd
 
@@ -277,19 +313,20 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
 }
 
 int pvd_p2p_allreduce_f16(const void* buffer_ptrs_dev, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
-                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, void* stream) {
+                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, uint32_t weak,
+                          void* stream) {
     PVD_REQUIRE(buffer_ptrs_dev != nullptr && signal_pad_ptrs_dev != nullptr && local_state != nullptr);
     PVD_REQUIRE((elem_offset % 8u) == 0 && (elem_count % 8u) == 0 && rank < world);
     const uint64_t n_vec = elem_count / 8u;
-    uint32_t grid = blocks ? blocks : 148u * 2u;
+    uint32_t grid = blocks ? blocks : 148u;
     grid = max(1u, min(grid, 148u * 4u));
     __half* const* bufs = reinterpret_cast<__half* const*>(buffer_ptrs_dev);
     uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pad_ptrs_dev);
     cudaStream_t st = (cudaStream_t)stream;
     switch (world) {
-        case 2: k_p2p_allreduce_f16<2><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
-        case 4: k_p2p_allreduce_f16<4><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
-        case 8: k_p2p_allreduce_f16<8><<<grid, 512, 0, st>>>(bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        case 2: p2p_launch<2>(grid, st, unroll, weak != 0, bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        case 4: p2p_launch<4>(grid, st, unroll, weak != 0, bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
+        case 8: p2p_launch<8>(grid, st, min(unroll, 2u), weak != 0, bufs, elem_offset / 8u, n_vec, pads, rank, local_state); break;
         default: return PVD_EUNSUPPORTED;
     }
     PVD_LAUNCH_CHECK();

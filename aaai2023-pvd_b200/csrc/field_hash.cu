@@ -294,6 +294,188 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
 #endif
 }
 
+// =============================================================================================== persistent inference kernel
+// The evaluation branch of NeRFRenderer.run_cuda (distill_mutual/renderer.py:450-543) is a HOST loop: march_rays (n_step <= 8 samples
+// per alive ray) -> NeRFNetwork.forward -> composite_rays -> compact_rays, one D2H read of the alive count per iteration, every
+// intermediate ([n_alive * n_step] xyzs / dirs / deltas / sigmas / rgbs) through HBM.  Here the whole loop is ONE persistent kernel
+// for a hash field: a CTA holds 16 ray slots x 8 steps = the 128 samples of one tensor-core tile and iterates
+//     refill dead slots from a global ray queue (atomicAdd) -> march each live ray by up to 8 samples (the reference's loop,
+//     raymarching.cu:705-793) -> gather + tcgen05 MLP for the 128 samples -> composite each ray's 8 samples in order
+//     (raymarching.cu:826-909, early termination at T < 1e-4) -> retire finished rays (write weights_sum / depth / image)
+// until the queue is empty and every slot has retired.  Nothing but the final per-ray outputs leaves the SM.  A ray's result does not
+// depend on how its samples are chunked (the march continues from the composited t, the termination test is per sample), so with
+// perturb off -- the reference's evaluation setting -- the outputs equal the host loop's bit for bit.
+constexpr uint32_t kRenderRays = 16, kRenderSteps = 8;
+static_assert(kRenderRays * kRenderSteps == kTile, "one MLP tile per iteration");
+
+struct RenderArgs {
+    const float* rays_o;
+    const float* rays_d;
+    const uint8_t* grid;
+    const float* nears;
+    const float* fars;
+    float bound, dt_gamma;
+    uint32_t max_steps, C, H, N;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_hash_render_persistent(FieldArgs a, RenderArgs ra, int32_t* __restrict__ queue,
+                                                                float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                                float* __restrict__ image, int32_t* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, wbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ LevelInfo lv[16];
+    __shared__ float s_pos[kTile * 3], s_dir[kRenderRays * 3], s_delta[kTile * 2], s_sig[kTile], s_rgb[kTile * 3];
+    __shared__ int32_t s_ray[kRenderRays], s_cnt[kRenderRays];
+    __shared__ float s_t[kRenderRays], s_ws[kRenderRays], s_d[kRenderRays], s_img[kRenderRays * 3];
+    uint8_t* smw = smem;
+    uint8_t* X = smem + PVD_FIELD_WBLOB_BYTES;
+    uint8_t* CIN = X;
+    uint8_t* HA = X + 8192;
+    uint8_t* HB = HA;
+    const uint32_t tid = threadIdx.x;
+    if (tid < 32) tc5::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) {
+        tc5::mbar_init(&bar, 1);
+        tc5::mbar_init(&wbar, 1);
+        tc5::mbar_fence_init();
+        stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);
+    }
+    level_info_init(lv, a.offsets, a.L, a.S, a.H);
+    if (tid < kRenderRays) s_ray[tid] = -1;
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    Pipe p{&bar, 0u, tmem_base_s, status};
+    p.wbar = &wbar;
+    const T* table = reinterpret_cast<const T*>(a.table);
+    const uint32_t lv_saddr = tc5::smem_u32(lv);
+
+    for (;;) {
+        // ---- refill + march: thread r < 16 owns ray slot r
+        int have_samples = 0;
+        if (tid < kRenderRays) {
+            if (s_ray[tid] == -1) {
+                const int32_t idx = atomicAdd(queue, 1);
+                if ((uint32_t)idx < ra.N) {
+                    s_ray[tid] = idx;
+                    s_t[tid] = __ldg(ra.nears + idx);
+                    s_ws[tid] = 0.0f; s_d[tid] = 0.0f;
+                    s_img[3 * tid] = 0.0f; s_img[3 * tid + 1] = 0.0f; s_img[3 * tid + 2] = 0.0f;
+                    s_cnt[tid] = 0;
+                } else {
+                    s_ray[tid] = -2;   // queue exhausted: this slot stays empty
+                }
+            }
+            uint32_t step = 0;
+            float* px = s_pos + 3 * kRenderSteps * tid;
+            float* pl = s_delta + 2 * kRenderSteps * tid;
+            if (s_ray[tid] >= 0) {
+                const int32_t index = s_ray[tid];
+                MarchCtx c;
+                march_ctx_init(c, ra.rays_o + 3 * (size_t)index, ra.rays_d + 3 * (size_t)index, ra.bound, ra.dt_gamma, ra.max_steps, ra.C, ra.H);
+                s_dir[3 * tid] = c.dx; s_dir[3 * tid + 1] = c.dy; s_dir[3 * tid + 2] = c.dz;
+                const float far = __ldg(ra.fars + index);
+                float t = s_t[tid];
+                float last_t = t;
+                while (t < far && step < kRenderSteps) {   // raymarching.cu:757-790
+                    float x, y, z, tt;
+                    march_pos(c, t, x, y, z);
+                    const float dt = march_dt(c, t);
+                    if (march_probe(c, ra.grid, t, dt, x, y, z, tt)) {
+                        px[3 * step] = x; px[3 * step + 1] = y; px[3 * step + 2] = z;
+                        t = __fadd_rn(t, dt);
+                        pl[2 * step] = dt;
+                        pl[2 * step + 1] = __fadd_rn(t, -last_t);
+                        last_t = t;
+                        ++step;
+                    } else {
+                        do { t = __fadd_rn(t, march_dt(c, t)); } while (t < tt);
+                    }
+                }
+            }
+            have_samples = step > 0;
+            for (uint32_t sidx = step; sidx < kRenderSteps; ++sidx) {   // unused slots: zeros, like the reference's fresh buffers
+                px[3 * sidx] = 0.0f; px[3 * sidx + 1] = 0.0f; px[3 * sidx + 2] = 0.0f;
+                pl[2 * sidx] = 0.0f; pl[2 * sidx + 1] = 0.0f;
+            }
+            if (s_ray[tid] < 0) { s_dir[3 * tid] = 0.0f; s_dir[3 * tid + 1] = 0.0f; s_dir[3 * tid + 2] = 0.0f; }
+        }
+        // ---- field query for the 128 samples (skipped when no ray of the CTA produced a sample)
+        if (__syncthreads_or(have_samples)) {
+            float pos[3], dir[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = s_pos[3 * tid + d];
+                dir[d] = s_dir[3 * (tid / kRenderSteps) + d];
+            }
+            float x01[3];
+            bool oob;
+            to_unit(pos, a.bound, x01, oob);
+            if (oob) x01[0] = x01[1] = x01[2] = 0.0f;
+#pragma unroll 1
+            for (uint32_t j = 0; j < 4; ++j) {
+                float f[8];
+                encode4<T>(table, lv_saddr, 4 * j, a.L, x01, oob, f);
+                *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, tid, j)) = tc5::pack8(f);
+            }
+            float sigma, o16[16];
+            FwdRegs r;
+            mlp_forward(p, a, smw, X, HA, CIN, HB, HA, dir, tid, sigma, o16, r);
+            s_sig[tid] = sigma;
+            s_rgb[3 * tid] = r.rgb[0]; s_rgb[3 * tid + 1] = r.rgb[1]; s_rgb[3 * tid + 2] = r.rgb[2];
+        }
+        __syncthreads();
+        // ---- composite each live ray's samples in order, retire finished rays (raymarching.cu:826-909)
+        int idle = 1;
+        if (tid < kRenderRays) {
+            if (s_ray[tid] >= 0) {
+                const int32_t index = s_ray[tid];
+                const float* ps = s_sig + kRenderSteps * tid;
+                const float* pc = s_rgb + 3 * kRenderSteps * tid;
+                const float* pl = s_delta + 2 * kRenderSteps * tid;
+                float t = s_t[tid], ws = s_ws[tid], d = s_d[tid];
+                float r = s_img[3 * tid], g = s_img[3 * tid + 1], b = s_img[3 * tid + 2];
+                uint32_t step = 0;
+                while (step < kRenderSteps) {
+                    if (pl[2 * step] == 0.0f) break;
+                    const float alpha = 1.0f - __expf(-ps[step] * pl[2 * step]);
+                    const float Tr = 1.0f - ws;
+                    const float w = alpha * Tr;
+                    ws += w;
+                    t += pl[2 * step + 1];
+                    d += w * t;
+                    r += w * pc[3 * step];
+                    g += w * pc[3 * step + 1];
+                    b += w * pc[3 * step + 2];
+                    if (Tr < 1e-4f) break;
+                    ++step;
+                }
+                s_cnt[tid] += (int32_t)kRenderSteps;
+                const bool dead = (step < kRenderSteps) || ((uint32_t)s_cnt[tid] >= ra.max_steps);
+                if (dead) {
+                    weights_sum[index] = ws;
+                    depth[index] = d;
+                    image[3 * (size_t)index] = r;
+                    image[3 * (size_t)index + 1] = g;
+                    image[3 * (size_t)index + 2] = b;
+                    s_ray[tid] = -1;
+                } else {
+                    s_t[tid] = t; s_ws[tid] = ws; s_d[tid] = d;
+                    s_img[3 * tid] = r; s_img[3 * tid + 1] = g; s_img[3 * tid + 2] = b;
+                }
+            }
+            idle = (s_ray[tid] == -2);
+        }
+        if (__syncthreads_and(idle)) break;   // queue exhausted and every slot retired
+    }
+    if (tid == 0) weights_ready(p);
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tc5::tmem_dealloc(p.tmem, 128);
+}
+
 // Stand-alone scatter of d(encoding) [M,32] fp16 into the fp32 table gradient: one thread per (sample, level), 256-thread CTAs,
 // ~40 registers -> full occupancy, so the reductions' issue latency is hidden by other warps instead of stalling a 128-thread
 // MLP CTA that also holds 88 KB of shared memory and 256 TMEM columns (gridencoder.cu:227-314 semantics, fp32 accumulation).
@@ -810,6 +992,35 @@ int pvd_hash_field_backward_rows(const PvdHashField* f, const float* xyzs, const
     PVD_REQUIRE(dx_ws != nullptr && (phases & (PVD_BWD_MLP | PVD_BWD_SCATTER)) != 0);
     return hash_backward_rows(f, xyzs, dirs, enc, grad_sigmas, grad_rgbs, grad_feat16, row0, rows, n_valid, grad_table, gw_ws, dx_ws,
                               status, phases, stream);
+}
+
+int pvd_hash_render_persistent(const PvdHashField* f, const float* rays_o, const float* rays_d, const uint8_t* grid, const float* nears,
+                               const float* fars, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, uint32_t N,
+                               int32_t* queue, float* weights_sum, float* depth, float* image, int32_t* status, void* stream) {
+    if (N == 0) return PVD_OK;
+    PVD_REQUIRE(f && f->table && f->offsets && f->wblob && rays_o && rays_d && grid && nears && fars && queue && weights_sum && depth && image && status);
+    PVD_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1);
+    if (f->L == 0 || f->L > 16) return PVD_EUNSUPPORTED;
+    const FieldArgs a = to_args(f);
+    RenderArgs ra{rays_o, rays_d, grid, nears, fars, bound, dt_gamma, max_steps, C, H, N};
+    const uint32_t groups = (N + kRenderRays - 1) / kRenderRays;
+    const uint32_t blocks = min(groups, (uint32_t)(4 * sm_count()));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    if (f->table_dtype == PVD_DTYPE_F16) {
+        e = cudaFuncSetAttribute(k_hash_render_persistent<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_hash_render_persistent<__half><<<blocks, 128, kFwdSmem, st>>>(a, ra, queue, weights_sum, depth, image, status);
+    } else if (f->table_dtype == PVD_DTYPE_F32) {
+        e = cudaFuncSetAttribute(k_hash_render_persistent<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        k_hash_render_persistent<float><<<blocks, 128, kFwdSmem, st>>>(a, ra, queue, weights_sum, depth, image, status);
+    } else {
+        return PVD_EUNSUPPORTED;
+    }
+    PVD_LAUNCH_CHECK();
+    return PVD_OK;
 }
 
 int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,

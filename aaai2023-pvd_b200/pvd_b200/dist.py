@@ -10,6 +10,8 @@ all-reduce one scalar (`global_l2_norm`) and back-propagate x / ||x||_global loc
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -112,6 +114,7 @@ class TableGradExchange:
         self.why = ""
         self.pre_scale = 1.0 / self.world
         self.fused_barrier, self.blocks, self.unroll = bool(fused_barrier), int(blocks), int(unroll)
+        self.weak = os.environ.get("PVD_P2P_WEAK", "1") != "0"
         self._side = torch.cuda.Stream(device=grad_table.device) if grad_table.is_cuda else None
         self.payload = None
         if mode in ("auto", "multimem", "p2p") and self.world > 1 and self.n % 8 == 0 and grad_table.is_cuda:
@@ -163,7 +166,8 @@ class TableGradExchange:
                                                      C.c_float(self.pre_scale), st))
         if self.kind == "p2p":
             nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(self._bufs), C.c_uint64(self._off), C.c_uint64(self._cnt), C.c_void_p(self._pads),
-                                                    C.c_uint32(self.rank), C.c_uint32(self.world), nv.ptr(self._local), C.c_uint32(self.blocks), st))
+                                                    C.c_uint32(self.rank), C.c_uint32(self.world), nv.ptr(self._local), C.c_uint32(self.blocks),
+                                                    C.c_uint32(self.unroll), C.c_uint32(1 if self.weak else 0), st))
         elif self.kind == "multimem" and self.fused_barrier:
             nv.check(nv.lib().pvd_multimem_allreduce_f16_fused(C.c_void_p(self._mc), C.c_uint64(self._off), C.c_uint64(self._cnt),
                                                                C.c_void_p(self._pads), C.c_uint32(self.rank), C.c_uint32(self.world),

@@ -263,6 +263,32 @@ class HashNeRFField(NeRFRenderer):
         self.color_l = color
         return sigma, color
 
+    @torch.no_grad()
+    def render_persistent(self, rays_o, rays_d, nears, fars, dt_gamma=0.0, max_steps=1024):
+        """The whole evaluation loop of run_cuda (renderer.py:450-543) in one persistent kernel: raw weights_sum [N], depth [N],
+        image [N,3] accumulators for rays_o / rays_d [N,3] (include/pvd_b200_fused.h::pvd_hash_render_persistent)."""
+        rays_o = rays_o.detach().float().contiguous()
+        rays_d = rays_d.detach().float().contiguous()
+        N, dev = rays_o.shape[0], rays_o.device
+        cfg = self.config()
+        cfg.density_scale = float(self.density_scale)      # renderer.py:517: sigmas = self.density_scale * sigmas
+        table = self._staged.table_for(self.encoder.embeddings, cfg.table_fp16)
+        wblob = self._staged.wblob_for((self.sigma_net[0].weight, self.sigma_net[1].weight, self.color_net[0].weight,
+                                        self.color_net[1].weight, self.color_net[2].weight), 2 * cfg.num_levels)
+        f = _cstruct(cfg, table, self.encoder.offsets, wblob)
+        ws = torch.zeros(N, dtype=torch.float32, device=dev)
+        depth = torch.zeros(N, dtype=torch.float32, device=dev)
+        image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+        queue = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with nv.on_device(rays_o):
+            nv.check(nv.lib().pvd_hash_render_persistent(C.byref(f), nv.ptr(rays_o), nv.ptr(rays_d), nv.ptr(self.density_bitfield), nv.ptr(nears),
+                                                         nv.ptr(fars), C.c_float(float(self.bound)), C.c_float(float(dt_gamma)), C.c_uint32(int(max_steps)),
+                                                         C.c_uint32(int(self.cascade)), C.c_uint32(int(self.grid_size)), C.c_uint32(N), nv.ptr(queue),
+                                                         nv.ptr(ws), nv.ptr(depth), nv.ptr(image), nv.ptr(status), nv.stream_of(rays_o)))
+        self._render_status = status
+        return ws, depth, image
+
     def density(self, x):
         """sigma only, for the density-grid upkeep (network.py:439-494; the colour half of the kernel output is discarded)."""
         x = x.reshape(-1, 3)

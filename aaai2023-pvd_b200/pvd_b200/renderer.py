@@ -112,7 +112,16 @@ class NeRFRenderer(nn.Module):
             return {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "inherited_params": inherited_params,
                     "sigmas": sigmas, "rays": rays}
 
-        # inference: march a few steps per alive ray, composite in place, compact (renderer.py:450-543)
+        # inference.  A hash field renders through ONE persistent kernel (march + field + composite fused, rays pulled from a device
+        # queue: csrc/field_hash.cu::k_hash_render_persistent) -- same per-ray results as the host loop below, no host round trips.
+        # PVD_PERSISTENT_INFER=0, a jittered march (perturb) or another field type take the reference's loop (renderer.py:450-543).
+        if (not perturb and os.environ.get("PVD_PERSISTENT_INFER", "1") != "0" and getattr(self, "model_type", None) == "hash"
+                and hasattr(self, "render_persistent")):
+            weights_sum, depth, image = self.render_persistent(rays_o, rays_d, nears, fars, dt_gamma, max_steps)
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+            depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            return {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "inherited_params": inherited_params}
+        # march a few steps per alive ray, composite in place, compact (renderer.py:450-543)
         weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
         depth = torch.zeros(N, dtype=torch.float32, device=device)
         image = torch.zeros(N, 3, dtype=torch.float32, device=device)

@@ -242,10 +242,23 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
                                      uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream);
 /* Two-shot all-reduce over peer pointers (plain NVLink loads / stores, fp32 accumulation, no switch reduction), barriers inside the
  * kernel: `buffer_ptrs_dev` = device array of the ranks' symmetric payload buffers; world 2, 4 or 8; the other arguments as above
- * (signal-pad slots [10W, 12W)). */
+ * (signal-pad slots [10W, 12W)); tuning knobs blocks (0 = 148 CTAs of 512 threads), unroll (1 | 2 | 4 vectors per thread and
+ * buffer in flight), weak (plain instead of relaxed.sys accesses; the barriers' system-scope fences order them). */
 int pvd_p2p_allreduce_f16(const void* buffer_ptrs_dev, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
-                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, void* stream);
+                          uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, uint32_t weak,
+                          void* stream);
 int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Persistent inference: the evaluation branch of NeRFRenderer.run_cuda (distill_mutual/renderer.py:450-543: a host loop of
+ * march_rays -> forward -> composite_rays -> compact_rays with one D2H read per iteration) as ONE kernel for a hash field: CTAs pull
+ * rays from a global queue, march / query / composite them 16 rays x 8 steps at a time and write only the final per-ray
+ * weights_sum [N], depth [N], image [N,3] (raw accumulators: the caller mixes the background and normalises the depth,
+ * renderer.py:540-541).  perturb is off (the reference's evaluation setting); `queue` is one int32 of scratch.
+ * ---------------------------------------------------------------------------------------- */
+int pvd_hash_render_persistent(const PvdHashField* field, const float* rays_o, const float* rays_d, const uint8_t* grid, const float* nears,
+                               const float* fars, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, uint32_t N,
+                               int32_t* queue, float* weights_sum, float* depth, float* image, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * "tensors" (Plenoxels-style) field: NeRFNetwork.forward for model_type "tensors" (distill_mutual/network.py:184-191,311-322,383-409):

@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""ms / frame of the evaluation path for a hash model, 800 x 800 rays of one synthetic Lego-scene camera:
+  persistent  ONE kernel: march + hash field + composite, rays from a device queue (k_hash_render_persistent)
+  host loop   the reference's loop structure (renderer.py:450-543) over this repo's kernels: one D2H read per iteration
+  reference   the same loop over the reference's own extensions + cuBLAS under autocast (oracle/ref_pipeline.py), when oracle/_ref loads
+Prints one JSON line; CUDA events, median of 10 frames after 3 warm-up frames."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "aaai2023-pvd_b200")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    from pvd_b200 import synthetic as syn
+    from pvd_b200.fused import HashNeRFField
+    from pvd_b200.rays import get_rays
+    dev = torch.device("cuda", 0)
+    _, bitfield, _ = syn.lego_bitfield()
+    torch.manual_seed(0)
+    net = HashNeRFField(num_levels=14, desired_resolution=2048).to(dev).eval()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    net.density_bitfield.copy_(torch.from_numpy(bitfield))
+    H = W = 800
+    pose = torch.from_numpy(syn.random_pose(np.random.default_rng(3)))[None].to(dev)
+    rays = get_rays(pose, (1111.1111, 1111.1111, W / 2, H / 2), H, W, N=-1)
+    ro, rd = rays["rays_o"], rays["rays_d"]
+    out = {"frame": f"{H}x{W}", "rays": H * W}
+
+    def render(persistent):
+        os.environ["PVD_PERSISTENT_INFER"] = "1" if persistent else "0"
+        with torch.no_grad():
+            return net.render(ro, rd, bg_color=1, perturb=False)
+
+    a, b = render(True), render(False)
+    out["hit_fraction"] = float((b["image"] != 1).any(-1).float().mean())
+    out["persistent_equals_loop"] = bool(torch.equal(a["image"], b["image"]) and torch.equal(a["depth"], b["depth"]))
+    out["ms_per_frame_persistent"] = timeit(lambda: render(True))
+    out["ms_per_frame_host_loop"] = timeit(lambda: render(False))
+    try:
+        from oracle import cpu, ref_glue, ref_pipeline as rp
+        ext = rp.load_ext()
+        offsets, pls = cpu.grid_offsets(3, 14, 16, 19, desired_resolution=2048)
+        ref = rp.RefHashNetwork(ext, offsets, pls).to(dev).eval()
+        with torch.no_grad():
+            ref.embeddings.copy_(net.encoder.embeddings)
+            for x, y in zip(list(ref.sigma_net) + list(ref.color_net), list(net.sigma_net) + list(net.color_net)):
+                x.weight.copy_(y.weight)
+        rm = ext["raymarching"]
+        bf = net.density_bitfield
+        aabb = net.aabb_infer
+        o, d = ro.view(-1, 3).contiguous(), rd.view(-1, 3).contiguous()
+        N = o.shape[0]
+
+        def ref_frame():  # renderer.py:450-543 over the reference's kernels
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                nears, fars = torch.empty(N, device=dev), torch.empty(N, device=dev)
+                rm.near_far_from_aabb(o, d, aabb, N, 0.2, nears, fars)
+                ws, depth, image = torch.zeros(N, device=dev), torch.zeros(N, device=dev), torch.zeros(N, 3, device=dev)
+                n_alive = N
+                counter = torch.zeros(1, dtype=torch.int32, device=dev)
+                alive = torch.zeros(2, N, dtype=torch.int32, device=dev)
+                rt = torch.zeros(2, N, device=dev)
+                step, i = 0, 0
+                while step < 1024:
+                    if step == 0:
+                        torch.arange(N, out=alive[0]); rt[0] = nears
+                    else:
+                        counter.zero_()
+                        rm.compact_rays(n_alive, alive[i % 2], alive[(i + 1) % 2], rt[i % 2], rt[(i + 1) % 2], counter)
+                        n_alive = counter.item()
+                    if n_alive <= 0:
+                        break
+                    n_step = max(min(N // n_alive, 8), 1)
+                    M = n_alive * n_step
+                    xyzs, dirs, deltas = torch.zeros(M, 3, device=dev), torch.zeros(M, 3, device=dev), torch.zeros(M, 2, device=dev)
+                    rm.march_rays(n_alive, n_step, alive[i % 2], rt[i % 2], o, d, 1.0, 0.0, 1024, 1, 128, bf, nears, fars, xyzs, dirs, deltas, 0)
+                    sig, rgb = ref(xyzs, dirs)
+                    rm.composite_rays(n_alive, n_step, alive[i % 2], rt[i % 2], sig.float(), rgb.float(), deltas, ws, depth, image)
+                    step += n_step
+                    i += 1
+                return image + (1 - ws).unsqueeze(-1)
+
+        img = ref_frame()
+        out["reference_vs_ours_max_abs"] = float((img.view(-1, 3) - b["image"].view(-1, 3)).abs().max())
+        out["ms_per_frame_reference_loop"] = timeit(ref_frame, n=5, warm=2)
+    except Exception as ex:  # noqa: BLE001
+        out["reference"] = f"unavailable: {ex!r}"[:200]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -86,16 +86,24 @@ except Exception as e:  # noqa: BLE001
 try:
     exp = TableGradExchange(g, small, mode="p2p")
     bestp = None
-    for blocks in (37, 74, 148, 296, 592):
-        exp.blocks = blocks
-        k = lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(exp._bufs), C.c_uint64(exp._off), C.c_uint64(exp._cnt), C.c_void_p(exp._pads),
-                                                            C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local), C.c_uint32(blocks), st()))
-        t = timeit(k, n=20, warm=3)
-        out[f"  p2p kernel only (barriers inside), {blocks} CTAs x 512"] = t
-        if exp.barrier_error():
-            out[f"  !! p2p barrier error at {blocks}"] = exp.barrier_error()
-        if bestp is None or t < bestp[0]:
-            bestp = (t, blocks)
+    small_cnt = 8 * world      # barrier cost alone: a shard of one vector per rank
+    exp.blocks, exp.unroll, exp.weak = 148, 1, True
+    out["  p2p kernel, barriers only (one vector)"] = timeit(lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(
+        C.c_void_p(exp._bufs), C.c_uint64(8 * rank), C.c_uint64(8), C.c_void_p(exp._pads), C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local),
+        C.c_uint32(148), C.c_uint32(1), C.c_uint32(1), st())), n=20, warm=3)
+    for weak in (1, 0):
+        for unroll in (1, 2, 4):
+            for blocks in (74, 148, 296):
+                k = lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(exp._bufs), C.c_uint64(exp._off), C.c_uint64(exp._cnt), C.c_void_p(exp._pads),
+                                                                    C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local), C.c_uint32(blocks),
+                                                                    C.c_uint32(unroll), C.c_uint32(weak), st()))
+                t = timeit(k, n=20, warm=3)
+                out[f"  p2p kernel only, {'plain' if weak else 'relaxed.sys'} accesses, unroll {unroll}, {blocks} CTAs x 512"] = t
+                if exp.barrier_error():
+                    out[f"  !! p2p barrier error at {weak}/{unroll}/{blocks}"] = exp.barrier_error()
+                if bestp is None or t < bestp[0]:
+                    bestp = (t, blocks, unroll, weak)
+    exp.unroll, exp.weak = bestp[2], bool(bestp[3])
     exp.blocks = bestp[1]
     out[f"p2p two-shot ({bestp[1]} CTAs): cast + kernel + small, total"] = timeit(exp)
     ref = (g * exp.pre_scale).clamp(-65504, 65504).to(torch.float16)
@@ -103,7 +111,7 @@ try:
     exp()
     torch.cuda.synchronize()
     out["p2p result vs NCCL: max rel err"] = float((exp.payload.float() - ref.float()).abs().max() / ref.float().abs().max())
-    out["best_p2p"] = {"blocks": bestp[1], "kernel_us": bestp[0]}
+    out["best_p2p"] = {"blocks": bestp[1], "unroll": bestp[2], "weak": bestp[3], "kernel_us": bestp[0]}
 except Exception as e:  # noqa: BLE001
     out["p2p"] = f"unavailable: {e!r}"[:200]
 if rank == 0:
