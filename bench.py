@@ -295,6 +295,37 @@ def roofline_kernels(eng):
     return out
 
 
+def l2_peaks():
+    """MEASURED random-access rates of this pool's B200 (scripts/micro/red_peak.cu -> profiles/r02_red_peak.json): 32-byte-sector loads and
+    reductions per second with every lane of a warp in a different sector -- what bounds the hash gather / scatter (their tables live in L2)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_red_peak.json")))
+        return {"ld": d["ld_4B_Gops"] * 1e9, "red": max(d["red_f32_v2_Gops"], d["red_f32_v4_Gops"], d["red_f32_x1_Gops"]) * 1e9}
+    except Exception:
+        return None
+
+
+def l2_roofline(kernel, ms):
+    """{"bound": "l2_sector_ld" | "l2_atomic", achieved / peak in G sector-ops/s} for a hash field kernel, from the sector count of the
+    committed ncu capture of the same workload and this run's event-timed duration; None when either is missing."""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"].get(kernel.split("(")[0])
+        pk = l2_peaks()
+        if not k or not pk:
+            return None
+        if "bwd" in kernel or "scatter" in kernel:
+            n, peak, bound = k.get("red_sectors"), pk["red"], "l2_atomic"
+        else:
+            n, peak, bound = k.get("ld_sectors"), pk["ld"], "l2_sector_ld"
+        if not n:
+            return None
+        ach = n / (ms * 1e-3)
+        return {"bound": bound, "sector_ops_per_launch": n, "achieved_Gops": ach / 1e9, "peak_Gops": peak / 1e9, "frac": ach / peak,
+                "peak_kind": "measured: scripts/micro/red_peak.cu (profiles/r02_red_peak.json)", "count_source": k.get("source")}
+    except Exception:
+        return None
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
     try:
@@ -579,6 +610,10 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
         roofs.append({"bound": bound, "kernel": kernel, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                       "traffic": traffic, "traffic_source": src, "peak_kind": peak_kind,
                       ("algorithmic_bytes_per_sample" if bound == "hbm" else "algorithmic_flops_per_sample"): per_sample})
+        if "hash" in kernel:   # the tables are L2-resident: the kernel's real bound is the L2 sector rate, quoted against a measured peak
+            l2 = l2_roofline(kernel, ms)
+            if l2:
+                roofs[-1]["l2"] = l2
     # the workload's bound: the table / plane traffic (HBM roofline) -- except mlp -> hash, where the teacher's GEMMs dominate
     want = "tensor" if workload == "mlp-hash" else "hbm"
     dom = max((r for r in roofs if r["bound"] == want), key=lambda r: r["ms"])
@@ -834,7 +869,7 @@ def main():
     ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (default 4096; 8192 for mlp-hash)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--grad-comm", default="fp16", choices=["auto", "p2p", "multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1: fp16 payload over NCCL (fp16), fp16 payload reduced in the NVSwitch by one kernel with device-side barriers (multimem; auto = multimem if it sets up and passes its self-check, else NCCL), or fp32 over NCCL")
+    ap.add_argument("--grad-comm", default="auto", choices=["auto", "p2p", "multimem", "fp16", "fp32"], help="big-gradient exchange for N > 1, fp16 payload unless fp32: auto (default) = p2p if torch symmetric memory sets up and the kernel passes its self-check against NCCL, else NCCL; p2p = two-shot reduction over NVLink peer pointers, one kernel with device-side barriers; multimem = the same shard reduced in the NVSwitch; fp16 = NCCL; fp32 = NCCL on the fp32 buffers")
     ap.add_argument("--mm-blocks", type=int, default=0, help="multimem exchange kernel: CTAs (0 = default)")
     ap.add_argument("--mm-unroll", type=int, default=4, help="multimem exchange kernel: 16-byte switch reductions in flight per thread (2 | 4 | 8)")
     ap.add_argument("--only", dest="all_workloads", action="store_false", help="measure only --workload (default: the other BASELINE configurations "
