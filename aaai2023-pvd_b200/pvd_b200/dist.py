@@ -134,6 +134,12 @@ class TableGradExchange:
                 if want_p2p:
                     if not (self._pads and self._bufs and self.world in (2, 4, 8)):
                         raise RuntimeError("peer pointers / signal pads not exposed by this torch, or world not in (2, 4, 8)")
+                    # the kernel's barriers are monotonic epoch flags in slots [12W, 13W) of the signal pads, counted from this
+                    # rank's local[3] = 0: start from zeroed slots on every rank (a pad may be recycled from an earlier buffer)
+                    pad = hdl.get_signal_pad(self.rank)
+                    pad.view(-1).view(torch.int32)[12 * self.world:13 * self.world].zero_()
+                    torch.cuda.synchronize(grad_table.device)
+                    dist.barrier(group=self.group)
                     self.kind = "p2p"
                 else:
                     if mc == 0:

@@ -242,11 +242,14 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
                                      uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, void* stream);
 /* Two-shot all-reduce over peer pointers (plain NVLink loads / stores, fp32 accumulation, no switch reduction), barriers inside the
  * kernel: `buffer_ptrs_dev` = device array of the ranks' symmetric payload buffers; world 2, 4 or 8; the other arguments as above
- * (signal-pad slots [10W, 12W)); tuning knobs blocks (0 = 148 CTAs of 512 threads), unroll (1 | 2 | 4 vectors per thread and
+ * (signal-pad slots [12W, 13W): monotonic epoch flags; `local_state[3]` carries the epoch between launches); tuning knobs blocks (0 = 148 CTAs of 512 threads), unroll (1 | 2 | 4 vectors per thread and
  * buffer in flight), weak (plain instead of relaxed.sys accesses; the barriers' system-scope fences order them). */
 int pvd_p2p_allreduce_f16(const void* buffer_ptrs_dev, uint64_t elem_offset, uint64_t elem_count, const void* signal_pad_ptrs_dev,
                           uint32_t rank, uint32_t world, uint32_t* local_state, uint32_t blocks, uint32_t unroll, uint32_t weak,
                           void* stream);
+/* NVLink rate probe (scripts/micro/exchange_probe.py): copy elem_count halves between this rank's and the next rank's symmetric
+ * buffer -- mode 0 pull, 1 push, 2 both directions on alternating vectors.  No synchronisation: timing only. */
+int pvd_p2p_copy_probe(const void* buffer_ptrs_dev, uint64_t elem_count, uint32_t rank, uint32_t world, uint32_t mode, uint32_t blocks, void* stream);
 int pvd_cast_f32_to_f16(const float* src, void* dst, uint64_t elem_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -91,8 +91,13 @@ try:
     out["  p2p kernel, barriers only (one vector)"] = timeit(lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(
         C.c_void_p(exp._bufs), C.c_uint64(8 * rank), C.c_uint64(8), C.c_void_p(exp._pads), C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local),
         C.c_uint32(148), C.c_uint32(1), C.c_uint32(1), st())), n=20, warm=3)
-    for weak in (1, 0):
-        for unroll in (1, 2, 4):
+    for mode, name in ((0, "pull (remote loads)"), (1, "push (remote stores)"), (2, "pull + push at once")):
+        t = timeit(lambda: nv.check(nv.lib().pvd_p2p_copy_probe(C.c_void_p(exp._bufs), C.c_uint64(exp.n), C.c_uint32(rank), C.c_uint32(world), C.c_uint32(mode),
+                                                                C.c_uint32(148), st())), n=20, warm=3)
+        out[f"  link probe, {name}: 21.2 MB to/from the next rank"] = t
+        out[f"  link probe, {name}: GB/s per direction"] = exp.n * 2 / (t * 1e-6) / 1e9 / (2 if mode == 2 else 1)
+    for weak in (1,):
+        for unroll in (2,):
             for blocks in (74, 148, 296):
                 k = lambda: nv.check(nv.lib().pvd_p2p_allreduce_f16(C.c_void_p(exp._bufs), C.c_uint64(exp._off), C.c_uint64(exp._cnt), C.c_void_p(exp._pads),
                                                                     C.c_uint32(rank), C.c_uint32(world), nv.ptr(exp._local), C.c_uint32(blocks),
