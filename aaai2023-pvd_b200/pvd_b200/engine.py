@@ -131,6 +131,9 @@ class FieldTrainEngine:
         self._alloc_samples(N * 32)
         self._coarse_valid = False
         # what surrounds forward + backward in a training iteration (all of it CUDA-graph capturable, see `_prologue` / `_epilogue`)
+        # stream the tables / planes the forward gathers from into L2 at the top of the step (side branch): matters when L2 is cold --
+        # another job's kernels, or bench.py's flush between timed steps -- and costs ~7 us of otherwise idle HBM time when it is warm
+        self.prefetch_l2 = os.environ.get("PVD_PREFETCH_L2", "1") != "0"
         self.restage_each_step = False   # parameters are changed by an EXTERNAL optimizer between steps: re-cast / re-pack at the top
         self.unpack_each_step = False    # leave the small weight gradients in parameter shapes (ops.wgrads) at the end of the step
         self.exchange = None             # dist.TableGradExchange: the one all-reduce of the multi-GPU path, after the backward
@@ -265,6 +268,8 @@ class FieldTrainEngine:
         latency-bound); parameter-only loss terms (the vm L1 penalty) follow it on the same branch."""
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
+            if self.prefetch_l2:         # first on this branch: the forward starts gathering within microseconds
+                self._prefetch(C.c_void_p(self._side.cuda_stream))
             if self.optimizer is None:   # a fused optimizer leaves the big gradient buffer zeroed (same pass as the update)
                 self.ops.clear_grads()
             if self.l1_reg_weight:
@@ -295,6 +300,9 @@ class FieldTrainEngine:
         self._loss_backward(st, rs, M, M_drop)
         self._field_backward(st, rs, M, cur)
         self._epilogue(st)
+
+    def _prefetch(self, st):
+        self.ops.prefetch(st)
 
     def _prologue(self, cur):
         if self.restage_each_step and self.optimizer is None:
@@ -558,6 +566,10 @@ class PairDistillEngine(FieldTrainEngine):
         self.feat_tea = torch.empty(M, 16, device=d)
         self.feat = torch.empty(M, 16, device=d)
         self.grad_feat = torch.zeros(M, 16, device=d)
+
+    def _prefetch(self, st):
+        self.ops.prefetch(st)
+        self.tea.prefetch(st)
 
     def stage(self):
         self.ops.stage(self.density_scale)

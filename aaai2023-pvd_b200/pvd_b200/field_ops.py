@@ -59,6 +59,11 @@ class HashOps:
         self.wblob = f._staged.wblob_for(self._weights(), 2 * cfg.num_levels)
         self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
 
+    def prefetch(self, st):
+        """Stream the table the forward gathers from into L2 (a side-stream TMA prefetch; see csrc/optim.cu::k_l2_prefetch)."""
+        t = self.table
+        nv.check(nv.lib().pvd_l2_prefetch(nv.ptr(t), C.c_uint64(t.numel() * t.element_size()), st))
+
     def alloc(self, M):
         if self.trainable:
             self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev)
@@ -213,6 +218,12 @@ class VmOps:
             self._shadow_key = key
         return self.shadow_groups
 
+    def prefetch(self, st):
+        groups = self.shadow_groups if (self.plane_f16 and self.shadow_groups) else self.groups
+        for grp in groups:
+            for p in grp:
+                nv.check(nv.lib().pvd_l2_prefetch(nv.ptr(p), C.c_uint64(p.numel() * p.element_size()), st))
+
     def alloc(self, M):
         if self.trainable and VM_SPLIT_SCATTER:
             l = nv.lib()
@@ -292,6 +303,9 @@ class MlpOps:
     def alloc(self, M):
         pass
 
+    def prefetch(self, st):
+        pass   # 876 KB of weights: L2-resident after the first tile
+
     def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
         nv.check(nv.lib().pvd_mlp_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
                                                 nv.ptr(feat), nv.ptr(status), st))
@@ -330,6 +344,9 @@ class TensorsOps:
 
     def alloc(self, M):
         pass
+
+    def prefetch(self, st):
+        pass   # 235 MB at 128^3: larger than L2, gathered from HBM either way
 
     def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
         assert feat is None, "the tensors field has no feature_sigma_color (network.py:407)"

@@ -81,6 +81,10 @@ typedef struct PvdCastDesc {
 } PvdCastDesc;
 int pvd_cast_f32_to_f16_multi(const PvdCastDesc* descs_dev, uint32_t n_descs, uint64_t max_n, void* stream);
 
+/* Stream `bytes` at `ptr` (16-byte aligned) into L2 with TMA prefetches: run on a side stream ahead of a kernel that gathers from the
+ * buffer at random (the hash table, the vm planes) when L2 is cold. */
+int pvd_l2_prefetch(const void* ptr, uint64_t bytes, void* stream);
+
 /* fp16 -> fp32 (the write-back of an exchanged gradient payload), scaled. */
 int pvd_cast_f16_to_f32(const void* src, float* dst, uint64_t elem_count, float scale, void* stream);
 /* fp32 -> fp16 with a scale and saturation to +-65504 (the payload of the multi-GPU exchange; never produces inf from finite input). */
