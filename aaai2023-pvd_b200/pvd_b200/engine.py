@@ -131,9 +131,11 @@ class FieldTrainEngine:
         self._alloc_samples(N * 32)
         self._coarse_valid = False
         # what surrounds forward + backward in a training iteration (all of it CUDA-graph capturable, see `_prologue` / `_epilogue`)
-        # stream the tables / planes the forward gathers from into L2 at the top of the step (side branch): matters when L2 is cold --
-        # another job's kernels, or bench.py's flush between timed steps -- and costs ~7 us of otherwise idle HBM time when it is warm
-        self.prefetch_l2 = os.environ.get("PVD_PREFETCH_L2", "1") != "0"
+        # PVD_PREFETCH_L2=1: stream the tables / planes the forward gathers from into L2 at the top of the step (TMA bulk prefetch on the
+        # memset branch).  MEASURED with bench.py's cold L2 (256 MiB flush between steps): hash step 112.8 vs 112.9 us (no effect: the
+        # forward's cold misses are not what bounds it), vm 242.5 vs 212.8 us and hash -> vm 281 vs 251 us (WORSE: 69 MB of planes + 69 MB
+        # of gradients do not fit L2 together, the prefetch evicts what the backward needs).  Off by default.
+        self.prefetch_l2 = os.environ.get("PVD_PREFETCH_L2", "0") != "0"
         self.restage_each_step = False   # parameters are changed by an EXTERNAL optimizer between steps: re-cast / re-pack at the top
         self.unpack_each_step = False    # leave the small weight gradients in parameter shapes (ops.wgrads) at the end of the step
         self.exchange = None             # dist.TableGradExchange: the one all-reduce of the multi-GPU path, after the backward
