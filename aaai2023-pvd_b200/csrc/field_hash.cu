@@ -213,8 +213,12 @@ __global__ void __launch_bounds__(128) k_hash_field_fwd(FieldArgs a, const float
         if (TMA_IN) tc5::mbar_init(&sbar, 1);
         tc5::mbar_fence_init();
         if (TMA_IN && blockIdx.x < n_tiles && tma_tile(blockIdx.x)) stage_samples(blockIdx.x);  // first: the gather waits on it
+        // programmatic dependent launch: this kernel may have started under the weight-pack kernel (a step that re-stages its
+        // parameters); samples and table are older than that, only the packed tiles must wait for it
+        pdl_wait();
         stage_blob_async(smw, a.wblob, PVD_FIELD_WBLOB_BYTES, &wbar);  // TMA: lands while the first tile is gathered
     }
+    pdl_launch_dependents();   // the loss kernel may be made resident now; it waits for this grid before it reads sigmas / rgbs
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     tc5::fence_before_sync();
     __syncthreads();
@@ -850,6 +854,7 @@ __global__ void __launch_bounds__(256) k_hash_scatter(FieldArgs a, const float* 
 __global__ void k_pack_weights(const float* __restrict__ ws0, const float* __restrict__ ws1, const float* __restrict__ wc0,
                                const float* __restrict__ wc1, const float* __restrict__ wc2, uint32_t in_dim,
                                uint8_t* __restrict__ blob) {
+    pdl_launch_dependents();   // the forward behind it (launch_pdl) gathers its first tile meanwhile and waits before it stages the tiles
     pack_matrix(ws0, 64, in_dim, blob + kWB1, 64, 32);
     pack_matrix(ws1, 16, 64, blob + kWB2, 16, 64);
     pack_matrix(wc0, 64, 31, blob + kWB3, 64, 32);
@@ -926,8 +931,8 @@ int pvd_hash_field_forward(const PvdHashField* f, const float* xyzs, const float
     auto launch = [&](auto kern) -> int {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, 128, kFwdSmem, st>>>(a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
-        return PVD_OK;
+        e = launch_pdl(kern, dim3(grid), dim3(128), kFwdSmem, st, a, xyzs, dirs, M, sigmas, rgbs, (__half*)enc, feat16, status);
+        return e == cudaSuccess ? PVD_OK : (int)e;
     };
     int rc;
     if (f->table_dtype == PVD_DTYPE_F16) {

@@ -784,6 +784,7 @@ __global__ void __launch_bounds__(32) k_composite_train_mse(const float* __restr
                                                            float* __restrict__ weights_sum, float* __restrict__ depth,
                                                            float* __restrict__ image, float* __restrict__ grad_sigmas,
                                                            float* __restrict__ grad_rgbs, float* __restrict__ loss_out) {
+    pdl_wait();                // (launched with launch_pdl behind the field forward: resident early, starts the moment that grid is done)
     pdl_launch_dependents();   // the field backward (launched with launch_pdl) may start its prologue + forward recomputation now
     const uint32_t n = blockIdx.x;
     const uint32_t lane = threadIdx.x;
@@ -1246,8 +1247,9 @@ int pvd_composite_rays_train_mse(const float* gt_rgb, const float* bg_color, flo
     if (N == 0) return PVD_OK;
     PVD_REQUIRE(gt_rgb && bg_color && sigmas && rgbs && deltas && rays && weights_sum && depth && image && grad_sigmas &&
                 grad_rgbs && loss_out);
-    k_composite_train_mse<<<N, 32, 0, (cudaStream_t)stream>>>(gt_rgb, bg_color, loss_scale, sigmas, rgbs, deltas, rays, M, N,
-                                                              weights_sum, depth, image, grad_sigmas, grad_rgbs, loss_out);
+    cudaError_t e = launch_pdl(k_composite_train_mse, dim3(N), dim3(32), 0, (cudaStream_t)stream, gt_rgb, bg_color, loss_scale, sigmas, rgbs, deltas, rays,
+                               M, N, weights_sum, depth, image, grad_sigmas, grad_rgbs, loss_out);
+    if (e != cudaSuccess) return (int)e;
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }
