@@ -1,102 +1,78 @@
 // field_mlp.cu -- fused "mlp" (NeRF) field FORWARD for sm_100a: frequency encoding -> 8 x 256 ReLU MLP with a skip
-// connection -> sigma_net / color_net tail, one kernel.  This is the teacher of BASELINE config 5 (mlp -> hash distillation);
-// it is evaluated under torch.no_grad (distill_mutual/utils.py:1008-1018), so only the forward is fused.
+// connection -> sigma_net / color_net tail, one kernel.  This is the teacher of BASELINE config 5 (mlp -> hash distillation),
+// evaluated under torch.no_grad (distill_mutual/utils.py:1008-1018), and -- with SAVE -- the forward of a TRAINED mlp model
+// (main_just_train_tea.py --model_type mlp), whose backward is field_mlp_bwd.cu.
 //
 // Replaces NeRFNetwork.forward for model_type "mlp" (distill_mutual/network.py:56-70,324-333,413-437 and
 // tools/encoding.py:6-49): 21 sin/cos/cat kernels, 8 cuBLAS GEMMs with bias + ReLU + cat kernels between them, then the
 // same 5-GEMM tail as the hash model -- 0.87 MFLOP per sample, the one part of the path where FLOPs dominate.
 //
-// Structure per 128-sample tile (one persistent CTA per SM, 128 threads, thread t owns sample row t):
-//   * PE(10): 63 features (x, then sin/cos(2^k x), k = 0..9) -> fp16 operand tile X0 [128 x 64].
-//   * every 256-wide layer is  D[128 x 256] (TMEM, 256 columns)  +=  A[128 x K] * W[256 x K]^T  streamed in K-chunks of 64:
-//     a chunk of W is a 32 KB fp16 operand tile (pre-packed on the host side), double-buffered in shared memory and moved by
-//     the TMA engine: ONE thread arms a "full" mbarrier with the byte count (mbarrier.arrive.expect_tx) and issues one
-//     cp.async.bulk.shared::cluster.global (UBLKCP) per chunk; the same thread waits for it, issues the four tcgen05.mma
-//     (N = 256, K = 16) of the chunk and commits them to the buffer's "empty" mbarrier, so the copy of chunk c+1 overlaps
-//     the MMAs of chunk c and no other thread takes part in weight streaming (no block-wide barrier per chunk).
-//   * the skip layer is two accumulating GEMMs: in_pts (X0, K = 64) and the 256 hidden units -- the concat never exists.
-//   * layer epilogue: each thread pulls its own row from TMEM 16 columns at a time, adds the bias, applies ReLU, and writes
-//     the next layer's A operand (fp16, chunk layout) over the previous one.
-//   * the last layer (256 -> 28) feeds the sigma_net / color_net tail of field_tail.cuh unchanged.
-#include <stdlib.h>
-#include "common.cuh"
-PVD_TRACE_TU(pvd_debug_trace_field_mlp)
-#include "field_tail.cuh"
-
-namespace pvd {
-
-constexpr uint32_t kMlpChunkBytes = 256 * 64 * 2;   // one K-chunk of a 256-row weight matrix
-constexpr uint32_t kMlpChunks = 26;                 // 1 (L0) + 3*4 (L1-3) + 1+4 (L4: in_pts part, hidden part) + 2*4 (L5-6)
-constexpr uint32_t kMlpL7Bytes = 4 * (32 * 64 * 2); // 256 -> 28 as four [32 x 64] chunks
-constexpr uint32_t kMlpBiasOff = kMlpChunks * kMlpChunkBytes + kMlpL7Bytes;
-constexpr uint32_t kMlpBiasBytes = 8 * 256 * 4;
-static_assert(kMlpBiasOff + kMlpBiasBytes == PVD_MLP_WBLOB_BYTES, "mlp blob size");
-
-struct MlpArgs {
-    const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
-    const uint8_t* tail_blob;  // PVD_FIELD_WBLOB_BYTES (sigma_net / color_net)
-    float clip_min, clip_max, density_scale;
-    uint32_t diag;   // timing diagnostics only (PVD_MLP_DIAG): 1 no bias loads, 2 no operand stores, 4 no TMEM loads, 8 no PE
-};
-
-// layer schedule: for each of the 26 streamed chunks, which layer it belongs to and where its A operand comes from
-struct ChunkDesc {
-    uint8_t layer;     // 0..6
-    uint8_t from_x0;   // A = X0 tile (in_pts) instead of the activation tile
-    uint8_t k_chunk;   // which 64-column slice of the activation tile
-    uint8_t last;      // last chunk of its layer
-};
-__constant__ ChunkDesc kSchedule[kMlpChunks] = {
-    {0, 1, 0, 1},
-    {1, 0, 0, 0}, {1, 0, 1, 0}, {1, 0, 2, 0}, {1, 0, 3, 1},
-    {2, 0, 0, 0}, {2, 0, 1, 0}, {2, 0, 2, 0}, {2, 0, 3, 1},
-    {3, 0, 0, 0}, {3, 0, 1, 0}, {3, 0, 2, 0}, {3, 0, 3, 1},
-    {4, 1, 0, 0}, {4, 0, 0, 0}, {4, 0, 1, 0}, {4, 0, 2, 0}, {4, 0, 3, 1},
-    {5, 0, 0, 0}, {5, 0, 1, 0}, {5, 0, 2, 0}, {5, 0, 3, 1},
-    {6, 0, 0, 0}, {6, 0, 1, 0}, {6, 0, 2, 0}, {6, 0, 3, 1},
-};
-
-// =============================================================================================== v2: warp-specialised, two tiles per CTA
-// One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream:
-//   warps 0-3 (warpgroup 0) own the rows of tile 0, warps 4-7 (warpgroup 1) the rows of tile 1: PE, layer epilogues (TMEM -> bias ->
-//     ReLU -> fp16 operand tile, in place), the sigma/colour tail and the outputs of their tile;
-//   warp 8, one lane: TMA producer.  The packed weights are streamed in 16 KB pieces ([256 x 32] fp16 = half of a v1 chunk, same
-//     blob) through a FOUR-stage ring; loads run up to four pieces ahead of the tensor core, across layers, tiles pairs and the
-//     tail, so their latency (the bound of v1: a two-stage ring serialised copy -> MMA -> copy) is off the critical path;
-//   warp 9, one lane: MMA issuer.  Every piece feeds 2 + 2 tcgen05.mma (tile 0, tile 1; N = 256, K = 16), so L2 -> shared weight
-//     traffic per sample is halved; accumulators: tile t in TMEM columns [256 t, 256 t + 256) -- all 512 columns of the SM.
+// One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream (18 warps):
+//   warps 0-7 own tile 0, warps 8-15 tile 1.  Inside a tile, warp w serves the TMEM lane quadrant w % 4 (= sample rows
+//     32 (w % 4) .. +31: a warp may only touch its own quadrant) and the COLUMN HALF (w / 4) % 2 of the 256-wide layer: two threads
+//     per sample row, 128 columns each.  PE, layer epilogues (TMEM -> bias -> ReLU -> fp16 operand tile, in place) are split that
+//     way; the sigma/colour tail and the outputs of a tile belong to its column-half-0 warpgroup.  Round 1 ran ONE thread per row
+//     (8 epilogue warps per SM, two per scheduler): the epilogue's dependent chain tcgen05.ld -> bias -> ReLU -> pack -> st.shared
+//     was latency-bound at ~3 us per layer against 1.1 us of MMAs; 16 warps halve the per-thread chain and double the warps a
+//     scheduler can switch between.
+//   warp 16, one lane: TMA producer.  The packed weights are streamed in 16 KB pieces ([256 x 32] fp16) through a FOUR-stage ring
+//     of cp.async.bulk copies; loads run up to four pieces ahead of the tensor core, across layers, tile pairs and the tail.
+//   warp 17, one lane: MMA issuer.  Accumulators: tile t in TMEM columns [256 t, 256 t + 256) -- all 512 columns of the SM.
 // Hand-offs are mbarriers only (no CTA-wide barrier in the steady state):
 //   ring_full[s] (TMA bytes) / ring_empty[s] (tcgen05.commit)        producer <-> issuer
-//   acc_full[t]  (tcgen05.commit after a layer's last MMA)           issuer   ->  warpgroup t: accumulator complete, operand tile dead
-//   act_ready[t] (128 arrivals)                                      warpgroup t -> issuer: next operand tile written, TMEM drained
+//   acc_full[t]  (tcgen05.commit after a layer's last MMA)           issuer   ->  the 8 warps of tile t: accumulator complete
+//   act_ready[t] (256 arrivals)                                      tile t's warps -> issuer: next operand tile written, TMEM drained
 // Shared memory: 2 x 64 KB operand tiles + 2 x 16 KB PE tiles + 4 x 16 KB ring = 224 KB.  The 20 KB tail weights are copied (TMA)
 // into the dead upper half of a tile's own operand buffer when its layer 7 has completed; biases are read through the constant-
 // like __ldg path (all threads of a warp read the same address).
-constexpr uint32_t kPiece = 16384;                    // bytes per streamed piece
-constexpr uint32_t kPieces = 2 * kMlpChunks + 1;      // 52 half-chunks of layers 0-6 + layer 7
-constexpr uint32_t kStages = 4;
-constexpr uint32_t kV2Threads = 320;
-constexpr uint32_t kTailWOff = 32768;
+// SAVE (training): every operand tile the tensor core consumed (PE tile, act_1..act_7; fp16 chunk layout, 464 KB per tile) and
+// the 28-wide trunk output (the tail's "encoding", [M,32] fp16) also go to global memory -- warp-wide 512-byte row stores -- for
+// the backward kernels.
+#include <stdlib.h>
+#include "field_mlp.cuh"
+PVD_TRACE_TU(pvd_debug_trace_field_mlp)
+
+namespace pvd {
+
+constexpr uint32_t kEpiWarps = 16;
+constexpr uint32_t kV2Threads = 32 * (kEpiWarps + 2);   // 576
+constexpr uint32_t kTailWOff = 32768;                   // tail weights inside a tile's operand buffer
 #ifndef PVD_MLP_STAGGER
 #define PVD_MLP_STAGGER 1
 #endif
 constexpr bool kStaggerDefault = PVD_MLP_STAGGER != 0;  // 1: per layer, tile 0's pass then tile 1's pass (weights streamed twice, MMA of one tile under
-                                                 // the epilogue of the other); 0: both tiles consume every piece (weights streamed once)                 // tail weights inside a tile's operand buffer
+                                                        // the epilogue of the other); 0: both tiles consume every piece (weights streamed once)
 
-struct V2Wait {  // bounded waits that stop costing time after the first failure (a wrong barrier must not hang the GPU)
-    int32_t* status;
-    bool dead = false;
-    __device__ __forceinline__ void operator()(uint64_t* bar, uint32_t parity) {
-        if (!tc5::mbar_wait(bar, parity, dead ? 1u : (1u << 22))) {
-            dead = true;
-            atomicExch(status, 2);
+// FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9 -> 63 features (+1 zero pad);
+// this thread's 32 of them (features 32 HALF .. 32 HALF + 31).  Feature 3 + 6k + d = sin(2^k x_d), 3 + 6k + 3 + d = cos(2^k x_d).
+template <int HALF>
+__device__ __forceinline__ void pe_half(const float (&pos)[3], float (&f)[32], bool skip) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = 0.0f;
+    if (HALF == 0) { f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2]; }
+    constexpr int k_lo = HALF == 0 ? 0 : 4, k_hi = HALF == 0 ? 4 : 9, lo = 32 * HALF, hi = 32 * HALF + 32;
+#pragma unroll
+    for (int k = k_lo; k <= k_hi; ++k) {
+        const float freq = (float)(1 << k);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int gs = 3 + 6 * k + d, gc = gs + 3;
+            const bool need_s = gs >= lo && gs < hi, need_c = gc >= lo && gc < hi;
+            if (need_s || need_c) {
+                float sn = 0.f, cs = 0.f;
+                if (!skip) sincosf(pos[d] * freq, &sn, &cs);
+                if (need_s) f[gs - lo] = sn;
+                if (need_c) f[gc - lo] = cs;
+            }
         }
     }
-};
+}
 
+template <bool SAVE>
 __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, const float* __restrict__ xyzs, const float* __restrict__ dirs,
                                                                 uint32_t M, float* __restrict__ sigmas, float* __restrict__ rgbs,
-                                                                float* __restrict__ feat16, int32_t* status) {
+                                                                float* __restrict__ feat16, uint8_t* __restrict__ save,
+                                                                __half* __restrict__ enc_out, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t ring_full[kStages], ring_empty[kStages], acc_full[2], act_ready[2], tail_bar[2], tail_w[2];
     __shared__ uint32_t tmem_base_s;
@@ -110,7 +86,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
         }
         for (uint32_t t = 0; t < 2; ++t) {
             tc5::mbar_init(&acc_full[t], 1);
-            tc5::mbar_init(&act_ready[t], 128);
+            tc5::mbar_init(&act_ready[t], 256);
             tc5::mbar_init(&tail_bar[t], 1);
             tc5::mbar_init(&tail_w[t], 1);
         }
@@ -126,7 +102,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
     V2Wait wait{status};
     const bool kStagger = kStaggerDefault != ((a.diag & 16u) != 0u);   // diag bit 16 flips the schedule
 
-    if (warp == 8) {
+    if (warp == kEpiWarps) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t pc = 0;  // pieces issued so far (ring position)
@@ -151,7 +127,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kEpiWarps + 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t pc = 0, acts = 0;  // pieces consumed; act_ready phases consumed (same count for both tiles)
@@ -162,7 +138,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                 for (uint32_t layer = 0; layer < 7; ++layer) {
                     const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : 8u);
                     if (kStagger) {
-                        // tile 0's whole layer, then tile 1's: while the tensor core runs tile 1, warpgroup 0 is already in its epilogue
+                        // tile 0's whole layer, then tile 1's: while the tensor core runs tile 1, tile 0's warps are already in their epilogue
                         for (uint32_t t = 0; t < 2; ++t) {
                             wait(&act_ready[t], acts & 1u);  // operand tile of this layer written, accumulator drained
                             for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
@@ -230,9 +206,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
             }
         }
     } else {
-        // ------------------------------------------------------------------ the two warpgroups: one tile each
-        const uint32_t t = warp >> 2;          // tile of the pair / warpgroup
-        const uint32_t r = tid & 127u;         // row inside the tile
+        // ------------------------------------------------------------------ the epilogue warps: 8 per tile, two threads per row
+        const uint32_t t = warp >> 3;                    // tile of the pair
+        const uint32_t half = (warp >> 2) & 1u;          // column half of the 256-wide layers
+        const uint32_t r = (warp & 3u) * 32u + lane;     // row inside the tile (TMEM lane)
         uint8_t* const A = smem + t * 65536;
         uint8_t* const X0 = smem + 2 * 65536 + t * 16384;
         const uint32_t trow = tc5::tmem_addr(tmem + 256u * t, (warp & 3u) * 32u, 0);
@@ -241,56 +218,52 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
         p.team = 1u + t;
         uint32_t accs = 0, pairs_done = 0;
         for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pairs_done) {
-            const uint32_t row = (2u * pair + t) * kTile + r;
+            const uint32_t tile = 2u * pair + t;
+            const uint32_t row = tile * kTile + r;
             const bool live = row < M;
-            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+            uint8_t* const sv = (SAVE && tile < n_tiles) ? save + (size_t)tile * kSaveTileBytes : nullptr;   // whole tiles: rows past M hold the image of x = 0
+            float pos[3] = {0.f, 0.f, 0.f};
             if (live) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
-                    dir[d] = __ldg(dirs + 3 * (size_t)row + d);
-                }
+                for (int d = 0; d < 3; ++d) pos[d] = __ldg(xyzs + 3 * (size_t)row + d);
             }
-            {   // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9
-                float f[64];
-                f[0] = pos[0]; f[1] = pos[1]; f[2] = pos[2];
-                float freq = 1.0f;
+            {
+                float f[32];
+                if (half == 0) pe_half<0>(pos, f, (a.diag & 8u) != 0u);
+                else pe_half<1>(pos, f, (a.diag & 8u) != 0u);
 #pragma unroll
-                for (int k = 0; k < 10; ++k) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        float sn = 0.f, cs = 0.f;
-                        if (!(a.diag & 8u)) sincosf(pos[d] * freq, &sn, &cs);
-                        f[3 + 6 * k + d] = sn;
-                        f[3 + 6 * k + 3 + d] = cs;
-                    }
-                    freq *= 2.0f;
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 u = tc5::pack8(f + 8 * j);
+                    const uint32_t off = tc5::chunk_off(kTile, r, 4 * half + j);
+                    *reinterpret_cast<uint4*>(X0 + off) = u;
+                    if (SAVE && sv) *reinterpret_cast<uint4*>(sv + kSavePe + off) = u;
                 }
-                f[63] = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(X0 + tc5::chunk_off(kTile, r, j)) = tc5::pack8(f + 8 * j);
             }
             tc5::fence_async_smem();
             tc5::fence_before_sync();
             tc5::mbar_arrive(&act_ready[t]);
-            // ---- layers 0..6: wait for the accumulator, bias + ReLU, rewrite the operand tile in place
+            // ---- layers 0..6: wait for the accumulator, bias + ReLU, rewrite this thread's half of the operand row in place
             for (uint32_t layer = 0; layer < 7; ++layer, ++accs) {
                 wait(&acc_full[t], accs & 1u);
                 tc5::fence_after_sync();
-                const float4* __restrict__ bl = reinterpret_cast<const float4*>(bias + 256 * layer);
-                uint32_t buf[2][32];
+                const float4* __restrict__ bl = reinterpret_cast<const float4*>(bias + 256 * layer + 128 * half);
+                const uint32_t tcol = trow + 128u * half;
+                uint8_t* const svl = (SAVE && sv) ? sv + kSaveAct + layer * 65536u : nullptr;
+                // 16 columns per tcgen05.ld, the next load in flight under bias + ReLU + pack + 2 x st.shared of the current one
+                // (18 warps = 5 on one scheduler: 96 registers per thread, so the x32 double buffer of the 8-warp version does not fit)
+                uint32_t buf[2][16];
                 const bool no_bias = a.diag & 1u, no_store = a.diag & 2u, no_ld = a.diag & 4u;
-                if (!no_ld) tc5::tmem_ld32_issue(trow, buf[0]);
+                if (!no_ld) tc5::tmem_ld16_issue(tcol, buf[0]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (!no_ld) {
                         tc5::tmem_ld_wait();
-                        if (c + 1 < 8) tc5::tmem_ld32_issue(trow + 32 * (c + 1), buf[(c + 1) & 1]);
+                        if (c + 1 < 8) tc5::tmem_ld16_issue(tcol + 16 * (c + 1), buf[(c + 1) & 1]);
                     }
-                    float v[32];
+                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b4 = no_bias ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bl + 8 * c + i);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = no_bias ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(bl + 4 * c + i);
                         v[4 * i + 0] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 0]) + b4.x, 0.0f);
                         v[4 * i + 1] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 1]) + b4.y, 0.0f);
                         v[4 * i + 2] = fmaxf(__uint_as_float(buf[c & 1][4 * i + 2]) + b4.z, 0.0f);
@@ -298,17 +271,28 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                     }
                     if (!no_store) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(A + tc5::chunk_off(kTile, r, 4 * c + i)) = tc5::pack8(v + 8 * i);
+                        for (int i = 0; i < 2; ++i) {
+                            const uint4 u = tc5::pack8(v + 8 * i);
+                            const uint32_t off = tc5::chunk_off(kTile, r, 16 * half + 2 * c + i);
+                            *reinterpret_cast<uint4*>(A + off) = u;
+                            if (SAVE && svl) *reinterpret_cast<uint4*>(svl + off) = u;
+                        }
                     }
                 }
                 tc5::fence_async_smem();
                 tc5::fence_before_sync();
                 tc5::mbar_arrive(&act_ready[t]);
             }
-            // ---- layer 7 -> x28; then the sigma / colour tail on this warpgroup's tile
+            // ---- layer 7 -> x28; then the sigma / colour tail on this tile's column-half-0 warpgroup
             wait(&acc_full[t], accs & 1u);
             ++accs;
+            if (half != 0u) continue;   // the other warpgroup goes on to the next pair's PE (X0 is free: layer 4 of this pair is complete)
             tc5::fence_after_sync();
+            float dir[3] = {0.f, 0.f, 0.f};
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) dir[d] = __ldg(dirs + 3 * (size_t)row + d);
+            }
             if (r == 0) {  // the operand tile is dead: fetch the tail weights into its upper half while x28 is formed
                 tc5::mbar_expect_tx(&tail_w[t], PVD_FIELD_WBLOB_BYTES);
                 tc5::bulk_g2s(tc5::smem_u32(A + kTailWOff), a.tail_blob, PVD_FIELD_WBLOB_BYTES, &tail_w[t]);
@@ -326,7 +310,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
 #pragma unroll
                 for (int i = 28; i < 32; ++i) v[i] = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, r, j)) = tc5::pack8(v + 8 * j);
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 u = tc5::pack8(v + 8 * j);
+                    *reinterpret_cast<uint4*>(X + tc5::chunk_off(kTile, r, j)) = u;
+                    if (SAVE && live) *reinterpret_cast<uint4*>(enc_out + (size_t)row * PVD_FIELD_ENC_STRIDE + 8 * j) = u;
+                }
             }
             FieldArgs fa;
             fa.clip_min = a.clip_min; fa.clip_max = a.clip_max; fa.density_scale = a.density_scale;
@@ -347,7 +335,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
                             make_float4(o16[4 * q], o16[4 * q + 1], o16[4 * q + 2], o16[4 * q + 3]);
                 }
             }
-            // the tail's last TMEM read / its tiles must be done before the next pair's PE arrival lets layer 0 overwrite them
+            // the tail's last TMEM read / its tiles must be done before this warpgroup's next PE arrival lets layer 0 overwrite them
             tc5::fence_before_sync();
             asm volatile("bar.sync %0, 128;" ::"r"(1u + t) : "memory");
         }
@@ -396,8 +384,6 @@ __global__ void k_mlp_pack(const float* const* __restrict__ w, const float* cons
     }
 }
 
-constexpr size_t kMlpSmem = 16384 + 65536 + 2 * kMlpChunkBytes + PVD_FIELD_WBLOB_BYTES + kMlpBiasBytes;  // 176128
-
 }  // namespace pvd
 
 using namespace pvd;
@@ -411,8 +397,8 @@ int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biase
     return PVD_OK;
 }
 
-int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
-                          float* feat16, int32_t* status, void* stream) {
+static int mlp_forward_launch(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                              float* feat16, void* save, void* enc, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
     PVD_REQUIRE(f && f->wblob && f->tail_wblob && xyzs && dirs && sigmas && rgbs && status);
     MlpArgs a;
@@ -424,11 +410,30 @@ int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* 
     const uint32_t tiles = (M + kTile - 1) / kTile;
     const uint32_t pairs = (tiles + 1) / 2;
     const uint32_t grid2 = min(pairs, (uint32_t)sm_count());
-    cudaError_t e2 = cudaFuncSetAttribute(k_mlp_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
-    if (e2 != cudaSuccess) return (int)e2;
-    k_mlp_field_fwd<<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, status);
+    cudaError_t e2;
+    if (save != nullptr) {
+        e2 = cudaFuncSetAttribute(k_mlp_field_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
+        if (e2 != cudaSuccess) return (int)e2;
+        k_mlp_field_fwd<true><<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, (uint8_t*)save,
+                                                                                        (__half*)enc, status);
+    } else {
+        e2 = cudaFuncSetAttribute(k_mlp_field_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmemV2);
+        if (e2 != cudaSuccess) return (int)e2;
+        k_mlp_field_fwd<false><<<grid2, kV2Threads, kMlpSmemV2, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16, nullptr, nullptr, status);
+    }
     PVD_LAUNCH_CHECK();
     return PVD_OK;
+}
+
+int pvd_mlp_field_forward(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                          float* feat16, int32_t* status, void* stream) {
+    return mlp_forward_launch(f, xyzs, dirs, M, sigmas, rgbs, feat16, nullptr, nullptr, status, stream);
+}
+
+int pvd_mlp_field_forward_train(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
+                                float* feat16, void* save_ws, void* enc, int32_t* status, void* stream) {
+    PVD_REQUIRE(save_ws && enc);
+    return mlp_forward_launch(f, xyzs, dirs, M, sigmas, rgbs, feat16, save_ws, enc, status, stream);
 }
 
 }  // extern "C"

@@ -487,6 +487,15 @@ class TensorsTrainEngine(FieldTrainEngine):
         super().__init__(field, *a, **k)
 
 
+class MLPTrainEngine(FieldTrainEngine):
+    """mlp (NeRF) teacher training (`main_just_train_tea.py --model_type mlp`): fused forward that saves its operand tiles, backward =
+    tail kernel -> trunk data gradients -> weight gradients on the tensor core (csrc/field_mlp_bwd.cu)."""
+
+    def __init__(self, field, *a, **k):
+        assert getattr(field, "model_type", None) == "mlp"
+        super().__init__(field, *a, **k)
+
+
 PAIR_SUM_STRIDE = 4   # PVD_PAIR_SUM_STRIDE
 PAIR_PARALLEL_FWD = os.environ.get("PVD_PAIR_PARALLEL_FWD", "1") != "0"
 

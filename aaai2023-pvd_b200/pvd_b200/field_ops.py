@@ -3,7 +3,7 @@ one model type (distill_mutual/network.py:335-437), on pre-allocated buffers, no
 
     HashOps  model_type "hash"  (fused.HashNeRFField)     forward + backward   csrc/field_hash.cu
     VmOps    model_type "vm"    (fused_vm.VMNeRFField)    forward + backward   csrc/field_vm.cu
-    MlpOps   model_type "mlp"   (fused_mlp.MLPNeRFField)  forward only (the frozen teacher of mlp -> hash distillation)
+    MlpOps   model_type "mlp"   (fused_mlp.MLPNeRFField)  forward (frozen teacher of mlp -> hash distillation) + backward   csrc/field_mlp*.cu
 
 Common protocol (all sample tensors are the engine's): `stage(density_scale)` refreshes staged parameters (fp16 table shadow,
 packed weight tiles); `alloc(M)` sizes per-sample scratch; `forward(st, xyzs, dirs, M, sigmas, rgbs, feat, status)`;
@@ -282,33 +282,113 @@ class VmOps:
 
 
 class MlpOps:
+    """model_type "mlp" (fused_mlp.MLPNeRFField).  Frozen teacher: forward only (csrc/field_mlp.cu).  Trainable (main_just_train_tea.py
+    --model_type mlp): the forward saves its operand tiles and the backward is tail kernel -> k_mlp_trunk_bwd -> k_mlp_wgrad
+    (csrc/field_mlp_bwd.cu); all scratch is allocated in alloc(M), nothing in the step."""
     kind = "mlp"
     kernels_fwd = 1
-    kernels_bwd = 0
-    trainable = False
+    NAMES = tuple(f"nerf_mlp.{i}.{k}" for i in range(8) for k in ("weight", "bias")) + \
+        ("sigma_net.0.weight", "sigma_net.1.weight", "color_net.0.weight", "color_net.1.weight", "color_net.2.weight")
 
     def __init__(self, field, dev, trainable: bool = False):
-        assert not trainable, "the fused NeRF-MLP field is forward only (it is the frozen teacher, distill_mutual/utils.py:1008-1018)"
-        self.field, self.dev = field, torch.device(dev)
+        from . import fused_mlp
+        self._fm = fused_mlp
+        self.field, self.dev, self.trainable = field, torch.device(dev), trainable
+        self.kernels_bwd = 3 if trainable else 0
+        self.save_ws = self.grad_ws = self.enc = self.d_x28 = None
+        self.grad_table = None
+        self.wgrads = []
+        if trainable:
+            d = self.dev
+            ps = self._params()
+            assert all(p.dtype == torch.float32 and p.is_contiguous() for p in ps), "trainable mlp parameters must be contiguous fp32"
+            self._wflat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=d)
+            off = 0
+            for p_ in ps:
+                self.wgrads.append(self._wflat[off:off + p_.numel()].view_as(p_))
+                off += p_.numel()
+            self.gw_mlp = torch.zeros(fused_mlp.MLP_GW_FLOATS, dtype=torch.float32, device=d)
+            self.wblob_t = torch.empty(fused_mlp.MLP_WBLOB_T_BYTES, dtype=torch.uint8, device=d)
+            # device arrays of device pointers (the ABI's float* const*): parameters and their gradient views never move
+            self._wp = fused_mlp._ptr_array([l.weight for l in field.nerf_mlp], d)
+            self._gwp = fused_mlp._ptr_array(self.wgrads[0:16:2], d)
+            self._gbp = fused_mlp._ptr_array(self.wgrads[1:16:2], d)
+            self._offsets = torch.arange(17, dtype=torch.int32, device=d) * 8
+            torch.cuda.current_stream(d).synchronize()
+
+    def _params(self):
+        f = self.field
+        return [p for l in f.nerf_mlp for p in (l.weight, l.bias)] + [f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight,
+                                                                      f.color_net[1].weight, f.color_net[2].weight]
+
+    def _tail(self):
+        f = self.field
+        return (f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
 
     def stage(self, density_scale=1.0):
-        from .fused_mlp import PvdMlpField
         f = self.field
-        self.tail = f._staged.wblob_for((f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight,
-                                         f.color_net[2].weight), f.in_dim)
+        self.tail = f._staged.wblob_for(self._tail(), f.in_dim)
         self.blob = f._blob()
-        self.cfield = PvdMlpField(wblob=self.blob.data_ptr(), tail_wblob=self.tail.data_ptr(), sigma_clip_min=float(f.args.sigma_clip_min),
-                                  sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
+        self.cfield = self._fm.PvdMlpField(wblob=self.blob.data_ptr(), tail_wblob=self.tail.data_ptr(), sigma_clip_min=float(f.args.sigma_clip_min),
+                                           sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
+        if self.trainable:
+            nv.check(nv.lib().pvd_mlp_pack_weights_t(nv.ptr(self._wp), nv.ptr(self.wblob_t), nv.stream_of(self.wblob_t)))
+            cfg = fused.HashFieldConfig(num_levels=14, base_resolution=16, per_level_scale=2.0, bound=1.0, sigma_clip_min=float(f.args.sigma_clip_min),
+                                        sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
+            self._tail_cfg = cfg
 
     def alloc(self, M):
-        pass
+        if self.trainable:
+            tiles = max((M + 127) // 128, 1)
+            self.save_ws = torch.empty(tiles * self._fm.MLP_SAVE_TILE_BYTES, dtype=torch.uint8, device=self.dev)
+            self.grad_ws = torch.empty(tiles * self._fm.MLP_GRAD_TILE_BYTES, dtype=torch.uint8, device=self.dev)
+            self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev)
+            self.d_x28 = torch.zeros(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev)
 
     def prefetch(self, st):
         pass   # 876 KB of weights: L2-resident after the first tile
 
     def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
-        nv.check(nv.lib().pvd_mlp_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
-                                                nv.ptr(feat), nv.ptr(status), st))
+        if self.trainable:
+            nv.check(nv.lib().pvd_mlp_field_forward_train(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
+                                                          nv.ptr(feat), nv.ptr(self.save_ws), nv.ptr(self.enc), nv.ptr(status), st))
+        else:
+            nv.check(nv.lib().pvd_mlp_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
+                                                    nv.ptr(feat), nv.ptr(status), st))
+
+    def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status, phases=None):
+        l = nv.lib()
+        f = fused._cstruct(self._tail_cfg, self.enc, self._offsets, self.tail)
+        # 1. sigma / colour tail: the hash model's tail backward in its d(encoding)-export mode; x28 plays the encoding
+        nv.check(l.pvd_hash_field_backward_rows(C.byref(f), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc), nv.ptr(grad_sigmas), nv.ptr(grad_rgbs),
+                                                nv.ptr(grad_feat), _u32(0), _u32(M), nv.ptr(n_valid), nv.ptr(gw_ws), nv.ptr(gw_ws), nv.ptr(self.d_x28),
+                                                nv.ptr(status), _u32(1), st))
+        # 2. data gradients through layers 7..1; 3. weight / bias gradients (reduction over all samples in TMEM)
+        nv.check(l.pvd_mlp_trunk_backward(nv.ptr(self.wblob_t), nv.ptr(self.save_ws), nv.ptr(self.d_x28), _u32(M), nv.ptr(n_valid),
+                                          nv.ptr(self.grad_ws), nv.ptr(status), st))
+        nv.check(l.pvd_mlp_weight_grads(nv.ptr(self.save_ws), nv.ptr(self.grad_ws), _u32(M), nv.ptr(self.gw_mlp), nv.ptr(status), st))
+
+    def clear_grads(self):
+        self.gw_mlp.zero_()
+
+    def big_grad(self):
+        return self.gw_mlp
+
+    def regularise(self, st, loss_scale, loss_slots, weight):
+        pass
+
+    def unpack_weight_grads(self, gw_ws, st):
+        """kernel-native workspaces -> self.wgrads (parameter shapes, NAMES order)."""
+        self._wflat.zero_()
+        nv.check(nv.lib().pvd_mlp_unpack_wgrads(nv.ptr(self.gw_mlp), nv.ptr(self._gwp), nv.ptr(self._gbp), st))
+        nv.check(nv.lib().pvd_field_unpack_wgrads(nv.ptr(gw_ws), _u32(self.field.in_dim), *[nv.ptr(g) for g in self.wgrads[16:]], st))
+
+    def weight_grads(self, gw_ws):
+        self.unpack_weight_grads(gw_ws, nv.stream_of(gw_ws))
+        return {n: g.clone() for n, g in zip(self.NAMES, self.wgrads)}
+
+    def grads(self, gw_ws):
+        return self.weight_grads(gw_ws)
 
     def algorithmic_bytes(self):
         return 0, 0   # FLOP-bound: 865 280 FLOP/sample forward (SURVEY 8d)

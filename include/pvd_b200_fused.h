@@ -165,7 +165,7 @@ int pvd_vm_field_backward_ws(const PvdVmField* field, const PvdVmGrads* grads, c
 int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, float* gw_color1, float* gw_color2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * "mlp" (NeRF) field, FORWARD only -- the frozen teacher of mlp -> hash distillation (BASELINE config 5):
+ * "mlp" (NeRF) field -- the frozen teacher of mlp -> hash distillation (BASELINE config 5), and a trainable model:
  * FreqEncoder PE(10) 3 -> 63 (tools/encoding.py:6-49), nerf_mlp = 8 Linear layers with bias, 256 wide, skip concat of the
  * encoding after the 4th (network.py:56-70,324-333), output 28, then the same sigma_net / color_net tail as the hash model.
  * ---------------------------------------------------------------------------------------- */
@@ -185,6 +185,34 @@ int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biase
 
 int pvd_mlp_field_forward(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
                           float* feat16, int32_t* status, void* stream);
+
+/* TRAINING an mlp model (main_just_train_tea.py --model_type mlp; network.py:324-333 under autograd in the reference).
+ * Forward: the same kernel, which additionally saves, per 128-sample tile, every fp16 operand tile the tensor core consumed
+ * (PE tile + the ReLU outputs of layers 0..6, PVD_MLP_SAVE_TILE_BYTES per tile; save_ws = ceil(M / 128) tiles) and the 28-wide trunk
+ * output `enc` [M, 32] fp16 (the tail's input, same role as the hash model's saved encoding).
+ * Backward, three launches:
+ *   1. the sigma/colour tail: pvd_hash_field_backward_rows(tail_field, ..., enc, ..., dx_ws = d_x28 [M,32] fp16, PVD_BWD_MLP) -- the
+ *      hash model's tcgen05 tail backward, which leaves d(loss)/d(x28) in dx_ws and the five tail weight gradients in its gw_ws;
+ *   2. pvd_mlp_trunk_backward: data gradients through layers 7..1 (transposed weight stream, masks from the saved activations);
+ *      writes G_7, G_0..G_6 = d(loss)/d(pre-activation) per tile into grad_ws (PVD_MLP_GRAD_TILE_BYTES per tile);
+ *   3. pvd_mlp_weight_grads: dW_l = G_l^T act_l, db_l = column sums of G_l, reduction over all samples on the tensor core
+ *      (accumulators in TMEM, one (layer, sample-split) job per CTA); ACCUMULATES into gw_ws, PVD_MLP_GW_FLOATS floats
+ *      (caller zeroes it): layers 0..6 as [256][320] (layer 4: columns 0..62 = in_pts part, 64..319 = hidden part; others from
+ *      column 0), layer 7 as [256 in][32 out], then 8 x 256 bias gradients.
+ *   pvd_mlp_unpack_wgrads adds them onto parameter-shaped buffers. */
+#define PVD_MLP_SAVE_TILE_BYTES 475136u
+#define PVD_MLP_GRAD_TILE_BYTES 466944u
+#define PVD_MLP_GW_FLOATS (7u * 256u * 320u + 256u * 32u + 8u * 256u)
+int pvd_mlp_field_forward_train(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas,
+                                float* rgbs, float* feat16, void* save_ws, void* enc, int32_t* status, void* stream);
+/* wblob_t: PVD_MLP_WBLOB_T_BYTES from pvd_mlp_pack_weights_t (the transposed weight stream of the backward). */
+#define PVD_MLP_WBLOB_T_BYTES (49u * 16384u)
+int pvd_mlp_pack_weights_t(const float* const* weights8, void* wblob_t, void* stream);
+/* n_valid (device pointer or NULL = all M): rows >= *n_valid are padding and receive zero gradients. */
+int pvd_mlp_trunk_backward(const void* wblob_t, const void* save_ws, const void* d_x28, uint32_t M, const int32_t* n_valid,
+                           void* grad_ws, int32_t* status, void* stream);
+int pvd_mlp_weight_grads(const void* save_ws, const void* grad_ws, uint32_t M, float* gw_ws, int32_t* status, void* stream);
+int pvd_mlp_unpack_wgrads(const float* gw_ws, float* const* grad_weights8, float* const* grad_biases8, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (teacher, student) distillation at SHARED samples: the loss side of Trainer.train_step, distill_mutual/utils.py:954-1189,
