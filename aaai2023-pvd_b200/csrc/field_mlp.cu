@@ -7,7 +7,7 @@
 // tools/encoding.py:6-49): 21 sin/cos/cat kernels, 8 cuBLAS GEMMs with bias + ReLU + cat kernels between them, then the
 // same 5-GEMM tail as the hash model -- 0.87 MFLOP per sample, the one part of the path where FLOPs dominate.
 //
-// One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream (18 warps):
+// One persistent CTA per SM works on PAIRS of 128-sample tiles with ONE weight stream (19 warps):
 //   warps 0-7 own tile 0, warps 8-15 tile 1.  Inside a tile, warp w serves the TMEM lane quadrant w % 4 (= sample rows
 //     32 (w % 4) .. +31: a warp may only touch its own quadrant) and the COLUMN HALF (w / 4) % 2 of the 256-wide layer: two threads
 //     per sample row, 128 columns each.  PE, layer epilogues (TMEM -> bias -> ReLU -> fp16 operand tile, in place) are split that
@@ -17,9 +17,10 @@
 //     scheduler can switch between.
 //   warp 16, one lane: TMA producer.  The packed weights are streamed in 16 KB pieces ([256 x 32] fp16) through a FOUR-stage ring
 //     of cp.async.bulk copies; loads run up to four pieces ahead of the tensor core, across layers, tile pairs and the tail.
-//   warp 17, one lane: MMA issuer.  Accumulators: tile t in TMEM columns [256 t, 256 t + 256) -- all 512 columns of the SM.
+//   warps 17 / 18, one lane each: MMA issuers of tile 0 / tile 1, both consuming every ring piece (a stage is released when both
+//     have committed).  Accumulators: tile t in TMEM columns [256 t, 256 t + 256) -- all 512 columns of the SM.
 // Hand-offs are mbarriers only (no CTA-wide barrier in the steady state):
-//   ring_full[s] (TMA bytes) / ring_empty[s] (tcgen05.commit)        producer <-> issuer
+//   ring_full[s] (TMA bytes) / ring_empty[s] (2 x tcgen05.commit)    producer <-> issuers
 //   acc_full[t]  (tcgen05.commit after a layer's last MMA)           issuer   ->  the 8 warps of tile t: accumulator complete
 //   act_ready[t] (256 arrivals)                                      tile t's warps -> issuer: next operand tile written, TMEM drained
 // Shared memory: 2 x 64 KB operand tiles + 2 x 16 KB PE tiles + 4 x 16 KB ring = 224 KB.  The 20 KB tail weights are copied (TMA)
@@ -35,14 +36,8 @@ PVD_TRACE_TU(pvd_debug_trace_field_mlp)
 namespace pvd {
 
 constexpr uint32_t kEpiWarps = 16;
-constexpr uint32_t kV2Threads = 32 * (kEpiWarps + 2);   // 576
+constexpr uint32_t kV2Threads = 32 * (kEpiWarps + 3);   // 608: 16 epilogue warps, TMA producer, two MMA issuers
 constexpr uint32_t kTailWOff = 32768;                   // tail weights inside a tile's operand buffer
-#ifndef PVD_MLP_STAGGER
-#define PVD_MLP_STAGGER 1
-#endif
-constexpr bool kStaggerDefault = PVD_MLP_STAGGER != 0;  // 1: per layer, tile 0's pass then tile 1's pass (weights streamed twice, MMA of one tile under
-                                                        // the epilogue of the other); 0: both tiles consume every piece (weights streamed once)
-
 // FreqEncoder (tools/encoding.py:36-49): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...], f_k = 2^k, k = 0..9 -> 63 features (+1 zero pad);
 // this thread's 32 of them (features 32 HALF .. 32 HALF + 31).  Feature 3 + 6k + d = sin(2^k x_d), 3 + 6k + 3 + d = cos(2^k x_d).
 template <int HALF>
@@ -82,7 +77,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
     if (tid == 0) {
         for (uint32_t s = 0; s < kStages; ++s) {
             tc5::mbar_init(&ring_full[s], 1);
-            tc5::mbar_init(&ring_empty[s], 1);
+            tc5::mbar_init(&ring_empty[s], 2);
         }
         for (uint32_t t = 0; t < 2; ++t) {
             tc5::mbar_init(&acc_full[t], 1);
@@ -100,109 +95,79 @@ __global__ void __launch_bounds__(kV2Threads, 1) k_mlp_field_fwd(MlpArgs a, cons
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     const uint32_t n_pairs = (n_tiles + 1) / 2;
     V2Wait wait{status};
-    const bool kStagger = kStaggerDefault != ((a.diag & 16u) != 0u);   // diag bit 16 flips the schedule
+    a.wblob += (size_t)(blockIdx.x % a.replicas) * PVD_MLP_WBLOB_BYTES;
 
     if (warp == kEpiWarps) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer: ONE weight stream for both tiles
         if (lane == 0) {
             uint32_t pc = 0;  // pieces issued so far (ring position)
-            auto load = [&](uint32_t q) {
-                const uint32_t s = pc % kStages;
-                if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
-                tc5::mbar_expect_tx(&ring_full[s], kPiece);
-                tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), a.wblob + (size_t)q * kPiece, kPiece, &ring_full[s]);
-                ++pc;
-            };
-            for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                if (kStagger) {   // per layer: the pieces for tile 0's pass, then the same pieces again for tile 1's pass
-                    uint32_t q0 = 0;
-                    for (uint32_t layer = 0; layer < 8; ++layer) {
-                        const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : (layer == 7 ? 1u : 8u));
-                        for (uint32_t t = 0; t < 2; ++t)
-                            for (uint32_t j = 0; j < n_pieces; ++j) load(q0 + j);
-                        q0 += n_pieces;
+            // diag (timing experiments only): bit 32 = no copies (the full barrier is just arrived on)
+            for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+                for (uint32_t q = 0; q < kPieces; ++q, ++pc) {
+                    const uint32_t s = pc % kStages;
+                    if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);   // BOTH issuers' MMAs on this stage are complete
+                    if (a.diag & 32u) {
+                        tc5::mbar_arrive(&ring_full[s]);
+                    } else {
+                        tc5::mbar_expect_tx(&ring_full[s], kPiece);
+                        tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), a.wblob + (size_t)q * kPiece, kPiece, &ring_full[s]);
                     }
-                } else {
-                    for (uint32_t q = 0; q < kPieces; ++q) load(q);
                 }
-            }
         }
-    } else if (warp == kEpiWarps + 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp > kEpiWarps) {
+        // ------------------------------------------------------------------ MMA issuers: warp 17 for tile 0, warp 18 for tile 1
+        // Both consume the SAME ring pieces (a stage is released when both have committed: ring_empty counts 2).  Measured with the
+        // kernel's diag bits (no copies, no MMAs, empty epilogues): one issuer lane spent ~450 cycles per piece in waits, fences and
+        // commits -- more than the 256 cycles of tensor-core time its two MMAs per piece are worth -- so ONE issuer could not keep the
+        // pipe half busy whatever the epilogue did.  Two issuer lanes halve the pieces per MMA and double the issue rate.
         if (lane == 0) {
-            uint32_t pc = 0, acts = 0;  // pieces consumed; act_ready phases consumed (same count for both tiles)
+            const uint32_t t = warp - (kEpiWarps + 1u);
+            uint32_t pc = 0, acts = 0;  // pieces consumed; act_ready phases consumed
             const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
             const uint32_t idesc7 = tc5::instr_desc_f16(128, 32, 0, 0);
+            const bool no_mma = (a.diag & 64u) != 0u;   // timing experiments only: commits without MMAs
+            const uint32_t a_tile0 = tc5::smem_u32(smem + t * 65536), x0_tile = tc5::smem_u32(smem + 2 * 65536 + t * 16384);
+            const uint32_t d_tmem = tmem + 256u * t;
             for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                uint32_t q0 = 0;
-                for (uint32_t layer = 0; layer < 7; ++layer) {
-                    const uint32_t n_pieces = (layer == 0) ? 2u : (layer == 4 ? 10u : 8u);
-                    if (kStagger) {
-                        // tile 0's whole layer, then tile 1's: while the tensor core runs tile 1, tile 0's warps are already in their epilogue
-                        for (uint32_t t = 0; t < 2; ++t) {
-                            wait(&act_ready[t], acts & 1u);  // operand tile of this layer written, accumulator drained
-                            for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
-                                const uint32_t q = q0 + j;
-                                const ChunkDesc cd = kSchedule[q >> 1];
-                                const uint32_t s = pc % kStages;
-                                wait(&ring_full[s], (pc / kStages) & 1u);
-                                tc5::fence_after_sync();
-                                const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
-                                const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
-                                                                   : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
-                                const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);
+                for (uint32_t layer = 0; layer < 7; ++layer, ++acts) {
+                    // pieces of this layer: [256 x 32] slices of its K range; layer 0 = the PE tile (2 pieces), layer 4 = PE tile
+                    // (2 pieces) then the 256 hidden units (8 pieces), the others 8 pieces of the activation tile
+                    const uint32_t n_x0 = (layer == 0u || layer == 4u) ? 2u : 0u, n_pieces = (layer == 0u) ? 2u : n_x0 + 8u;
+                    wait(&act_ready[t], acts & 1u);   // operand tile of this layer written, accumulator drained
+                    for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
+                        const uint32_t s = pc % kStages;
+                        wait(&ring_full[s], (pc / kStages) & 1u);
+                        tc5::fence_after_sync();
+                        const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                        const uint32_t a_tile = (j < n_x0) ? x0_tile + j * 4u * (kTile * 16u) : a_tile0 + (j - n_x0) * 4u * (kTile * 16u);
+                        if (!no_mma) {
 #pragma unroll
-                                for (uint32_t k0 = 0; k0 < 32; k0 += 16)
-                                    tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                                    !(j == 0 && k0 == 0));
-                                tc5::mma_commit(&ring_empty[s]);
-                            }
-                            tc5::mma_commit(&acc_full[t]);
+                            for (uint32_t k0 = 0; k0 < 32; k0 += 16)
+                                tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc, !(j == 0 && k0 == 0));
                         }
-                    } else {
-                        for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
-                            const uint32_t q = q0 + j;
-                            const ChunkDesc cd = kSchedule[q >> 1];
-                            const uint32_t s = pc % kStages;
-                            wait(&ring_full[s], (pc / kStages) & 1u);
-                            const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
-                            for (uint32_t t = 0; t < 2; ++t) {
-                                if (j == 0) wait(&act_ready[t], acts & 1u);
-                                tc5::fence_after_sync();
-                                const uint32_t a_base = cd.from_x0 ? tc5::smem_u32(smem + 2 * 65536 + t * 16384)
-                                                                   : tc5::smem_u32(smem + t * 65536) + (uint32_t)cd.k_chunk * 8u * (kTile * 16u);
-                                const uint32_t a_tile = a_base + (q & 1u) * 4u * (kTile * 16u);   // which 32-column half of the 64-column slice
-#pragma unroll
-                                for (uint32_t k0 = 0; k0 < 32; k0 += 16)
-                                    tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                                    !(j == 0 && k0 == 0));
-                                if (j + 1 == n_pieces) tc5::mma_commit(&acc_full[t]);
-                            }
-                            tc5::mma_commit(&ring_empty[s]);
-                        }
+                        tc5::mma_commit(&ring_empty[s]);
                     }
-                    q0 += n_pieces;
-                    ++acts;
+                    tc5::mma_commit(&acc_full[t]);
                 }
                 // layer 7: 256 -> 28 (N = 32); the piece holds four [32 x 64] operand tiles
-                for (uint32_t t = 0; t < 2; ++t) {
+                {
                     const uint32_t s = pc % kStages;
-                    if (kStagger || t == 0) wait(&ring_full[s], (pc / kStages) & 1u);
-                    const uint32_t b_base = tc5::smem_u32(ring + s * kPiece);
                     wait(&act_ready[t], acts & 1u);
+                    wait(&ring_full[s], (pc / kStages) & 1u);
                     tc5::fence_after_sync();
-                    for (uint32_t c = 0; c < 4; ++c)
+                    const uint32_t b_base = tc5::smem_u32(ring + s * kPiece);
+                    if (!no_mma) {
+                        for (uint32_t c = 0; c < 4; ++c)
 #pragma unroll
-                        for (uint32_t k0 = 0; k0 < 64; k0 += 16)
-                            tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(tc5::smem_u32(smem + t * 65536) + c * 8u * (kTile * 16u), kTile, k0),
-                                            tc5::desc_kmajor(b_base + c * (32u * 64u * 2u), 32, k0), idesc7, !(c == 0 && k0 == 0));
-                    tc5::mma_commit(&acc_full[t]);
-                    if (kStagger || t == 1) {
-                        tc5::mma_commit(&ring_empty[s]);
-                        ++pc;
+                            for (uint32_t k0 = 0; k0 < 64; k0 += 16)
+                                tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(a_tile0 + c * 8u * (kTile * 16u), kTile, k0),
+                                                tc5::desc_kmajor(b_base + c * (32u * 64u * 2u), 32, k0), idesc7, !(c == 0 && k0 == 0));
                     }
+                    tc5::mma_commit(&acc_full[t]);
+                    tc5::mma_commit(&ring_empty[s]);
+                    ++pc;
+                    ++acts;
                 }
-                ++acts;
             }
         }
     } else {
@@ -397,6 +362,15 @@ int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biase
     return PVD_OK;
 }
 
+int pvd_mlp_replicate_weights(void* wblob, uint64_t bytes, uint32_t replicas, void* stream) {
+    PVD_REQUIRE(wblob && bytes);
+    for (uint32_t r = 1; r < replicas; ++r) {
+        cudaError_t e = cudaMemcpyAsync((uint8_t*)wblob + (size_t)r * bytes, wblob, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return PVD_OK;
+}
+
 static int mlp_forward_launch(const PvdMlpField* f, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
                               float* feat16, void* save, void* enc, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
@@ -405,6 +379,7 @@ static int mlp_forward_launch(const PvdMlpField* f, const float* xyzs, const flo
     a.wblob = reinterpret_cast<const uint8_t*>(f->wblob);
     a.tail_blob = reinterpret_cast<const uint8_t*>(f->tail_wblob);
     a.clip_min = f->sigma_clip_min; a.clip_max = f->sigma_clip_max; a.density_scale = f->density_scale;
+    a.replicas = f->replicas ? f->replicas : 1u;
     static const uint32_t diag = []() { const char* v = getenv("PVD_MLP_DIAG"); return v ? (uint32_t)atoi(v) : 0u; }();
     a.diag = diag;
     const uint32_t tiles = (M + kTile - 1) / kTile;

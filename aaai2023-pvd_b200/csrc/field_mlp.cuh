@@ -14,7 +14,8 @@ constexpr uint32_t kMlpBiasBytes = 8 * 256 * 4;
 static_assert(kMlpBiasOff + kMlpBiasBytes == PVD_MLP_WBLOB_BYTES, "mlp blob size");
 
 struct MlpArgs {
-    const uint8_t* wblob;      // PVD_MLP_WBLOB_BYTES
+    const uint8_t* wblob;      // this CTA's replica is selected in the kernel: wblob + (blockIdx.x % replicas) * PVD_MLP_WBLOB_BYTES
+    uint32_t replicas;
     const uint8_t* tail_blob;  // PVD_FIELD_WBLOB_BYTES (sigma_net / color_net)
     float clip_min, clip_max, density_scale;
     uint32_t diag;   // timing diagnostics only (PVD_MLP_DIAG): 1 no bias loads, 2 no operand stores, 4 no TMEM loads, 8 no PE

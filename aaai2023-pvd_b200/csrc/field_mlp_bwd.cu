@@ -6,7 +6,7 @@
 // d(loss)/d(x28) [M,32] fp16.  From there, two kernels:
 //
 // k_mlp_trunk_bwd  -- DATA gradients, the forward's structure run backwards.  One persistent CTA per SM, pairs of 128-sample
-//   tiles, 16 epilogue warps (two threads per sample row), one TMA producer lane, one MMA issuer lane.  Round rho = 0..6 computes
+//   tiles, 16 epilogue warps (two threads per sample row), one TMA producer lane, two MMA issuer lanes (one per tile, same ring pieces).  Round rho = 0..6 computes
 //   d(act_{7-rho}) [128 x 256] = G_{7-rho} [128 x K] * W_{7-rho} [K x 256] on the tensor core (accumulator in TMEM), the weights
 //   streamed as the TRANSPOSED operand pieces of pvd_mlp_pack_weights_t ([256 in x 32 out] fp16, 16 KB, four-stage ring -- the
 //   forward's machinery with the roles of in and out swapped; layer 4 contributes only its hidden part, d(in_pts) has no consumer),
@@ -30,7 +30,7 @@ namespace pvd {
 constexpr uint32_t kBwdPieces = 49;                     // layer 7^T (1) + layers 6..1 (8 each)
 static_assert(kBwdPieces * kPiece == PVD_MLP_WBLOB_T_BYTES, "transposed blob size");
 constexpr uint32_t kEpiWarpsB = 16;
-constexpr uint32_t kBwdThreads = 32 * (kEpiWarpsB + 2);  // 576
+constexpr uint32_t kBwdThreads = 32 * (kEpiWarpsB + 3);  // 608: 16 epilogue warps, TMA producer, two MMA issuers
 constexpr size_t kTrunkSmem = 2 * 65536 + kStages * kPiece;  // 196608
 
 // piece q of the transposed stream: B operand [256 rows = layer INPUT index] x [32 cols = 32 of the layer's OUTPUTS], K-major
@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t pos_mask2(uint32_t act2) {   // 0xFFFF per h
     return __hgt2_mask(*reinterpret_cast<const __half2*>(&act2), __float2half2_rn(0.0f));
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_trunk_bwd(const uint8_t* __restrict__ wblob_t, const uint8_t* __restrict__ save,
+__global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_trunk_bwd(const uint8_t* __restrict__ wblob_t, uint32_t replicas, const uint8_t* __restrict__ save,
                                                 const __half* __restrict__ d_x28, uint32_t M, const int32_t* __restrict__ n_valid_p,
                                                 uint8_t* __restrict__ grad_ws, int32_t* status) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_trunk_bwd(const uint8_t*
     if (tid == 0) {
         for (uint32_t s = 0; s < kStages; ++s) {
             tc5::mbar_init(&ring_full[s], 1);
-            tc5::mbar_init(&ring_empty[s], 1);
+            tc5::mbar_init(&ring_empty[s], 2);
         }
         for (uint32_t t = 0; t < 2; ++t) {
             tc5::mbar_init(&acc_full[t], 1);
@@ -88,47 +88,44 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_trunk_bwd(const uint8_t*
     // rows >= *n_valid are padding (the tail kernel did not write their d_x28): they get zero gradients
     const uint32_t m_end = n_valid_p ? min((uint32_t)max(*n_valid_p, 0), M) : M;
     V2Wait wait{status};
+    wblob_t += (size_t)(blockIdx.x % replicas) * PVD_MLP_WBLOB_T_BYTES;
 
     if (warp == kEpiWarpsB) {
-        // ------------------------------------------------------------------ TMA producer: per round, tile 0's pieces then tile 1's
+        // ------------------------------------------------------------------ TMA producer: ONE transposed weight stream for both tiles
         if (lane == 0) {
             uint32_t pc = 0;
             for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-                for (uint32_t rho = 0; rho < 7; ++rho) {
-                    const uint32_t n_pieces = rho == 0 ? 1u : 8u, q0 = rho == 0 ? 0u : 1u + 8u * (rho - 1u);
-                    for (uint32_t t = 0; t < 2; ++t)
-                        for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
-                            const uint32_t s = pc % kStages;
-                            if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
-                            tc5::mbar_expect_tx(&ring_full[s], kPiece);
-                            tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), wblob_t + (size_t)(q0 + j) * kPiece, kPiece, &ring_full[s]);
-                        }
+                for (uint32_t q = 0; q < kBwdPieces; ++q, ++pc) {
+                    const uint32_t s = pc % kStages;
+                    if (pc >= kStages) wait(&ring_empty[s], ((pc / kStages) - 1u) & 1u);
+                    tc5::mbar_expect_tx(&ring_full[s], kPiece);
+                    tc5::bulk_g2s(tc5::smem_u32(ring + s * kPiece), wblob_t + (size_t)q * kPiece, kPiece, &ring_full[s]);
                 }
         }
-    } else if (warp == kEpiWarpsB + 1) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp > kEpiWarpsB) {
+        // ------------------------------------------------------------------ MMA issuers: one lane per tile, both on the same ring pieces
+        // (see k_mlp_field_fwd: one issuer lane cannot keep the tensor pipe busy at two MMAs per piece)
         if (lane == 0) {
+            const uint32_t t = warp - (kEpiWarpsB + 1u);
             uint32_t pc = 0, acts = 0;
             const uint32_t idesc = tc5::instr_desc_f16(128, 256, 0, 0);
+            const uint32_t a_tile0 = tc5::smem_u32(smem + t * 65536), d_tmem = tmem + 256u * t;
             for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
                 for (uint32_t rho = 0; rho < 7; ++rho, ++acts) {
                     const uint32_t n_pieces = rho == 0 ? 1u : 8u;
-                    for (uint32_t t = 0; t < 2; ++t) {
-                        wait(&act_ready[t], acts & 1u);   // G operand tile written, accumulator drained
-                        for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
-                            const uint32_t s = pc % kStages;
-                            wait(&ring_full[s], (pc / kStages) & 1u);
-                            tc5::fence_after_sync();
-                            const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
-                            const uint32_t a_tile = tc5::smem_u32(smem + t * 65536) + j * 4u * (kTile * 16u);   // G columns 32 j .. 32 j + 31
+                    wait(&act_ready[t], acts & 1u);   // G operand tile written, accumulator drained
+                    for (uint32_t j = 0; j < n_pieces; ++j, ++pc) {
+                        const uint32_t s = pc % kStages;
+                        wait(&ring_full[s], (pc / kStages) & 1u);
+                        tc5::fence_after_sync();
+                        const uint32_t b_tile = tc5::smem_u32(ring + s * kPiece);
+                        const uint32_t a_tile = a_tile0 + j * 4u * (kTile * 16u);   // G columns 32 j .. 32 j + 31
 #pragma unroll
-                            for (uint32_t k0 = 0; k0 < 32; k0 += 16)
-                                tc5::mma_f16_ss(tmem + 256u * t, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc,
-                                                !(j == 0 && k0 == 0));
-                            tc5::mma_commit(&ring_empty[s]);
-                        }
-                        tc5::mma_commit(&acc_full[t]);
+                        for (uint32_t k0 = 0; k0 < 32; k0 += 16)
+                            tc5::mma_f16_ss(d_tmem, tc5::desc_kmajor(a_tile, kTile, k0), tc5::desc_kmajor(b_tile, 256, k0), idesc, !(j == 0 && k0 == 0));
+                        tc5::mma_commit(&ring_empty[s]);
                     }
+                    tc5::mma_commit(&acc_full[t]);
                 }
         }
     } else {
@@ -433,15 +430,15 @@ int pvd_mlp_pack_weights_t(const float* const* weights8, void* wblob_t, void* st
     return PVD_OK;
 }
 
-int pvd_mlp_trunk_backward(const void* wblob_t, const void* save_ws, const void* d_x28, uint32_t M, const int32_t* n_valid, void* grad_ws,
-                           int32_t* status, void* stream) {
+int pvd_mlp_trunk_backward(const void* wblob_t, uint32_t replicas, const void* save_ws, const void* d_x28, uint32_t M, const int32_t* n_valid,
+                           void* grad_ws, int32_t* status, void* stream) {
     if (M == 0) return PVD_OK;
     PVD_REQUIRE(wblob_t && save_ws && d_x28 && grad_ws && status);
     const uint32_t tiles = (M + kTile - 1) / kTile, pairs = (tiles + 1) / 2;
     const uint32_t grid = min(pairs, (uint32_t)sm_count());
     cudaError_t e = cudaFuncSetAttribute(k_mlp_trunk_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrunkSmem);
     if (e != cudaSuccess) return (int)e;
-    k_mlp_trunk_bwd<<<grid, kBwdThreads, kTrunkSmem, (cudaStream_t)stream>>>((const uint8_t*)wblob_t, (const uint8_t*)save_ws, (const __half*)d_x28, M,
+    k_mlp_trunk_bwd<<<grid, kBwdThreads, kTrunkSmem, (cudaStream_t)stream>>>((const uint8_t*)wblob_t, replicas ? replicas : 1u, (const uint8_t*)save_ws, (const __half*)d_x28, M,
                                                                             n_valid, (uint8_t*)grad_ws, status);
     PVD_LAUNCH_CHECK();
     return PVD_OK;

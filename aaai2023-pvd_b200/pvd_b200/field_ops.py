@@ -308,7 +308,7 @@ class MlpOps:
                 self.wgrads.append(self._wflat[off:off + p_.numel()].view_as(p_))
                 off += p_.numel()
             self.gw_mlp = torch.zeros(fused_mlp.MLP_GW_FLOATS, dtype=torch.float32, device=d)
-            self.wblob_t = torch.empty(fused_mlp.MLP_WBLOB_T_BYTES, dtype=torch.uint8, device=d)
+            self.wblob_t = torch.empty(fused_mlp.MLP_WBLOB_T_BYTES * fused_mlp.REPLICAS, dtype=torch.uint8, device=d)
             # device arrays of device pointers (the ABI's float* const*): parameters and their gradient views never move
             self._wp = fused_mlp._ptr_array([l.weight for l in field.nerf_mlp], d)
             self._gwp = fused_mlp._ptr_array(self.wgrads[0:16:2], d)
@@ -330,9 +330,10 @@ class MlpOps:
         self.tail = f._staged.wblob_for(self._tail(), f.in_dim)
         self.blob = f._blob()
         self.cfield = self._fm.PvdMlpField(wblob=self.blob.data_ptr(), tail_wblob=self.tail.data_ptr(), sigma_clip_min=float(f.args.sigma_clip_min),
-                                           sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
+                                           sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale), replicas=self._fm.REPLICAS)
         if self.trainable:
             nv.check(nv.lib().pvd_mlp_pack_weights_t(nv.ptr(self._wp), nv.ptr(self.wblob_t), nv.stream_of(self.wblob_t)))
+            self._fm.replicate(self.wblob_t, self._fm.MLP_WBLOB_T_BYTES)
             cfg = fused.HashFieldConfig(num_levels=14, base_resolution=16, per_level_scale=2.0, bound=1.0, sigma_clip_min=float(f.args.sigma_clip_min),
                                         sigma_clip_max=float(f.args.sigma_clip_max), density_scale=float(density_scale))
             self._tail_cfg = cfg
@@ -364,7 +365,7 @@ class MlpOps:
                                                 nv.ptr(grad_feat), _u32(0), _u32(M), nv.ptr(n_valid), nv.ptr(gw_ws), nv.ptr(gw_ws), nv.ptr(self.d_x28),
                                                 nv.ptr(status), _u32(1), st))
         # 2. data gradients through layers 7..1; 3. weight / bias gradients (reduction over all samples in TMEM)
-        nv.check(l.pvd_mlp_trunk_backward(nv.ptr(self.wblob_t), nv.ptr(self.save_ws), nv.ptr(self.d_x28), _u32(M), nv.ptr(n_valid),
+        nv.check(l.pvd_mlp_trunk_backward(nv.ptr(self.wblob_t), _u32(self._fm.REPLICAS), nv.ptr(self.save_ws), nv.ptr(self.d_x28), _u32(M), nv.ptr(n_valid),
                                           nv.ptr(self.grad_ws), nv.ptr(status), st))
         nv.check(l.pvd_mlp_weight_grads(nv.ptr(self.save_ws), nv.ptr(self.grad_ws), _u32(M), nv.ptr(self.gw_mlp), nv.ptr(status), st))
 

@@ -199,6 +199,58 @@ class _FusedHashField(Function):
         return (None, None, grad_table.to(embeddings.dtype), g[0], g[1], g[2], g[3], g[4], None, None, None, None)
 
 
+class PvdFieldWeightsF32(C.Structure):
+    _fields_ = [("sigma0", C.c_void_p), ("sigma1", C.c_void_p), ("color0", C.c_void_p), ("color1", C.c_void_p), ("color2", C.c_void_p)]
+
+
+class _FusedHashFieldF32(Function):
+    """The hash field in fp32 end to end (csrc/field_hash_f32.cu): fp32 table gather, fp32 MLPs on the CUDA cores, fp32 gradients.
+    What the reference computes without --fp16; the path north_star's 1e-4 fp32 bound is checked on."""
+
+    @staticmethod
+    def _structs(cfg, table, offsets, ws):
+        f = _cstruct(cfg, table, offsets, table)          # wblob is not used by the fp32 kernels
+        w = PvdFieldWeightsF32(*[x.data_ptr() for x in ws])
+        return f, w
+
+    @staticmethod
+    def forward(ctx, xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg):
+        xyzs = xyzs.detach().float().contiguous().view(-1, 3)
+        dirs = dirs.detach().float().contiguous().view(-1, 3)
+        table = embeddings.detach().float().contiguous()
+        ws = [w.detach().float().contiguous() for w in (w0, w1, w2, w3, w4)]
+        M, dev = xyzs.shape[0], xyzs.device
+        sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        feat = torch.empty(M, 16, dtype=torch.float32, device=dev)
+        f, w = _FusedHashFieldF32._structs(cfg, table, offsets, ws)
+        with nv.on_device(xyzs):
+            nv.check(nv.lib().pvd_hash_field_forward_f32(C.byref(f), C.byref(w), nv.ptr(xyzs), nv.ptr(dirs), C.c_uint32(M), nv.ptr(sigmas),
+                                                         nv.ptr(rgbs), nv.ptr(feat), nv.stream_of(xyzs)))
+        ctx.save_for_backward(xyzs, dirs, offsets, embeddings, w0, w1, w2, w3, w4)
+        ctx.cfg = cfg
+        return sigmas, rgbs, feat
+
+    @staticmethod
+    def backward(ctx, grad_sigmas, grad_rgbs, grad_feat):
+        xyzs, dirs, offsets, embeddings, w0, w1, w2, w3, w4 = ctx.saved_tensors
+        cfg, dev, M = ctx.cfg, xyzs.device, xyzs.shape[0]
+        table = embeddings.detach().float().contiguous()
+        ws = [w.detach().float().contiguous() for w in (w0, w1, w2, w3, w4)]
+        gs = (grad_sigmas if grad_sigmas is not None else torch.zeros(M, device=dev)).float().contiguous()
+        gc = (grad_rgbs if grad_rgbs is not None else torch.zeros(M, 3, device=dev)).float().contiguous()
+        gf = grad_feat.float().contiguous() if grad_feat is not None else None
+        grad_table = torch.zeros(embeddings.shape, dtype=torch.float32, device=dev)
+        gw_ws = torch.zeros(GW_WS_FLOATS, dtype=torch.float32, device=dev)
+        f, w = _FusedHashFieldF32._structs(cfg, table, offsets, ws)
+        with nv.on_device(xyzs):
+            nv.check(nv.lib().pvd_hash_field_backward_f32(C.byref(f), C.byref(w), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(gs), nv.ptr(gc), nv.ptr(gf),
+                                                          C.c_uint32(M), None, nv.ptr(grad_table), nv.ptr(gw_ws), nv.stream_of(xyzs)))
+        g = unpack_wgrads(gw_ws, 2 * cfg.num_levels, (w0, w1, w2, w3, w4))
+        g = [gi.to(x.dtype) for gi, x in zip(g, (w0, w1, w2, w3, w4))]
+        return (None, None, grad_table.to(embeddings.dtype), g[0], g[1], g[2], g[3], g[4], None, None)
+
+
 def fused_hash_field(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat=False):
     return _FusedHashField.apply(xyzs, dirs, embeddings, w0, w1, w2, w3, w4, offsets, cfg, staged, want_feat)
 
@@ -223,7 +275,7 @@ class HashNeRFField(NeRFRenderer):
     """
 
     def __init__(self, num_levels=14, desired_resolution=2048, bound=1, hidden_dim=64, geo_feat_dim=15, args=None,
-                 density_scale=1.0, table_fp16=True, is_teacher=False, **renderer_kwargs):
+                 density_scale=1.0, table_fp16=True, is_teacher=False, fp32=False, **renderer_kwargs):
         super().__init__(bound=bound, density_scale=density_scale, **renderer_kwargs)
         self.is_teacher = is_teacher
         self.model_type = "hash"
@@ -239,6 +291,7 @@ class HashNeRFField(NeRFRenderer):
         self.color_net = nn.ModuleList([nn.Linear(31, 64, bias=False), nn.Linear(64, 64, bias=False),
                                         nn.Linear(64, 3, bias=False)])
         self.table_fp16 = table_fp16
+        self.fp32 = bool(fp32)   # fp32 end to end (csrc/field_hash_f32.cu): the reference without --fp16; fp16 tensor-core path otherwise
         self._staged = StagedParams()
         self.feature_sigma_color = None
         self.sigma_l = None
@@ -252,9 +305,14 @@ class HashNeRFField(NeRFRenderer):
 
     def forward(self, x, d):
         # x [M,3] in [-bound, bound], d [M,3] unit -> sigma [M], color [M,3]   (network.py:335-437, hash branch)
-        out = fused_hash_field(x, d, self.encoder.embeddings, self.sigma_net[0].weight, self.sigma_net[1].weight,
-                               self.color_net[0].weight, self.color_net[1].weight, self.color_net[2].weight,
-                               self.encoder.offsets, self.config(), self._staged, True)
+        if self.fp32:
+            shape = x.shape[:-1]
+            sigma, color, feat = _FusedHashFieldF32.apply(x, d, self.encoder.embeddings, self.sigma_net[0].weight, self.sigma_net[1].weight,
+                                                          self.color_net[0].weight, self.color_net[1].weight, self.color_net[2].weight,
+                                                          self.encoder.offsets, self.config())
+            out = (sigma.view(shape), color.view(*shape, 3), feat.view(*shape, 16))
+        else:
+            out = self._fp16_forward(x, d)
         sigma, color, feat = out
         self.feature_sigma_color = feat
         if self.training and self.args.global_step < self.args.stage_iters["stage1"]:
@@ -262,6 +320,11 @@ class HashNeRFField(NeRFRenderer):
         self.sigma_l = feat[..., 0]
         self.color_l = color
         return sigma, color
+
+    def _fp16_forward(self, x, d):
+        return fused_hash_field(x, d, self.encoder.embeddings, self.sigma_net[0].weight, self.sigma_net[1].weight,
+                                self.color_net[0].weight, self.color_net[1].weight, self.color_net[2].weight,
+                                self.encoder.offsets, self.config(), self._staged, True)
 
     @torch.no_grad()
     def render_persistent(self, rays_o, rays_d, nears, fars, dt_gamma=0.0, max_steps=1024):

@@ -30,11 +30,20 @@ MLP_SAVE_TILE_BYTES = 475136
 MLP_GRAD_TILE_BYTES = 466944
 MLP_GW_FLOATS = 7 * 256 * 320 + 256 * 32 + 8 * 256
 TORCH_TRAIN = os.environ.get("PVD_MLP_TORCH_TRAIN", "0") == "1"
+# copies of the packed weight streams in global memory; CTA b reads copy b mod R (include/pvd_b200_fused.h::PvdMlpField.replicas)
+REPLICAS = max(1, int(os.environ.get("PVD_MLP_REPLICAS", "1")))
+
+
+def replicate(blob, bytes_each):
+    """Fill replicas 1.. of a packed stream from replica 0 (stream-ordered device copies)."""
+    if REPLICAS > 1:
+        with nv.on_device(blob):
+            nv.check(nv.lib().pvd_mlp_replicate_weights(nv.ptr(blob), C.c_uint64(bytes_each), C.c_uint32(REPLICAS), nv.stream_of(blob)))
 
 
 class PvdMlpField(C.Structure):
     _fields_ = [("wblob", C.c_void_p), ("tail_wblob", C.c_void_p), ("sigma_clip_min", C.c_float), ("sigma_clip_max", C.c_float),
-                ("density_scale", C.c_float)]
+                ("density_scale", C.c_float), ("replicas", C.c_uint32)]
 
 
 def _ptr_array(tensors, dev):
@@ -91,7 +100,7 @@ class _FusedMlpField(Function):
         tail_blob = field._staged.wblob_for(tail, field.in_dim)
         d_x28, gw_tail = mlp_tail_backward(field.args, tail_blob, x, d, enc, gs, gc, gf, status)
         w32 = [w.detach().float().contiguous() for w in ws]
-        wblob_t = torch.empty(MLP_WBLOB_T_BYTES, dtype=torch.uint8, device=dev)
+        wblob_t = torch.empty(MLP_WBLOB_T_BYTES * REPLICAS, dtype=torch.uint8, device=dev)
         grad_ws = torch.empty(max((M + 127) // 128, 1) * MLP_GRAD_TILE_BYTES, dtype=torch.uint8, device=dev)
         gw = torch.zeros(MLP_GW_FLOATS, dtype=torch.float32, device=dev)
         gws = [torch.zeros(w.shape, dtype=torch.float32, device=dev) for w in ws]
@@ -100,7 +109,8 @@ class _FusedMlpField(Function):
         with nv.on_device(x):
             st = nv.stream_of(x)
             nv.check(nv.lib().pvd_mlp_pack_weights_t(nv.ptr(wp), nv.ptr(wblob_t), st))
-            nv.check(nv.lib().pvd_mlp_trunk_backward(nv.ptr(wblob_t), nv.ptr(save_ws), nv.ptr(d_x28), C.c_uint32(M), None, nv.ptr(grad_ws), nv.ptr(status), st))
+            replicate(wblob_t, MLP_WBLOB_T_BYTES)
+            nv.check(nv.lib().pvd_mlp_trunk_backward(nv.ptr(wblob_t), C.c_uint32(REPLICAS), nv.ptr(save_ws), nv.ptr(d_x28), C.c_uint32(M), None, nv.ptr(grad_ws), nv.ptr(status), st))
             nv.check(nv.lib().pvd_mlp_weight_grads(nv.ptr(save_ws), nv.ptr(grad_ws), C.c_uint32(M), nv.ptr(gw), nv.ptr(status), st))
             nv.check(nv.lib().pvd_mlp_unpack_wgrads(nv.ptr(gw), nv.ptr(gwp), nv.ptr(gbp), st))
         gt = fused.unpack_wgrads(gw_tail, field.in_dim, tail)
@@ -152,7 +162,7 @@ class MLPNeRFField(NeRFRenderer):
             return self._mlp_blob
         dev = ps[0].device
         if self._mlp_blob is None or self._mlp_blob.device != dev:
-            self._mlp_blob = torch.empty(MLP_WBLOB_BYTES, dtype=torch.uint8, device=dev)
+            self._mlp_blob = torch.empty(MLP_WBLOB_BYTES * REPLICAS, dtype=torch.uint8, device=dev)
             self._ptr_key = None
         in_place = all(p.dtype == torch.float32 and p.is_contiguous() for p in ps)
         if in_place:
@@ -170,6 +180,7 @@ class MLPNeRFField(NeRFRenderer):
             with nv.on_device(self._mlp_blob):
                 nv.check(nv.lib().pvd_mlp_pack_weights(nv.ptr(wp), nv.ptr(bp), nv.ptr(self._mlp_blob), nv.stream_of(self._mlp_blob)))
             torch.cuda.current_stream(dev).synchronize()  # the temporaries may be freed after this scope
+        replicate(self._mlp_blob, MLP_WBLOB_BYTES)
         self._mlp_key = key
         return self._mlp_blob
 
@@ -180,7 +191,7 @@ class MLPNeRFField(NeRFRenderer):
         tail = self._staged.wblob_for((self.sigma_net[0].weight, self.sigma_net[1].weight, self.color_net[0].weight,
                                        self.color_net[1].weight, self.color_net[2].weight), self.in_dim)
         f = PvdMlpField(wblob=self._blob().data_ptr(), tail_wblob=tail.data_ptr(), sigma_clip_min=float(self.args.sigma_clip_min),
-                        sigma_clip_max=float(self.args.sigma_clip_max), density_scale=1.0)
+                        sigma_clip_max=float(self.args.sigma_clip_max), density_scale=1.0, replicas=REPLICAS)
         sigmas = torch.empty(M, dtype=torch.float32, device=dev)
         rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
         feat = torch.empty(M, 16, dtype=torch.float32, device=dev)

@@ -195,6 +195,22 @@ def for_engine(engine, lr=1e-2, lr2=1e-3, betas=(0.9, 0.99), eps=1e-15, weight_d
         entries.append(dict(param=vol.data, grad=ops._flat, lr=lrs[id(vol)], grad_f16=gh_all, zero_grad=True, grad_mul=big_mul))
         ws, wg = [], []
         pre = post = lambda st: None
+    elif ops.kind == "mlp":
+        assert exchange is None, "the mlp model's fused optimizer is single-GPU"
+        from .fused_mlp import _ptr_array
+        ws = ops._params()                     # nerf_mlp.{0..7}.{weight,bias}, sigma_net.{0,1}.weight, color_net.{0,1,2}.weight
+        wg = [torch.zeros_like(w, dtype=torch.float32) for w in ws]
+        gwp, gbp = _ptr_array(wg[0:16:2], engine.dev), _ptr_array(wg[1:16:2], engine.dev)
+        torch.cuda.current_stream(engine.dev).synchronize()
+        opt_ptrs = (gwp, gbp)                  # kept alive by the closure below
+
+        def pre(st):
+            nv.check(l.pvd_mlp_unpack_wgrads(nv.ptr(ops.gw_mlp), nv.ptr(opt_ptrs[0]), nv.ptr(opt_ptrs[1]), st))
+            nv.check(l.pvd_field_unpack_wgrads(nv.ptr(engine.gw_ws), C.c_uint32(field.in_dim), *[nv.ptr(g) for g in wg[16:]], st))
+            ops.gw_mlp.zero_()                 # the weight-gradient kernel accumulates into it
+
+        def post(st):
+            ops.stage(engine.density_scale)    # forward stream, transposed stream and tail tiles re-packed from the updated masters
     else:
         raise ValueError(f"no fused optimizer wiring for model_type {ops.kind!r}")
     for w, g in zip(ws, wg):

@@ -127,11 +127,15 @@ WORKLOADS = {
                "losses), both networks queried at the SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
     "mlp-hash": "mlp (NeRF 8x256, PE 10) teacher -> hash (L={L}) student distillation (main_distill_mutual stage 3), both networks queried at the "
                 "SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
+    "mlp": "mlp (NeRF 8x256, PE 10, skip) teacher training (main_just_train_tea.py --model_type mlp; not a BASELINE config, reported beside them), "
+           "{R} rays/GPU x 1024 max steps, cuda_ray, synthetic 800x800 Lego-shaped scene, fwd+bwd (MSE), random-init weights",
 }
-DEFAULT_RAYS = {"hash": 4096, "vm": 4096, "hash-vm": 4096, "mlp-hash": 8192}
+DEFAULT_RAYS = {"hash": 4096, "vm": 4096, "hash-vm": 4096, "mlp-hash": 8192, "mlp": 4096}
+ALL_WORKLOADS = ("hash", "vm", "hash-vm", "mlp-hash", "mlp")
 PAIR_RATES = (1.0, 0.002, 0.002, 0.002)   # main_distill_mutual.py:174-177
 L1_REG = 1e-4                             # main_distill_mutual.py:178 / main_just_train_tea.py:170
 MLP_FLOPS_PER_SAMPLE = 865280             # 2 * (63*256 + 5*256^2 + 319*256 + 256*28)
+MLP_BWD_FLOPS_PER_SAMPLE = 2 * (28 * 256 + 6 * 256 * 256) + MLP_FLOPS_PER_SAMPLE   # data gradients (layers 7..1, hidden parts) + weight gradients
 TAIL_FLOPS_FWD_BWD = 54500                # sigma_net + color_net, 18.2 kFLOP forward, x3 with both gradient GEMMs
 
 
@@ -161,11 +165,14 @@ def cpu_baseline(workload, levels, n_rays, budget_s=15.0):
         fn = lambda x, d: field.vm_field_forward(x, d, sm, sv, cm, cv, bw, cw, aabb)
         return fn, sm + sv + cm + cv + [bw] + cw, (sm, sv)
 
-    def mlp_model():
+    def mlp_model(train=False):
         dims = [(63, 256)] + [(256, 256)] * 3 + [(319, 256)] + [(256, 256)] * 2 + [(256, 28)]
         ls = [torch.nn.Linear(i, o) for i, o in dims]
         nw, nb, tw = [l.weight.detach() for l in ls], [l.bias.detach() for l in ls], [w.detach() for w in lin(((28, 64),) + TAIL[1:])]
-        return lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw)
+        for t in (nw + nb + tw) if train else ():
+            t.requires_grad_(True)
+        fn = lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw)
+        return (fn, nw + nb + tw) if train else fn
 
     if workload == "hash":
         f_s, params = hash_model(True)
@@ -177,6 +184,9 @@ def cpu_baseline(workload, levels, n_rays, budget_s=15.0):
         f_t, _ = hash_model(False)
         f_s, params, (sm, sv) = vm_model()
         one = lambda ro, rd, gt: field.pair_distill_step(ro, rd, bitfield, f_s, f_t, PAIR_RATES, l1_reg=L1_REG * field.vm_density_loss(sm, sv))["loss"]
+    elif workload == "mlp":
+        f_s, params = mlp_model(True)
+        one = lambda ro, rd, gt: field.render_train_step(ro, rd, bitfield, gt, lambda x, d: f_s(x, d)[:2])["loss"]
     else:
         f_t = mlp_model()
         f_s, params = hash_model(True)
@@ -223,6 +233,9 @@ def build_engine(args, dev, bitfield):
         tea = HashNeRFField(num_levels=args.levels, desired_resolution=2048, is_teacher=True).to(dev)
         return PairDistillEngine(tea, VMNeRFField(resolution0=300).to(dev), bf, args.rays, rates=PAIR_RATES, stage=3, l1_reg_weight=L1_REG, **kw)
     from pvd_b200.fused_mlp import MLPNeRFField
+    if w == "mlp":
+        from pvd_b200.engine import MLPTrainEngine
+        return MLPTrainEngine(MLPNeRFField().to(dev), bf, args.rays, **kw)
     tea = MLPNeRFField().to(dev)
     return PairDistillEngine(tea, HashNeRFField(num_levels=args.levels, desired_resolution=2048, table_fp16=False).to(dev), bf, args.rays,
                              rates=PAIR_RATES, stage=3, **kw)
@@ -281,7 +294,10 @@ def roofline_kernels(eng):
             out.append(("k_mlp_field_fwd", "teacher_fwd", "tensor", MLP_FLOPS_PER_SAMPLE))
     o = eng.ops
     fb, bb = o.algorithmic_bytes()
-    if o.kind == "hash":
+    if o.kind == "mlp":
+        out.append(("k_mlp_field_fwd", "field_fwd", "tensor", MLP_FLOPS_PER_SAMPLE))
+        out.append(("k_mlp_trunk_bwd+k_mlp_wgrad", "field_bwd", "tensor", MLP_BWD_FLOPS_PER_SAMPLE))
+    elif o.kind == "hash":
         out.append(("k_hash_field_fwd", "field_fwd", "hbm", fb))
         if o.dx_ws is not None:
             out.append(("k_hash_field_bwd", "mlp_bwd", "tensor", TAIL_FLOPS_FWD_BWD))   # the MLP backward GEMMs (forward recomputed)
@@ -355,7 +371,9 @@ def _timed(fn_load, fn_step, flush, steps, world, dev):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    per = sorted(a.elapsed_time(b) for a, b in ev)
+    _timed.last_percentiles = {"median": per[len(per) // 2], "p10": per[len(per) // 10], "p90": per[(9 * len(per)) // 10]}   # this rank's steps
+    tt = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     return float(tt.item())
@@ -497,6 +515,7 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
     sampler.start()
     # ---- timed region: K steps, each bracketed by events, L2 flushed between steps (outside the brackets)
     t_ms = _timed(load_next, run_step, flush, steps, world, dev)
+    step_pct = dict(_timed.last_percentiles)
 
     # ---- per-kernel pass (same steps again, events around the field kernels; used for the roofline only)
     plan = phase_plan(eng)
@@ -615,13 +634,13 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
             if l2:
                 roofs[-1]["l2"] = l2
     # the workload's bound: the table / plane traffic (HBM roofline) -- except mlp -> hash, where the teacher's GEMMs dominate
-    want = "tensor" if workload == "mlp-hash" else "hbm"
+    want = "tensor" if workload in ("mlp-hash", "mlp") else "hbm"
     dom = max((r for r in roofs if r["bound"] == want), key=lambda r: r["ms"])
-    n_extra = 2 + (1 if eng.ops.kind == "hash" else 0)   # per step: weight pack, weight-gradient unpack (+ the table cast for hash)
+    n_extra = 2 + (1 if eng.ops.kind == "hash" else 0) + (3 if eng.ops.kind == "mlp" else 0)   # per step: weight pack, weight-gradient unpack (+ the table cast for hash)
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic", "impl": "ours",
+        "ms_per_step": t_ms / steps, "ms_per_step_percentiles": step_pct, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOADS[workload].format(L=L, R=n_rays), "workload_key": workload,
                    "rays_per_gpu": n_rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
                    "precision": "fp16 tcgen05 MLP (fp32 accumulate); trained hash table gathered as fp32 master, frozen teacher table / vm planes as fp16 shadows; fp32 composite / gradients", "loss_scale": 65536,
@@ -668,7 +687,7 @@ def run_ours(args, rank, world, local):
     # the other BASELINE configurations in the same line (shorter runs): configs[1]-[4] all measured by one invocation
     others = {}
     if args.all_workloads:
-        for w in ("hash", "vm", "hash-vm", "mlp-hash"):
+        for w in ALL_WORKLOADS:
             if w == args.workload:
                 continue
             try:
@@ -724,6 +743,8 @@ def build_reference(args, dev, ext, bitfield):
         return rp.RefTrainer(ext, rp.RefVmNetwork(ext).to(dev), bf, l1_reg_weight=L1_REG)
     if w == "hash-vm":
         return rp.RefPairTrainer(ext, rp.RefVmNetwork(ext).to(dev), hash_net(), bf, rates=PAIR_RATES, l1_reg_weight=L1_REG)
+    if w == "mlp":
+        return rp.RefTrainer(ext, rp.RefMlpNetwork(ext).to(dev), bf)
     return rp.RefPairTrainer(ext, hash_net(), rp.RefMlpNetwork(ext).to(dev), bf, rates=PAIR_RATES, l1_reg_weight=0.0)
 
 
@@ -842,7 +863,7 @@ def run_reference(args, rank, world, local):
         out["note"] = f"launched under torchrun with {world} ranks: ONE-GPU reference (the reference has no multi-GPU path), rank 0 only"
     out["workloads"] = {args.workload: {k: out[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "iteration") if k in out}}
     if args.all_workloads:
-        for w in ("hash", "vm", "hash-vm", "mlp-hash"):
+        for w in ALL_WORKLOADS:
             if w == args.workload:
                 continue
             try:

@@ -106,6 +106,27 @@ int pvd_hash_field_backward_rows(const PvdHashField* field, const float* xyzs, c
                                  uint32_t rows, const int32_t* n_valid, float* grad_table, float* gw_ws, void* dx_ws, int32_t* status,
                                  uint32_t phases, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The same field in FP32 end to end (csrc/field_hash_f32.cu): what NeRFNetwork.forward computes when the reference runs WITHOUT
+ * --fp16 (fp32 table gather, gridencoder.cu with scalar_t = float, fp32 GEMMs; network.py:335-437), and the path north_star's
+ * 1e-4 fp32 parity bound is measured on.  field->table must be the fp32 table (table_dtype PVD_DTYPE_F32); field->wblob is not
+ * used: the five weight matrices are read in place as fp32 row-major [out, in].  No saved encoding: the backward recomputes the
+ * forward.  Gradients go to the same grad_table / gw_ws (PVD_FIELD_GW_COPIES x PVD_FIELD_GW_FLOATS, pvd_field_unpack_wgrads)
+ * as the fp16 path.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct PvdFieldWeightsF32 {
+    const float* sigma0; /* [64, 2L] */
+    const float* sigma1; /* [16, 64] */
+    const float* color0; /* [64, 31] */
+    const float* color1; /* [64, 64] */
+    const float* color2; /* [3, 64]  */
+} PvdFieldWeightsF32;
+int pvd_hash_field_forward_f32(const PvdHashField* field, const PvdFieldWeightsF32* weights, const float* xyzs, const float* dirs,
+                               uint32_t M, float* sigmas, float* rgbs, float* feat16, void* stream);
+int pvd_hash_field_backward_f32(const PvdHashField* field, const PvdFieldWeightsF32* weights, const float* xyzs, const float* dirs,
+                                const float* grad_sigmas, const float* grad_rgbs, const float* grad_feat16, uint32_t M,
+                                const int32_t* n_valid, float* grad_table, float* gw_ws, void* stream);
+
 /* gw_* += un-padded / transposed views of gw_ws; shapes [64,in_dim], [16,64], [64,31], [64,64], [3,64]. */
 int pvd_field_unpack_wgrads(const float* gw_ws, uint32_t in_dim, float* gw_sigma0, float* gw_sigma1, float* gw_color0,
                             float* gw_color1, float* gw_color2, void* stream);
@@ -172,16 +193,20 @@ int pvd_vm_unpack_wgrads(const float* gw_ws, float* g_basis, float* gw_color0, f
 #define PVD_MLP_WBLOB_BYTES 876544u
 
 typedef struct PvdMlpField {
-    const void* wblob;       /* PVD_MLP_WBLOB_BYTES from pvd_mlp_pack_weights */
+    const void* wblob;       /* `replicas` x PVD_MLP_WBLOB_BYTES: pvd_mlp_pack_weights fills the first, pvd_mlp_replicate_weights the rest */
     const void* tail_wblob;  /* PVD_FIELD_WBLOB_BYTES from pvd_field_pack_weights (in_dim = 28) */
     float sigma_clip_min;
     float sigma_clip_max;
     float density_scale;
+    uint32_t replicas;       /* 0 / 1: one copy.  R > 1: CTA b streams replica b mod R -- every CTA walks the SAME 876 KB in the same order,
+                                so one copy concentrates all 148 TMA streams on the few L2 slices that hold the current piece */
 } PvdMlpField;
 
 /* weights8 / biases8: DEVICE arrays of 8 device pointers to nerf_mlp.{0..7}.weight ([256,63] [256,256]x3 [256,319] [256,256]x2
  * [28,256], fp32 row-major) and .bias. */
 int pvd_mlp_pack_weights(const float* const* weights8, const float* const* biases8, void* wblob, void* stream);
+/* copy replica 0 of a packed stream (`bytes` each) into replicas 1 .. replicas-1 behind it */
+int pvd_mlp_replicate_weights(void* wblob, uint64_t bytes, uint32_t replicas, void* stream);
 
 int pvd_mlp_field_forward(const PvdMlpField* field, const float* xyzs, const float* dirs, uint32_t M, float* sigmas, float* rgbs,
                           float* feat16, int32_t* status, void* stream);
@@ -209,8 +234,8 @@ int pvd_mlp_field_forward_train(const PvdMlpField* field, const float* xyzs, con
 #define PVD_MLP_WBLOB_T_BYTES (49u * 16384u)
 int pvd_mlp_pack_weights_t(const float* const* weights8, void* wblob_t, void* stream);
 /* n_valid (device pointer or NULL = all M): rows >= *n_valid are padding and receive zero gradients. */
-int pvd_mlp_trunk_backward(const void* wblob_t, const void* save_ws, const void* d_x28, uint32_t M, const int32_t* n_valid,
-                           void* grad_ws, int32_t* status, void* stream);
+int pvd_mlp_trunk_backward(const void* wblob_t, uint32_t replicas, const void* save_ws, const void* d_x28, uint32_t M,
+                           const int32_t* n_valid, void* grad_ws, int32_t* status, void* stream);
 int pvd_mlp_weight_grads(const void* save_ws, const void* grad_ws, uint32_t M, float* gw_ws, int32_t* status, void* stream);
 int pvd_mlp_unpack_wgrads(const float* gw_ws, float* const* grad_weights8, float* const* grad_biases8, void* stream);
 

@@ -1,0 +1,74 @@
+"""north_star's fp32 bound: the fused hash field in fp32 end to end (csrc/field_hash_f32.cu, HashNeRFField(fp32=True)) against the
+oracle's fp32 restatement of NeRFNetwork.forward (oracle/field.py, pinned to the reference's own forward by
+tests/golden/ref_network_golden.npz) -- values AND every gradient within 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL_SCALE = 1e-4     # the tolerance north_star states for fp32
+
+
+def _close(a, b, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    tol = ATOL_SCALE * float(b.abs().max()) + RTOL * b.abs()
+    bad = (a - b).abs() > tol
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())} of {bad.numel()} beyond 1e-4, worst abs {float((a - b).abs().max()):.3e} at scale {float(b.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("M", [128 * 3 + 50, 128 * 200])
+def test_fp32_hash_field_matches_oracle_values_and_gradients(M):
+    from oracle import cpu, field
+    from pvd_b200.fused import HashNeRFField
+    torch.manual_seed(0)
+    net = HashNeRFField(num_levels=14, desired_resolution=2048, fp32=True).cuda()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    net.train()
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.999
+    d = torch.randn(M, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    cs, cc, cf = torch.randn(M, generator=g) * 0.05, torch.randn(M, 3, generator=g), torch.randn(M, 16, generator=g) * 0.1
+    sigma, color = net(x.cuda(), d.cuda())
+    feat = net.feature_sigma_color
+    ((sigma * cs.cuda()).sum() + (color * cc.cuda()).sum() + (feat * cf.cuda()).sum()).backward()
+    # oracle: the same network in fp32 on the CPU
+    e = net.encoder
+    P = {"emb": e.embeddings.detach().cpu().clone().requires_grad_(True)}
+    ws = [m.weight.detach().cpu().clone().requires_grad_(True) for m in list(net.sigma_net) + list(net.color_net)]
+    so, co, fo = field.hash_field_forward(x, d, P["emb"], e.offsets.cpu().numpy(), float(e.per_level_scale), e.base_resolution, ws)
+    ((so * cs).sum() + (co * cc).sum() + (fo * cf).sum()).backward()
+    _close(sigma, so, "sigma")
+    _close(color, co, "color")
+    _close(feat, fo, "feature_sigma_color")
+    _close(e.embeddings.grad, P["emb"].grad, "d/d embeddings")
+    for m, w, n in zip(list(net.sigma_net) + list(net.color_net), ws, ("sigma_net.0", "sigma_net.1", "color_net.0", "color_net.1", "color_net.2")):
+        _close(m.weight.grad, w.grad, f"d/d {n}.weight")
+
+
+def test_fp32_training_step_through_the_renderer(scene):
+    """run_cuda with the fp32 field: loss and gradients equal the oracle's fp32 training step on the same rays (1e-4)."""
+    from oracle import field
+    from pvd_b200.fused import HashNeRFField
+    torch.manual_seed(2)
+    net = HashNeRFField(num_levels=14, desired_resolution=2048, fp32=True).cuda()
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    net.density_bitfield.copy_(torch.from_numpy(scene["bitfield"]))
+    net.train()
+    ro, rd = scene["batches"][0]
+    ro, rd = ro[:512].contiguous(), rd[:512].contiguous()
+    gt = torch.rand(512, 3, generator=torch.Generator().manual_seed(3))
+    out = net.render(ro.cuda().unsqueeze(0), rd.cuda().unsqueeze(0), bg_color=1, perturb=True)
+    loss = torch.mean((out["image"][0] - gt.cuda()) ** 2)
+    loss.backward()
+    e = net.encoder
+    emb = e.embeddings.detach().cpu().clone().requires_grad_(True)
+    ws = [m.weight.detach().cpu().clone().requires_grad_(True) for m in list(net.sigma_net) + list(net.color_net)]
+    fn = lambda x, d: field.hash_field_forward(x, d, emb, e.offsets.cpu().numpy(), float(e.per_level_scale), e.base_resolution, ws)[:2]
+    o = field.render_train_step(ro, rd, scene["bitfield"], gt, fn)
+    o["loss"].backward()
+    assert abs(float(loss) - float(o["loss"])) <= 1e-4 * float(o["loss"])
+    _close(e.embeddings.grad, emb.grad, "d/d embeddings")
+    for m, w in zip(list(net.sigma_net) + list(net.color_net), ws):
+        _close(m.weight.grad, w.grad, "weight gradient")

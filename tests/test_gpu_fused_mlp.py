@@ -134,7 +134,7 @@ def test_mlp_engine_step_matches_module_path_and_fp32_autograd(scene):
     reproduces the eager step."""
     import raymarching
     from pvd_b200.engine import MLPTrainEngine
-    n_rays, scale = 1024, 256.0
+    n_rays, scale = 1024, 16384.0      # GradScaler's role: the data gradients travel as fp16 operand tiles
     net = _make(8)
     net.train()
     eng = MLPTrainEngine(net, torch.from_numpy(scene["bitfield"]), n_rays, loss_scale=scale)
@@ -157,6 +157,9 @@ def test_mlp_engine_step_matches_module_path_and_fp32_autograd(scene):
         xyzs, dirs, deltas, rays = eng.xyzs[:eng.M], eng.dirs[:eng.M], eng.deltas[:eng.M], eng.rays
         if kind == "module":
             sigma, color = net(xyzs, dirs)
+        elif kind == "amp":
+            with torch.autocast("cuda", dtype=torch.float16):
+                sigma, color, _ = net._torch_forward(xyzs, dirs)
         else:
             sigma, color, _ = net._torch_forward(xyzs, dirs)
         ws, depth, image = raymarching.composite_rays_train(sigma.float(), color.float(), deltas, rays)
@@ -167,11 +170,13 @@ def test_mlp_engine_step_matches_module_path_and_fp32_autograd(scene):
 
     loss_m, g_m = reference("module")
     loss_t, g_t = reference("fp32")
+    _, g_a = reference("amp")
     assert abs(loss_e - loss_m) < 1e-5 * max(1.0, loss_m)
     assert abs(loss_e - loss_t) < 1e-2 * max(1e-3, loss_t)
     for n in g_t:
         assert _rel(g_e[n], g_m[n]) < 1e-3, (n, _rel(g_e[n], g_m[n]))          # same kernels; float reductions reorder
-        assert _rel(g_e[n], g_t[n]) < 3e-2, (n, _rel(g_e[n], g_t[n]))
+        oa, af = _rel(g_e[n], g_t[n]), _rel(g_a[n], g_t[n])                   # ours vs fp32; the reference's autocast vs fp32
+        assert oa <= max(1e-2, 1.25 * af), (n, oa, af)
     # CUDA graph of the step
     eng.unpack_each_step = True
     eng.capture()

@@ -55,7 +55,7 @@ def _net(mt):
 
 def _reference_autocast(mt, ref_ext):
     """{record: value} of the reference's OWN autocast path on the golden's parameters / points (None without oracle/_ref)."""
-    if ref_ext is None or mt in ("mlp", "tensors"):
+    if ref_ext is None or mt == "tensors":
         return None
     from oracle import ref_pipeline as rp
     P = netgold.seeded_params(mt)
@@ -64,6 +64,9 @@ def _reference_autocast(mt, ref_ext):
         offsets, pls = cpu.grid_offsets(3, 14, 16, 19, desired_resolution=2048)
         net = rp.RefHashNetwork(ref_ext, offsets, pls).cuda()
         P = {("embeddings" if k == "encoder.embeddings" else k): v for k, v in P.items()}
+    elif mt == "mlp":
+        net = rp.RefMlpNetwork(ref_ext).cuda()      # a TRAINED mlp model: autograd through cuBLAS under autocast in the reference
+        offsets = None
     else:
         net = rp.RefVmNetwork(ref_ext, resolution=netgold.VM_RES).cuda()
         offsets = None
@@ -101,7 +104,8 @@ def test_fused_field_matches_reference_network_golden(gold, ref_ext, mt):
     x, d, cs, cc, cf = (t.cuda() for t in netgold.query_points(mt))
     sigma, color = net(x, d)
     feat = net.feature_sigma_color
-    netgold.scalar(sigma, color, feat, cs, cc, cf).backward()
+    scale = 128.0 if mt == "mlp" else 1.0   # mlp: the data gradients travel between layers as fp16 tiles, as under the reference's autocast + GradScaler
+    (netgold.scalar(sigma, color, feat, cs, cc, cf) * scale).backward()
     torch.cuda.synchronize()
     rec, noise = {}, {}
 
@@ -123,7 +127,7 @@ def test_fused_field_matches_reference_network_golden(gold, ref_ext, mt):
     for name, p in net.named_parameters():
         if p.grad is None:
             continue
-        for k, v in netgold.summarise_grad(name, p.grad, offsets).items():
+        for k, v in netgold.summarise_grad(name, p.grad / scale, offsets).items():
             judge(k, v, gold[f"{mt}/{k}"], amp and amp.get(k))
             seen += 1
     assert seen == sum(1 for k in gold if k.startswith(mt + "/grad")), "a parameter received no gradient"
