@@ -688,7 +688,7 @@ def run_ours(args, rank, world, local):
     others = {}
     if args.all_workloads:
         for w in ALL_WORKLOADS:
-            if w == args.workload:
+            if w == args.workload or (w == "mlp" and world > 1):   # mlp training is not a BASELINE config: reported on one GPU only
                 continue
             try:
                 r = measure_ours(args, w, DEFAULT_RAYS[w], rank, world, local, headline=False)

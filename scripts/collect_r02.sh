@@ -23,4 +23,8 @@ ncu -i $O/${T}_pair_full.ncu-rep --page raw --csv > $O/${T}_pair_ncu_full_raw.cs
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:k_mlp_field_fwd' -s 20 -c 1 -o $O/${T}_mlp_full \
     python bench.py --workload mlp-hash --steps 2 --warmup 3 --only --no-cpu-baseline --no-graph > $O/ncu_fm.log 2>&1
 ncu -i $O/${T}_mlp_full.ncu-rep --page raw --csv > $O/${T}_mlp_ncu_full_raw.csv 2>/dev/null
+# the NeRF-MLP training kernels: forward that saves its tiles, trunk data gradients, tensor-core weight gradients
+timeout 500 ncu --set full --clock-control none --import-source on -k 'regex:k_mlp_field_fwd|k_mlp_trunk_bwd|k_mlp_wgrad' -s 30 -c 3 -o $O/${T}_mlptrain_full \
+    python bench.py --workload mlp --steps 2 --warmup 3 --only --no-cpu-baseline --no-graph > $O/ncu_fmt.log 2>&1
+ncu -i $O/${T}_mlptrain_full.ncu-rep --page raw --csv > $O/${T}_mlptrain_ncu_full_raw.csv 2>/dev/null
 ls -la $O | grep ${T}_ | tail -20
