@@ -31,7 +31,8 @@ class HashOps:
         self.field, self.dev, self.trainable = field, torch.device(dev), trainable
         self.grad_table = torch.zeros(field.encoder.embeddings.shape, dtype=torch.float32, device=self.dev) if trainable else None
         self.enc = self.dx_ws = None
-        self.kernels_bwd = 2 if fused.SPLIT_SCATTER else 1
+        self.fp32 = bool(getattr(field, "fp32", False))   # fp32 end to end: csrc/field_hash_f32.cu (no saved encoding, no packed tiles)
+        self.kernels_bwd = 1 if self.fp32 else (2 if fused.SPLIT_SCATTER else 1)
         self.table = self.wblob = self.cfield = None
         ws = self._weights()
         # the small weight gradients in parameter shapes, ONE flat buffer (one memset), for callers with an external optimizer
@@ -55,6 +56,13 @@ class HashOps:
         cfg = f.config()
         cfg.density_scale = density_scale
         self.cfg = cfg
+        if self.fp32:
+            ws = self._weights()
+            assert f.encoder.embeddings.dtype == torch.float32 and all(w.dtype == torch.float32 and w.is_contiguous() for w in ws)
+            self.table = f.encoder.embeddings.detach()
+            self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.table)
+            self.cweights = fused.PvdFieldWeightsF32(*[w.data_ptr() for w in ws])     # read in place: nothing to re-stage after an optimizer step
+            return
         self.table = f._staged.table_for(f.encoder.embeddings, cfg.table_fp16)
         self.wblob = f._staged.wblob_for(self._weights(), 2 * cfg.num_levels)
         self.cfield = fused._cstruct(cfg, self.table, f.encoder.offsets, self.wblob)
@@ -65,16 +73,25 @@ class HashOps:
         nv.check(nv.lib().pvd_l2_prefetch(nv.ptr(t), C.c_uint64(t.numel() * t.element_size()), st))
 
     def alloc(self, M):
-        if self.trainable:
+        if self.trainable and not self.fp32:
             self.enc = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev)
             self.dx_ws = torch.empty(M, fused.ENC_STRIDE, dtype=torch.float16, device=self.dev) if fused.SPLIT_SCATTER else None
 
     def forward(self, st, xyzs, dirs, M, sigmas, rgbs, feat, status):
+        if self.fp32:
+            nv.check(nv.lib().pvd_hash_field_forward_f32(C.byref(self.cfield), C.byref(self.cweights), nv.ptr(xyzs), nv.ptr(dirs), _u32(M),
+                                                         nv.ptr(sigmas), nv.ptr(rgbs), nv.ptr(feat), st))
+            return
         nv.check(nv.lib().pvd_hash_field_forward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), _u32(M), nv.ptr(sigmas), nv.ptr(rgbs),
                                                  nv.ptr(self.enc), nv.ptr(feat), nv.ptr(status), st))
 
     def backward(self, st, xyzs, dirs, grad_sigmas, grad_rgbs, grad_feat, M, n_valid, gw_ws, status, phases=None):
         """phases: None = the whole backward; PVD_BWD_MLP (1) / PVD_BWD_SCATTER (2) = one of its two kernels (needs dx_ws)."""
+        if self.fp32:
+            nv.check(nv.lib().pvd_hash_field_backward_f32(C.byref(self.cfield), C.byref(self.cweights), nv.ptr(xyzs), nv.ptr(dirs),
+                                                          nv.ptr(grad_sigmas), nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid),
+                                                          nv.ptr(self.grad_table), nv.ptr(gw_ws), st))
+            return
         if phases is None:
             nv.check(nv.lib().pvd_hash_field_backward(C.byref(self.cfield), nv.ptr(xyzs), nv.ptr(dirs), nv.ptr(self.enc),
                                                       nv.ptr(grad_sigmas), nv.ptr(grad_rgbs), nv.ptr(grad_feat), _u32(M), nv.ptr(n_valid),

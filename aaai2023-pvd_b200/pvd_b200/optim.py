@@ -170,7 +170,8 @@ def for_engine(engine, lr=1e-2, lr2=1e-3, betas=(0.9, 0.99), eps=1e-15, weight_d
             nv.check(l.pvd_field_unpack_wgrads(nv.ptr(engine.gw_ws), C.c_uint32(in_dim), *[nv.ptr(g) for g in wg], st))
 
         def post(st):
-            nv.check(l.pvd_field_pack_weights(*[nv.ptr(w.data) for w in ws], C.c_uint32(in_dim), nv.ptr(ops.wblob), st))
+            if not getattr(ops, "fp32", False):     # the fp32 kernels read the parameters in place
+                nv.check(l.pvd_field_pack_weights(*[nv.ptr(w.data) for w in ws], C.c_uint32(in_dim), nv.ptr(ops.wblob), st))
     elif ops.kind == "vm":
         off, k = 0, 0
         for grp, views in zip(ops.groups, ops.grad_groups):

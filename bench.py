@@ -127,11 +127,14 @@ WORKLOADS = {
                "losses), both networks queried at the SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
     "mlp-hash": "mlp (NeRF 8x256, PE 10) teacher -> hash (L={L}) student distillation (main_distill_mutual stage 3), both networks queried at the "
                 "SAME samples, {R} rays/GPU x 1024 max steps, synthetic Lego-shaped scene, random-init weights",
+    "hash-fp32": "hash (INGP L={L}) teacher training in FP32 END TO END (the reference without --fp16; north_star's fp32 bound; not a BASELINE config, "
+                 "reported beside them), {R} rays/GPU x 1024 max steps, cuda_ray, synthetic Lego-shaped scene, fwd+bwd (MSE), random-init weights",
     "mlp": "mlp (NeRF 8x256, PE 10, skip) teacher training (main_just_train_tea.py --model_type mlp; not a BASELINE config, reported beside them), "
            "{R} rays/GPU x 1024 max steps, cuda_ray, synthetic 800x800 Lego-shaped scene, fwd+bwd (MSE), random-init weights",
 }
-DEFAULT_RAYS = {"hash": 4096, "vm": 4096, "hash-vm": 4096, "mlp-hash": 8192, "mlp": 4096}
-ALL_WORKLOADS = ("hash", "vm", "hash-vm", "mlp-hash", "mlp")
+DEFAULT_RAYS = {"hash": 4096, "vm": 4096, "hash-vm": 4096, "mlp-hash": 8192, "mlp": 4096, "hash-fp32": 4096}
+ALL_WORKLOADS = ("hash", "vm", "hash-vm", "mlp-hash", "mlp", "hash-fp32")
+ONE_GPU_ONLY = ("mlp", "hash-fp32")       # not BASELINE configs: reported beside them on one GPU
 PAIR_RATES = (1.0, 0.002, 0.002, 0.002)   # main_distill_mutual.py:174-177
 L1_REG = 1e-4                             # main_distill_mutual.py:178 / main_just_train_tea.py:170
 MLP_FLOPS_PER_SAMPLE = 865280             # 2 * (63*256 + 5*256^2 + 319*256 + 256*28)
@@ -174,7 +177,7 @@ def cpu_baseline(workload, levels, n_rays, budget_s=15.0):
         fn = lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw)
         return (fn, nw + nb + tw) if train else fn
 
-    if workload == "hash":
+    if workload in ("hash", "hash-fp32"):
         f_s, params = hash_model(True)
         one = lambda ro, rd, gt: field.render_train_step(ro, rd, bitfield, gt, lambda x, d: f_s(x, d)[:2])["loss"]
     elif workload == "vm":
@@ -225,6 +228,8 @@ def build_engine(args, dev, bitfield):
     # distillation pair keeps its fp16 shadow (cast once, half the L2 footprint).
     if w == "hash":
         return HashTrainEngine(HashNeRFField(num_levels=args.levels, desired_resolution=2048, table_fp16=False).to(dev), bf, args.rays, **kw)
+    if w == "hash-fp32":
+        return HashTrainEngine(HashNeRFField(num_levels=args.levels, desired_resolution=2048, table_fp16=False, fp32=True).to(dev), bf, args.rays, **kw)
     if w == "vm":
         from pvd_b200.fused_vm import VMNeRFField
         return VMTrainEngine(VMNeRFField(resolution0=300).to(dev), bf, args.rays, l1_reg_weight=L1_REG, **kw)
@@ -297,6 +302,9 @@ def roofline_kernels(eng):
     if o.kind == "mlp":
         out.append(("k_mlp_field_fwd", "field_fwd", "tensor", MLP_FLOPS_PER_SAMPLE))
         out.append(("k_mlp_trunk_bwd+k_mlp_wgrad", "field_bwd", "tensor", MLP_BWD_FLOPS_PER_SAMPLE))
+    elif o.kind == "hash" and o.fp32:
+        out.append(("k_hash_field_fwd_f32", "field_fwd", "hbm", fb))
+        out.append(("k_hash_field_bwd_f32", "field_bwd", "hbm", bb))
     elif o.kind == "hash":
         out.append(("k_hash_field_fwd", "field_fwd", "hbm", fb))
         if o.dx_ws is not None:
@@ -640,10 +648,12 @@ def measure_ours(args, workload, n_rays, rank, world, local, headline):
     out = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": t_ms / steps, "ms_per_step_percentiles": step_pct, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16", "data": "synthetic", "impl": "ours",
+        "dtype": "f32" if workload == "hash-fp32" else "f16", "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOADS[workload].format(L=L, R=n_rays), "workload_key": workload,
                    "rays_per_gpu": n_rays, "levels": L, "samples_per_step": S_mean, "M_rows": eng.M,
-                   "precision": "fp16 tcgen05 MLP (fp32 accumulate); trained hash table gathered as fp32 master, frozen teacher table / vm planes as fp16 shadows; fp32 composite / gradients", "loss_scale": 65536,
+                   "precision": ("fp32 end to end: fp32 table gather, fp32 MLPs on the CUDA cores, fp32 composite / gradients" if workload == "hash-fp32" else
+                                 "fp16 tcgen05 MLP (fp32 accumulate); trained hash table gathered as fp32 master, frozen teacher table / vm planes as fp16 shadows; fp32 composite / gradients"),
+                   "loss_scale": 65536,
                    "step": "fwd+bwd of a trainer with an external optimizer: fp16 table shadow re-cast + weight tiles re-packed at the top of "
                            "EVERY timed step, small weight gradients unpacked to parameter shapes at its end" + ("; gradient exchange inside" if world > 1 else ""),
                    "parallelism": (f"rays sharded over {world} GPU(s), one all-reduce of the gradients per step inside the step graph ({exchange.kind}: "
@@ -688,7 +698,7 @@ def run_ours(args, rank, world, local):
     others = {}
     if args.all_workloads:
         for w in ALL_WORKLOADS:
-            if w == args.workload or (w == "mlp" and world > 1):   # mlp training is not a BASELINE config: reported on one GPU only
+            if w == args.workload or (w in ONE_GPU_ONLY and world > 1):
                 continue
             try:
                 r = measure_ours(args, w, DEFAULT_RAYS[w], rank, world, local, headline=False)
@@ -739,6 +749,8 @@ def build_reference(args, dev, ext, bitfield):
     w = args.workload
     if w == "hash":
         return rp.RefTrainer(ext, hash_net(), bf)
+    if w == "hash-fp32":
+        return rp.RefTrainer(ext, hash_net(), bf, autocast=False)
     if w == "vm":
         return rp.RefTrainer(ext, rp.RefVmNetwork(ext).to(dev), bf, l1_reg_weight=L1_REG)
     if w == "hash-vm":
@@ -815,7 +827,7 @@ def measure_reference(args, workload, n_rays, local, ext, steps):
     clocks = sampler.stop()
     rays_total = n_rays * steps
     cfg = {"workload": WORKLOADS[workload].format(L=args.levels, R=n_rays), "workload_key": workload, "rays_per_gpu": n_rays, "levels": args.levels,
-           "M_rows": tr.mean_count + (128 - tr.mean_count % 128), "precision": "torch autocast fp16 (the reference's -O default), GradScaler-style loss scale 65536",
+           "M_rows": tr.mean_count + (128 - tr.mean_count % 128), "precision": ("fp32 (the reference without --fp16)" if workload == "hash-fp32" else "torch autocast fp16 (the reference's -O default), GradScaler-style loss scale 65536"),
            "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)", "scene_bitfield_sha256": sha[:16],
            "what": "unmodified reference CUDA extensions (oracle/_ref, sm_100a rebuild) + cuBLAS GEMMs via F.linear + F.grid_sample + torch "
                    "autograd, Python flow restated in oracle/ref_pipeline.py"}

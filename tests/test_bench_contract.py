@@ -46,7 +46,7 @@ def test_our_arm_has_no_cpu_path():
 def test_roofline_tables_cover_every_workload():
     sys.path.insert(0, ROOT)
     import bench
-    assert set(bench.WORKLOADS) == {"hash", "vm", "hash-vm", "mlp-hash", "mlp"} == set(bench.DEFAULT_RAYS) == set(bench.ALL_WORKLOADS)
+    assert set(bench.WORKLOADS) == {"hash", "vm", "hash-vm", "mlp-hash", "mlp", "hash-fp32"} == set(bench.DEFAULT_RAYS) == set(bench.ALL_WORKLOADS)
     t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
     for k in ("k_hash_field_fwd", "k_hash_field_bwd", "k_vm_field_fwd", "k_vm_field_bwd", "k_vm_scatter", "k_mlp_field_fwd", "k_pair_composite"):
         assert k in t and t[k]["dram_bytes"] > 0 and t[k]["source"].startswith("profiles/") and os.path.exists(os.path.join(ROOT, t[k]["source"])), k
