@@ -60,7 +60,7 @@ __device__ __forceinline__ void stage_weights_f32(float* sw, const F32Args& a, b
 }
 
 // out[o] = sum_k Wt[k][o] * in[k][tid]   for o in [0, OUT), OUT a multiple of 16 (or 4): accumulation in input order
-template <uint32_t K, uint32_t OUT, bool RELU>
+template <uint32_t K, uint32_t OUT, bool RELU, uint32_t LD = kLD>
 __device__ __forceinline__ void layer_fwd(const float* __restrict__ wt, const float* __restrict__ in, float* __restrict__ outp, uint32_t tid) {
     constexpr uint32_t OB = OUT < 16 ? OUT : 16;
 #pragma unroll 1
@@ -70,7 +70,7 @@ __device__ __forceinline__ void layer_fwd(const float* __restrict__ wt, const fl
         for (uint32_t i = 0; i < OB; ++i) acc[i] = 0.0f;
 #pragma unroll 4
         for (uint32_t k = 0; k < K; ++k) {
-            const float x = in[k * kLD + tid];
+            const float x = in[k * LD + tid];
 #pragma unroll
             for (uint32_t i = 0; i < OB; i += 4) {
                 const float4 w = *reinterpret_cast<const float4*>(wt + k * OUT + ob + i);
@@ -81,7 +81,7 @@ __device__ __forceinline__ void layer_fwd(const float* __restrict__ wt, const fl
             }
         }
 #pragma unroll
-        for (uint32_t i = 0; i < OB; ++i) outp[(ob + i) * kLD + tid] = RELU ? fmaxf(acc[i], 0.0f) : acc[i];
+        for (uint32_t i = 0; i < OB; ++i) outp[(ob + i) * LD + tid] = RELU ? fmaxf(acc[i], 0.0f) : acc[i];
     }
 }
 
@@ -164,6 +164,7 @@ struct F32Tile {   // shared-memory column blocks of one tile (floats)
 };
 
 // forward of this thread's sample into the tile's column blocks; returns sigma (scaled), rgb, o16 (channel 0 clamped), raw o0
+template <uint32_t LD = kLD>
 __device__ __forceinline__ void f32_forward(const F32Args& a, const float* sw, const F32Tile& t, uint32_t lv_saddr, const float (&pos)[3],
                                             const float (&dir)[3], bool live, uint32_t tid, float& sigma, float (&rgb)[3], float (&o16)[16],
                                             float& o0_raw) {
@@ -174,12 +175,12 @@ __device__ __forceinline__ void f32_forward(const F32Args& a, const float* sw, c
         float f[8];
         encode4<float>(a.table, lv_saddr, l0, a.L, x01, oob || !live, f);
 #pragma unroll
-        for (uint32_t i = 0; i < 8; ++i) t.X[(2 * l0 + i) * kLD + tid] = f[i];
+        for (uint32_t i = 0; i < 8; ++i) t.X[(2 * l0 + i) * LD + tid] = f[i];
     }
-    layer_fwd<32, 64, true>(sw + kT1, t.X, t.H1, tid);
-    layer_fwd<64, 16, false>(sw + kT2, t.H1, t.G16, tid);     // G16 doubles as the 16-wide sigma_net output column block
+    layer_fwd<32, 64, true, LD>(sw + kT1, t.X, t.H1, tid);
+    layer_fwd<64, 16, false, LD>(sw + kT2, t.H1, t.G16, tid);     // G16 doubles as the 16-wide sigma_net output column block
 #pragma unroll
-    for (uint32_t i = 0; i < 16; ++i) o16[i] = t.G16[i * kLD + tid];
+    for (uint32_t i = 0; i < 16; ++i) o16[i] = t.G16[i * LD + tid];
     o0_raw = o16[0];
     const float o0c = clampf(o16[0], a.clip_min, a.clip_max);  // network.py:418-420
     o16[0] = o0c;
@@ -187,18 +188,20 @@ __device__ __forceinline__ void f32_forward(const F32Args& a, const float* sw, c
     float sh[16];
     sh_basis4(dir[0], dir[1], dir[2], sh);
 #pragma unroll
-    for (uint32_t i = 0; i < 16; ++i) t.CIN[i * kLD + tid] = sh[i];
+    for (uint32_t i = 0; i < 16; ++i) t.CIN[i * LD + tid] = sh[i];
 #pragma unroll
-    for (uint32_t i = 0; i < 15; ++i) t.CIN[(16 + i) * kLD + tid] = o16[i + 1];
-    t.CIN[31 * kLD + tid] = 0.0f;
-    layer_fwd<32, 64, true>(sw + kT3, t.CIN, t.H3, tid);
-    layer_fwd<64, 64, true>(sw + kT4, t.H3, t.H4, tid);
-    layer_fwd<64, 4, false>(sw + kT5, t.H4, t.G5, tid);
+    for (uint32_t i = 0; i < 15; ++i) t.CIN[(16 + i) * LD + tid] = o16[i + 1];
+    t.CIN[31 * LD + tid] = 0.0f;
+    layer_fwd<32, 64, true, LD>(sw + kT3, t.CIN, t.H3, tid);
+    layer_fwd<64, 64, true, LD>(sw + kT4, t.H3, t.H4, tid);
+    layer_fwd<64, 4, false, LD>(sw + kT5, t.H4, t.G5, tid);
 #pragma unroll
-    for (uint32_t i = 0; i < 3; ++i) rgb[i] = 1.0f / (1.0f + expf(-t.G5[i * kLD + tid]));
+    for (uint32_t i = 0; i < 3; ++i) rgb[i] = 1.0f / (1.0f + expf(-t.G5[i * LD + tid]));
 }
 
-__global__ void __launch_bounds__(kB) k_hash_field_fwd_f32(F32Args a, const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M,
+// forward: 256 samples per block (8 warps per SM; the column blocks of 256 samples + the weights fill the SM's shared memory)
+constexpr uint32_t kBF = 256, kLDF = kBF + 4;
+__global__ void __launch_bounds__(kBF) k_hash_field_fwd_f32(F32Args a, const float* __restrict__ xyzs, const float* __restrict__ dirs, uint32_t M,
                                                           float* __restrict__ sigmas, float* __restrict__ rgbs, float* __restrict__ feat16) {
     extern __shared__ __align__(16) float smf[];
     __shared__ LevelInfo lv[16];
@@ -206,18 +209,18 @@ __global__ void __launch_bounds__(kB) k_hash_field_fwd_f32(F32Args a, const floa
     float* col = smf + kTEnd;
     F32Tile t;
     t.X = col; t.CIN = col;                           // 32 rows, CIN over X (dead after sigma_net.0)
-    t.H1 = col + 32 * kLD; t.H3 = t.H1;               // 64 rows
-    t.H4 = t.H1 + 64 * kLD;                           // 64 rows
-    t.G16 = t.H4 + 64 * kLD;                          // 16 rows
-    t.G5 = t.G16 + 16 * kLD;                          // 4 rows
+    t.H1 = col + 32 * kLDF; t.H3 = t.H1;               // 64 rows
+    t.H4 = t.H1 + 64 * kLDF;                           // 64 rows
+    t.G16 = t.H4 + 64 * kLDF;                          // 16 rows
+    t.G5 = t.G16 + 16 * kLDF;                          // 4 rows
     const uint32_t tid = threadIdx.x;
     stage_weights_f32(sw, a, false);
     level_info_init(lv, a.offsets, a.L, a.S, a.H);
     __syncthreads();
     const uint32_t lv_saddr = (uint32_t)__cvta_generic_to_shared(lv);
-    const uint32_t n_tiles = (M + kB - 1) / kB;
+    const uint32_t n_tiles = (M + kBF - 1) / kBF;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t row = tile * kB + tid;
+        const uint32_t row = tile * kBF + tid;
         const bool live = row < M;
         float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         if (live) {
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kB) k_hash_field_fwd_f32(F32Args a, const floa
             }
         }
         float sigma, rgb[3], o16[16], o0_raw;
-        f32_forward(a, sw, t, lv_saddr, pos, dir, live, tid, sigma, rgb, o16, o0_raw);   // thread-private columns: no barrier needed
+        f32_forward<kLDF>(a, sw, t, lv_saddr, pos, dir, live, tid, sigma, rgb, o16, o0_raw);   // thread-private columns: no barrier needed
         if (live) {
             sigmas[row] = sigma;
             rgbs[3 * (size_t)row] = rgb[0]; rgbs[3 * (size_t)row + 1] = rgb[1]; rgbs[3 * (size_t)row + 2] = rgb[2];
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(kB, 1) k_hash_field_bwd_f32(F32Args a, const f
     }
 }
 
-constexpr size_t kF32FwdSmem = (kTEnd + (32 + 64 + 64 + 16 + 4) * kLD) * sizeof(float);              // 132 928
+constexpr size_t kF32FwdSmem = (kTEnd + (32 + 64 + 64 + 16 + 4) * kLDF) * sizeof(float);             // 225 088
 constexpr size_t kF32BwdSmem = (kOEnd + (32 + 64 + 32 + 64 + 64 + 16 + 4) * kLD) * sizeof(float);    // 221 504
 
 static F32Args to_f32_args(const PvdHashField* f, const PvdFieldWeightsF32* w) {
@@ -426,8 +429,8 @@ int pvd_hash_field_forward_f32(const PvdHashField* f, const PvdFieldWeightsF32* 
     const F32Args a = to_f32_args(f, w);
     cudaError_t e = cudaFuncSetAttribute(k_hash_field_fwd_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF32FwdSmem);
     if (e != cudaSuccess) return (int)e;
-    const uint32_t tiles = (M + kB - 1) / kB, grid = min(tiles, (uint32_t)sm_count());
-    k_hash_field_fwd_f32<<<grid, kB, kF32FwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16);
+    const uint32_t tiles = (M + kBF - 1) / kBF, grid = min(tiles, (uint32_t)sm_count());
+    k_hash_field_fwd_f32<<<grid, kBF, kF32FwdSmem, (cudaStream_t)stream>>>(a, xyzs, dirs, M, sigmas, rgbs, feat16);
     PVD_LAUNCH_CHECK();
     return PVD_OK;
 }

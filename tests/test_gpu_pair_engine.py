@@ -275,3 +275,46 @@ def test_pair_engine_graph_and_pipeline_equal_eager(scene):
     assert abs(float(eng.loss[0]) - loss) < 1e-5 * loss
     for k, v in eng.grads().items():
         assert _rel_l2(v, want[k]) < 1e-3, k
+
+
+def test_pair_engine_hash_to_mlp(scene):
+    """hash teacher -> NeRF-MLP STUDENT (INGP -> NeRF, one of the paper's conversions): the student's backward is the fused mlp
+    backward (csrc/field_mlp_bwd.cu) driven by the pair losses, including d(loss)/d(feature_sigma_color).  Checked against the
+    oracle's pair step with the same loss scale; the bound per tensor is 3e-2 or 1.25 x the deviation of the oracle's OWN fp16
+    model from its fp32 evaluation (the deep trunk amplifies fp16 rounding more than the two-layer heads do)."""
+    from oracle import field
+    from pvd_b200.engine import PairDistillEngine
+    from pvd_b200.fused import _Args
+    from pvd_b200.fused_mlp import MLPNeRFField
+    tea = _hash_net(21, True)
+    torch.manual_seed(22)
+    stu = MLPNeRFField(args=_Args(), is_teacher=False).cuda()
+    ro, rd = scene["batches"][1]
+    ro, rd = ro[:384].contiguous(), rd[:384].contiguous()
+    scale = 4096.0
+    eng = PairDistillEngine(tea, stu, torch.from_numpy(scene["bitfield"]), 384, rates=RATES, stage=3, loss_scale=scale)
+    _run_engine(eng, ro.cuda(), rd.cuda())
+    f_t, _ = _hash_oracle(tea, False)
+
+    def oracle_grads(q):
+        nw = [l.weight.detach().cpu().clone().requires_grad_(True) for l in stu.nerf_mlp]
+        nb = [l.bias.detach().cpu().clone().requires_grad_(True) for l in stu.nerf_mlp]
+        tw = [m.weight.detach().cpu().clone().requires_grad_(True) for m in list(stu.sigma_net) + list(stu.color_net)]
+        f_s = lambda x, d: field.mlp_field_forward(x, d, nw, nb, tw, quantize_fp16=q)
+        o = field.pair_distill_step(ro, rd, scene["bitfield"], f_s, f_t, RATES, stage=3, M=eng.M)
+        (o["loss"] * scale).backward()
+        named = {}
+        for i in range(8):
+            named[f"nerf_mlp.{i}.weight"], named[f"nerf_mlp.{i}.bias"] = nw[i].grad, nb[i].grad
+        for n, w in zip(("sigma_net.0", "sigma_net.1", "color_net.0", "color_net.1", "color_net.2"), tw):
+            named[n + ".weight"] = w.grad
+        return o, named
+
+    o16, g16 = oracle_grads(True)
+    _, g32 = oracle_grads(False)
+    assert abs(float(eng.loss[0]) - float(o16["loss"])) < 2e-2 * float(o16["loss"])
+    got = eng.grads()
+    assert set(got) == set(g32)
+    for k in g32:
+        ours, noise = _rel_l2(got[k], g32[k]), _rel_l2(g16[k], g32[k])
+        assert ours < max(3e-2, 1.25 * noise), f"{k}: ours vs fp32 oracle {ours:.3e}, fp16 oracle vs fp32 oracle {noise:.3e}"
