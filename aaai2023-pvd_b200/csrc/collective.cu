@@ -103,9 +103,10 @@ __device__ __forceinline__ void epoch_barrier(uint32_t* const* pads, uint32_t ra
 template <int UNROLL>
 __global__ void __launch_bounds__(256) k_multimem_allreduce_f16_fused(__half* __restrict__ mc, uint64_t first_vec, uint64_t n_vec,
                                                                       uint32_t* const* __restrict__ pads, uint32_t rank, uint32_t world,
-                                                                      uint32_t* __restrict__ local /* [0] flag, [1] done, [2] error */) {
+                                                                      uint32_t* __restrict__ local /* [0] flag, [1] done, [2] error, [3] epoch */) {
+    const uint32_t epoch0 = local[3];   // written only by block 0 at the very end of the previous launch: stable here
     if (blockIdx.x == 0) {
-        cross_rank_barrier(pads, rank, world, 8u, local + 2);
+        epoch_barrier(pads, rank, world, 12u, epoch0 + 1u, local + 2);   // every rank's payload is written (its cast precedes its kernel)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -158,9 +159,10 @@ __global__ void __launch_bounds__(256) k_multimem_allreduce_f16_fused(__half* __
             __threadfence_system();
         }
         __syncthreads();
-        cross_rank_barrier(pads, rank, world, 9u, local + 2);
+        epoch_barrier(pads, rank, world, 12u, epoch0 + 2u, local + 2);   // every rank's multicast stores are issued and fenced
         __syncthreads();
         if (threadIdx.x == 0) {
+            local[3] = epoch0 + 2u;
             local[1] = 0u;
             __threadfence();
             local[0] = 0u;
@@ -335,7 +337,7 @@ int pvd_multimem_allreduce_f16_fused(void* multicast_ptr, uint64_t elem_offset, 
     PVD_REQUIRE((elem_offset % 8u) == 0 && (elem_count % 8u) == 0 && world >= 1 && world <= 32 && rank < world);
     PVD_REQUIRE((reinterpret_cast<uintptr_t>(multicast_ptr) & 15u) == 0);
     const uint64_t n_vec = elem_count / 8u;
-    uint32_t grid = blocks ? blocks : 148u * 4u;
+    uint32_t grid = blocks ? blocks : 64u;   // measured on 4 and 8 GPUs: 32-64 CTAs x unroll 2-4 (scripts/micro/exchange_probe.py)
     grid = max(1u, min(grid, 148u * 8u));
     uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pad_ptrs_dev);
     cudaStream_t st = (cudaStream_t)stream;

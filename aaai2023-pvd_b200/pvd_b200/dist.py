@@ -96,7 +96,7 @@ class TableGradExchange:
 
     Kinds: "nccl" (cast kernel + ncclAllReduce of the payload); "p2p" (the payload lives in a torch symmetric-memory buffer; each
     rank loads ITS 1/W shard from every rank over NVLink, sums in fp32 and stores the result into every rank's buffer -- one kernel,
-    device-side barriers, csrc/collective.cu::k_p2p_allreduce_f16; what mode "auto" picks on 2 / 4 / 8 ranks); "multimem" (the same
+    device-side barriers, csrc/collective.cu::k_p2p_allreduce_f16; what mode "auto" picks on 2 / 4 ranks); "multimem" (what "auto" picks on 8: the same
     shard reduced BY THE SWITCH through the buffer's multicast address, multimem.ld_reduce / multimem.st, barriers inside the kernel
     (`fused_barrier`) or as two signal-pad launches).  Anything that does not set up falls back to NCCL with the same result layout.
     """
@@ -130,16 +130,27 @@ class TableGradExchange:
                 self._bufs = int(getattr(hdl, "buffer_ptrs_dev", 0) or 0)
                 self._local = torch.zeros(4, dtype=torch.int32, device=grad_table.device)
                 mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-                want_p2p = mode == "p2p" or (mode == "auto" and self.world in (2, 4, 8))
-                if want_p2p:
-                    if not (self._pads and self._bufs and self.world in (2, 4, 8)):
-                        raise RuntimeError("peer pointers / signal pads not exposed by this torch, or world not in (2, 4, 8)")
-                    # the kernel's barriers are monotonic epoch flags in slots [12W, 13W) of the signal pads, counted from this
+                # "auto": measured totals (cast + kernel + small, scripts/micro/exchange_probe.py, profiles/r02_exchange_probe_N*):
+                # 2 ranks p2p 73 vs multimem 98 us; 4 ranks 85 vs 88; 8 ranks 98 vs 90 -- the switch reduction wins once 7/8 of the
+                # payload would have to cross the links in both directions
+                p2p_ok = bool(self._pads and self._bufs and self.world in (2, 4, 8))
+                mm_ok = bool(mc and self._pads)
+                if mode == "auto":
+                    want_p2p = p2p_ok and not (self.world >= 8 and mm_ok)
+                    if not want_p2p and not mm_ok:
+                        raise RuntimeError("neither peer pointers nor a multicast mapping are available")
+                else:
+                    want_p2p = mode == "p2p"
+                if self._pads:
+                    # the kernels' barriers are monotonic epoch flags in slots [12W, 13W) of the signal pads, counted from this
                     # rank's local[3] = 0: start from zeroed slots on every rank (a pad may be recycled from an earlier buffer)
                     pad = hdl.get_signal_pad(self.rank)
                     pad.view(-1).view(torch.int32)[12 * self.world:13 * self.world].zero_()
                     torch.cuda.synchronize(grad_table.device)
                     dist.barrier(group=self.group)
+                if want_p2p:
+                    if not p2p_ok:
+                        raise RuntimeError("peer pointers / signal pads not exposed by this torch, or world not in (2, 4, 8)")
                     self.kind = "p2p"
                 else:
                     if mc == 0:
@@ -147,6 +158,8 @@ class TableGradExchange:
                     if self._pads == 0:
                         self.fused_barrier = False
                     self.kind = "multimem"
+                    if self.blocks == 0:
+                        self.blocks, self.unroll = 64, 2
                 self.payload, self._hdl, self._mc = buf, hdl, mc
             except Exception as ex:  # noqa: BLE001  (any failure: NCCL carries the exchange)
                 self.why = repr(ex)[:160]
