@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: bash scripts/_scale.sh N   (bench.py exactly as the driver launches it for N GPUs)
+# usage: bash scripts/scale_run.sh N   (bench.py exactly as the driver launches it for N GPUs)
 N=$1; O=gpurun_out; mkdir -p $O
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N --steps 50 --warmup 10 > $O/r02b_bench_ours_N$N.json 2> $O/bench_N$N.err
 tail -3 $O/bench_N$N.err
