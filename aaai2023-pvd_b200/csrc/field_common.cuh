@@ -18,6 +18,8 @@ struct Pipe {
     uint32_t wphase = 0;       // parity of `wbar` to wait for
     uint32_t team = 0;         // 0: the whole CTA works on one tile (barrier 0, leader = thread 0); n > 0: a 128-thread warpgroup
                                // works on its own tile (named barrier n, leader = the warpgroup's first thread)
+    bool dead = false;         // a bounded wait of this thread has timed out: later waits poll once instead of 2^22 times, so a wedged
+                               // pipeline costs one long wait per thread, not one per layer
 };
 
 __device__ __forceinline__ bool team_leader(const Pipe& p) { return p.team ? ((threadIdx.x & 127u) == 0u) : (threadIdx.x == 0u); }
@@ -37,7 +39,10 @@ __device__ __forceinline__ void operands_ready(const Pipe& p) {
 }
 // Every thread: wait for the MMAs committed by thread 0.
 __device__ __forceinline__ void mma_wait(Pipe& p) {
-    if (!tc5::mbar_wait(p.bar, p.phase)) atomicExch(p.status, 1);
+    if (!tc5::mbar_wait(p.bar, p.phase, p.dead ? 1u : (1u << 22))) {
+        p.dead = true;
+        atomicExch(p.status, 1);
+    }
     p.phase ^= 1u;
     tc5::fence_after_sync();
 }
@@ -121,7 +126,10 @@ __device__ __forceinline__ void flush_acc(uint32_t tmem_base, uint32_t col, uint
 // core reads shared memory through the async proxy, the same proxy TMA wrote it through: no proxy fence is needed.
 __device__ __forceinline__ void weights_ready(Pipe& p) {
     if (p.wbar != nullptr) {
-        if (!tc5::mbar_wait(p.wbar, p.wphase)) atomicExch(p.status, 1);
+        if (!tc5::mbar_wait(p.wbar, p.wphase, p.dead ? 1u : (1u << 22))) {
+            p.dead = true;
+            atomicExch(p.status, 1);
+        }
         p.wbar = nullptr;
     }
 }
