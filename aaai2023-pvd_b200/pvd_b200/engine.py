@@ -36,6 +36,7 @@ _u32, _f32 = C.c_uint32, C.c_float
 # opt-in experiment (measured SLOWER on B200, 0.129 vs 0.120 ms/step: the full-occupancy scatter CTAs crowd out the MLP CTAs of the
 # other half instead of overlapping with them); the default issues MLP backward and scatter back to back on one stream
 SPLIT_HALVES = os.environ.get("PVD_SPLIT_HALVES", "0") == "1"
+LOSS_D2H_EARLY = os.environ.get("PVD_LOSS_D2H_EARLY", "1") != "0"   # host-fed graphs: read the loss back beside the backward
 
 
 @contextlib.contextmanager
@@ -398,13 +399,21 @@ class FieldTrainEngine:
             march_branch()
         cur.wait_stream(self._side)    # before the loss kernel (see step()): the backward follows it as a programmatic dependent launch
         self._loss_backward(st, rs, M, M)
+        if host_io and LOSS_D2H_EARLY:
+            # the loss words are final once the loss kernel has run: their D2H copy goes on a side branch, beside the field backward,
+            # instead of between the backward and the epilogue on the critical path
+            self._side3.wait_stream(cur)
+            with torch.cuda.stream(self._side3):
+                self.host_loss.copy_(self._loss_dev(), non_blocking=True)
         self._field_backward(st, rs, M, cur)
-        if host_io:
+        if host_io and not LOSS_D2H_EARLY:
             self.host_loss.copy_(self._loss_dev(), non_blocking=True)
         if where == "exchange":
             march_branch()
         self._epilogue(st)
         cur.wait_stream(self._side2)
+        if host_io and LOSS_D2H_EARLY:
+            cur.wait_stream(self._side3)
 
     def capture_pipelined(self, host_io: bool = False):
         """Two graphs (even / odd steps).  Protocol: write batch 0 into sets[0], call march(0); then for step i write batch i+1
