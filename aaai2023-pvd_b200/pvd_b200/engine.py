@@ -36,6 +36,7 @@ _u32, _f32 = C.c_uint32, C.c_float
 # opt-in experiment (measured SLOWER on B200, 0.129 vs 0.120 ms/step: the full-occupancy scatter CTAs crowd out the MLP CTAs of the
 # other half instead of overlapping with them); the default issues MLP backward and scatter back to back on one stream
 SPLIT_HALVES = os.environ.get("PVD_SPLIT_HALVES", "0") == "1"
+PACK_LAST = os.environ.get("PVD_PACK_LAST", "1") != "0"             # weight-pack kernel immediately before the forward (PDL edge)
 LOSS_D2H_EARLY = os.environ.get("PVD_LOSS_D2H_EARLY", "1") != "0"   # host-fed graphs: read the loss back beside the backward
 
 
@@ -275,6 +276,8 @@ class FieldTrainEngine:
                 self._prefetch(C.c_void_p(self._side.cuda_stream))
             if self.optimizer is None:   # a fused optimizer leaves the big gradient buffer zeroed (same pass as the update)
                 self.ops.clear_grads()
+                if self.unpack_each_step:    # the parameter-shaped weight gradients the epilogue's unpack kernel accumulates into
+                    self.ops.zero_weight_grads()
             if self.l1_reg_weight:
                 self.ops.regularise(C.c_void_p(self._side.cuda_stream), self.loss_scale, self.loss_slots, self.l1_reg_weight)
 
@@ -308,10 +311,15 @@ class FieldTrainEngine:
         self.ops.prefetch(st)
 
     def _prologue(self, cur):
-        if self.restage_each_step and self.optimizer is None:
+        restage = self.restage_each_step and self.optimizer is None
+        if restage and not PACK_LAST:
             self.ops.stage(self.density_scale)     # trainable parameters only: a frozen teacher stays staged
         self._zeros.zero_()                    # loss, weight-gradient workspace
         self._clear_big(cur)
+        if restage and PACK_LAST:
+            # the pack kernel LAST: the field forward then follows a KERNEL in stream order and starts as its programmatic dependent
+            # (it gathers its first tile while the tiles are packed); behind a memset node the launch is an ordinary full dependency
+            self.ops.stage(self.density_scale)
 
     def _epilogue(self, st):
         """After the backward: gradient exchange (multi-GPU), then either the fused optimizer or -- for an external optimizer -- the
@@ -321,7 +329,7 @@ class FieldTrainEngine:
         if self.optimizer is not None:
             self.optimizer.step()
         elif self.unpack_each_step:
-            self.ops.unpack_weight_grads(self.gw_ws, st)
+            self.ops.unpack_weight_grads(self.gw_ws, st, zero=False)   # zeroed on the memset branch (_clear_big), off the critical path
 
     def attach_optimizer(self, optimizer):
         """From here on every step ends with `optimizer.step()` (graphs must be captured afterwards)."""

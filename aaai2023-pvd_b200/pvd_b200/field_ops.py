@@ -46,9 +46,14 @@ class HashOps:
         f = self.field
         return (f.sigma_net[0].weight, f.sigma_net[1].weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
 
-    def unpack_weight_grads(self, gw_ws, st):
-        """gw_ws (kernel-native, 16 replicas) -> self.wgrads (parameter shapes); two nodes: memset + k_unpack_wgrads."""
+    def zero_weight_grads(self):
         self._wflat.zero_()
+
+    def unpack_weight_grads(self, gw_ws, st, zero=True):
+        """gw_ws (kernel-native, 16 replicas) -> self.wgrads (parameter shapes): memset (unless the caller has zeroed them already,
+        `zero_weight_grads`, off the critical path) + k_unpack_wgrads, which accumulates."""
+        if zero:
+            self._wflat.zero_()
         nv.check(nv.lib().pvd_field_unpack_wgrads(nv.ptr(gw_ws), _u32(2 * self.cfg.num_levels), *[nv.ptr(g) for g in self.wgrads], st))
 
     def stage(self, density_scale=1.0):
@@ -191,8 +196,12 @@ class VmOps:
         f = self.field
         return (f.basis_mat.weight, f.color_net[0].weight, f.color_net[1].weight, f.color_net[2].weight)
 
-    def unpack_weight_grads(self, gw_ws, st):
+    def zero_weight_grads(self):
         self._wflat.zero_()
+
+    def unpack_weight_grads(self, gw_ws, st, zero=True):
+        if zero:
+            self._wflat.zero_()
         nv.check(nv.lib().pvd_vm_unpack_wgrads(nv.ptr(gw_ws), *[nv.ptr(g) for g in self.wgrads], st))
 
     def stage(self, density_scale=1.0):
@@ -395,9 +404,13 @@ class MlpOps:
     def regularise(self, st, loss_scale, loss_slots, weight):
         pass
 
-    def unpack_weight_grads(self, gw_ws, st):
-        """kernel-native workspaces -> self.wgrads (parameter shapes, NAMES order)."""
+    def zero_weight_grads(self):
         self._wflat.zero_()
+
+    def unpack_weight_grads(self, gw_ws, st, zero=True):
+        """kernel-native workspaces -> self.wgrads (parameter shapes, NAMES order)."""
+        if zero:
+            self._wflat.zero_()
         nv.check(nv.lib().pvd_mlp_unpack_wgrads(nv.ptr(self.gw_mlp), nv.ptr(self._gwp), nv.ptr(self._gbp), st))
         nv.check(nv.lib().pvd_field_unpack_wgrads(nv.ptr(gw_ws), _u32(self.field.in_dim), *[nv.ptr(g) for g in self.wgrads[16:]], st))
 
@@ -463,7 +476,10 @@ class TensorsOps:
     def regularise(self, st, loss_scale, loss_slots, weight):
         pass
 
-    def unpack_weight_grads(self, gw_ws, st):
+    def zero_weight_grads(self):
+        pass
+
+    def unpack_weight_grads(self, gw_ws, st, zero=True):
         pass
 
     def weight_grads(self, gw_ws):
