@@ -112,3 +112,25 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert l.pvd_vm_field_backward(None, None, None, None, None, None, None, u32(0), None, None, None, None) == 0
     assert l.pvd_mlp_field_forward(None, None, None, u32(0), None, None, None, None, None) == 0
     assert l.pvd_hash_field_backward(None, None, None, None, None, None, None, u32(0), None, None, None, None, None, None) == 0
+
+
+def test_python_constants_match_the_header():
+    """Sizes the host side allocates by (pvd_b200/fused*.py) are the header's #defines, not copies that can drift."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "pvd_b200_fused.h")).read()
+
+    def define(name):
+        m = re.search(rf"#define\s+{name}\s+(.+)", hdr)
+        assert m, name
+        expr = re.sub(r"(\d+)u\b", r"\1", m.group(1).split("/*")[0].strip())
+        return int(eval(expr, {"__builtins__": {}}, {}))
+
+    from pvd_b200 import fused, fused_mlp
+    assert fused.WBLOB_BYTES == define("PVD_FIELD_WBLOB_BYTES")
+    assert fused.GW_WS_FLOATS == define("PVD_FIELD_GW_FLOATS") * define("PVD_FIELD_GW_COPIES")
+    assert fused.LOSS_SLOTS == define("PVD_LOSS_SLOTS")
+    assert fused_mlp.MLP_WBLOB_BYTES == define("PVD_MLP_WBLOB_BYTES")
+    assert fused_mlp.MLP_WBLOB_T_BYTES == define("PVD_MLP_WBLOB_T_BYTES")
+    assert fused_mlp.MLP_SAVE_TILE_BYTES == define("PVD_MLP_SAVE_TILE_BYTES")
+    assert fused_mlp.MLP_GRAD_TILE_BYTES == define("PVD_MLP_GRAD_TILE_BYTES")
+    assert fused_mlp.MLP_GW_FLOATS == define("PVD_MLP_GW_FLOATS")
